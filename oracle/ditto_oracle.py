@@ -1,0 +1,337 @@
+"""CPU oracle for the DiTTo-TTS DiT denoiser hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-PyTorch (CPU, fp32 or fp64) restatement of the reference
+algorithm.  It is the *checker*: only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The
+product path (``ditto_tts_b200``) never imports anything from ``oracle/`` and
+fails loudly when the CUDA library is missing.
+
+Parity status: PINNED.  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so the pin is "outputs of the reference itself run here":
+``tests/golden/make_golden.py`` imports the unmodified reference modules from
+``/root/reference/src`` (NAC stubbed), runs them on seeded
+weights/inputs and stores the results under ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks this restatement against those fixtures
+(fp32: rel-L2 <= 2e-6, i.e. re-association noise only).
+
+Every function cites the reference file:line it follows
+(paths relative to the reference repo root).
+
+All tensors: x [n,T,H], text_emb [n,S,text_dim], t [n] int64.  ``sd`` is a
+state_dict with the reference's key names.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+@dataclass(frozen=True)
+class OracleConfig:
+    """Shapes of one DiTTO instance.  Defaults = ConfigDiTTO, src/utils/Config.py:109-116."""
+
+    hidden_dim: int = 768
+    num_layers: int = 5
+    num_heads: int = 1
+    time_dim: int = 256
+    text_dim: int = 768
+    diffusion_steps: int = 1000
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_dim // self.num_heads
+
+
+# --------------------------------------------------------------------------
+# schedule  (src/model/DiTTO.py:96-104, src/model/SpeechGenerator.py:70-72)
+# --------------------------------------------------------------------------
+def cosine_beta_schedule(timesteps: int, s: float = 0.008) -> Tensor:
+    """Returns the clipped *betas* (the reference's name notwithstanding).  DiTTO.py:96-104."""
+    steps = timesteps + 1
+    x = torch.linspace(0, timesteps, steps)
+    alphas_cumprod = torch.cos(((x / timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+    alphas_cumprod = alphas_cumprod / alphas_cumprod[0]
+    betas = 1 - (alphas_cumprod[1:] / alphas_cumprod[:-1])
+    return torch.clip(betas, 0.0001, 0.9999)
+
+
+def sampler_tables(timesteps: int):
+    """betas, alphas, alphas_cumprod as the sampler builds them.  SpeechGenerator.py:70-72."""
+    betas = cosine_beta_schedule(timesteps)
+    alphas = 1.0 - betas
+    alphas_cumprod = torch.cumprod(alphas, dim=0)
+    return betas, alphas, alphas_cumprod
+
+
+# --------------------------------------------------------------------------
+# components  (src/components/DiT.py)
+# --------------------------------------------------------------------------
+def rotary_angles(seq_len: int, head_dim: int, dtype=torch.float32) -> Tensor:
+    """RotaryEmbedding.__init__ + forward: [T, head_dim] angles = cat(freqs, freqs).  DiT.py:46-59."""
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, head_dim, 2).float() / head_dim))  # DiT.py:49 (fp32 buffer)
+    inv_freq = inv_freq.to(dtype)
+    t = torch.arange(seq_len).to(dtype)                                            # DiT.py:57
+    freqs = torch.einsum("i,j->ij", t, inv_freq)                                   # DiT.py:58
+    return torch.cat((freqs, freqs), dim=-1)                                       # DiT.py:59
+
+
+def rotate_half(x: Tensor) -> Tensor:
+    """DiT.py:52-54."""
+    x1, x2 = x.chunk(2, dim=-1)
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rope(pos: Tensor, t: Tensor) -> Tensor:
+    """t: [n, T, heads, d]; pos: [T, d].  DiT.py:61-72."""
+    pos = pos.unsqueeze(0).unsqueeze(2)
+    return t * pos.cos() + rotate_half(t) * pos.sin()
+
+
+def global_adaln(sd: Dict[str, Tensor], x: Tensor, time_emb: Tensor, text_emb: Tensor) -> Tensor:
+    """GlobalAdaLN.forward.  DiT.py:25-40."""
+    text_mean = torch.mean(text_emb, dim=1)                                                       # :27
+    tm = F.linear(F.silu(time_emb), sd["ada_ln.time_mlp.1.weight"], sd["ada_ln.time_mlp.1.bias"])  # :30
+    xm = F.linear(F.silu(text_mean), sd["ada_ln.text_mlp.1.weight"], sd["ada_ln.text_mlp.1.bias"])  # :31
+    time_scale, time_shift = tm.chunk(2, dim=-1)
+    text_scale, text_shift = xm.chunk(2, dim=-1)
+    scale = 1 + time_scale + text_scale                                                           # :34
+    shift = time_shift + text_shift                                                               # :35
+    x = F.layer_norm(x, (x.shape[-1],), None, None, 1e-5)                                         # :38 (no affine)
+    return x * scale.unsqueeze(1) + shift.unsqueeze(1)                                            # :39
+
+
+def self_attention(sd, prefix: str, x: Tensor, rotary_pos: Tensor, num_heads: int) -> Tensor:
+    """LN1 -> manual q/k/v from attn.in_proj -> RoPE(q,k) -> softmax(qk^T/sqrt(d))v -> +residual.
+    No out_proj, no mask.  DiT.py:103-139."""
+    n, T, H = x.shape
+    d = H // num_heads
+    residual = x
+    u = F.layer_norm(x, (H,), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], 1e-5)  # :105
+    w = sd[prefix + "attn.in_proj_weight"]
+    b = sd[prefix + "attn.in_proj_bias"]
+    q = F.linear(u, w[:H], b[:H])                     # :112
+    k = F.linear(u, w[H:2 * H], b[H:2 * H])           # :113
+    v = F.linear(u, w[2 * H:], b[2 * H:])             # :114
+    q = q.reshape(n, T, num_heads, d)                 # :117-119 (einops 'b n (h d) -> b n h d')
+    k = k.reshape(n, T, num_heads, d)
+    v = v.reshape(n, T, num_heads, d)
+    q = apply_rope(rotary_pos, q)                     # :122
+    k = apply_rope(rotary_pos, k)                     # :123
+    q, k, v = (z.permute(0, 2, 1, 3) for z in (q, k, v))                # :126-128
+    scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(d)        # :131-132
+    attn = torch.softmax(scores, dim=-1)                                # :133
+    out = torch.matmul(attn, v)                                         # :134
+    out = out.permute(0, 2, 1, 3).reshape(n, T, H)                      # :137-138
+    return out + residual                                               # :139
+
+
+def cross_attention(sd, prefix: str, x: Tensor, text_emb: Tensor, num_heads: int) -> Tensor:
+    """LN2 -> nn.MultiheadAttention(q=x, k=v=text) math path (eval: dropout off) -> +residual.
+    DiT.py:141-148; torch/nn/functional.py multi_head_attention_forward, need_weights branch:
+    q is pre-scaled by sqrt(1/d), softmax over S, out_proj applied; the head-averaged
+    weights are computed and dropped by the caller ([0])."""
+    n, T, H = x.shape
+    S = text_emb.shape[1]
+    d = H // num_heads
+    residual = x
+    u = F.layer_norm(x, (H,), sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], 1e-5)  # :143
+    w = sd[prefix + "cross_attn.in_proj_weight"]
+    b = sd[prefix + "cross_attn.in_proj_bias"]
+    q = F.linear(u, w[:H], b[:H])
+    k = F.linear(text_emb, w[H:2 * H], b[H:2 * H])
+    v = F.linear(text_emb, w[2 * H:], b[2 * H:])
+    q = q.reshape(n, T, num_heads, d).permute(0, 2, 1, 3)
+    k = k.reshape(n, S, num_heads, d).permute(0, 2, 1, 3)
+    v = v.reshape(n, S, num_heads, d).permute(0, 2, 1, 3)
+    q = q * math.sqrt(1.0 / d)
+    attn = torch.softmax(torch.matmul(q, k.transpose(-2, -1)), dim=-1)
+    out = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(n, T, H)
+    out = F.linear(out, sd[prefix + "cross_attn.out_proj.weight"], sd[prefix + "cross_attn.out_proj.bias"])
+    return out + residual                                                                     # :148
+
+
+def gated_mlp(sd, prefix: str, x: Tensor) -> Tensor:
+    """LN3 -> fc2(GELU_erf(fc1(h)) * sigmoid(gate(h))) + residual.  DiT.py:150-155."""
+    H = x.shape[-1]
+    residual = x
+    u = F.layer_norm(x, (H,), sd[prefix + "norm3.weight"], sd[prefix + "norm3.bias"], 1e-5)  # :152
+    a = F.gelu(F.linear(u, sd[prefix + "mlp_fc1.weight"], sd[prefix + "mlp_fc1.bias"]))       # :153 (exact erf)
+    g = torch.sigmoid(F.linear(u, sd[prefix + "gate.weight"], sd[prefix + "gate.bias"]))      # :154
+    return F.linear(a * g, sd[prefix + "mlp_fc2.weight"], sd[prefix + "mlp_fc2.bias"]) + residual  # :155
+
+
+def dit_block(sd, i: int, x: Tensor, text_emb: Tensor, rotary_pos: Tensor, num_heads: int) -> Tensor:
+    """DiT.forward; time_emb is accepted and ignored by the reference.  DiT.py:100-157."""
+    p = f"blocks.{i}."
+    x = self_attention(sd, p, x, rotary_pos, num_heads)
+    x = cross_attention(sd, p, x, text_emb, num_heads)
+    return gated_mlp(sd, p, x)
+
+
+# --------------------------------------------------------------------------
+# model  (src/model/DiTTO.py)
+# --------------------------------------------------------------------------
+def time_embedding(sd, t: Tensor) -> Tensor:
+    """t_embedding lookup + time_embed MLP.  DiTTO.py:75-76 (params :37-44)."""
+    e = sd["t_embedding.weight"][t]
+    e = F.linear(e, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    e = F.silu(e)
+    return F.linear(e, sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+
+
+def ditto_forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, text_emb: Tensor, t: Tensor,
+                  taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """DiTTO.forward.  DiTTO.py:66-94.  ``taps`` (optional dict) receives intermediates for kernel tests."""
+    dtype = x.dtype
+    te = time_embedding(sd, t)                                             # :75-76
+    rotary_pos = rotary_angles(x.shape[1], cfg.head_dim, dtype)            # :79-80
+    x_skip = F.linear(x, sd["proj_in.weight"], sd["proj_in.bias"])         # :83
+    h = global_adaln(sd, x, te, text_emb)                                  # :86
+    if taps is not None:
+        taps["time_emb"] = te
+        taps["x_skip"] = x_skip
+        taps["adaln"] = h
+    for i in range(cfg.num_layers):                                        # :89-90
+        h = dit_block(sd, i, h, text_emb, rotary_pos, cfg.num_heads)
+        if taps is not None:
+            taps[f"block{i}"] = h
+    out = F.linear(h, sd["proj_out.weight"], sd["proj_out.bias"])          # :93
+    return x_skip + out                                                    # :94
+
+
+def q_sample(sd, x_start: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+    """DiTTO.q_sample incl. the reference quirk: the ``alphas_cumprod`` buffer holds the clipped
+    betas (DiTTO.py:63-64 registers cosine_beta_schedule's return value).  DiTTO.py:106-126."""
+    ac = sd["alphas_cumprod"][t.long()]
+    a = (ac ** 0.5).reshape(-1, 1, 1)
+    b = ((1 - ac) ** 0.5).reshape(-1, 1, 1)
+    return a * x_start + b * noise
+
+
+# --------------------------------------------------------------------------
+# sampler  (src/model/SpeechGenerator.py:131-164), plus the CFG extension
+# --------------------------------------------------------------------------
+def predict_noise(sd, cfg: OracleConfig, x: Tensor, text_emb: Tensor, t: Tensor,
+                  guidance_scale: Optional[float] = None, null_text_emb: Optional[Tensor] = None) -> Tensor:
+    """eps_hat.  Without guidance this is the reference call SpeechGenerator.py:135.
+    EXTENSION (not in the reference): classifier-free guidance
+    eps = eps_u + w (eps_c - eps_u), unconditional branch = zero text embedding unless given."""
+    eps_c = ditto_forward(sd, cfg, x, text_emb, t)
+    if guidance_scale is None:
+        return eps_c
+    null = torch.zeros_like(text_emb) if null_text_emb is None else null_text_emb
+    eps_u = ditto_forward(sd, cfg, x, null, t)
+    return eps_u + guidance_scale * (eps_c - eps_u)
+
+
+def p_sample_update(x: Tensor, noise_pred: Tensor, noise: Tensor, t: Tensor,
+                    betas: Tensor, alphas: Tensor, alphas_cumprod: Tensor) -> Tensor:
+    """The DDPM ancestral update, term by term as the reference writes it.  SpeechGenerator.py:137-147."""
+    beta_t = betas[t].view(-1, 1, 1)
+    alpha_t = alphas[t].view(-1, 1, 1)
+    alpha_cumprod_t = alphas_cumprod[t].view(-1, 1, 1)
+    mask = (t > 0).to(x.dtype).view(-1, 1, 1)
+    return (1 / torch.sqrt(alpha_t)) * (
+        x - (1 - alpha_t) / torch.sqrt(1 - alpha_cumprod_t) * noise_pred
+    ) + mask * torch.sqrt(beta_t) * noise
+
+
+def sample_latents(sd, cfg: OracleConfig, text_emb: Tensor, x_init: Tensor, noise: Tensor,
+                   guidance_scale: Optional[float] = None, record: Optional[List[Tensor]] = None) -> Tensor:
+    """__sample_latents: for t = steps-1 .. 0: x = p_sample(x, t).  SpeechGenerator.py:150-164.
+    ``noise`` [steps, B, T, H] replaces the reference's in-loop randn_like (index = t_val), so that
+    CPU and CUDA runs see the same draws.  ``record`` collects the per-step eps_hat."""
+    steps = cfg.diffusion_steps
+    betas, alphas, alphas_cumprod = (z.to(x_init.dtype) for z in sampler_tables(steps))
+    x = x_init
+    for t_val in reversed(range(steps)):                                       # :161
+        t = torch.full((x.shape[0],), t_val, dtype=torch.long)                 # :162
+        eps = predict_noise(sd, cfg, x, text_emb, t, guidance_scale)           # :135
+        if record is not None:
+            record.append(eps)
+        x = p_sample_update(x, eps, noise[t_val], t, betas, alphas, alphas_cumprod)  # :137-147
+    return x
+
+
+# --------------------------------------------------------------------------
+# deterministic synthetic weights (used by tests, bench and the golden script alike)
+# --------------------------------------------------------------------------
+def state_dict_keys(cfg: OracleConfig):
+    """(key, shape, kind) for every tensor of the reference DiTTO state_dict that the hot path reads
+    (SURVEY.md section 8b), plus the dead self-attn out_proj so that load_state_dict(strict) works."""
+    H, Td, Xd, L, St = cfg.hidden_dim, cfg.time_dim, cfg.text_dim, cfg.num_layers, cfg.diffusion_steps
+    ks = [("t_embedding.weight", (St, Td), "emb"),
+          ("time_embed.0.weight", (Td, Td), "w"), ("time_embed.0.bias", (Td,), "b"),
+          ("time_embed.2.weight", (Td, Td), "w"), ("time_embed.2.bias", (Td,), "b"),
+          ("ada_ln.time_mlp.1.weight", (2 * H, Td), "w"), ("ada_ln.time_mlp.1.bias", (2 * H,), "b"),
+          ("ada_ln.text_mlp.1.weight", (2 * H, Xd), "w"), ("ada_ln.text_mlp.1.bias", (2 * H,), "b")]
+    for i in range(L):
+        p = f"blocks.{i}."
+        ks += [(p + "norm1.weight", (H,), "g"), (p + "norm1.bias", (H,), "b"),
+               (p + "attn.in_proj_weight", (3 * H, H), "w"), (p + "attn.in_proj_bias", (3 * H,), "b"),
+               (p + "attn.out_proj.weight", (H, H), "w"), (p + "attn.out_proj.bias", (H,), "b"),
+               (p + "norm2.weight", (H,), "g"), (p + "norm2.bias", (H,), "b"),
+               (p + "cross_attn.in_proj_weight", (3 * H, H), "w"), (p + "cross_attn.in_proj_bias", (3 * H,), "b"),
+               (p + "cross_attn.out_proj.weight", (H, H), "w"), (p + "cross_attn.out_proj.bias", (H,), "b"),
+               (p + "norm3.weight", (H,), "g"), (p + "norm3.bias", (H,), "b"),
+               (p + "mlp_fc1.weight", (4 * H, H), "w"), (p + "mlp_fc1.bias", (4 * H,), "b"),
+               (p + "gate.weight", (4 * H, H), "w"), (p + "gate.bias", (4 * H,), "b"),
+               (p + "mlp_fc2.weight", (H, 4 * H), "w"), (p + "mlp_fc2.bias", (H,), "b")]
+    ks += [("proj_in.weight", (H, H), "w"), ("proj_in.bias", (H,), "b"),
+           ("proj_out.weight", (H, H), "w"), ("proj_out.bias", (H,), "b")]
+    return ks
+
+
+def make_state_dict(cfg: OracleConfig, seed: int = 0) -> Dict[str, Tensor]:
+    """Seeded random-init weights with torch-default-like scales (uniform +-1/sqrt(fan_in) for
+    matrices, N(0,1) embedding) but NON-trivial biases and LayerNorm affine parameters, so that a
+    dropped bias / gamma cannot hide.  Pure CPU torch.Generator => identical on every box."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    for key, shape, kind in state_dict_keys(cfg):
+        if kind == "emb":
+            v = torch.randn(shape, generator=g)
+        elif kind == "w":
+            bound = 1.0 / math.sqrt(shape[1])
+            v = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        elif kind == "g":
+            v = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            v = 0.05 * torch.randn(shape, generator=g)
+        sd[key] = v
+    sd["alphas_cumprod"] = cosine_beta_schedule(cfg.diffusion_steps)        # DiTTO.py:63-64 (betas!)
+    inv = 1.0 / (10000 ** (torch.arange(0, cfg.head_dim, 2).float() / cfg.head_dim))
+    sd["rotary.inv_freq"] = inv.clone()
+    for i in range(cfg.num_layers):
+        sd[f"blocks.{i}.rotary.inv_freq"] = inv.clone()
+    return sd
+
+
+def make_inputs(B: int, T: int, S: int, cfg: OracleConfig, seed: int = 1, steps_noise: int = 0):
+    """x_T ~ N(0,1) [B,T,H], text_emb ~ N(0,1) [B,S,text_dim], optional noise [steps,B,T,H].
+    SURVEY.md section 8d 'Synthetic inputs'."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, cfg.hidden_dim, generator=g)
+    text = torch.randn(B, S, cfg.text_dim, generator=g)
+    noise = torch.randn(steps_noise, B, T, cfg.hidden_dim, generator=g) if steps_noise else None
+    return x, text, noise
+
+
+def rel_l2(a: Tensor, b: Tensor) -> float:
+    """||a-b||_2 / ||b||_2 in fp64 (b = reference)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def forward_flops(T: int, S: int, cfg: OracleConfig) -> float:
+    """Algorithmic flops per sequence per forward, SURVEY.md section 8a:
+    L(34 T H^2 + 4 T^2 H + 4 T S H) + 4 T H^2 (dead self-attn out_proj excluded)."""
+    H, L = cfg.hidden_dim, cfg.num_layers
+    return L * (34.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * S * H) + 4.0 * T * H * H
