@@ -1,0 +1,81 @@
+"""ctypes binding of libditto_b200.so (include/ditto_b200.h).  There is no fallback: if the library
+is missing or no B200 is visible, the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libditto_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+F_FUSED_ROPE, F_FOLD_CROSS = 1, 2
+
+
+class DittoError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("hidden_dim", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
+                ("time_dim", C.c_int32), ("text_dim", C.c_int32), ("diffusion_steps", C.c_int32),
+                ("precision", C.c_int32), ("max_seq_len", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
+
+
+_P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+# name -> (restype, argtypes); mirrors include/ditto_b200.h one to one
+SIGNATURES = {
+    "ditto_abi_version": (_I32, []),
+    "ditto_last_error": (C.c_char_p, []),
+    "ditto_kernel_launch_count": (_I64, []),
+    "ditto_engine_create": (_I32, [C.POINTER(Config), C.POINTER(_P)]),
+    "ditto_engine_destroy": (_I32, [_P]),
+    "ditto_engine_load_weight": (_I32, [_P, C.c_char_p, _P, _I64, _P]),
+    "ditto_engine_load_schedule": (_I32, [_P, _P, _P, _P, _I64, _P]),
+    "ditto_engine_finalize": (_I32, [_P, _P]),
+    "ditto_text_context_bytes": (_I64, [_P, _I64, _I64]),
+    "ditto_workspace_bytes": (_I64, [_P, _I64, _I64, _I64]),
+    "ditto_text_context": (_I32, [_P, _P, _I64, _I64, _P, _P, _I64, _P]),
+    "ditto_forward": (_I32, [_P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "ditto_cfg_ddpm_update": (_I32, [_P, _P, _P, _P, _P, _P, _F, _P, _I64, _I64, _P]),
+    "ditto_p_sample": (_I32, [_P, _P, _P, _P, _P, _I32, _F, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
+    "ditto_q_sample": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "ditto_layernorm": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _P]),
+    "ditto_gemm_f32": (_I32, [_P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64, _I64, _P, _P, _F, _I64, _I64, _I64,
+                              _I64, _P]),
+    "ditto_gemm_bf16": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _I64, _F, _I64, _I64, _I64, _P]),
+    "ditto_cast_bf16": (_I32, [_P, _P, _I64, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises DittoError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DittoError(f"{LIB_PATH} not found: build it with `python -m ditto_tts_b200.build` "
+                         "(nvcc, sm_100a).  There is no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ditto_abi_version() != 1:
+        raise DittoError("libditto_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ditto_last_error().decode("utf-8", "replace")
+        raise DittoError(f"{what or 'libditto_b200'} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().ditto_kernel_launch_count())

@@ -1,0 +1,482 @@
+// HBM-bound kernels of the DiT denoiser hot path: LayerNorm / AdaLN, RoPE, softmax, gated activation,
+// CFG-combine + DDPM update, q_sample, casts and weight packing.  All coalesced + 128-bit vectorised.
+#include "kernels.cuh"
+
+namespace ditto {
+
+// =====================================================================================================
+// casts / packing
+// =====================================================================================================
+__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(y + i) = o;
+  }
+  if (i < n) {  // tail (n % 4 != 0): the one thread that lands on it
+    for (int64_t j = i; j < n && j < i + 4; ++j) y[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+int launch_cast_bf16(const float* x, bf16* y, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  DITTO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                DITTO_E_BADARG, "cast_bf16: misaligned pointer");
+  int64_t blocks = std::min<int64_t>(ceil_div(n, 4 * 256), 148 * 16);
+  cast_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, y, n);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// rows [rows, K] fp32 -> bf16 with an output-row permutation: y[r] = x[perm(r)]
+//  mode 0: identity; mode 1: GLU interleave (16-row blocks: [fc1 16 | gate 16]); src = [fc1 (R/2 rows); gate (R/2)]
+//  mode 2: RoPE pairing for the q and k thirds of in_proj (see pack notes in engine.cu)
+__global__ void pack_rows_kernel(const float* __restrict__ x, bf16* __restrict__ y, float* __restrict__ bias_out,
+                                 const float* __restrict__ bias_in, const int* __restrict__ perm, int rows, int K) {
+  const int r = blockIdx.x;
+  const int src = perm ? perm[r] : r;
+  const float* xr = x + static_cast<int64_t>(src) * K;
+  bf16* yr = y + static_cast<int64_t>(r) * K;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) yr[c] = __float2bfloat16_rn(xr[c]);
+  if (bias_out && threadIdx.x == 0) bias_out[r] = bias_in[src];
+}
+
+int launch_pack_rows(const float* x, bf16* y, float* bias_out, const float* bias_in, const int* perm, int rows, int K,
+                     cudaStream_t st) {
+  pack_rows_kernel<<<rows, 256, 0, st>>>(x, y, bias_out, bias_in, perm, rows, K);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// LayerNorm (eps 1e-5, biased variance, two-pass statistics in fp32) -- one warp per row
+// =====================================================================================================
+constexpr int LN_MAXV = 8;  // float4 per lane kept in registers -> H <= 1024
+
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c, float d) {
+  uint2 o;
+  o.x = pack_bf16x2(a, b);
+  o.y = pack_bf16x2(c, d);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+// statistics of a row held in registers: v[i] valid for i < nv (per-lane float4 slots)
+__device__ __forceinline__ void row_stats(const float4 (&v)[LN_MAXV], int nv_lane, int H, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) / static_cast<float>(H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  rstd = rsqrtf(warp_sum(q) / static_cast<float>(H) + 1e-5f);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, OutT* __restrict__ y,
+                                                        int64_t rows, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = H >> 2;                            // float4 per row
+  const int nv_lane = (nvec - lane + 31) >> 5;        // slots of this lane
+  const float* xr = x + row * H;
+  float4 v[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) v[i] = *reinterpret_cast<const float4*>(xr + ((i << 5) + lane) * 4);
+  float mean, rstd;
+  row_stats(v, nv_lane, H, mean, rstd);
+  OutT* yr = y + row * H;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) {
+      const int c = ((i << 5) + lane) * 4;
+      float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 b = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      store4<OutT>(yr + c, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    }
+}
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* y, bool out_bf16, int64_t rows, int H,
+                     cudaStream_t st) {
+  DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128 && H > 0, DITTO_E_UNSUPPORTED, "layernorm: need H % 4 == 0 and H <= 1024");
+  if (rows <= 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(ceil_div(rows, 8));
+  if (out_bf16)
+    layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x, gamma, beta, static_cast<bf16*>(y), rows, H);
+  else
+    layernorm_kernel<float><<<blocks, 256, 0, st>>>(x, gamma, beta, static_cast<float*>(y), rows, H);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// Global AdaLN fused with the first block's LayerNorm (DiT.py:25-40 then DiT.py:105):
+//   h = LN_noaffine(x) * (1 + ts + xs) + (tb + xb)      -> fp32 residual stream
+//   u = LN(h) * gamma1 + beta1                          -> GEMM operand (bf16 or fp32)
+//   xcast = bf16(x)                                     -> operand of proj_in (written once per distinct x row)
+// ts|tb = time_table[t[seq]] (per-step constants), xs|xb = text_mod[seq] (per-utterance constants).
+// =====================================================================================================
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+    adaln_ln_kernel(const float* __restrict__ x, int64_t n_x, const float* __restrict__ time_table,
+                    const float* __restrict__ text_mod, const int64_t* __restrict__ t, int steps,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ h,
+                    OutT* __restrict__ u, bf16* __restrict__ xcast, int64_t n_seq, int T, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_seq * T) return;
+  const int64_t seq = row / T;
+  const int64_t pos = row - seq * T;
+  const int64_t xrow = (seq % n_x) * T + pos;
+  int64_t tt = t[seq];
+  tt = tt < 0 ? 0 : (tt >= steps ? steps - 1 : tt);
+  const float* tm = time_table + tt * 2 * H;
+  const float* xm = text_mod + seq * 2 * H;
+  const int nvec = H >> 2;
+  const int nv_lane = (nvec - lane + 31) >> 5;
+  const float* xr = x + xrow * H;
+  float4 v[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) v[i] = *reinterpret_cast<const float4*>(xr + ((i << 5) + lane) * 4);
+  if (xcast != nullptr && seq < n_x) {
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv_lane) store4<bf16>(xcast + xrow * H + ((i << 5) + lane) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
+  }
+  float mean, rstd;
+  row_stats(v, nv_lane, H, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) {
+      const int c = ((i << 5) + lane) * 4;
+      const float4 ts = *reinterpret_cast<const float4*>(tm + c);
+      const float4 tb = *reinterpret_cast<const float4*>(tm + H + c);
+      const float4 xs = *reinterpret_cast<const float4*>(xm + c);
+      const float4 xb = *reinterpret_cast<const float4*>(xm + H + c);
+      // scale = 1 + time_scale + text_scale ; shift = time_shift + text_shift   (DiT.py:34-35, same order)
+      v[i].x = (v[i].x - mean) * rstd * ((1.f + ts.x) + xs.x) + (tb.x + xb.x);
+      v[i].y = (v[i].y - mean) * rstd * ((1.f + ts.y) + xs.y) + (tb.y + xb.y);
+      v[i].z = (v[i].z - mean) * rstd * ((1.f + ts.z) + xs.z) + (tb.z + xb.z);
+      v[i].w = (v[i].w - mean) * rstd * ((1.f + ts.w) + xs.w) + (tb.w + xb.w);
+      *reinterpret_cast<float4*>(h + row * H + c) = v[i];
+    }
+  row_stats(v, nv_lane, H, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv_lane) {
+      const int c = ((i << 5) + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c);
+      store4<OutT>(u + row * H + c, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    }
+}
+
+int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
+                    int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
+                    int64_t n_seq, int T, int H, cudaStream_t st) {
+  DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128, DITTO_E_UNSUPPORTED, "adaln: need H % 4 == 0 and H <= 1024");
+  const unsigned blocks = static_cast<unsigned>(ceil_div(n_seq * T, 8));
+  if (u_bf16)
+    adaln_ln_kernel<bf16><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
+                                                  static_cast<bf16*>(u), xcast, n_seq, T, H);
+  else
+    adaln_ln_kernel<float><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
+                                                   static_cast<float*>(u), xcast, n_seq, T, H);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// RoPE tables and application (DiT.py:46-72): angle[p][j] = float(p) * inv_freq[j] (fp32 product, as einsum)
+// =====================================================================================================
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cos_t, float* __restrict__ sin_t,
+                                  int max_T, int half, int head_dim) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(max_T) * half) return;
+  const int p = static_cast<int>(i / half), j = static_cast<int>(i % half);
+  const float f = inv_freq ? inv_freq[j] : 1.0f / powf(10000.f, static_cast<float>(2 * j) / static_cast<float>(head_dim));
+  const float a = static_cast<float>(p) * f;
+  cos_t[i] = cosf(a);  // accurate (non fast-math) range reduction: angles reach ~2.2e3 rad
+  sin_t[i] = sinf(a);
+}
+
+int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, int max_T, int half, int head_dim, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(max_T) * half;
+  rope_table_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(inv_freq, cos_t, sin_t, max_T, half, head_dim);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// in place on the q and k thirds of qkv [M, ld] (q at col 0, k at col H); pairs (j, j + d/2) inside each head
+template <typename T>
+__global__ void rope_kernel(T* __restrict__ qkv, int64_t ld, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, int64_t rows, int seq_T, int H, int head_dim) {
+  const int half = head_dim >> 1;
+  const int pairs_per_row = H >> 1;                 // per q (and per k)
+  const int64_t total = rows * pairs_per_row * 2;   // q and k
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / (pairs_per_row * 2);
+    int r = static_cast<int>(i - row * pairs_per_row * 2);
+    const int which = r / pairs_per_row;            // 0 = q, 1 = k
+    r -= which * pairs_per_row;
+    const int head = r / half, j = r - head * half;
+    const int pos = static_cast<int>(row % seq_T);
+    const float c = cos_t[static_cast<int64_t>(pos) * half + j], s = sin_t[static_cast<int64_t>(pos) * half + j];
+    T* p = qkv + row * ld + which * H + head * head_dim + j;
+    const float x1 = static_cast<float>(p[0]), x2 = static_cast<float>(p[half]);
+    p[0] = static_cast<T>(x1 * c - x2 * s);       // t*cos + (-x2)*sin
+    p[half] = static_cast<T>(x2 * c + x1 * s);    // t*cos + ( x1)*sin
+  }
+}
+
+int launch_rope(void* qkv, bool is_bf16, int64_t ld, const float* cos_t, const float* sin_t, int64_t rows, int seq_T,
+                int H, int head_dim, cudaStream_t st) {
+  const int64_t total = rows * H;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(total, 256), 148 * 32));
+  if (is_bf16)
+    rope_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<bf16*>(qkv), ld, cos_t, sin_t, rows, seq_T, H, head_dim);
+  else
+    rope_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(qkv), ld, cos_t, sin_t, rows, seq_T, H, head_dim);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// row softmax over fp32 scores -> P (bf16 or fp32, may alias the input when fp32).  One warp per row.
+// =====================================================================================================
+template <typename OutT, bool kFast>
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ s, int64_t lds, OutT* __restrict__ p,
+                                                      int64_t ldp, int64_t rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* sr = s + row * lds;
+  OutT* pr = p + row * ldp;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, sr[c]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += kFast ? __expf(sr[c] - m) : expf(sr[c] - m);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int c = lane; c < cols; c += 32) {
+    const float e = kFast ? __expf(sr[c] - m) : expf(sr[c] - m);
+    pr[c] = static_cast<OutT>(e * inv);
+  }
+  // zero the padding columns so that a full-width read never sees garbage
+  for (int c = cols + lane; c < ldp; c += 32) pr[c] = static_cast<OutT>(0.f);
+}
+
+int launch_softmax(const float* s, int64_t lds, void* p, bool p_bf16, int64_t ldp, int64_t rows, int cols, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(ceil_div(rows, 8));
+  if (p_bf16)
+    softmax_kernel<bf16, true><<<blocks, 256, 0, st>>>(s, lds, static_cast<bf16*>(p), ldp, rows, cols);
+  else
+    softmax_kernel<float, false><<<blocks, 256, 0, st>>>(s, lds, static_cast<float*>(p), ldp, rows, cols);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// fp32-path gated activation: hid = GELU_erf(a) * sigmoid(g)  (DiT.py:153-155)
+// =====================================================================================================
+__global__ void geglu_f32_kernel(const float* __restrict__ a, const float* __restrict__ g, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    const float4 av = *reinterpret_cast<const float4*>(a + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float4 o;
+    o.x = gelu_erf_f(av.x) * (1.0f / (1.0f + expf(-gv.x)));
+    o.y = gelu_erf_f(av.y) * (1.0f / (1.0f + expf(-gv.y)));
+    o.z = gelu_erf_f(av.z) * (1.0f / (1.0f + expf(-gv.z)));
+    o.w = gelu_erf_f(av.w) * (1.0f / (1.0f + expf(-gv.w)));
+    *reinterpret_cast<float4*>(out + i) = o;
+  }
+}
+int launch_geglu_f32(const float* a, const float* g, float* out, int64_t n, cudaStream_t st) {
+  DITTO_REQUIRE(n % 4 == 0, DITTO_E_UNSUPPORTED, "geglu: n % 4");
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(n, 1024), 148 * 16));
+  geglu_f32_kernel<<<blocks, 256, 0, st>>>(a, g, out, n);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void silu_kernel(float* __restrict__ x, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    x[i] = v / (1.0f + expf(-v));
+  }
+}
+int launch_silu(float* x, int64_t n, cudaStream_t st) {
+  silu_kernel<<<static_cast<unsigned>(std::min<int64_t>(ceil_div(n, 256), 148 * 8)), 256, 0, st>>>(x, n);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// silu(mean_S(text)) : text [n, S, D] -> out [n, D]   (DiT.py:27 + the SiLU of text_mlp, DiT.py:19)
+__global__ void mean_silu_kernel(const float* __restrict__ text, float* __restrict__ out, int S, int D) {
+  const int seq = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const float* p = text + static_cast<int64_t>(seq) * S * D + c;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += p[static_cast<int64_t>(s) * D];
+  const float m = acc / static_cast<float>(S);
+  out[static_cast<int64_t>(seq) * D + c] = m / (1.0f + expf(-m));
+}
+int launch_mean_silu(const float* text, float* out, int64_t n, int S, int D, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(ceil_div(D, 128)), static_cast<unsigned>(n));
+  mean_silu_kernel<<<grid, 128, 0, st>>>(text, out, S, D);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// V [T, d] slices of qkv (ld) -> Vt [n*heads, d, Tp] (keys contiguous): fallback operand layout for P@V
+__global__ void transpose_v_kernel(const bf16* __restrict__ v, int64_t ld, bf16* __restrict__ vt, int T, int Tp, int heads,
+                                   int d) {
+  __shared__ bf16 tile[32][33];
+  const int b = blockIdx.z;  // seq * heads + head
+  const int seq = b / heads, head = b % heads;
+  const bf16* src = v + (static_cast<int64_t>(seq) * T) * ld + head * d;
+  bf16* dst = vt + static_cast<int64_t>(b) * d * Tp;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int tt = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (tt < T && c < d) ? src[static_cast<int64_t>(tt) * ld + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, tt = t0 + threadIdx.x;
+    if (c < d && tt < Tp) dst[static_cast<int64_t>(c) * Tp + tt] = tile[threadIdx.x][i];
+  }
+}
+int launch_transpose_v(const bf16* v, int64_t ld, bf16* vt, int64_t n_seq, int T, int Tp, int heads, int d, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(ceil_div(Tp, 32)), static_cast<unsigned>(ceil_div(d, 32)), static_cast<unsigned>(n_seq * heads));
+  transpose_v_kernel<<<grid, dim3(32, 8), 0, st>>>(v, ld, vt, T, Tp, heads, d);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// CFG combine + DDPM ancestral update, one pass (SpeechGenerator.py:137-147 + the guidance extension)
+//   coef[t] = { 1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-acp_t), [t>0]*sqrt(beta_t) }
+// 20 B/element with guidance + noise (4 reads, 1 write), 128-bit accesses, grid = multiple of 148.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+    cfg_ddpm_update_kernel(const float4* __restrict__ eps_c, const float4* __restrict__ eps_u, const float4* __restrict__ x,
+                           const float4* __restrict__ z, const int64_t* __restrict__ t, const float* __restrict__ coef,
+                           int steps, float w, float4* __restrict__ out, int64_t vec_per_seq, int64_t total_vec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t seq = i / vec_per_seq;
+    int64_t tt = t[seq];
+    tt = tt < 0 ? 0 : (tt >= steps ? steps - 1 : tt);
+    const float c1 = coef[tt * 3 + 0], c2 = coef[tt * 3 + 1], c3 = coef[tt * 3 + 2];
+    float4 e = eps_c[i];
+    if (eps_u != nullptr) {
+      const float4 u = eps_u[i];
+      e.x = u.x + w * (e.x - u.x);
+      e.y = u.y + w * (e.y - u.y);
+      e.z = u.z + w * (e.z - u.z);
+      e.w = u.w + w * (e.w - u.w);
+    }
+    const float4 xv = x[i];
+    float4 o;
+    o.x = c1 * (xv.x - c2 * e.x);
+    o.y = c1 * (xv.y - c2 * e.y);
+    o.z = c1 * (xv.z - c2 * e.z);
+    o.w = c1 * (xv.w - c2 * e.w);
+    if (z != nullptr) {
+      const float4 zv = z[i];
+      o.x += c3 * zv.x;
+      o.y += c3 * zv.y;
+      o.z += c3 * zv.z;
+      o.w += c3 * zv.w;
+    }
+    out[i] = o;
+  }
+}
+
+int launch_cfg_ddpm_update(const float* eps_c, const float* eps_u, const float* x, const float* z, const int64_t* t,
+                           const float* coef, int steps, float w, float* out, int64_t B, int64_t elems_per_seq,
+                           cudaStream_t st) {
+  DITTO_REQUIRE(elems_per_seq % 4 == 0, DITTO_E_UNSUPPORTED, "cfg_ddpm_update: elems_per_seq % 4");
+  const int64_t total_vec = B * elems_per_seq / 4;
+  if (total_vec == 0) return 0;
+  const int64_t want = ceil_div(total_vec, 256 * 4);  // ~4 vectors per thread
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(round_up(want, 148), 148 * 32));
+  cfg_ddpm_update_kernel<<<blocks, 256, 0, st>>>(
+      reinterpret_cast<const float4*>(eps_c), reinterpret_cast<const float4*>(eps_u), reinterpret_cast<const float4*>(x),
+      reinterpret_cast<const float4*>(z), t, coef, steps, w, reinterpret_cast<float4*>(out), elems_per_seq / 4, total_vec);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// coef table from the host-provided schedule (device arithmetic mirrors torch: 1/sqrt(a), (1-a)/sqrt(1-acp), sqrt(b))
+__global__ void schedule_coef_kernel(const float* __restrict__ betas, const float* __restrict__ alphas,
+                                     const float* __restrict__ acp, float* __restrict__ coef, int steps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= steps) return;
+  coef[i * 3 + 0] = __fdiv_rn(1.0f, __fsqrt_rn(alphas[i]));
+  coef[i * 3 + 1] = __fdiv_rn(__fsub_rn(1.0f, alphas[i]), __fsqrt_rn(__fsub_rn(1.0f, acp[i])));
+  coef[i * 3 + 2] = i > 0 ? __fsqrt_rn(betas[i]) : 0.0f;
+}
+int launch_schedule_coef(const float* betas, const float* alphas, const float* acp, float* coef, int steps, cudaStream_t st) {
+  schedule_coef_kernel<<<static_cast<unsigned>(ceil_div(steps, 128)), 128, 0, st>>>(betas, alphas, acp, coef, steps);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// q_sample with the reference's buffer (betas stored as "alphas_cumprod"): sqrt(b_t) x0 + sqrt(1-b_t) noise
+__global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise, const int64_t* __restrict__ t,
+                                const float* __restrict__ buf, int steps, float4* __restrict__ out, int64_t vec_per_seq,
+                                int64_t total_vec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t seq = i / vec_per_seq;
+    int64_t tt = t[seq];
+    tt = tt < 0 ? 0 : (tt >= steps ? steps - 1 : tt);
+    const float a = __fsqrt_rn(buf[tt]), b = __fsqrt_rn(__fsub_rn(1.0f, buf[tt]));
+    const float4 xv = x0[i], nv = noise[i];
+    out[i] = make_float4(__fadd_rn(__fmul_rn(a, xv.x), __fmul_rn(b, nv.x)), __fadd_rn(__fmul_rn(a, xv.y), __fmul_rn(b, nv.y)),
+                         __fadd_rn(__fmul_rn(a, xv.z), __fmul_rn(b, nv.z)), __fadd_rn(__fmul_rn(a, xv.w), __fmul_rn(b, nv.w)));
+  }
+}
+int launch_q_sample(const float* x0, const float* noise, const int64_t* t, const float* buf, int steps, float* out, int64_t B,
+                    int64_t elems_per_seq, cudaStream_t st) {
+  DITTO_REQUIRE(elems_per_seq % 4 == 0, DITTO_E_UNSUPPORTED, "q_sample: elems_per_seq % 4");
+  const int64_t total_vec = B * elems_per_seq / 4;
+  if (total_vec == 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(round_up(ceil_div(total_vec, 1024), 148), 148 * 32));
+  q_sample_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x0), reinterpret_cast<const float4*>(noise), t, buf,
+                                          steps, reinterpret_cast<float4*>(out), elems_per_seq / 4, total_vec);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ditto

@@ -1,0 +1,679 @@
+// C-ABI entry points (include/ditto_b200.h) and the host-side orchestration of one DiTTO forward / sampler step.
+// Semantics follow the reference line by line (citations: src/model/DiTTO.py, src/components/DiT.py,
+// src/model/SpeechGenerator.py of Tikai7/DiTTO-TTS); the arithmetic runs in the kernels of this library only.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace ditto {
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+std::atomic<long long> g_launches{0};
+void set_error(const std::string& msg) { t_last_error = msg; }
+int cuda_fail(cudaError_t err, const char* what, const char* file, int line) {
+  t_last_error = std::string("CUDA error ") + std::to_string(static_cast<int>(err)) + " (" + cudaGetErrorString(err) + ") at " +
+                 what + " [" + file + ":" + std::to_string(line) + "]";
+  return DITTO_E_CUDA;
+}
+
+// bump allocator over a caller buffer; with base == nullptr it only measures
+struct Arena {
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(int64_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += static_cast<size_t>(n) * sizeof(T);
+    return p;
+  }
+};
+
+struct LayerPack {
+  bf16 *w_qkv = nullptr, *wc_in = nullptr, *wc_o = nullptr, *w_glu = nullptr, *w_fc2 = nullptr;
+  float *b_qkv = nullptr, *b_glu = nullptr;  // permuted / interleaved copies
+};
+
+}  // namespace ditto
+
+using namespace ditto;
+
+struct ditto_engine {
+  ditto_config_t cfg;
+  int H = 0, L = 0, heads = 0, d = 0, half = 0, Td = 0, Xd = 0, steps = 0, maxT = 0;
+  bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
+  int rope_pd = 0;
+  int pv_transpose = 0;  // debug: use the transposed-V operand instead of the MN-major descriptor
+  std::map<std::string, int64_t> expected;  // key -> numel
+  std::map<std::string, float*> w;          // device fp32 copies (owned)
+  std::vector<void*> owned;                 // everything else cudaMalloc'ed by the engine
+  float *time_table = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *coef = nullptr, *qs_buf = nullptr;
+  bf16 *w_in16 = nullptr, *w_out16 = nullptr;
+  std::vector<LayerPack> layers;
+
+  const float* W(const std::string& k) const {
+    auto it = w.find(k);
+    return it == w.end() ? nullptr : it->second;
+  }
+  const float* LW(int i, const char* name) const { return W("blocks." + std::to_string(i) + "." + name); }
+};
+
+namespace ditto {
+
+static int dev_alloc(ditto_engine* e, void** p, size_t bytes) {
+  DITTO_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  e->owned.push_back(*p);
+  return 0;
+}
+
+static void build_expected(ditto_engine* e) {
+  const int64_t H = e->H, Td = e->Td, Xd = e->Xd, St = e->steps;
+  auto& m = e->expected;
+  m["t_embedding.weight"] = St * Td;
+  m["time_embed.0.weight"] = Td * Td; m["time_embed.0.bias"] = Td;
+  m["time_embed.2.weight"] = Td * Td; m["time_embed.2.bias"] = Td;
+  m["ada_ln.time_mlp.1.weight"] = 2 * H * Td; m["ada_ln.time_mlp.1.bias"] = 2 * H;
+  m["ada_ln.text_mlp.1.weight"] = 2 * H * Xd; m["ada_ln.text_mlp.1.bias"] = 2 * H;
+  for (int i = 0; i < e->L; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    for (const char* n : {"norm1", "norm2", "norm3"}) { m[p + n + ".weight"] = H; m[p + n + ".bias"] = H; }
+    m[p + "attn.in_proj_weight"] = 3 * H * H; m[p + "attn.in_proj_bias"] = 3 * H;
+    m[p + "cross_attn.in_proj_weight"] = 3 * H * H; m[p + "cross_attn.in_proj_bias"] = 3 * H;
+    m[p + "cross_attn.out_proj.weight"] = H * H; m[p + "cross_attn.out_proj.bias"] = H;
+    m[p + "mlp_fc1.weight"] = 4 * H * H; m[p + "mlp_fc1.bias"] = 4 * H;
+    m[p + "gate.weight"] = 4 * H * H; m[p + "gate.bias"] = 4 * H;
+    m[p + "mlp_fc2.weight"] = 4 * H * H; m[p + "mlp_fc2.bias"] = H;
+  }
+  m["proj_in.weight"] = H * H; m["proj_in.bias"] = H;
+  m["proj_out.weight"] = H * H; m["proj_out.bias"] = H;
+  m["rotary.inv_freq"] = e->half;  // optional
+}
+
+static bool ignorable_key(const std::string& k) {
+  if (k.rfind("nac.", 0) == 0) return true;
+  if (k == "alphas_cumprod") return true;  // the sampler tables come through ditto_engine_load_schedule
+  if (k.size() > 9 && k.compare(k.size() - 9, 9, ".inv_freq") == 0 && k != "rotary.inv_freq") return true;
+  if (k.find(".attn.out_proj.") != std::string::npos) return true;  // dead weights (DiT.py:137-139 never applies them)
+  return false;
+}
+
+// simple fp32 GEMM helper: C[M,N] = alpha * A[M,K] @ W[N,K]^T + bias (+resid)
+static int sgemm_nt(const float* A, int64_t lda, const float* Wt, int64_t ldw, float* C, int64_t ldc, const float* bias,
+                    const float* resid, int64_t ldr, float alpha, int M, int N, int K, cudaStream_t st) {
+  SgemmParams p;
+  p.A = A; p.lda = lda; p.B = Wt; p.ldb = ldw; p.C = C; p.ldc = ldc; p.bias = bias; p.resid = resid; p.ldr = ldr;
+  p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.b_is_nk = true;
+  return launch_sgemm(p, st);
+}
+
+// bf16 tensor-core helper: out = alpha * A[M,K] @ W[N,K]^T (+bias) (+resid)
+static int tc_nt(const bf16* A, int64_t lda, const bf16* Wt, int64_t ldw, void* out, bool out_bf16, int64_t ldo,
+                 const float* bias, const float* resid, int64_t ldr, int64_t resid_row_mod, bf16* out2, int64_t ldo2,
+                 int M, int N, int K, cudaStream_t st) {
+  TcGemmParams p;
+  p.A.ptr = A; p.A.rows = M; p.A.cols = K; p.A.ld = lda;
+  p.B.ptr = Wt; p.B.rows = N; p.B.cols = K; p.B.ld = ldw;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.out = out; p.out_bf16 = out_bf16; p.ldo = ldo;
+  p.resid = resid; p.ldr = ldr; p.resid_row_mod = resid_row_mod; p.out2 = out2; p.ldo2 = ldo2;
+  return launch_tc_gemm(p, st);
+}
+
+struct CtxLayout {
+  float* text_mod = nullptr;  // [n, 2H]
+  void* kv0 = nullptr;        // layer 0 K|V [n*S, 2H] (bf16 or fp32); layers are kv_stride bytes apart
+  size_t kv_stride = 0;
+  size_t total = 0;
+};
+static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_t S) {
+  Arena a(base);
+  CtxLayout c;
+  c.text_mod = a.take<float>(n * 2 * e->H);
+  const int64_t kv_elems = n * S * 2 * e->H;
+  a.take<char>(0);
+  const size_t kv_bytes = ((static_cast<size_t>(kv_elems) * (e->bf16_mode ? 2 : 4)) + 255) & ~static_cast<size_t>(255);
+  c.kv0 = a.take<char>(static_cast<int64_t>(kv_bytes) * e->L);
+  c.kv_stride = kv_bytes;
+  c.total = a.off + 256;
+  return c;
+}
+
+struct Workspace {
+  float *h = nullptr, *xskip = nullptr, *scores = nullptr;
+  void *u = nullptr, *qkv = nullptr, *P = nullptr, *qc = nullptr, *oc = nullptr, *hid = nullptr, *xb16 = nullptr;
+  float *fc1 = nullptr, *gate = nullptr;  // fp32 path only
+  bf16* vt = nullptr;                     // transposed-V fallback
+  float* tmp_small = nullptr;             // [n, Xd] pooled text
+  bf16* text16 = nullptr;                 // [n*S, Xd]
+  int64_t Tp = 0, Sp = 0, ldp = 0;
+  size_t total = 0;
+};
+static Workspace ws_layout(const ditto_engine* e, void* base, int64_t n, int64_t T, int64_t S) {
+  Arena a(base);
+  Workspace w;
+  const int64_t H = e->H, M = n * T;
+  const int es = e->bf16_mode ? 2 : 4;
+  w.Tp = round_up(T, 8);
+  w.Sp = round_up(S, 8);
+  w.ldp = std::max(w.Tp, w.Sp);
+  w.h = a.take<float>(M * H);
+  w.xskip = a.take<float>(M * H);
+  w.u = a.take<char>(M * H * es);
+  w.xb16 = a.take<char>(M * H * 2);
+  w.qkv = a.take<char>(M * 3 * H * es);
+  w.scores = a.take<float>(n * e->heads * T * w.ldp);
+  w.P = e->bf16_mode ? static_cast<void*>(a.take<bf16>(n * e->heads * T * w.ldp)) : static_cast<void*>(w.scores);
+  w.qc = a.take<char>(M * H * es);
+  w.oc = a.take<char>(M * H * es);
+  w.hid = a.take<char>(M * 4 * H * es);
+  if (!e->bf16_mode) {
+    w.fc1 = a.take<float>(M * 4 * H);
+    w.gate = a.take<float>(M * 4 * H);
+  } else if (e->pv_transpose) {
+    w.vt = a.take<bf16>(n * e->heads * e->d * w.ldp);
+  }
+  w.tmp_small = a.take<float>(n * e->Xd);
+  w.text16 = a.take<bf16>(n * S * e->Xd);
+  w.total = a.off + 256;
+  return w;
+}
+
+}  // namespace ditto
+
+// ---------------------------------------------------------------------------------------------------
+// attention cores (materialised scores; see DESIGN.md for the roofline discussion)
+// ---------------------------------------------------------------------------------------------------
+namespace ditto {
+
+// bf16: scores = alpha * Q K^T (tcgen05) -> softmax -> P V (tcgen05, V as MN-major operand) (+ fp32 residual)
+static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, int64_t ldq, int64_t q_seq_stride, const bf16* k,
+                          int64_t ldk, int64_t k_seq_stride, const bf16* v, int64_t ldv, int64_t v_seq_stride, int64_t n, int Tq,
+                          int Tk, float alpha, void* out, bool out_bf16, int64_t ldo, int64_t o_seq_stride, const float* resid,
+                          cudaStream_t st) {
+  const int d = e->d, heads = e->heads;
+  const int64_t ldp = round_up(Tk, 8);
+  TcGemmParams g;
+  g.A.ptr = q; g.A.rows = Tq; g.A.cols = d; g.A.ld = ldq; g.A.s_inner = d; g.A.s_outer = q_seq_stride;
+  g.B.ptr = k; g.B.rows = Tk; g.B.cols = d; g.B.ld = ldk; g.B.s_inner = d; g.B.s_outer = k_seq_stride;
+  g.M = Tq; g.N = Tk; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+  g.alpha = alpha; g.out = w.scores; g.out_bf16 = false; g.ldo = ldp; g.so_inner = static_cast<int64_t>(Tq) * ldp;
+  g.so_outer = static_cast<int64_t>(heads) * Tq * ldp;
+  DITTO_TRY(launch_tc_gemm(g, st));
+  DITTO_TRY(launch_softmax(w.scores, ldp, w.P, true, ldp, n * heads * Tq, Tk, st));
+  TcGemmParams o;
+  o.A.ptr = static_cast<const bf16*>(w.P); o.A.rows = Tq; o.A.cols = Tk; o.A.ld = ldp; o.A.s_inner = static_cast<int64_t>(Tq) * ldp;
+  o.A.s_outer = static_cast<int64_t>(heads) * Tq * ldp;
+  if (e->pv_transpose && w.vt) {  // fallback operand: V^T [d, Tp] per (seq, head), keys contiguous
+    DITTO_TRY(launch_transpose_v(v, ldv, w.vt, n, Tk, static_cast<int>(ldp), heads, d, st));
+    o.B.ptr = w.vt; o.B.rows = d; o.B.cols = Tk; o.B.ld = ldp; o.B.s_inner = static_cast<int64_t>(d) * ldp;
+    o.B.s_outer = static_cast<int64_t>(heads) * d * ldp;
+    o.b_kn = false;
+  } else {
+    o.B.ptr = v; o.B.rows = Tk; o.B.cols = d; o.B.ld = ldv; o.B.s_inner = d; o.B.s_outer = v_seq_stride;
+    o.b_kn = true;
+  }
+  o.M = Tq; o.N = d; o.K = Tk; o.batch_inner = heads; o.batch_outer = static_cast<int>(n);
+  o.out = out; o.out_bf16 = out_bf16; o.ldo = ldo; o.so_inner = d; o.so_outer = o_seq_stride;
+  o.resid = resid; o.ldr = ldo; o.sr_inner = d; o.sr_outer = o_seq_stride;
+  DITTO_TRY(launch_tc_gemm(o, st));
+  return 0;
+}
+
+static int attention_f32(ditto_engine* e, const Workspace& w, const float* q, int64_t ldq, int64_t q_seq_stride, const float* k,
+                         int64_t ldk, int64_t k_seq_stride, const float* v, int64_t ldv, int64_t v_seq_stride, int64_t n, int Tq,
+                         int Tk, float alpha, float* out, int64_t ldo, int64_t o_seq_stride, const float* resid, cudaStream_t st) {
+  const int d = e->d, heads = e->heads;
+  const int64_t ldp = round_up(Tk, 8);
+  SgemmParams g;
+  g.A = q; g.lda = ldq; g.sA_inner = d; g.sA_outer = q_seq_stride;
+  g.B = k; g.ldb = ldk; g.sB_inner = d; g.sB_outer = k_seq_stride; g.b_is_nk = true;
+  g.C = w.scores; g.ldc = ldp; g.sC_inner = static_cast<int64_t>(Tq) * ldp; g.sC_outer = static_cast<int64_t>(heads) * Tq * ldp;
+  g.alpha = alpha; g.M = Tq; g.N = Tk; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+  DITTO_TRY(launch_sgemm(g, st));
+  DITTO_TRY(launch_softmax(w.scores, ldp, w.scores, false, ldp, n * heads * Tq, Tk, st));
+  SgemmParams o;
+  o.A = w.scores; o.lda = ldp; o.sA_inner = static_cast<int64_t>(Tq) * ldp; o.sA_outer = static_cast<int64_t>(heads) * Tq * ldp;
+  o.B = v; o.ldb = ldv; o.sB_inner = d; o.sB_outer = v_seq_stride; o.b_is_nk = false;
+  o.C = out; o.ldc = ldo; o.sC_inner = d; o.sC_outer = o_seq_stride;
+  o.resid = resid; o.ldr = ldo; o.sR_inner = d; o.sR_outer = o_seq_stride;
+  o.M = Tq; o.N = d; o.K = Tk; o.batch_inner = heads; o.batch_outer = static_cast<int>(n);
+  DITTO_TRY(launch_sgemm(o, st));
+  return 0;
+}
+
+static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void* ctx, const int64_t* t, int64_t n, int64_t T,
+                        int64_t S, float* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const int H = e->H, d = e->d;
+  const int64_t M = n * T;
+  DITTO_REQUIRE(M < (1ll << 31) / 8, DITTO_E_UNSUPPORTED, "forward: batch too large for one call (split it)");
+  Workspace w = ws_layout(e, workspace, n, T, S);
+  DITTO_REQUIRE(static_cast<int64_t>(w.total) <= workspace_bytes, DITTO_E_WORKSPACE, "forward: workspace too small");
+  CtxLayout c = ctx_layout(e, const_cast<void*>(ctx), n, S);
+  const bool b16 = e->bf16_mode;
+  const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(d));          // DiT.py:131-132: scores / sqrt(d)
+  const float sqrt_inv_d = sqrtf(1.0f / static_cast<float>(d));          // torch MHA: q * sqrt(1/d)
+
+  // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
+  DITTO_TRY(launch_adaln_ln(x, n_x, e->time_table, c.text_mod, t, e->steps, e->LW(0, "norm1.weight"), e->LW(0, "norm1.bias"), w.h, w.u,
+                            b16, b16 ? static_cast<bf16*>(w.xb16) : nullptr, n, static_cast<int>(T), H, st));
+  // x_skip = proj_in(x), once per distinct x                               DiTTO.py:83
+  const int Mx = static_cast<int>(n_x * T);
+  if (b16)
+    DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_in16, H, w.xskip, false, H, e->W("proj_in.bias"), nullptr, 0, 0, nullptr, 0, Mx, H,
+                    H, st));
+  else
+    DITTO_TRY(sgemm_nt(x, H, e->W("proj_in.weight"), H, w.xskip, H, e->W("proj_in.bias"), nullptr, 0, 1.f, Mx, H, H, st));
+
+  for (int i = 0; i < e->L; ++i) {
+    const LayerPack& lp = e->layers[i];
+    const bool last = (i == e->L - 1);
+    void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
+    if (b16) {
+      bf16* u = static_cast<bf16*>(w.u);
+      bf16* qkv = static_cast<bf16*>(w.qkv);
+      // ---- self-attention: QKV projection (+RoPE), softmax(QK^T/sqrt d)V, + residual (no out_proj)   DiT.py:103-139
+      {
+        TcGemmParams g;
+        g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
+        g.B.ptr = lp.w_qkv; g.B.rows = 3 * H; g.B.cols = H; g.B.ld = H;
+        g.M = static_cast<int>(M); g.N = 3 * H; g.K = H; g.bias = lp.b_qkv; g.out = qkv; g.out_bf16 = true; g.ldo = 3 * H;
+        if (e->fused_rope) {
+          g.epilogue = TC_EPI_QKV_ROPE; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_half = e->half;
+          g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(T); g.hidden = H;
+        }
+        DITTO_TRY(launch_tc_gemm(g, st));
+        if (!e->fused_rope) DITTO_TRY(launch_rope(qkv, true, 3 * H, e->rope_cos, e->rope_sin, M, static_cast<int>(T), H, d, st));
+      }
+      DITTO_TRY(attention_bf16(e, w, qkv, 3 * H, T * 3 * H, qkv + H, 3 * H, T * 3 * H, qkv + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
+                               static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st));
+      // ---- cross-attention (torch MHA math path)                                                     DiT.py:141-148
+      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
+      bf16* qc = static_cast<bf16*>(w.qc);
+      bf16* oc = static_cast<bf16*>(w.oc);
+      DITTO_TRY(tc_nt(u, H, lp.wc_in, H, qc, true, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 0, nullptr, 0, static_cast<int>(M), H,
+                      H, st));
+      const bf16* kc = static_cast<const bf16*>(kv);
+      DITTO_TRY(attention_bf16(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
+                               sqrt_inv_d, oc, true, H, T * H, nullptr, st));
+      DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, nullptr, 0, static_cast<int>(M), H,
+                      H, st));
+      // ---- gated MLP                                                                                  DiT.py:150-155
+      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
+      {
+        TcGemmParams g;
+        g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
+        g.B.ptr = lp.w_glu; g.B.rows = 8 * H; g.B.cols = H; g.B.ld = H;
+        g.M = static_cast<int>(M); g.N = 8 * H; g.K = H; g.bias = lp.b_glu; g.out = w.hid; g.out_bf16 = true; g.ldo = 4 * H;
+        g.epilogue = TC_EPI_GEGLU;
+        DITTO_TRY(launch_tc_gemm(g, st));
+      }
+      DITTO_TRY(tc_nt(static_cast<bf16*>(w.hid), 4 * H, lp.w_fc2, 4 * H, w.h, false, H, e->LW(i, "mlp_fc2.bias"), w.h, H, 0,
+                      last ? static_cast<bf16*>(w.xb16) : nullptr, H, static_cast<int>(M), H, 4 * H, st));
+      if (!last)
+        DITTO_TRY(launch_layernorm(w.h, e->LW(i + 1, "norm1.weight"), e->LW(i + 1, "norm1.bias"), u, true, M, H, st));
+    } else {
+      float* u = static_cast<float*>(w.u);
+      float* qkv = static_cast<float*>(w.qkv);
+      DITTO_TRY(sgemm_nt(u, H, e->LW(i, "attn.in_proj_weight"), H, qkv, 3 * H, e->LW(i, "attn.in_proj_bias"), nullptr, 0, 1.f,
+                         static_cast<int>(M), 3 * H, H, st));
+      DITTO_TRY(launch_rope(qkv, false, 3 * H, e->rope_cos, e->rope_sin, M, static_cast<int>(T), H, d, st));
+      DITTO_TRY(attention_f32(e, w, qkv, 3 * H, T * 3 * H, qkv + H, 3 * H, T * 3 * H, qkv + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
+                              static_cast<int>(T), inv_sqrt_d, w.h, H, T * H, w.h, st));
+      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, false, M, H, st));
+      float* qc = static_cast<float*>(w.qc);
+      float* oc = static_cast<float*>(w.oc);
+      DITTO_TRY(sgemm_nt(u, H, e->LW(i, "cross_attn.in_proj_weight"), H, qc, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 1.f,
+                         static_cast<int>(M), H, H, st));
+      const float* kc = static_cast<const float*>(kv);
+      DITTO_TRY(attention_f32(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
+                              sqrt_inv_d, oc, H, T * H, nullptr, st));
+      DITTO_TRY(sgemm_nt(oc, H, e->LW(i, "cross_attn.out_proj.weight"), H, w.h, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 1.f,
+                         static_cast<int>(M), H, H, st));
+      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, false, M, H, st));
+      DITTO_TRY(sgemm_nt(u, H, e->LW(i, "mlp_fc1.weight"), H, w.fc1, 4 * H, e->LW(i, "mlp_fc1.bias"), nullptr, 0, 1.f, static_cast<int>(M),
+                         4 * H, H, st));
+      DITTO_TRY(sgemm_nt(u, H, e->LW(i, "gate.weight"), H, w.gate, 4 * H, e->LW(i, "gate.bias"), nullptr, 0, 1.f, static_cast<int>(M),
+                         4 * H, H, st));
+      DITTO_TRY(launch_geglu_f32(w.fc1, w.gate, static_cast<float*>(w.hid), M * 4 * H, st));
+      DITTO_TRY(sgemm_nt(static_cast<float*>(w.hid), 4 * H, e->LW(i, "mlp_fc2.weight"), 4 * H, w.h, H, e->LW(i, "mlp_fc2.bias"), w.h, H, 1.f,
+                         static_cast<int>(M), H, 4 * H, st));
+      if (!last)
+        DITTO_TRY(launch_layernorm(w.h, e->LW(i + 1, "norm1.weight"), e->LW(i + 1, "norm1.bias"), u, false, M, H, st));
+    }
+  }
+  // eps = x_skip + proj_out(h)                                              DiTTO.py:93-94
+  if (b16) {
+    DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_out16, H, out, false, H, e->W("proj_out.bias"), w.xskip, H, n_x * T, nullptr, 0,
+                    static_cast<int>(M), H, H, st));
+  } else {
+    // residual rows repeat with period n_x*T: one GEMM per group of n_x sequences
+    for (int64_t g0 = 0; g0 < n; g0 += n_x)
+      DITTO_TRY(sgemm_nt(w.h + g0 * T * H, H, e->W("proj_out.weight"), H, out + g0 * T * H, H, e->W("proj_out.bias"), w.xskip, H, 1.f, Mx,
+                         H, H, st));
+  }
+  return 0;
+}
+
+}  // namespace ditto
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+int32_t ditto_abi_version(void) { return DITTO_ABI_VERSION; }
+const char* ditto_last_error(void) { return t_last_error.c_str(); }
+int64_t ditto_kernel_launch_count(void) { return g_launches.load(); }
+
+int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
+  DITTO_REQUIRE(cfg && out, DITTO_E_BADARG, "engine_create: null argument");
+  DITTO_REQUIRE(cfg->hidden_dim > 0 && cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->time_dim > 0 && cfg->diffusion_steps > 0,
+                DITTO_E_BADARG, "engine_create: non-positive dimension");
+  DITTO_REQUIRE(cfg->hidden_dim % cfg->num_heads == 0 && (cfg->hidden_dim / cfg->num_heads) % 2 == 0, DITTO_E_BADARG,
+                "engine_create: hidden_dim must split into heads of even size");
+  DITTO_REQUIRE(cfg->text_dim == cfg->hidden_dim, DITTO_E_UNSUPPORTED,
+                "engine_create: text_dim must equal hidden_dim (nn.MultiheadAttention without kdim, DiT.py:90-91)");
+  DITTO_REQUIRE(cfg->hidden_dim % 8 == 0 && cfg->hidden_dim <= 1024 && cfg->time_dim % 4 == 0, DITTO_E_UNSUPPORTED,
+                "engine_create: need hidden_dim % 8 == 0, hidden_dim <= 1024, time_dim % 4 == 0");
+  DITTO_REQUIRE(cfg->precision == DITTO_PREC_FP32 || cfg->precision == DITTO_PREC_BF16, DITTO_E_BADARG, "engine_create: precision");
+  int ndev = 0;
+  DITTO_CUDA(cudaGetDeviceCount(&ndev));
+  DITTO_REQUIRE(ndev > 0, DITTO_E_CUDA, "engine_create: no CUDA device (there is no CPU fallback)");
+  ditto_engine* e = new ditto_engine();
+  e->cfg = *cfg;
+  e->H = cfg->hidden_dim; e->L = cfg->num_layers; e->heads = cfg->num_heads; e->d = e->H / e->heads; e->half = e->d / 2;
+  e->Td = cfg->time_dim; e->Xd = cfg->text_dim; e->steps = cfg->diffusion_steps;
+  e->maxT = cfg->max_seq_len > 0 ? cfg->max_seq_len : 4096;
+  e->bf16_mode = cfg->precision == DITTO_PREC_BF16;
+  if (e->bf16_mode) {
+    if (e->bf16_mode && e->d % 8 != 0) {
+      delete e;
+      set_error("engine_create: bf16 path needs head_dim % 8 == 0 (16-byte TMA rows)");
+      return DITTO_E_UNSUPPORTED;
+    }
+    int rc = tc_gemm_init();
+    if (rc != 0) { delete e; return rc; }
+    // RoPE pair distance inside a GEMM tile: largest of 128/64/32 dividing d/2 (d=768 -> 128, d=64 -> 32)
+    for (int pd : {128, 64, 32})
+      if (e->half % pd == 0 && e->H % (2 * pd) == 0) { e->rope_pd = pd; break; }
+    e->fused_rope = (cfg->flags & DITTO_F_FUSED_ROPE) && e->rope_pd != 0;
+    const char* env = getenv("DITTO_PV_TRANSPOSE");
+    e->pv_transpose = env && env[0] == '1';
+  }
+  build_expected(e);
+  e->layers.resize(e->L);
+  *out = e;
+  return 0;
+}
+
+int32_t ditto_engine_destroy(ditto_engine_t* e) {
+  if (!e) return 0;
+  for (auto& kv : e->w) cudaFree(kv.second);
+  for (void* p : e->owned) cudaFree(p);
+  delete e;
+  return 0;
+}
+
+int32_t ditto_engine_load_weight(ditto_engine_t* e, const char* key, const float* data, int64_t numel, void* stream) {
+  DITTO_REQUIRE(e && key && data, DITTO_E_BADARG, "load_weight: null argument");
+  const std::string k(key);
+  if (ignorable_key(k)) return 0;
+  auto it = e->expected.find(k);
+  if (it == e->expected.end()) {
+    set_error("load_weight: unknown state_dict key '" + k + "'");
+    return DITTO_E_BADARG;
+  }
+  if (it->second != numel) {
+    set_error("load_weight: '" + k + "' has " + std::to_string(numel) + " elements, expected " + std::to_string(it->second));
+    return DITTO_E_BADARG;
+  }
+  float*& dst = e->w[k];
+  if (!dst) DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&dst), static_cast<size_t>(numel) * sizeof(float)));
+  DITTO_CUDA(cudaMemcpyAsync(dst, data, static_cast<size_t>(numel) * sizeof(float), cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+  e->finalized = false;
+  return 0;
+}
+
+int32_t ditto_engine_load_schedule(ditto_engine_t* e, const float* betas, const float* alphas, const float* alphas_cumprod,
+                                   int64_t steps, void* stream) {
+  DITTO_REQUIRE(e && betas && alphas && alphas_cumprod, DITTO_E_BADARG, "load_schedule: null argument");
+  DITTO_REQUIRE(steps == e->steps, DITTO_E_BADARG, "load_schedule: steps != diffusion_steps");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!e->coef) {
+    DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->coef), sizeof(float) * 3 * steps));
+    DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->qs_buf), sizeof(float) * steps));
+  }
+  DITTO_TRY(launch_schedule_coef(betas, alphas, alphas_cumprod, e->coef, static_cast<int>(steps), st));
+  // DiTTO.py:63-64: the module's "alphas_cumprod" buffer is cosine_beta_schedule(), i.e. the betas
+  DITTO_CUDA(cudaMemcpyAsync(e->qs_buf, betas, sizeof(float) * steps, cudaMemcpyDeviceToDevice, st));
+  e->have_schedule = true;
+  return 0;
+}
+
+int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
+  DITTO_REQUIRE(e, DITTO_E_BADARG, "finalize: null engine");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& kv : e->expected) {
+    if (kv.first == "rotary.inv_freq") continue;
+    if (!e->w.count(kv.first)) {
+      set_error("finalize: missing weight '" + kv.first + "'");
+      return DITTO_E_STATE;
+    }
+  }
+  const int H = e->H, Td = e->Td, St = e->steps;
+  // ---- per-step modulation table: time_mlp(SiLU(time_embed(t_embedding[t])))  (DiTTO.py:75-76, DiT.py:30)
+  if (!e->time_table) DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->time_table), sizeof(float) * St * 2 * H));
+  float *t1 = nullptr, *t2 = nullptr;
+  DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t1), sizeof(float) * St * Td));
+  DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t2), sizeof(float) * St * Td));
+  int rc = sgemm_nt(e->W("t_embedding.weight"), Td, e->W("time_embed.0.weight"), Td, t1, Td, e->W("time_embed.0.bias"), nullptr, 0,
+                    1.f, St, Td, Td, st);
+  if (!rc) rc = launch_silu(t1, static_cast<int64_t>(St) * Td, st);
+  if (!rc) rc = sgemm_nt(t1, Td, e->W("time_embed.2.weight"), Td, t2, Td, e->W("time_embed.2.bias"), nullptr, 0, 1.f, St, Td, Td, st);
+  if (!rc) rc = launch_silu(t2, static_cast<int64_t>(St) * Td, st);
+  if (!rc) rc = sgemm_nt(t2, Td, e->W("ada_ln.time_mlp.1.weight"), Td, e->time_table, 2 * H, e->W("ada_ln.time_mlp.1.bias"), nullptr,
+                         0, 1.f, St, 2 * H, Td, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(t1);
+  cudaFree(t2);
+  if (rc) return rc;
+  DITTO_CUDA(se);
+  // ---- RoPE tables (DiT.py:46-59)
+  if (!e->rope_cos) {
+    DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->rope_cos), sizeof(float) * e->maxT * e->half));
+    DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->rope_sin), sizeof(float) * e->maxT * e->half));
+  }
+  DITTO_TRY(launch_rope_table(e->W("rotary.inv_freq"), e->rope_cos, e->rope_sin, e->maxT, e->half, e->d, st));
+
+  // ---- bf16 packing
+  if (e->bf16_mode) {
+    auto cast_new = [&](const float* src, int64_t n, bf16** dst) -> int {
+      if (!*dst) DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(dst), sizeof(bf16) * n));
+      return launch_cast_bf16(src, *dst, n, st);
+    };
+    DITTO_TRY(cast_new(e->W("proj_in.weight"), static_cast<int64_t>(H) * H, &e->w_in16));
+    DITTO_TRY(cast_new(e->W("proj_out.weight"), static_cast<int64_t>(H) * H, &e->w_out16));
+    // row permutations (host-built, tiny)
+    std::vector<int> glu_perm(8 * H), qkv_perm(3 * H);
+    for (int r = 0; r < 8 * H; ++r) {
+      const int blk = r / 32, i = r % 32;
+      glu_perm[r] = i < 16 ? 16 * blk + i : 4 * H + 16 * blk + (i - 16);
+    }
+    for (int r = 0; r < 3 * H; ++r) qkv_perm[r] = r;
+    if (e->fused_rope) {
+      const int pd = e->rope_pd, half = e->half;
+      for (int region = 0; region < 2; ++region)
+        for (int lp = 0; lp < H; ++lp) {
+          const int g = lp / (2 * pd), w = lp % (2 * pd);
+          const int e0 = g * pd, head = e0 / half, j0 = e0 % half;
+          const int x1 = head * 2 * half + j0 + (w % pd);
+          qkv_perm[region * H + lp] = region * H + (w < pd ? x1 : x1 + half);
+        }
+    }
+    int *d_glu = nullptr, *d_qkv = nullptr;
+    float* cat = nullptr;
+    DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_glu), sizeof(int) * glu_perm.size()));
+    DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_qkv), sizeof(int) * qkv_perm.size()));
+    DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&cat), sizeof(float) * (8ll * H * H + 8 * H)));
+    DITTO_CUDA(cudaMemcpyAsync(d_glu, glu_perm.data(), sizeof(int) * glu_perm.size(), cudaMemcpyHostToDevice, st));
+    DITTO_CUDA(cudaMemcpyAsync(d_qkv, qkv_perm.data(), sizeof(int) * qkv_perm.size(), cudaMemcpyHostToDevice, st));
+    float* cat_bias = cat + 8ll * H * H;
+    rc = 0;
+    for (int i = 0; i < e->L && !rc; ++i) {
+      LayerPack& lp = e->layers[i];
+      if (!lp.w_qkv) {
+        rc = dev_alloc(e, reinterpret_cast<void**>(&lp.w_qkv), sizeof(bf16) * 3ll * H * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.b_qkv), sizeof(float) * 3 * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.w_glu), sizeof(bf16) * 8ll * H * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.b_glu), sizeof(float) * 8 * H);
+        if (rc) break;
+      }
+      rc = launch_pack_rows(e->LW(i, "attn.in_proj_weight"), lp.w_qkv, lp.b_qkv, e->LW(i, "attn.in_proj_bias"), d_qkv, 3 * H, H, st);
+      if (!rc) rc = cast_new(e->LW(i, "cross_attn.in_proj_weight"), 3ll * H * H, &lp.wc_in);
+      if (!rc) rc = cast_new(e->LW(i, "cross_attn.out_proj.weight"), static_cast<int64_t>(H) * H, &lp.wc_o);
+      if (!rc) rc = cast_new(e->LW(i, "mlp_fc2.weight"), 4ll * H * H, &lp.w_fc2);
+      if (rc) break;
+      cudaMemcpyAsync(cat, e->LW(i, "mlp_fc1.weight"), sizeof(float) * 4ll * H * H, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(cat + 4ll * H * H, e->LW(i, "gate.weight"), sizeof(float) * 4ll * H * H, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(cat_bias, e->LW(i, "mlp_fc1.bias"), sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(cat_bias + 4 * H, e->LW(i, "gate.bias"), sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
+      rc = launch_pack_rows(cat, lp.w_glu, lp.b_glu, cat_bias, d_glu, 8 * H, H, st);
+    }
+    se = cudaStreamSynchronize(st);
+    cudaFree(d_glu);
+    cudaFree(d_qkv);
+    cudaFree(cat);
+    if (rc) return rc;
+    DITTO_CUDA(se);
+  }
+  DITTO_CUDA(cudaStreamSynchronize(st));
+  e->finalized = true;
+  return 0;
+}
+
+int64_t ditto_text_context_bytes(const ditto_engine_t* e, int64_t n_seq, int64_t S) {
+  if (!e || n_seq <= 0 || S <= 0) return -1;
+  return static_cast<int64_t>(ctx_layout(e, nullptr, n_seq, S).total);
+}
+int64_t ditto_workspace_bytes(const ditto_engine_t* e, int64_t n_seq, int64_t T, int64_t S) {
+  if (!e || n_seq <= 0 || T <= 0 || S <= 0) return -1;
+  return static_cast<int64_t>(ws_layout(e, nullptr, n_seq, T, S).total);
+}
+
+int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, int64_t S, void* ctx, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && text_emb && ctx && workspace, DITTO_E_BADARG, "text_context: null argument");
+  DITTO_REQUIRE(e->finalized, DITTO_E_STATE, "text_context: engine not finalized");
+  DITTO_REQUIRE(n > 0 && S > 0, DITTO_E_BADARG, "text_context: empty input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int H = e->H, Xd = e->Xd;
+  // only the small tail of the workspace is needed here; lay it out with T = 1
+  Workspace w = ws_layout(e, workspace, n, 1, S);
+  DITTO_REQUIRE(static_cast<int64_t>(w.total) <= workspace_bytes, DITTO_E_WORKSPACE, "text_context: workspace too small");
+  CtxLayout c = ctx_layout(e, ctx, n, S);
+  // text modulation: text_mlp(SiLU(mean_S(text)))  (DiT.py:27,31)
+  DITTO_TRY(launch_mean_silu(text_emb, w.tmp_small, n, static_cast<int>(S), Xd, st));
+  DITTO_TRY(sgemm_nt(w.tmp_small, Xd, e->W("ada_ln.text_mlp.1.weight"), Xd, c.text_mod, 2 * H, e->W("ada_ln.text_mlp.1.bias"), nullptr,
+                     0, 1.f, static_cast<int>(n), 2 * H, Xd, st));
+  // per-layer K|V = text @ in_proj[H:3H]^T + b  (torch MHA packed in_proj, rows H..3H)
+  if (e->bf16_mode) DITTO_TRY(launch_cast_bf16(text_emb, w.text16, n * S * Xd, st));
+  for (int i = 0; i < e->L; ++i) {
+    void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
+    const float* bias = e->LW(i, "cross_attn.in_proj_bias") + H;
+    if (e->bf16_mode) {
+      DITTO_TRY(tc_nt(w.text16, Xd, e->layers[i].wc_in + static_cast<int64_t>(H) * H, H, kv, true, 2 * H, bias, nullptr, 0, 0, nullptr, 0,
+                      static_cast<int>(n * S), 2 * H, Xd, st));
+    } else {
+      DITTO_TRY(sgemm_nt(text_emb, Xd, e->LW(i, "cross_attn.in_proj_weight") + static_cast<int64_t>(H) * H, H, static_cast<float*>(kv),
+                         2 * H, bias, nullptr, 0, 1.f, static_cast<int>(n * S), 2 * H, Xd, st));
+    }
+  }
+  return 0;
+}
+
+int32_t ditto_forward(ditto_engine_t* e, const float* x, int64_t n_x, const void* ctx, const int64_t* t, int64_t n_seq, int64_t T,
+                      int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && x && ctx && t && out && workspace, DITTO_E_BADARG, "forward: null argument");
+  DITTO_REQUIRE(e->finalized, DITTO_E_STATE, "forward: engine not finalized");
+  DITTO_REQUIRE(n_seq > 0 && T > 0 && S > 0 && n_x > 0 && n_seq % n_x == 0, DITTO_E_BADARG, "forward: bad batch sizes");
+  DITTO_REQUIRE(T <= e->maxT, DITTO_E_UNSUPPORTED, "forward: T exceeds max_seq_len of the engine");
+  return forward_impl(e, x, n_x, ctx, t, n_seq, T, S, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_cfg_ddpm_update(ditto_engine_t* e, const float* eps_c, const float* eps_u, const float* x, const float* z,
+                              const int64_t* t, float guidance_scale, float* x_out, int64_t B, int64_t elems_per_seq, void* stream) {
+  DITTO_REQUIRE(e && eps_c && x && t && x_out, DITTO_E_BADARG, "cfg_ddpm_update: null argument");
+  DITTO_REQUIRE(e->have_schedule, DITTO_E_STATE, "cfg_ddpm_update: schedule not loaded");
+  DITTO_REQUIRE(B >= 0 && elems_per_seq >= 0, DITTO_E_BADARG, "cfg_ddpm_update: negative size");
+  return launch_cfg_ddpm_update(eps_c, eps_u, x, z, t, e->coef, e->steps, guidance_scale, x_out, B, elems_per_seq,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_p_sample(ditto_engine_t* e, const float* x, const void* ctx, const int64_t* t, const float* z, int32_t guided,
+                       float guidance_scale, int64_t B, int64_t T, int64_t S, float* eps_scratch, float* x_out, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && x && ctx && t && eps_scratch && x_out && workspace, DITTO_E_BADARG, "p_sample: null argument");
+  DITTO_REQUIRE(e->finalized && e->have_schedule, DITTO_E_STATE, "p_sample: engine not finalized / schedule not loaded");
+  DITTO_REQUIRE(B > 0 && T > 0 && S > 0 && T <= e->maxT, DITTO_E_BADARG, "p_sample: bad sizes");
+  const int64_t n = guided ? 2 * B : B;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DITTO_TRY(forward_impl(e, x, B, ctx, t, n, T, S, eps_scratch, workspace, workspace_bytes, st));
+  const int64_t per = T * e->H;
+  return launch_cfg_ddpm_update(eps_scratch, guided ? eps_scratch + B * per : nullptr, x, z, t, e->coef, e->steps, guidance_scale, x_out,
+                                B, per, st);
+}
+
+int32_t ditto_q_sample(ditto_engine_t* e, const float* x_start, const float* noise, const int64_t* t, float* out, int64_t B,
+                       int64_t elems_per_seq, void* stream) {
+  DITTO_REQUIRE(e && x_start && noise && t && out, DITTO_E_BADARG, "q_sample: null argument");
+  DITTO_REQUIRE(e->have_schedule, DITTO_E_STATE, "q_sample: schedule not loaded");
+  return launch_q_sample(x_start, noise, t, e->qs_buf, e->steps, out, B, elems_per_seq, static_cast<cudaStream_t>(stream));
+}
+
+// ---- single operators ---------------------------------------------------------------------------------
+int32_t ditto_layernorm(const float* x, const float* gamma, const float* beta, void* y, int32_t out_bf16, int64_t rows, int64_t H,
+                        void* stream) {
+  DITTO_REQUIRE(x && y && rows >= 0 && H > 0, DITTO_E_BADARG, "layernorm: bad argument");
+  return launch_layernorm(x, gamma, beta, y, out_bf16 != 0, rows, static_cast<int>(H), static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_gemm_f32(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb, int64_t strideB, int32_t b_is_nk,
+                       float* C, int64_t ldc, int64_t strideC, const float* bias, const float* resid, float alpha, int64_t M, int64_t N,
+                       int64_t K, int64_t batch, void* stream) {
+  DITTO_REQUIRE(A && B && C && batch >= 1, DITTO_E_BADARG, "gemm_f32: bad argument");
+  SgemmParams p;
+  p.A = A; p.lda = lda; p.sA_outer = strideA; p.B = B; p.ldb = ldb; p.sB_outer = strideB; p.b_is_nk = b_is_nk != 0;
+  p.C = C; p.ldc = ldc; p.sC_outer = strideC; p.bias = bias; p.resid = resid; p.ldr = ldc; p.sR_outer = strideC; p.alpha = alpha;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.batch_outer = static_cast<int>(batch);
+  return launch_sgemm(p, static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t out_bf16,
+                        const float* bias, const float* resid, int64_t ldr, float alpha, int64_t M, int64_t N, int64_t K, void* stream) {
+  DITTO_REQUIRE(A && W && C, DITTO_E_BADARG, "gemm_bf16: null argument");
+  TcGemmParams p;
+  p.A.ptr = static_cast<const bf16*>(A); p.A.rows = M; p.A.cols = K; p.A.ld = lda;
+  p.B.ptr = static_cast<const bf16*>(W); p.B.rows = N; p.B.cols = K; p.B.ld = ldw;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.alpha = alpha; p.bias = bias; p.out = C; p.out_bf16 = out_bf16 != 0; p.ldo = ldc; p.resid = resid; p.ldr = ldr;
+  return launch_tc_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
+  DITTO_REQUIRE(x && y && n >= 0, DITTO_E_BADARG, "cast_bf16: bad argument");
+  return launch_cast_bf16(x, static_cast<bf16*>(y), n, static_cast<cudaStream_t>(stream));
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Internal launcher interface shared by the translation units of libditto_b200.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ditto {
+
+// ---- elementwise.cu ----------------------------------------------------------------------------------
+int launch_cast_bf16(const float* x, bf16* y, int64_t n, cudaStream_t st);
+int launch_pack_rows(const float* x, bf16* y, float* bias_out, const float* bias_in, const int* perm, int rows, int K,
+                     cudaStream_t st);
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* y, bool out_bf16, int64_t rows, int H,
+                     cudaStream_t st);
+int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
+                    int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
+                    int64_t n_seq, int T, int H, cudaStream_t st);
+int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, int max_T, int half, int head_dim, cudaStream_t st);
+int launch_rope(void* qkv, bool is_bf16, int64_t ld, const float* cos_t, const float* sin_t, int64_t rows, int seq_T,
+                int H, int head_dim, cudaStream_t st);
+int launch_softmax(const float* s, int64_t lds, void* p, bool p_bf16, int64_t ldp, int64_t rows, int cols, cudaStream_t st);
+int launch_geglu_f32(const float* a, const float* g, float* out, int64_t n, cudaStream_t st);
+int launch_silu(float* x, int64_t n, cudaStream_t st);
+int launch_mean_silu(const float* text, float* out, int64_t n, int S, int D, cudaStream_t st);
+int launch_transpose_v(const bf16* v, int64_t ld, bf16* vt, int64_t n_seq, int T, int Tp, int heads, int d, cudaStream_t st);
+int launch_cfg_ddpm_update(const float* eps_c, const float* eps_u, const float* x, const float* z, const int64_t* t,
+                           const float* coef, int steps, float w, float* out, int64_t B, int64_t elems_per_seq,
+                           cudaStream_t st);
+int launch_schedule_coef(const float* betas, const float* alphas, const float* acp, float* coef, int steps, cudaStream_t st);
+int launch_q_sample(const float* x0, const float* noise, const int64_t* t, const float* buf, int steps, float* out, int64_t B,
+                    int64_t elems_per_seq, cudaStream_t st);
+
+// ---- gemm_f32.cu -------------------------------------------------------------------------------------
+struct SgemmParams {
+  const float* A = nullptr; int64_t lda = 0, sA_inner = 0, sA_outer = 0;
+  const float* B = nullptr; int64_t ldb = 0, sB_inner = 0, sB_outer = 0;
+  float* C = nullptr;       int64_t ldc = 0, sC_inner = 0, sC_outer = 0;
+  const float* resid = nullptr; int64_t ldr = 0, sR_inner = 0, sR_outer = 0;
+  const float* bias = nullptr;
+  float alpha = 1.f;
+  int M = 0, N = 0, K = 0;
+  int batch_inner = 1, batch_outer = 1;
+  bool b_is_nk = true;  // B [N,K] (x W^T) else B [K,N]
+};
+int launch_sgemm(const SgemmParams& p, cudaStream_t st);
+
+// ---- gemm_tc.cu (tcgen05 / TMEM / TMA) ---------------------------------------------------------------
+enum TcEpilogue { TC_EPI_STORE = 0, TC_EPI_GEGLU = 1, TC_EPI_QKV_ROPE = 2 };
+
+// 2-D operand view with two batch levels; strides in ELEMENTS (bf16).  rows x cols with `cols` contiguous.
+struct TcOperand {
+  const bf16* ptr = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+  int64_t s_inner = 0, s_outer = 0;  // batch strides; 0 => operand shared by every batch item
+};
+
+struct TcGemmParams {
+  // C[b] (M x N) = alpha * A[b] (M x K) @ B[b]^T  where B is [N, K] (b_kn == false) or [K, N] (b_kn == true)
+  TcOperand A, B;
+  bool b_kn = false;
+  int M = 0, N = 0, K = 0;
+  int batch_inner = 1, batch_outer = 1;
+  int epilogue = TC_EPI_STORE;
+  float alpha = 1.f;
+  const float* bias = nullptr;                 // [N], indexed by GEMM column
+  void* out = nullptr; bool out_bf16 = false;  // [M, ldo] per batch item
+  int64_t ldo = 0, so_inner = 0, so_outer = 0;
+  const float* resid = nullptr;                // fp32, added after bias
+  int64_t ldr = 0, sr_inner = 0, sr_outer = 0;
+  int64_t resid_row_mod = 0;                   // >0: residual row = row % resid_row_mod (x_skip shared by CFG branches)
+  bf16* out2 = nullptr; int64_t ldo2 = 0;      // optional bf16 copy of the (fp32) result, batch strides as `out`
+  // TC_EPI_QKV_ROPE
+  const float* rope_cos = nullptr; const float* rope_sin = nullptr;
+  int rope_half = 0, rope_pd = 0, seq_T = 0, hidden = 0;
+};
+int launch_tc_gemm(const TcGemmParams& p, cudaStream_t st);
+int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
+
+}  // namespace ditto

@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's DiT modules (src/model/DiTTO.py, src/components/DiT.py).
+
+Same class names, constructor arguments, parameter names (state_dict keys) and call signatures as the
+reference, so a ``TrainDiTTO.py``-style inference script can switch by changing the import.  The modules
+are PARAMETER CONTAINERS: their arithmetic runs in libditto_b200.so (hand-written sm_100a CUDA behind the
+C-ABI of include/ditto_b200.h).  Inference only; no autograd; no CPU fallback (CPU tensors raise).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import DittoError
+
+__all__ = ["DiTTO", "DiT", "GlobalAdaLN", "RotaryEmbedding", "DittoError"]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda_f32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise DittoError(f"{name} must be a CUDA tensor: ditto_tts_b200 has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise DittoError(f"{name} must be float32 (the reference path is fp32 end to end), got {t.dtype}")
+    return t.contiguous()
+
+
+class GlobalAdaLN(nn.Module):
+    """Parameters of the global AdaLN (reference: components/DiT.py:8-23).  The modulation
+    LN(x)*(1+ts+xs)+(tb+xb) (DiT.py:25-40) is fused with block 0's LayerNorm inside the engine."""
+
+    def __init__(self, hidden_dim, time_dim, text_dim):
+        super().__init__()
+        self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_dim, 2 * hidden_dim))
+        self.text_mlp = nn.Sequential(nn.SiLU(), nn.Linear(text_dim, 2 * hidden_dim))
+        self.norm = nn.LayerNorm(hidden_dim, elementwise_affine=False)
+
+    def forward(self, x, time_emb, text_emb):
+        raise DittoError("GlobalAdaLN runs fused inside DiTTO.forward (libditto_b200); call the DiTTO module")
+
+
+class RotaryEmbedding(nn.Module):
+    """RoPE angle table (reference: components/DiT.py:43-59).  ``forward`` returns the same [T, d] angle
+    tensor as the reference (host-side table building); rotation itself happens in the QKV kernels."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
+        self.register_buffer("inv_freq", inv_freq)
+
+    def forward(self, seq_len, device):
+        t = torch.arange(seq_len, device=device).type_as(self.inv_freq)
+        freqs = torch.einsum("i,j->ij", t, self.inv_freq)
+        return torch.cat((freqs, freqs), dim=-1)
+
+
+class DiT(nn.Module):
+    """Parameters of one DiT block (reference: components/DiT.py:78-98), same names and init order."""
+
+    def __init__(self, hidden_dim, num_heads, time_dim, text_dim):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = hidden_dim // num_heads
+        self.norm1 = nn.LayerNorm(hidden_dim)
+        self.attn = nn.MultiheadAttention(hidden_dim, num_heads)
+        self.rotary = RotaryEmbedding(self.head_dim)
+        self.norm2 = nn.LayerNorm(hidden_dim)
+        self.cross_attn = nn.MultiheadAttention(hidden_dim, num_heads, dropout=0.1)
+        self.norm3 = nn.LayerNorm(hidden_dim)
+        self.mlp_fc1 = nn.Linear(hidden_dim, 4 * hidden_dim)
+        self.act = nn.GELU()
+        self.gate = nn.Linear(hidden_dim, 4 * hidden_dim)
+        self.mlp_fc2 = nn.Linear(4 * hidden_dim, hidden_dim)
+
+    def forward(self, x, text_emb, time_emb, rotary_pos):
+        raise DittoError("DiT blocks run fused inside DiTTO.forward (libditto_b200); call the DiTTO module")
+
+
+class _Buffers:
+    """Caller-owned device scratch for the C-ABI (workspace / text context), cached by size."""
+
+    def __init__(self):
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int, device) -> torch.Tensor:
+        b = self._bufs.get(name)
+        if b is None or b.numel() < nbytes or b.device != device:
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self._bufs[name] = b
+        return b
+
+
+class DiTTO(nn.Module):
+    """Drop-in for ``model.DiTTO.DiTTO`` (reference: src/model/DiTTO.py:7-126) on the inference path.
+
+    Same constructor keywords; ``forward(x, text_emb, t)`` -> eps_hat with x [n,T,H] fp32, text_emb
+    [n,S,text_dim] fp32, t [n] int64, all CUDA.  Differences, all outside the hot path:
+      * the NAC (HF EnCodec/GPT-2 + a checkpoint file, DiTTO.py:22-34) is not constructed: pass
+        ``nac=<module>`` to attach one; ``nac.*`` keys of reference checkpoints are ignored on load;
+      * extra keywords ``precision`` ("bf16" tensor-core path | "fp32" CUDA-core parity path),
+        ``max_seq_len`` (RoPE table rows) and ``fused_rope``.
+    """
+
+    def __init__(self, hidden_dim=768, num_layers=12, num_heads=12, time_dim=256, text_dim=768,
+                 diffusion_steps=1000, lambda_factor=0.1, nac_model_path=None, *, nac: Optional[nn.Module] = None,
+                 precision: str = "bf16", max_seq_len: int = 4096, fused_rope: bool = True):
+        super().__init__()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.hidden_dim, self.num_layers, self.num_heads = hidden_dim, num_layers, num_heads
+        self.time_dim, self.text_dim, self.diffusion_steps = time_dim, text_dim, diffusion_steps
+        self.lambda_factor, self.nac_model_path = lambda_factor, nac_model_path
+        self.precision, self.max_seq_len, self.fused_rope = precision, max_seq_len, fused_rope
+        if nac is not None:
+            self.nac = nac
+        # construction order == reference (DiTTO.py:36-64): seeded default init gives the same weights
+        self.t_embedding = nn.Embedding(diffusion_steps, time_dim)
+        self.time_embed = nn.Sequential(nn.Linear(time_dim, time_dim), nn.SiLU(), nn.Linear(time_dim, time_dim))
+        self.ada_ln = GlobalAdaLN(hidden_dim, time_dim, text_dim)
+        self.blocks = nn.ModuleList([DiT(hidden_dim, num_heads, time_dim, text_dim) for _ in range(num_layers)])
+        self.proj_in = nn.Linear(hidden_dim, hidden_dim)
+        self.proj_out = nn.Linear(hidden_dim, hidden_dim)
+        self.rotary = RotaryEmbedding(hidden_dim // num_heads)
+        self.register_buffer("alphas_cumprod", self.cosine_beta_schedule(diffusion_steps))
+        self._engine = None
+        self._engine_key = None
+        self._schedule_loaded = False
+        self._bufs = _Buffers()
+        self.eval()
+
+    # ------------------------------------------------------------------ reference API (host side)
+    def cosine_beta_schedule(self, timesteps, s=0.008):
+        """Identical arithmetic to DiTTO.py:96-104 (host torch ops; returns the clipped betas)."""
+        steps = timesteps + 1
+        x = torch.linspace(0, timesteps, steps)
+        alphas_cumprod = torch.cos(((x / timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+        alphas_cumprod = alphas_cumprod / alphas_cumprod[0]
+        betas = 1 - (alphas_cumprod[1:] / alphas_cumprod[:-1])
+        return torch.clip(betas, 0.0001, 0.9999)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts reference checkpoints: ``nac.*`` entries are dropped unless a NAC is attached."""
+        if not hasattr(self, "nac"):
+            state_dict = {k: v for k, v in state_dict.items() if not k.startswith("nac.")}
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._engine_key = None
+        return out
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _weights_key(self):
+        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items()
+                     if not k.startswith("nac."))
+
+    def engine(self):
+        """Create / refresh the native engine from the current parameters (must live on a CUDA device)."""
+        lib = _lib.load()
+        dev = self.proj_in.weight.device
+        if dev.type != "cuda":
+            raise DittoError("DiTTO parameters are on the CPU: move the module to a B200 (model.cuda()); "
+                             "there is no CPU fallback")
+        key = self._weights_key()
+        if self._engine is not None and key == self._engine_key:
+            return self._engine
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                cfg = _lib.Config(hidden_dim=self.hidden_dim, num_layers=self.num_layers, num_heads=self.num_heads,
+                                  time_dim=self.time_dim, text_dim=self.text_dim,
+                                  diffusion_steps=self.diffusion_steps,
+                                  precision=_lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32,
+                                  max_seq_len=self.max_seq_len,
+                                  flags=_lib.F_FUSED_ROPE if self.fused_rope else 0)
+                h = C.c_void_p()
+                _lib.check(lib.ditto_engine_create(C.byref(cfg), C.byref(h)), "ditto_engine_create")
+                self._engine = h
+            for k, v in self.state_dict().items():
+                if k.startswith("nac."):
+                    continue
+                w = v.detach().to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(lib.ditto_engine_load_weight(self._engine, k.encode(), _ptr(w), w.numel(), _stream()),
+                           f"ditto_engine_load_weight({k})")
+            _lib.check(lib.ditto_engine_finalize(self._engine, _stream()), "ditto_engine_finalize")
+        self._engine_key = key
+        return self._engine
+
+    def load_schedule(self, betas: torch.Tensor, alphas: torch.Tensor, alphas_cumprod: torch.Tensor):
+        """Hand the sampler tables (SpeechGenerator.py:70-72) to the engine."""
+        eng = self.engine()
+        dev = self.proj_in.weight.device
+        tabs = [z.detach().to(device=dev, dtype=torch.float32).contiguous() for z in (betas, alphas, alphas_cumprod)]
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ditto_engine_load_schedule(eng, _ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]),
+                                                             tabs[0].numel(), _stream()), "ditto_engine_load_schedule")
+            torch.cuda.current_stream().synchronize()
+        self._schedule_loaded = True
+
+    def _ensure_schedule(self):
+        if not self._schedule_loaded:
+            betas = self.cosine_beta_schedule(self.diffusion_steps)
+            alphas = 1.0 - betas
+            self.load_schedule(betas, alphas, torch.cumprod(alphas, dim=0))
+
+    def workspace(self, n_seq: int, T: int, S: int) -> torch.Tensor:
+        eng = self.engine()
+        nbytes = _lib.load().ditto_workspace_bytes(eng, n_seq, T, S)
+        if nbytes < 0:
+            raise DittoError("ditto_workspace_bytes: bad sizes")
+        return self._bufs.get("ws", nbytes, self.proj_in.weight.device)
+
+    def text_context(self, text_emb: torch.Tensor, name: str = "ctx", T_hint: int = 1) -> torch.Tensor:
+        """Step-invariant text work (cross-attention K/V of every layer + text modulation) for a batch."""
+        eng = self.engine()
+        lib = _lib.load()
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        n, S, Xd = text_emb.shape
+        if Xd != self.text_dim:
+            raise DittoError(f"text_emb last dim {Xd} != text_dim {self.text_dim}")
+        with torch.cuda.device(text_emb.device):
+            ctx = self._bufs.get(name, lib.ditto_text_context_bytes(eng, n, S), text_emb.device)
+            ws = self.workspace(n, T_hint, S)
+            _lib.check(lib.ditto_text_context(eng, _ptr(text_emb), n, S, _ptr(ctx), _ptr(ws), ws.numel(), _stream()),
+                       "ditto_text_context")
+        return ctx
+
+    def forward_with_context(self, x: torch.Tensor, ctx: torch.Tensor, t: torch.Tensor, n_seq: int, S: int,
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """eps_hat for n_seq sequences whose text context is already built; x [n_x,T,H] with n_seq % n_x == 0."""
+        eng = self.engine()
+        lib = _lib.load()
+        x = _need_cuda_f32("x", x)
+        n_x, T, H = x.shape
+        if H != self.hidden_dim:
+            raise DittoError(f"x last dim {H} != hidden_dim {self.hidden_dim}")
+        if not t.is_cuda or t.dtype != torch.int64 or t.numel() != n_seq:
+            raise DittoError("t must be a CUDA int64 tensor with one entry per sequence")
+        t = t.contiguous()
+        if out is None:
+            out = torch.empty((n_seq, T, H), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = self.workspace(n_seq, T, S)
+            _lib.check(lib.ditto_forward(eng, _ptr(x), n_x, _ptr(ctx), _ptr(t), n_seq, T, S, _ptr(out), _ptr(ws),
+                                         ws.numel(), _stream()), "ditto_forward")
+        return out
+
+    @torch.no_grad()
+    def forward(self, x, text_emb, t):
+        """eps_hat = DiTTO.forward(x, text_emb, t)  (reference: DiTTO.py:66-94)."""
+        x = _need_cuda_f32("x", x)
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        if x.dim() != 3 or text_emb.dim() != 3 or x.shape[0] != text_emb.shape[0]:
+            raise DittoError("expected x [n,T,H] and text_emb [n,S,text_dim] with the same n")
+        t = t.to(device=x.device, dtype=torch.int64)
+        ctx = self.text_context(text_emb, T_hint=x.shape[1])
+        return self.forward_with_context(x, ctx, t, x.shape[0], text_emb.shape[1])
+
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """Forward diffusion (reference: DiTTO.py:106-126, incl. its betas-as-alphas_cumprod buffer)."""
+        x_start = _need_cuda_f32("x_start", x_start)
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        noise = _need_cuda_f32("noise", noise)
+        self._ensure_schedule()
+        t = t.to(device=x_start.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(x_start)
+        B = x_start.shape[0]
+        with torch.cuda.device(x_start.device):
+            _lib.check(_lib.load().ditto_q_sample(self.engine(), _ptr(x_start), _ptr(noise), _ptr(t), _ptr(out), B,
+                                                  x_start.numel() // B, _stream()), "ditto_q_sample")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None) is not None:
+                _lib.load().ditto_engine_destroy(self._engine)
+        except Exception:
+            pass

@@ -1,0 +1,134 @@
+"""DDPM ancestral sampler around the native DiTTO engine.
+
+Mirrors the sampling part of the reference's ``SpeechGenerator`` (src/model/SpeechGenerator.py):
+schedule tables :70-72, ``__p_sample`` :131-147, ``__sample_latents`` :150-164 -- same arithmetic, same
+argument meaning -- plus the classifier-free-guidance extension BASELINE.json asks for
+(eps = eps_u + w (eps_c - eps_u), unconditional branch = zero text embedding unless supplied).
+One sampler iteration is a single C-ABI call (ditto_p_sample): the 2B-sequence forward and the fused
+CFG-combine + update kernel; the text K/V and modulation vectors are built once per utterance batch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import DittoError
+from .model import DiTTO, _need_cuda_f32, _ptr, _stream
+
+__all__ = ["DiTTOSampler"]
+
+
+class DiTTOSampler:
+    def __init__(self, model: DiTTO, guidance_scale: Optional[float] = None):
+        self.model = model
+        self.guidance_scale = guidance_scale
+        steps = model.diffusion_steps
+        # SpeechGenerator.py:70-72 (host torch ops => bit-identical tables)
+        self.betas = model.cosine_beta_schedule(steps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        model.load_schedule(self.betas, self.alphas, self.alphas_cumprod)
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _context(self, text_emb: torch.Tensor, guided: bool, null_text_emb: Optional[torch.Tensor], T: int):
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        if guided:
+            null = torch.zeros_like(text_emb) if null_text_emb is None else _need_cuda_f32("null_text_emb", null_text_emb)
+            if null.shape != text_emb.shape:
+                raise DittoError("null_text_emb must have the shape of text_emb")
+            text_emb = torch.cat([text_emb, null], dim=0)  # [cond(B); uncond(B)]
+        return self.model.text_context(text_emb, name="sampler_ctx", T_hint=T)
+
+    def _p_sample_raw(self, x, ctx, t_n, z, guided, w, S, eps, x_out):
+        m = self.model
+        B, T, H = x.shape
+        n = 2 * B if guided else B
+        with torch.cuda.device(x.device):
+            ws = m.workspace(n, T, S)
+            _lib.check(_lib.load().ditto_p_sample(m.engine(), _ptr(x), _ptr(ctx), _ptr(t_n), _ptr(z), 1 if guided else 0,
+                                                  float(w), B, T, S, _ptr(eps), _ptr(x_out), _ptr(ws), ws.numel(),
+                                                  _stream()), "ditto_p_sample")
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def predict_noise(self, x, t, text_emb, guidance_scale=None, null_text_emb=None):
+        """eps_hat (guided when a scale is given): the call at SpeechGenerator.py:135 + CFG combine."""
+        w = self.guidance_scale if guidance_scale is None else guidance_scale
+        guided = w is not None
+        x = _need_cuda_f32("x", x)
+        B, T, H = x.shape
+        ctx = self._context(text_emb, guided, null_text_emb, T)
+        t = t.to(device=x.device, dtype=torch.int64)
+        t_n = torch.cat([t, t]) if guided else t
+        eps = self.model.forward_with_context(x, ctx, t_n.contiguous(), t_n.numel(), text_emb.shape[1])
+        if not guided:
+            return eps
+        return eps[B:] + w * (eps[:B] - eps[B:])
+
+    @torch.no_grad()
+    def p_sample(self, x, t, text_emb, noise=None, guidance_scale=None, null_text_emb=None):
+        """One reverse step (reference: __p_sample, SpeechGenerator.py:131-147).  ``noise`` replaces the
+        reference's in-place ``torch.randn_like(x)``; when omitted it is drawn the same way."""
+        w = self.guidance_scale if guidance_scale is None else guidance_scale
+        guided = w is not None
+        x = _need_cuda_f32("x", x)
+        B, T, H = x.shape
+        ctx = self._context(text_emb, guided, null_text_emb, T)
+        t = t.to(device=x.device, dtype=torch.int64)
+        t_n = (torch.cat([t, t]) if guided else t).contiguous()
+        z = torch.randn_like(x) if noise is None else _need_cuda_f32("noise", noise)
+        eps = torch.empty((t_n.numel(), T, H), dtype=torch.float32, device=x.device)
+        out = torch.empty_like(x)
+        self._p_sample_raw(x, ctx, t_n, z, guided, w if guided else 0.0, text_emb.shape[1], eps, out)
+        return out
+
+    @torch.no_grad()
+    def sample_latents(self, text_emb, audio_emb=None, *, x_init=None, noise=None, guidance_scale=None,
+                       null_text_emb=None, cond_by_audio=False, record: Optional[List[torch.Tensor]] = None,
+                       generator: Optional[torch.Generator] = None):
+        """All reverse steps (reference: __sample_latents, SpeechGenerator.py:150-164).
+
+        text_emb [B,S,text_dim]; ``audio_emb`` [B,T,H] gives the latent shape (and the start point when
+        ``cond_by_audio``), exactly as in the reference; ``x_init`` overrides the initial N(0,I) draw;
+        ``noise`` [steps,B,T,H] (indexed by t) replaces the per-step randn_like for parity runs;
+        ``record`` collects the guided eps_hat of every step (parity tests)."""
+        m = self.model
+        w = self.guidance_scale if guidance_scale is None else guidance_scale
+        guided = w is not None
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        dev = text_emb.device
+        if x_init is not None:
+            x = _need_cuda_f32("x_init", x_init).clone()
+        elif audio_emb is not None:
+            audio_emb = _need_cuda_f32("audio_emb", audio_emb)
+            x = audio_emb.clone() if cond_by_audio else torch.randn(audio_emb.shape, device=dev, generator=generator)
+        else:
+            raise DittoError("sample_latents needs audio_emb (shape donor) or x_init")
+        B, T, H = x.shape
+        S = text_emb.shape[1]
+        steps = m.diffusion_steps
+        ctx = self._context(text_emb, guided, null_text_emb, T)
+        n = 2 * B if guided else B
+        # t for every step, all sequences share it (SpeechGenerator.py:162)
+        t_all = torch.arange(steps - 1, -1, -1, device=dev, dtype=torch.int64).unsqueeze(1).repeat(1, n).contiguous()
+        eps = torch.empty((n, T, H), dtype=torch.float32, device=dev)
+        x_next = torch.empty_like(x)
+        z_buf = None if noise is not None else torch.empty_like(x)
+        for i in range(steps):
+            t_val = steps - 1 - i
+            if noise is not None:
+                z = noise[t_val]
+                if not z.is_cuda:
+                    raise DittoError("noise must live on the GPU")
+                z = z.contiguous()
+            else:
+                z = z_buf.normal_(generator=generator)  # drawn every step incl. t = 0, as the reference does
+            self._p_sample_raw(x, ctx, t_all[i], z, guided, w if guided else 0.0, S, eps, x_next)
+            if record is not None:
+                record.append((eps[B:] + w * (eps[:B] - eps[B:])).clone() if guided else eps.clone())
+            x, x_next = x_next, x
+        return x

@@ -1,0 +1,152 @@
+/*
+ * ditto_b200.h -- C-ABI of the B200-native DiTTo-TTS denoiser hot path (libditto_b200.so).
+ *
+ * The reference (Tikai7/DiTTO-TTS) is pure Python/PyTorch and has NO FFI / plugin layer
+ * (SURVEY.md section 8b): its boundary for this path is the nn.Module call signatures
+ *     DiTTO.forward(x, text_emb, t)                 src/model/DiTTO.py:66-94
+ *     GlobalAdaLN.forward / DiT.forward             src/components/DiT.py:25-40, 100-157
+ *     SpeechGenerator.__p_sample/__sample_latents   src/model/SpeechGenerator.py:131-164
+ * Each entry point below names the reference code it replaces.  The Python host
+ * (ditto_tts_b200/model.py, sampler.py) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor pointer is a DEVICE pointer (sm_100a, B200),
+ *     fp32 contiguous row-major unless stated; `stream` is a cudaStream_t passed as void*.
+ *   - the caller allocates outputs, the text context and the workspace (query the *_bytes functions);
+ *     hot-path calls never allocate, never synchronise, and are CUDA-graph capturable.
+ *   - return value: 0 = ok, <0 = error (DITTO_E_*); ditto_last_error() gives the message for the
+ *     calling thread.  Nothing throws across the ABI.  There is NO CPU fallback.
+ */
+#ifndef DITTO_B200_H_
+#define DITTO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DITTO_ABI_VERSION 1
+
+enum {
+  DITTO_OK = 0,
+  DITTO_E_BADARG = -1,      /* null pointer, negative size, unknown key, wrong numel        */
+  DITTO_E_UNSUPPORTED = -2, /* shape outside what the kernels cover         */
+  DITTO_E_CUDA = -3,        /* a CUDA runtime/driver call failed; message has the code      */
+  DITTO_E_STATE = -4,       /* engine not finalized / weights missing                      */
+  DITTO_E_WORKSPACE = -5    /* workspace or context buffer too small                       */
+};
+
+/* arithmetic mode of the engine (BASELINE.json: fp32 bar 1e-4, bf16 bar 2e-2 vs the fp32 reference) */
+enum {
+  DITTO_PREC_FP32 = 0, /* CUDA-core fp32 FMA GEMMs/attention: correctness path                  */
+  DITTO_PREC_BF16 = 1  /* tcgen05 bf16 tensor-core GEMMs, fp32 accumulate / residual / statistics */
+};
+
+/* optional features of the bf16 path (bit mask in ditto_config_t.flags); 0 = the plain composition */
+enum {
+  DITTO_F_FUSED_ROPE = 1 << 0, /* RoPE fused into the QKV GEMM epilogue (column-permuted weights) */
+  DITTO_F_FOLD_CROSS = 1 << 1  /* fold cross-attn q/out projections into the per-utterance text K/V */
+};
+
+/* Shapes of one DiTTO instance == ctor arguments of the reference, src/model/DiTTO.py:10-19
+ * (ConfigDiTTO defaults: src/utils/Config.py:109-116). */
+typedef struct ditto_config {
+  int32_t hidden_dim;      /* H, multiple of 8                                   */
+  int32_t num_layers;      /* L                                                  */
+  int32_t num_heads;       /* h, H % h == 0, (H/h) even                          */
+  int32_t time_dim;        /* width of t_embedding / time_embed                  */
+  int32_t text_dim;        /* must equal hidden_dim (nn.MultiheadAttention kdim) */
+  int32_t diffusion_steps; /* rows of t_embedding and of the sampler tables      */
+  int32_t precision;       /* DITTO_PREC_*                                       */
+  int32_t max_seq_len;     /* RoPE table rows to precompute (T <= max_seq_len)   */
+  int32_t flags;           /* DITTO_F_*                                          */
+  int32_t reserved[7];
+} ditto_config_t;
+
+typedef struct ditto_engine ditto_engine_t; /* opaque */
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int32_t ditto_abi_version(void);
+const char* ditto_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+int64_t ditto_kernel_launch_count(void);
+
+/* ---- engine life cycle == DiTTO.__init__ + load_state_dict (src/model/DiTTO.py:10-64) -------------- */
+int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out);
+int32_t ditto_engine_destroy(ditto_engine_t* e);
+/* Copy one state_dict tensor (reference key name) from device fp32 memory into the engine.
+ * Keys starting with "nac." and the dead "blocks.i.attn.out_proj.*" / "*.inv_freq" / "alphas_cumprod"
+ * entries are accepted and ignored. */
+int32_t ditto_engine_load_weight(ditto_engine_t* e, const char* key, const float* data, int64_t numel, void* stream);
+/* Sampler tables betas/alphas/alphas_cumprod [diffusion_steps] fp32, computed by the host exactly as
+ * src/model/SpeechGenerator.py:70-72 does. */
+int32_t ditto_engine_load_schedule(ditto_engine_t* e, const float* betas, const float* alphas,
+                                   const float* alphas_cumprod, int64_t steps, void* stream);
+/* Pack weights (bf16 copies, interleaved [fc1;gate], permuted QKV), build the per-step modulation table
+ * time_mlp(SiLU(time_embed(t_embedding))) [steps, 2H] (DiTTO.py:75-76 + DiT.py:30) and the RoPE cos/sin
+ * tables (DiT.py:46-59).  Synchronises the stream. */
+int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream);
+
+/* ---- sizes ------------------------------------------------------------------------------------------ */
+int64_t ditto_text_context_bytes(const ditto_engine_t* e, int64_t n_seq, int64_t S);
+int64_t ditto_workspace_bytes(const ditto_engine_t* e, int64_t n_seq, int64_t T, int64_t S);
+
+/* ---- hot path --------------------------------------------------------------------------------------- */
+/* Step-invariant text work for n_seq sequences: mean-pooled text modulation text_mlp(SiLU(mean_S(text)))
+ * (DiT.py:27,31) and every layer's cross-attention K/V projection (DiT.py:144-148 -> torch MHA in_proj).
+ * text_emb [n_seq, S, text_dim].  ctx: caller buffer of ditto_text_context_bytes(). */
+int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n_seq, int64_t S, void* ctx,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* eps_hat = DiTTO.forward(x, text_emb, t)   (src/model/DiTTO.py:66-94)
+ * x [n_x, T, H]; sequence i of n_seq reads x[i % n_x] (n_seq % n_x == 0; CFG: n_seq = 2 n_x shares x
+ * between the conditional and unconditional branch); t [n_seq] int64 (device); out [n_seq, T, H]. */
+int32_t ditto_forward(ditto_engine_t* e, const float* x, int64_t n_x, const void* ctx, const int64_t* t,
+                      int64_t n_seq, int64_t T, int64_t S, float* out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* Fused classifier-free-guidance combine + DDPM ancestral update (SpeechGenerator.py:137-147):
+ *   eps = eps_u + w (eps_c - eps_u)           (eps_u == NULL: eps = eps_c, the reference's no-guidance case)
+ *   x_out = 1/sqrt(alpha_t) (x - (1-alpha_t)/sqrt(1-acp_t) eps) + [t>0] sqrt(beta_t) z
+ * all [B, T*H] fp32; t [B] int64 (device); z == NULL: no noise term.  x_out may alias x. */
+int32_t ditto_cfg_ddpm_update(ditto_engine_t* e, const float* eps_c, const float* eps_u, const float* x,
+                              const float* z, const int64_t* t, float guidance_scale, float* x_out,
+                              int64_t B, int64_t elems_per_seq, void* stream);
+
+/* One sampler iteration == SpeechGenerator.__p_sample (SpeechGenerator.py:131-147) with the CFG
+ * extension: ditto_forward on n_seq = (guided ? 2B : B) sequences sharing x, then ditto_cfg_ddpm_update.
+ * ctx holds [cond(B); uncond(B)] when guided.  t [n_seq] int64.  eps_scratch [n_seq, T, H]. */
+int32_t ditto_p_sample(ditto_engine_t* e, const float* x, const void* ctx, const int64_t* t, const float* z,
+                       int32_t guided, float guidance_scale, int64_t B, int64_t T, int64_t S,
+                       float* eps_scratch, float* x_out, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* DiTTO.q_sample (DiTTO.py:106-126) with the reference's betas-as-alphas_cumprod buffer. */
+int32_t ditto_q_sample(ditto_engine_t* e, const float* x_start, const float* noise, const int64_t* t,
+                       float* out, int64_t B, int64_t elems_per_seq, void* stream);
+
+/* ---- single operators (unit-tested against the oracle; also usable on their own) --------------------- */
+/* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5, biased variance; DiT.py:84,89,94).
+ * gamma/beta may be NULL (no affine, DiT.py:23).  out_bf16 != 0: y is written as bf16. */
+int32_t ditto_layernorm(const float* x, const float* gamma, const float* beta, void* y, int32_t out_bf16,
+                        int64_t rows, int64_t H, void* stream);
+/* C[b] = alpha * A[b] @ op(B[b]) (+ bias) (+ resid), fp32 CUDA-core path.  A [M,K] lda; b_is_nk: B [N,K]
+ * (y = x W^T, F.linear) else B [K,N].  batch strides in elements. */
+int32_t ditto_gemm_f32(const float* A, int64_t lda, int64_t strideA, const float* B, int64_t ldb,
+                       int64_t strideB, int32_t b_is_nk, float* C, int64_t ldc, int64_t strideC,
+                       const float* bias, const float* resid, float alpha, int64_t M, int64_t N, int64_t K,
+                       int64_t batch, void* stream);
+/* C = alpha * A @ W^T (+bias) (+resid) with bf16 operands on tcgen05 tensor cores, fp32 accumulation in
+ * TMEM.  A [M,K] bf16 (lda), W [N,K] bf16 (ldw); out fp32 or bf16 (out_bf16).  K % 8 == 0. */
+int32_t ditto_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                        int32_t out_bf16, const float* bias, const float* resid, int64_t ldr, float alpha,
+                        int64_t M, int64_t N, int64_t K, void* stream);
+/* fp32 -> bf16 (round to nearest even) */
+int32_t ditto_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DITTO_B200_H_ */
