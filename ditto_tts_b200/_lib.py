@@ -30,6 +30,12 @@ SIGNATURES = {
     "ditto_abi_version": (_I32, []),
     "ditto_last_error": (C.c_char_p, []),
     "ditto_kernel_launch_count": (_I64, []),
+    "ditto_profile_start": (_I32, []),
+    "ditto_profile_stop": (_I32, []),
+    "ditto_profile_num_classes": (_I32, []),
+    "ditto_profile_class_name": (C.c_char_p, [_I32]),
+    "ditto_profile_get": (_I32, [_I32, C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double)]),
     "ditto_engine_create": (_I32, [C.POINTER(Config), C.POINTER(_P)]),
     "ditto_engine_destroy": (_I32, [_P]),
     "ditto_engine_load_weight": (_I32, [_P, C.c_char_p, _P, _I64, _P]),
@@ -79,3 +85,21 @@ def check(rc: int, what: str = ""):
 
 def launch_count() -> int:
     return int(load().ditto_kernel_launch_count())
+
+
+def profile_start():
+    check(load().ditto_profile_start(), "ditto_profile_start")
+
+
+def profile_stop():
+    """Returns {class_name: dict(launches, ms, flops, bytes)} for the classes that launched."""
+    lib = load()
+    check(lib.ditto_profile_stop(), "ditto_profile_stop")
+    out = {}
+    for i in range(lib.ditto_profile_num_classes()):
+        n, ms, fl, by = _I64(), C.c_double(), C.c_double(), C.c_double()
+        check(lib.ditto_profile_get(i, C.byref(n), C.byref(ms), C.byref(fl), C.byref(by)))
+        if n.value:
+            out[lib.ditto_profile_class_name(i).decode()] = dict(launches=n.value, ms=ms.value, flops=fl.value,
+                                                                 bytes=by.value)
+    return out

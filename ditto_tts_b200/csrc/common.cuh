@@ -51,6 +51,20 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     if (_rc != 0) return _rc;                                                    \
   } while (0)
 
+// ---------------------------------------------------------------- per-kernel-class timing (CUDA events, opt-in)
+enum ProfClass {
+  PC_TC_PROJ_IN = 0, PC_TC_QKV, PC_TC_SELF_SCORES, PC_TC_SELF_PV, PC_TC_CROSS_Q, PC_TC_CROSS_SCORES, PC_TC_CROSS_PV,
+  PC_TC_CROSS_OUT, PC_TC_GLU, PC_TC_FC2, PC_TC_PROJ_OUT, PC_TC_TEXT_KV, PC_TC_OTHER,
+  PC_SGEMM, PC_LAYERNORM, PC_ADALN, PC_ROPE, PC_SOFTMAX, PC_CFG_UPDATE, PC_ELEMENTWISE, PC_COUNT
+};
+extern bool g_prof_enabled;
+struct ProfScope {  // records start/stop events around the launches issued in its lifetime (no-op unless enabled)
+  int slot = -1;
+  cudaStream_t st;
+  ProfScope(int cls, cudaStream_t stream, double flops, double bytes);
+  ~ProfScope();
+};
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -27,6 +27,7 @@ int launch_cast_bf16(const float* x, bf16* y, int64_t n, cudaStream_t st) {
   DITTO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
                 DITTO_E_BADARG, "cast_bf16: misaligned pointer");
   int64_t blocks = std::min<int64_t>(ceil_div(n, 4 * 256), 148 * 16);
+  ProfScope prof(PC_ELEMENTWISE, st, 0.0, static_cast<double>(n) * 6);
   cast_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, y, n);
   DITTO_LAUNCH_CHECK();
   return 0;
@@ -121,6 +122,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128 && H > 0, DITTO_E_UNSUPPORTED, "layernorm: need H % 4 == 0 and H <= 1024");
   if (rows <= 0) return 0;
   const unsigned blocks = static_cast<unsigned>(ceil_div(rows, 8));
+  ProfScope prof(PC_LAYERNORM, st, 0.0, static_cast<double>(rows) * H * (out_bf16 ? 6 : 8));
   if (out_bf16)
     layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x, gamma, beta, static_cast<bf16*>(y), rows, H);
   else
@@ -198,6 +200,7 @@ int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const 
                     int64_t n_seq, int T, int H, cudaStream_t st) {
   DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128, DITTO_E_UNSUPPORTED, "adaln: need H % 4 == 0 and H <= 1024");
   const unsigned blocks = static_cast<unsigned>(ceil_div(n_seq * T, 8));
+  ProfScope prof(PC_ADALN, st, 0.0, static_cast<double>(n_seq) * T * H * (u_bf16 ? 10 + 2 : 12));
   if (u_bf16)
     adaln_ln_kernel<bf16><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
                                                   static_cast<bf16*>(u), xcast, n_seq, T, H);
@@ -256,6 +259,7 @@ int launch_rope(void* qkv, bool is_bf16, int64_t ld, const float* cos_t, const f
                 int H, int head_dim, cudaStream_t st) {
   const int64_t total = rows * H;
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(total, 256), 148 * 32));
+  ProfScope prof(PC_ROPE, st, 0.0, static_cast<double>(rows) * H * 2 * (is_bf16 ? 4 : 8));
   if (is_bf16)
     rope_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<bf16*>(qkv), ld, cos_t, sin_t, rows, seq_T, H, head_dim);
   else
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
 int launch_softmax(const float* s, int64_t lds, void* p, bool p_bf16, int64_t ldp, int64_t rows, int cols, cudaStream_t st) {
   if (rows <= 0) return 0;
   const unsigned blocks = static_cast<unsigned>(ceil_div(rows, 8));
+  ProfScope prof(PC_SOFTMAX, st, 0.0, static_cast<double>(rows) * cols * (p_bf16 ? 6 : 8));
   if (p_bf16)
     softmax_kernel<bf16, true><<<blocks, 256, 0, st>>>(s, lds, static_cast<bf16*>(p), ldp, rows, cols);
   else
@@ -430,6 +435,7 @@ int launch_cfg_ddpm_update(const float* eps_c, const float* eps_u, const float* 
   if (total_vec == 0) return 0;
   const int64_t want = ceil_div(total_vec, 256 * 4);  // ~4 vectors per thread
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(round_up(want, 148), 148 * 32));
+  ProfScope prof(PC_CFG_UPDATE, st, 0.0, static_cast<double>(total_vec) * 16 * (3 + (eps_u ? 1 : 0) + (z ? 1 : 0)));
   cfg_ddpm_update_kernel<<<blocks, 256, 0, st>>>(
       reinterpret_cast<const float4*>(eps_c), reinterpret_cast<const float4*>(eps_u), reinterpret_cast<const float4*>(x),
       reinterpret_cast<const float4*>(z), t, coef, steps, w, reinterpret_cast<float4*>(out), elems_per_seq / 4, total_vec);

@@ -24,6 +24,33 @@ int cuda_fail(cudaError_t err, const char* what, const char* file, int line) {
   return DITTO_E_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// opt-in profiler: one CUDA event pair per launcher call, accumulated per class on ditto_profile_stop()
+// ---------------------------------------------------------------------------------------------------
+bool g_prof_enabled = false;
+namespace {
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+std::vector<ProfRec> g_prof_recs;
+struct ProfAcc { long long launches = 0; double ms = 0, flops = 0, bytes = 0; };
+ProfAcc g_prof_acc[PC_COUNT];
+const char* kProfNames[PC_COUNT] = {"tc_gemm.proj_in", "tc_gemm.qkv_rope", "tc_gemm.self_scores", "tc_gemm.self_pv", "tc_gemm.cross_q",
+                                    "tc_gemm.cross_scores", "tc_gemm.cross_pv", "tc_gemm.cross_out", "tc_gemm.glu", "tc_gemm.fc2",
+                                    "tc_gemm.proj_out", "tc_gemm.text_kv", "tc_gemm.other", "sgemm_f32", "layernorm", "adaln_ln",
+                                    "rope", "softmax", "cfg_ddpm_update", "elementwise"};
+}  // namespace
+ProfScope::ProfScope(int cls, cudaStream_t stream, double flops, double bytes) : st(stream) {
+  if (!g_prof_enabled) return;
+  ProfRec r;
+  r.cls = cls; r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+  slot = static_cast<int>(g_prof_recs.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof_recs[slot].b, st);
+}
+
 // bump allocator over a caller buffer; with base == nullptr it only measures
 struct Arena {
   char* base;
@@ -118,8 +145,9 @@ static int sgemm_nt(const float* A, int64_t lda, const float* Wt, int64_t ldw, f
 // bf16 tensor-core helper: out = alpha * A[M,K] @ W[N,K]^T (+bias) (+resid)
 static int tc_nt(const bf16* A, int64_t lda, const bf16* Wt, int64_t ldw, void* out, bool out_bf16, int64_t ldo,
                  const float* bias, const float* resid, int64_t ldr, int64_t resid_row_mod, bf16* out2, int64_t ldo2,
-                 int M, int N, int K, cudaStream_t st) {
+                 int M, int N, int K, cudaStream_t st, int tag = PC_TC_OTHER) {
   TcGemmParams p;
+  p.tag = tag;
   p.A.ptr = A; p.A.rows = M; p.A.cols = K; p.A.ld = lda;
   p.B.ptr = Wt; p.B.rows = N; p.B.cols = K; p.B.ld = ldw;
   p.M = M; p.N = N; p.K = K;
@@ -198,7 +226,7 @@ namespace ditto {
 static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, int64_t ldq, int64_t q_seq_stride, const bf16* k,
                           int64_t ldk, int64_t k_seq_stride, const bf16* v, int64_t ldv, int64_t v_seq_stride, int64_t n, int Tq,
                           int Tk, float alpha, void* out, bool out_bf16, int64_t ldo, int64_t o_seq_stride, const float* resid,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool cross) {
   const int d = e->d, heads = e->heads;
   const int64_t ldp = round_up(Tk, 8);
   TcGemmParams g;
@@ -207,6 +235,7 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
   g.M = Tq; g.N = Tk; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
   g.alpha = alpha; g.out = w.scores; g.out_bf16 = false; g.ldo = ldp; g.so_inner = static_cast<int64_t>(Tq) * ldp;
   g.so_outer = static_cast<int64_t>(heads) * Tq * ldp;
+  g.tag = cross ? PC_TC_CROSS_SCORES : PC_TC_SELF_SCORES;
   DITTO_TRY(launch_tc_gemm(g, st));
   DITTO_TRY(launch_softmax(w.scores, ldp, w.P, true, ldp, n * heads * Tq, Tk, st));
   TcGemmParams o;
@@ -224,6 +253,7 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
   o.M = Tq; o.N = d; o.K = Tk; o.batch_inner = heads; o.batch_outer = static_cast<int>(n);
   o.out = out; o.out_bf16 = out_bf16; o.ldo = ldo; o.so_inner = d; o.so_outer = o_seq_stride;
   o.resid = resid; o.ldr = ldo; o.sr_inner = d; o.sr_outer = o_seq_stride;
+  o.tag = cross ? PC_TC_CROSS_PV : PC_TC_SELF_PV;
   DITTO_TRY(launch_tc_gemm(o, st));
   return 0;
 }
@@ -269,7 +299,7 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
   const int Mx = static_cast<int>(n_x * T);
   if (b16)
     DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_in16, H, w.xskip, false, H, e->W("proj_in.bias"), nullptr, 0, 0, nullptr, 0, Mx, H,
-                    H, st));
+                    H, st, PC_TC_PROJ_IN));
   else
     DITTO_TRY(sgemm_nt(x, H, e->W("proj_in.weight"), H, w.xskip, H, e->W("proj_in.bias"), nullptr, 0, 1.f, Mx, H, H, st));
 
@@ -286,6 +316,7 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
         g.B.ptr = lp.w_qkv; g.B.rows = 3 * H; g.B.cols = H; g.B.ld = H;
         g.M = static_cast<int>(M); g.N = 3 * H; g.K = H; g.bias = lp.b_qkv; g.out = qkv; g.out_bf16 = true; g.ldo = 3 * H;
+        g.tag = PC_TC_QKV;
         if (e->fused_rope) {
           g.epilogue = TC_EPI_QKV_ROPE; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_half = e->half;
           g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(T); g.hidden = H;
@@ -294,18 +325,18 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         if (!e->fused_rope) DITTO_TRY(launch_rope(qkv, true, 3 * H, e->rope_cos, e->rope_sin, M, static_cast<int>(T), H, d, st));
       }
       DITTO_TRY(attention_bf16(e, w, qkv, 3 * H, T * 3 * H, qkv + H, 3 * H, T * 3 * H, qkv + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
-                               static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st));
+                               static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st, false));
       // ---- cross-attention (torch MHA math path)                                                     DiT.py:141-148
       DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
       bf16* qc = static_cast<bf16*>(w.qc);
       bf16* oc = static_cast<bf16*>(w.oc);
       DITTO_TRY(tc_nt(u, H, lp.wc_in, H, qc, true, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 0, nullptr, 0, static_cast<int>(M), H,
-                      H, st));
+                      H, st, PC_TC_CROSS_Q));
       const bf16* kc = static_cast<const bf16*>(kv);
       DITTO_TRY(attention_bf16(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
-                               sqrt_inv_d, oc, true, H, T * H, nullptr, st));
+                               sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
       DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, nullptr, 0, static_cast<int>(M), H,
-                      H, st));
+                      H, st, PC_TC_CROSS_OUT));
       // ---- gated MLP                                                                                  DiT.py:150-155
       DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
       {
@@ -314,10 +345,11 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         g.B.ptr = lp.w_glu; g.B.rows = 8 * H; g.B.cols = H; g.B.ld = H;
         g.M = static_cast<int>(M); g.N = 8 * H; g.K = H; g.bias = lp.b_glu; g.out = w.hid; g.out_bf16 = true; g.ldo = 4 * H;
         g.epilogue = TC_EPI_GEGLU;
+        g.tag = PC_TC_GLU;
         DITTO_TRY(launch_tc_gemm(g, st));
       }
       DITTO_TRY(tc_nt(static_cast<bf16*>(w.hid), 4 * H, lp.w_fc2, 4 * H, w.h, false, H, e->LW(i, "mlp_fc2.bias"), w.h, H, 0,
-                      last ? static_cast<bf16*>(w.xb16) : nullptr, H, static_cast<int>(M), H, 4 * H, st));
+                      last ? static_cast<bf16*>(w.xb16) : nullptr, H, static_cast<int>(M), H, 4 * H, st, PC_TC_FC2));
       if (!last)
         DITTO_TRY(launch_layernorm(w.h, e->LW(i + 1, "norm1.weight"), e->LW(i + 1, "norm1.bias"), u, true, M, H, st));
     } else {
@@ -353,7 +385,7 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
   // eps = x_skip + proj_out(h)                                              DiTTO.py:93-94
   if (b16) {
     DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_out16, H, out, false, H, e->W("proj_out.bias"), w.xskip, H, n_x * T, nullptr, 0,
-                    static_cast<int>(M), H, H, st));
+                    static_cast<int>(M), H, H, st, PC_TC_PROJ_OUT));
   } else {
     // residual rows repeat with period n_x*T: one GEMM per group of n_x sequences
     for (int64_t g0 = 0; g0 < n; g0 += n_x)
@@ -374,6 +406,36 @@ extern "C" {
 int32_t ditto_abi_version(void) { return DITTO_ABI_VERSION; }
 const char* ditto_last_error(void) { return t_last_error.c_str(); }
 int64_t ditto_kernel_launch_count(void) { return g_launches.load(); }
+
+int32_t ditto_profile_start(void) {
+  for (auto& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof_recs.clear();
+  for (auto& a : g_prof_acc) a = ProfAcc();
+  g_prof_enabled = true;
+  return 0;
+}
+int32_t ditto_profile_stop(void) {
+  g_prof_enabled = false;
+  DITTO_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ProfAcc& a = g_prof_acc[r.cls];
+      a.launches += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  return 0;
+}
+int32_t ditto_profile_num_classes(void) { return PC_COUNT; }
+const char* ditto_profile_class_name(int32_t i) { return (i >= 0 && i < PC_COUNT) ? kProfNames[i] : ""; }
+int32_t ditto_profile_get(int32_t i, int64_t* launches, double* total_ms, double* flops, double* bytes) {
+  DITTO_REQUIRE(i >= 0 && i < PC_COUNT && launches && total_ms && flops && bytes, DITTO_E_BADARG, "profile_get: bad argument");
+  *launches = g_prof_acc[i].launches; *total_ms = g_prof_acc[i].ms; *flops = g_prof_acc[i].flops; *bytes = g_prof_acc[i].bytes;
+  return 0;
+}
 
 int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
   DITTO_REQUIRE(cfg && out, DITTO_E_BADARG, "engine_create: null argument");
@@ -593,7 +655,7 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
     const float* bias = e->LW(i, "cross_attn.in_proj_bias") + H;
     if (e->bf16_mode) {
       DITTO_TRY(tc_nt(w.text16, Xd, e->layers[i].wc_in + static_cast<int64_t>(H) * H, H, kv, true, 2 * H, bias, nullptr, 0, 0, nullptr, 0,
-                      static_cast<int>(n * S), 2 * H, Xd, st));
+                      static_cast<int>(n * S), 2 * H, Xd, st, PC_TC_TEXT_KV));
     } else {
       DITTO_TRY(sgemm_nt(text_emb, Xd, e->LW(i, "cross_attn.in_proj_weight") + static_cast<int64_t>(H) * H, H, static_cast<float*>(kv),
                          2 * H, bias, nullptr, 0, 1.f, static_cast<int>(n * S), 2 * H, Xd, st));

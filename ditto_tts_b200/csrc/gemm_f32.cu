@@ -130,6 +130,7 @@ int launch_sgemm(const SgemmParams& p, cudaStream_t st) {
   if (p.M == 0 || p.N == 0) return 0;
   const int64_t batch = static_cast<int64_t>(p.batch_inner) * p.batch_outer;
   DITTO_REQUIRE(batch <= 65535 && ceil_div(p.M, BM) <= 65535, DITTO_E_UNSUPPORTED, "sgemm: grid too large");
+  ProfScope prof(PC_SGEMM, st, 2.0 * p.M * p.N * p.K * batch, 0.0);
   dim3 grid(static_cast<unsigned>(ceil_div(p.N, BN)), static_cast<unsigned>(ceil_div(p.M, BM)), static_cast<unsigned>(batch));
   if (p.b_is_nk)
     sgemm_kernel<true><<<grid, TPB, 0, st>>>(p);

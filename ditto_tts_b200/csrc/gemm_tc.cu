@@ -431,6 +431,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
 
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
+  ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
   if (q.epilogue == TC_EPI_STORE && !q.b_kn)
     tc_gemm_kernel<TC_EPI_STORE, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
   else if (q.epilogue == TC_EPI_STORE && q.b_kn)

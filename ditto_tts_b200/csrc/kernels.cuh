@@ -61,6 +61,7 @@ struct TcGemmParams {
   int M = 0, N = 0, K = 0;
   int batch_inner = 1, batch_outer = 1;
   int epilogue = TC_EPI_STORE;
+  int tag = PC_TC_OTHER;                       // profiling class (call site)
   float alpha = 1.f;
   const float* bias = nullptr;                 // [N], indexed by GEMM column
   void* out = nullptr; bool out_bf16 = false;  // [M, ldo] per batch item

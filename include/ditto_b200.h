@@ -73,6 +73,15 @@ const char* ditto_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
 int64_t ditto_kernel_launch_count(void);
 
+/* Opt-in per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline numbers).
+ * start: reset + enable; stop: device-synchronise, accumulate, disable.  Not for use under graph capture.
+ * get: launches, summed duration [ms], summed algorithmic flops and bytes of class i. */
+int32_t ditto_profile_start(void);
+int32_t ditto_profile_stop(void);
+int32_t ditto_profile_num_classes(void);
+const char* ditto_profile_class_name(int32_t i);
+int32_t ditto_profile_get(int32_t i, int64_t* launches, double* total_ms, double* flops, double* bytes);
+
 /* ---- engine life cycle == DiTTO.__init__ + load_state_dict (src/model/DiTTO.py:10-64) -------------- */
 int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out);
 int32_t ditto_engine_destroy(ditto_engine_t* e);
