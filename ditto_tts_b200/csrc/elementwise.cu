@@ -361,6 +361,31 @@ int launch_mean_silu(const float* text, float* out, int64_t n, int S, int D, cud
   return 0;
 }
 
+// folded cross-attention score bias: sb[seq, head, s] = scale * sum_i K[seq*S + s, head*d + i] * bq[head*d + i]; zero pad
+__global__ void fold_bias_kernel(const bf16* __restrict__ kv, int64_t ld, const float* __restrict__ bq, float* __restrict__ sb,
+                                 int64_t total, int S, int Sp, int heads, int d, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (seq, head, s in [0, Sp))
+  if (o >= total) return;
+  const int s_idx = static_cast<int>(o % Sp);
+  const int head = static_cast<int>((o / Sp) % heads);
+  const int64_t seq = o / (static_cast<int64_t>(Sp) * heads);
+  float acc = 0.f;
+  if (s_idx < S) {
+    const bf16* row = kv + (seq * S + s_idx) * ld + head * d;
+    for (int i = lane; i < d; i += 32) acc += __bfloat162float(row[i]) * bq[head * d + i];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) sb[o] = s_idx < S ? scale * acc : 0.f;
+}
+int launch_fold_bias(const bf16* kv, int64_t ld, const float* bq, float* sb, int64_t n, int S, int Sp, int heads, int d, float scale,
+                     cudaStream_t st) {
+  const int64_t total = n * heads * Sp;
+  fold_bias_kernel<<<static_cast<unsigned>(ceil_div(total, 8)), 256, 0, st>>>(kv, ld, bq, sb, total, S, Sp, heads, d, scale);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
 // V [T, d] slices of qkv (ld) -> Vt [n*heads, d, Tp] (keys contiguous): fallback operand layout for P@V
 __global__ void transpose_v_kernel(const bf16* __restrict__ v, int64_t ld, bf16* __restrict__ vt, int T, int Tp, int heads,
                                    int d) {

@@ -79,6 +79,7 @@ struct ditto_engine {
   int H = 0, L = 0, heads = 0, d = 0, half = 0, Td = 0, Xd = 0, steps = 0, maxT = 0;
   bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
   int rope_pd = 0;
+  bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
   int pv_transpose = 0;  // debug: use the transposed-V operand instead of the MN-major descriptor
   std::map<std::string, int64_t> expected;  // key -> numel
   std::map<std::string, float*> w;          // device fp32 copies (owned)
@@ -160,8 +161,19 @@ struct CtxLayout {
   float* text_mod = nullptr;  // [n, 2H]
   void* kv0 = nullptr;        // layer 0 K|V [n*S, 2H] (bf16 or fp32); layers are kv_stride bytes apart
   size_t kv_stride = 0;
+  // folded cross-attention (bf16 path, DITTO_F_FOLD_CROSS): per layer
+  //   kfold [n, heads, S, H]   = K_h Wq_h           (scores = u . kfold^T + sbias)
+  //   vfold [n, heads*Sp, H]   = V_h Wo_h^T         (out = P . vfold + bo), zero rows for s >= S
+  //   sbias [n, heads, Sp] f32 = sqrt(1/d) K_h bq_h
+  bf16 *kfold0 = nullptr, *vfold0 = nullptr;
+  float* sbias0 = nullptr;
+  size_t kfold_stride = 0, vfold_stride = 0, sbias_stride = 0;  // elements between layers
   size_t total = 0;
 };
+static bool fold_active(const ditto_engine* e, int64_t S) {
+  // folding trades the two M x H x H projections for (heads*S)-wide products: only worth it when heads*S << H
+  return e->bf16_mode && e->fold_cross && e->heads * round_up(S, 8) * 2 <= e->H;
+}
 static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_t S) {
   Arena a(base);
   CtxLayout c;
@@ -171,6 +183,15 @@ static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_
   const size_t kv_bytes = ((static_cast<size_t>(kv_elems) * (e->bf16_mode ? 2 : 4)) + 255) & ~static_cast<size_t>(255);
   c.kv0 = a.take<char>(static_cast<int64_t>(kv_bytes) * e->L);
   c.kv_stride = kv_bytes;
+  if (fold_active(e, S)) {
+    const int64_t Sp = round_up(S, 8);
+    c.kfold_stride = static_cast<size_t>(n * e->heads * S * e->H);
+    c.vfold_stride = static_cast<size_t>(n * e->heads * Sp * e->H);
+    c.sbias_stride = static_cast<size_t>(n * e->heads * Sp);
+    c.kfold0 = a.take<bf16>(static_cast<int64_t>(c.kfold_stride) * e->L);
+    c.vfold0 = a.take<bf16>(static_cast<int64_t>(c.vfold_stride) * e->L);
+    c.sbias0 = a.take<float>(static_cast<int64_t>(c.sbias_stride) * e->L);
+  }
   c.total = a.off + 256;
   return c;
 }
@@ -328,15 +349,40 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
                                static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st, false));
       // ---- cross-attention (torch MHA math path)                                                     DiT.py:141-148
       DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
-      bf16* qc = static_cast<bf16*>(w.qc);
-      bf16* oc = static_cast<bf16*>(w.oc);
-      DITTO_TRY(tc_nt(u, H, lp.wc_in, H, qc, true, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 0, nullptr, 0, static_cast<int>(M), H,
-                      H, st, PC_TC_CROSS_Q));
-      const bf16* kc = static_cast<const bf16*>(kv);
-      DITTO_TRY(attention_bf16(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
-                               sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
-      DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, nullptr, 0, static_cast<int>(M), H,
-                      H, st, PC_TC_CROSS_OUT));
+      if (fold_active(e, S)) {
+        // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
+        const int heads = e->heads;
+        const int64_t Sp = w.Sp;
+        TcGemmParams g;
+        g.A.ptr = u; g.A.rows = T; g.A.cols = H; g.A.ld = H; g.A.s_inner = 0; g.A.s_outer = T * H;
+        g.B.ptr = c.kfold0 + c.kfold_stride * i; g.B.rows = S; g.B.cols = H; g.B.ld = H; g.B.s_inner = S * H;
+        g.B.s_outer = static_cast<int64_t>(heads) * S * H;
+        g.M = static_cast<int>(T); g.N = static_cast<int>(S); g.K = H; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+        g.alpha = sqrt_inv_d; g.bias = c.sbias0 + c.sbias_stride * i; g.sb_inner = Sp; g.sb_outer = heads * Sp;
+        g.out = w.scores; g.out_bf16 = false; g.ldo = heads * Sp; g.so_inner = Sp; g.so_outer = T * heads * Sp;
+        g.tag = PC_TC_CROSS_SCORES;
+        DITTO_TRY(launch_tc_gemm(g, st));
+        DITTO_TRY(launch_softmax(w.scores, Sp, w.P, true, Sp, n * T * heads, static_cast<int>(S), st));
+        TcGemmParams o;
+        o.A.ptr = static_cast<const bf16*>(w.P); o.A.rows = T; o.A.cols = heads * Sp; o.A.ld = heads * Sp; o.A.s_outer = T * heads * Sp;
+        o.B.ptr = c.vfold0 + c.vfold_stride * i; o.B.rows = heads * Sp; o.B.cols = H; o.B.ld = H; o.B.s_outer = heads * Sp * H;
+        o.b_kn = true;
+        o.M = static_cast<int>(T); o.N = H; o.K = static_cast<int>(heads * Sp); o.batch_inner = 1; o.batch_outer = static_cast<int>(n);
+        o.bias = e->LW(i, "cross_attn.out_proj.bias");
+        o.out = w.h; o.out_bf16 = false; o.ldo = H; o.so_outer = T * H; o.resid = w.h; o.ldr = H; o.sr_outer = T * H;
+        o.tag = PC_TC_CROSS_PV;
+        DITTO_TRY(launch_tc_gemm(o, st));
+      } else {
+        bf16* qc = static_cast<bf16*>(w.qc);
+        bf16* oc = static_cast<bf16*>(w.oc);
+        DITTO_TRY(tc_nt(u, H, lp.wc_in, H, qc, true, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 0, nullptr, 0, static_cast<int>(M), H,
+                        H, st, PC_TC_CROSS_Q));
+        const bf16* kc = static_cast<const bf16*>(kv);
+        DITTO_TRY(attention_bf16(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
+                                 sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
+        DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, nullptr, 0, static_cast<int>(M), H,
+                        H, st, PC_TC_CROSS_OUT));
+      }
       // ---- gated MLP                                                                                  DiT.py:150-155
       DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
       {
@@ -469,6 +515,7 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     for (int pd : {128, 64, 32})
       if (e->half % pd == 0 && e->H % (2 * pd) == 0) { e->rope_pd = pd; break; }
     e->fused_rope = (cfg->flags & DITTO_F_FUSED_ROPE) && e->rope_pd != 0;
+    e->fold_cross = (cfg->flags & DITTO_F_FOLD_CROSS) != 0;
     const char* env = getenv("DITTO_PV_TRANSPOSE");
     e->pv_transpose = env && env[0] == '1';
   }
@@ -656,6 +703,34 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
     if (e->bf16_mode) {
       DITTO_TRY(tc_nt(w.text16, Xd, e->layers[i].wc_in + static_cast<int64_t>(H) * H, H, kv, true, 2 * H, bias, nullptr, 0, 0, nullptr, 0,
                       static_cast<int>(n * S), 2 * H, Xd, st, PC_TC_TEXT_KV));
+      if (fold_active(e, S)) {
+        const int d = e->d, heads = e->heads;
+        const int64_t Sp = round_up(S, 8);
+        const bf16* kvb = static_cast<const bf16*>(kv);
+        bf16* kf = c.kfold0 + c.kfold_stride * i;
+        bf16* vf = c.vfold0 + c.vfold_stride * i;
+        float* sb = c.sbias0 + c.sbias_stride * i;
+        DITTO_CUDA(cudaMemsetAsync(vf, 0, c.vfold_stride * sizeof(bf16), st));
+        // kfold[seq, h] (S x H) = K[seq][:, h*d:(h+1)*d] (S x d) @ Wq[h*d:(h+1)*d, :] (d x H, "KN" operand)
+        TcGemmParams g;
+        g.A.ptr = kvb; g.A.rows = S; g.A.cols = d; g.A.ld = 2 * H; g.A.s_inner = d; g.A.s_outer = S * 2 * H;
+        g.B.ptr = e->layers[i].wc_in; g.B.rows = d; g.B.cols = H; g.B.ld = H; g.B.s_inner = static_cast<int64_t>(d) * H; g.B.s_outer = 0;
+        g.b_kn = true;
+        g.M = static_cast<int>(S); g.N = H; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+        g.out = kf; g.out_bf16 = true; g.ldo = H; g.so_inner = S * H; g.so_outer = static_cast<int64_t>(heads) * S * H;
+        g.tag = PC_TC_TEXT_KV;
+        DITTO_TRY(launch_tc_gemm(g, st));
+        // vfold[seq, h*Sp + s, :] = V[seq][:, h*d:(h+1)*d] (S x d) @ Wo[:, h*d:(h+1)*d]^T
+        TcGemmParams v;
+        v.A.ptr = kvb + H; v.A.rows = S; v.A.cols = d; v.A.ld = 2 * H; v.A.s_inner = d; v.A.s_outer = S * 2 * H;
+        v.B.ptr = e->layers[i].wc_o; v.B.rows = H; v.B.cols = d; v.B.ld = H; v.B.s_inner = d; v.B.s_outer = 0;
+        v.M = static_cast<int>(S); v.N = H; v.K = d; v.batch_inner = heads; v.batch_outer = static_cast<int>(n);
+        v.out = vf; v.out_bf16 = true; v.ldo = H; v.so_inner = Sp * H; v.so_outer = static_cast<int64_t>(heads) * Sp * H;
+        v.tag = PC_TC_TEXT_KV;
+        DITTO_TRY(launch_tc_gemm(v, st));
+        DITTO_TRY(launch_fold_bias(kvb, 2 * H, e->LW(i, "cross_attn.in_proj_bias"), sb, n, static_cast<int>(S), static_cast<int>(Sp), heads, d,
+                                   sqrtf(1.0f / static_cast<float>(d)), st));
+      }
     } else {
       DITTO_TRY(sgemm_nt(text_emb, Xd, e->LW(i, "cross_attn.in_proj_weight") + static_cast<int64_t>(H) * H, H, static_cast<float*>(kv),
                          2 * H, bias, nullptr, 0, 1.f, static_cast<int>(n * S), 2 * H, Xd, st));

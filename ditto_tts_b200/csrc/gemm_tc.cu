@@ -26,7 +26,10 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BARRIER_BYTES = 256;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BARRIER_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
 
 struct DevParams {
   int M, N, K;
@@ -34,7 +37,7 @@ struct DevParams {
   int m_tiles, n_tiles, num_tiles, num_kb;
   int a_bi, a_bo, b_bi, b_bo;  // which batch coordinates each operand consumes
   float alpha;
-  const float* bias;
+  const float* bias; long long sb_inner, sb_outer;
   void* out; int out_bf16;
   long long ldo, so_inner, so_outer;
   const float* resid;
@@ -44,67 +47,135 @@ struct DevParams {
   int rope_half, rope_pd, seq_T, hidden;
 };
 
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], int ncols) {
-  if (ncols == 32) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) dst[j] = v[j];
-  }
+// ---------------------------------------------------------------------------------------------------
+// epilogue math
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32], int ncols) {
-  if (ncols == 32) {
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU_erf(a) * sigmoid(g) with 3 MUFU ops (2x ex2, 1x rcp shared by both factors).
+//   Phi(a) = 0.5 (1 + erf(a / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), exact-erf semantics of nn.GELU()
+__device__ __forceinline__ float geglu_fast(float a, float g) {
+  const float z = fabsf(a) * 0.70710678118654752440f;
+  const float e1 = ex2_approx(-z * z * 1.4426950408889634f);                 // exp(-z^2)
+  const float e2 = ex2_approx(fminf(-g * 1.4426950408889634f, 80.f));        // exp(-g), clamped: no inf * 0
+  const float da = fmaf(0.3275911f, z, 1.0f);                                // 1 + p z
+  const float db = 1.0f + e2;                                                // 1 + exp(-g)
+  const float r = rcp_approx(da * db);
+  const float t = db * r;                                                    // 1 / (1 + p z)
+  const float sig = da * r;                                                  // sigmoid(g)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float half_erfc = 0.5f * t * poly * e1;                              // 0.5 erfc(z)
+  const float phi = a >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return a * phi * sig;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue staging: each epilogue warp owns a 32 x 32 fp32 tile in shared memory (4 KiB, 16-byte chunks XOR-swizzled
+// by row) used to turn the TMEM layout (thread = row) into a coalesced global layout (quarter-warp = 128 B of a row).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int stage_idx(int row, int chunk) { return row * 8 + (chunk ^ (row & 7)); }
+
+__device__ __forceinline__ void stage_put_row(float4* stage, int lane, const float (&v)[32]) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 o;
-      o.x = pack_bf16x2(v[j], v[j + 1]);
-      o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-      o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-      o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-      *reinterpret_cast<uint4*>(dst + j) = o;
+  for (int j = 0; j < 8; ++j) stage[stage_idx(lane, j)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// Residual prefetch for one 32 x ncols chunk in the coalesced layout (lane -> 4 columns x 8 rows).  Issued BEFORE the
+// TMEM load / staging of the chunk so that the (HBM-latency) loads overlap them; out and resid alias for the in-place
+// residual update, so loads and stores of one chunk must not be interleaved.
+__device__ __forceinline__ void resid_prefetch(const DevParams& p, int lane, long long row0, int ocol0, int ncols,
+                                               long long res_off, float4 (&rv)[8]) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int c = c4 * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c >= ncols) return;
+  const bool full = c + 3 < ncols;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long row = row0 + i * 4 + rsub;
+    if (row >= p.M) break;
+    const long long rrow = p.resid_row_mod > 0 ? row % p.resid_row_mod : row;
+    const float* rp = p.resid + res_off + rrow * p.ldr + ocol0 + c;
+    if (full) {
+      rv[i] = *reinterpret_cast<const float4*>(rp);
+    } else {
+      rv[i].x = rp[0];
+      if (c + 1 < ncols) rv[i].y = rp[1];
+      if (c + 2 < ncols) rv[i].z = rp[2];
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
   }
 }
 
-// generic chunk store used by STORE and by the v-part / fallback of QKV_ROPE
-__device__ __forceinline__ void epilogue_store_chunk(const DevParams& p, const uint32_t (&r)[32], long long row, int col0,
-                                                     long long out_off, long long res_off, bool row_ok) {
-  const int ncols = min(32, p.N - col0);
-  if (!row_ok || ncols <= 0) return;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
-  if (p.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
-  }
-  if (p.resid) {
-    const long long rrow = p.resid_row_mod > 0 ? row % p.resid_row_mod : row;
-    const float* rp = p.resid + res_off + rrow * p.ldr + col0;
-    if (ncols == 32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(rp + j);
-        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-      }
+// Flush a staged 32 x ncols tile: v = alpha * staged (+bias) (+rv) -> out (fp32 or bf16) (+ bf16 copy).
+// Row r of the tile is global row row0 + r; column c is output column ocol0 + c (bias indexed by bias + c).
+__device__ __forceinline__ void stage_flush(const DevParams& p, const float4* stage, int lane, long long row0, int ocol0,
+                                            const float* bias, int ncols, long long out_off, bool out_bf16,
+                                            const float4 (&rv)[8]) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int c = c4 * 4;
+  if (c >= ncols) return;                      // after the caller's __syncwarp; no further warp-collectives inside
+  const bool full = c + 3 < ncols;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias != nullptr) {
+    if (full) {
+      b4 = *reinterpret_cast<const float4*>(bias + c);
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] += rp[j];
+      b4.x = bias[c];
+      if (c + 1 < ncols) b4.y = bias[c + 1];
+      if (c + 2 < ncols) b4.z = bias[c + 2];
     }
   }
-  if (p.out_bf16)
-    store_bf16x32(static_cast<bf16*>(p.out) + out_off + row * p.ldo + col0, v, ncols);
-  else
-    store_f32x32(static_cast<float*>(p.out) + out_off + row * p.ldo + col0, v, ncols);
-  if (p.out2) store_bf16x32(p.out2 + out_off + row * p.ldo2 + col0, v, ncols);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const long long row = row0 + r;
+    if (row >= p.M) break;
+    float4 v = stage[stage_idx(r, c4)];
+    v.x = fmaf(p.alpha, v.x, b4.x) + rv[i].x; v.y = fmaf(p.alpha, v.y, b4.y) + rv[i].y;
+    v.z = fmaf(p.alpha, v.z, b4.z) + rv[i].z; v.w = fmaf(p.alpha, v.w, b4.w) + rv[i].w;
+    const long long o = out_off + row * p.ldo + ocol0 + c;
+    if (out_bf16) {
+      bf16* dst = static_cast<bf16*>(p.out) + o;
+      if (full) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      } else {
+        dst[0] = __float2bfloat16_rn(v.x);
+        if (c + 1 < ncols) dst[1] = __float2bfloat16_rn(v.y);
+        if (c + 2 < ncols) dst[2] = __float2bfloat16_rn(v.z);
+      }
+    } else {
+      float* dst = static_cast<float*>(p.out) + o;
+      if (full) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        dst[0] = v.x;
+        if (c + 1 < ncols) dst[1] = v.y;
+        if (c + 2 < ncols) dst[2] = v.z;
+      }
+    }
+    if (p.out2) {
+      bf16* d2 = p.out2 + out_off + row * p.ldo2 + ocol0 + c;
+      if (full) {
+        *reinterpret_cast<uint2*>(d2) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      } else {
+        d2[0] = __float2bfloat16_rn(v.x);
+        if (c + 1 < ncols) d2[1] = __float2bfloat16_rn(v.y);
+        if (c + 2 < ncols) d2[2] = __float2bfloat16_rn(v.z);
+      }
+    }
+  }
 }
 
 template <int EPI, bool B_KN>
@@ -118,6 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float4* stage_base = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + BARRIER_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,10 +277,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // =========================== epilogue: TMEM -> registers -> global ===========================
+    // =========================== epilogue: TMEM -> registers -> swizzled smem -> coalesced global ===========================
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may touch
     const int half_sel = ew >> 2;  // which 4 of the 8 column chunks
+    float4* stage = stage_base + ew * 256;
+    float4 zero8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) zero8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -219,93 +295,139 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
       const long long out_off = bo * p.so_outer + bi * p.so_inner;
       const long long res_off = bo * p.sr_outer + bi * p.sr_inner;
-      const long long row = static_cast<long long>(m_blk) * BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const long long bias_off = bo * p.sb_outer + bi * p.sb_inner;
+      const long long row0 = static_cast<long long>(m_blk) * BLOCK_M + quarter * 32;
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
+      const bool rows_live = row0 < p.M;  // warp-uniform: nothing to store for a fully out-of-range row group
 
       if (EPI == TC_EPI_STORE) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           const int tcol = (half_sel * 4 + c) * 32;
           const int col0 = n_blk * BLOCK_N + tcol;
-          if (col0 >= p.N) break;  // warp-uniform
+          if (col0 >= p.N || !rows_live) break;  // warp-uniform
+          const int ncols = min(32, p.N - col0);
+          float4 rv[8];
+          if (p.resid != nullptr) {
+            resid_prefetch(p, lane, row0, col0, ncols, res_off, rv);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           uint32_t r[32];
           tmem_ld_32x32(t_row + tcol, r);
           tmem_ld_wait();
-          epilogue_store_chunk(p, r, row, col0, out_off, res_off, row_ok);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          stage_put_row(stage, lane, v);
+          __syncwarp();
+          stage_flush(p, stage, lane, row0, col0, p.bias ? p.bias + bias_off + col0 : nullptr, ncols, out_off, p.out_bf16 != 0, rv);
+          __syncwarp();
         }
       } else if (EPI == TC_EPI_GEGLU) {
+        // two 32-column accumulator chunks [a16|g16][a16|g16] -> 32 hidden values per row -> one staged tile
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int tcol = (half_sel * 4 + c) * 32;
+        for (int c = 0; c < 2; ++c) {
+          const int tcol = (half_sel * 4 + c * 2) * 32;
           const int col0 = n_blk * BLOCK_N + tcol;
-          if (col0 >= p.N) break;
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + tcol, r);
+          if (col0 >= p.N || !rows_live) break;
+          const bool second = col0 + 32 < p.N;  // N % 32 == 0, so the second chunk is all-or-nothing
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_row + tcol, r0);
+          if (second) tmem_ld_32x32(t_row + tcol + 32, r1);
           tmem_ld_wait();
-          if (row_ok) {
-            uint32_t o[8];
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float a0 = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
-              const float a1 = __uint_as_float(r[j + 1]) + __ldg(p.bias + col0 + j + 1);
-              const float g0 = __uint_as_float(r[16 + j]) + __ldg(p.bias + col0 + 16 + j);
-              const float g1 = __uint_as_float(r[16 + j + 1]) + __ldg(p.bias + col0 + 16 + j + 1);
-              o[j >> 1] = pack_bf16x2(gelu_erf_f(a0) * sigmoid_f(g0), gelu_erf_f(a1) * sigmoid_f(g1));
-            }
-            bf16* dst = static_cast<bf16*>(p.out) + out_off + row * p.ldo + (col0 >> 1);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          for (int j = 0; j < 16; ++j)
+            v[j] = geglu_fast(__uint_as_float(r0[j]) + __ldg(p.bias + col0 + j), __uint_as_float(r0[16 + j]) + __ldg(p.bias + col0 + 16 + j));
+          if (second) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              v[16 + j] = geglu_fast(__uint_as_float(r1[j]) + __ldg(p.bias + col0 + 32 + j),
+                                     __uint_as_float(r1[16 + j]) + __ldg(p.bias + col0 + 48 + j));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
           }
+          stage_put_row(stage, lane, v);
+          __syncwarp();
+          stage_flush(p, stage, lane, row0, col0 >> 1, nullptr, second ? 32 : 16, out_off, true, zero8);
+          __syncwarp();
         }
       } else {  // TC_EPI_QKV_ROPE
         const int cpp = p.rope_pd >> 5;  // 32-column chunks per PD block
+        const int c4 = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int pi = half_sel * 2 + c;
           const int ch1 = (pi / cpp) * (2 * cpp) + (pi % cpp);
           const int ch2 = ch1 + cpp;
           const int pc1 = n_blk * BLOCK_N + ch1 * 32, pc2 = n_blk * BLOCK_N + ch2 * 32;
-          if (pc1 >= p.N) continue;  // warp-uniform
+          if (pc1 >= p.N || !rows_live) continue;  // warp-uniform
           uint32_t r1[32], r2[32];
           tmem_ld_32x32(t_row + ch1 * 32, r1);
           tmem_ld_32x32(t_row + ch2 * 32, r2);
           tmem_ld_wait();
-          if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store
-            epilogue_store_chunk(p, r1, row, pc1, out_off, res_off, row_ok);
-            epilogue_store_chunk(p, r2, row, pc2, out_off, res_off, row_ok);
+          float v[32];
+          if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store of both chunks
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+            stage_put_row(stage, lane, v);
+            __syncwarp();
+            stage_flush(p, stage, lane, row0, pc1, p.bias + pc1, 32, out_off, true, zero8);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
+            stage_put_row(stage, lane, v);
+            __syncwarp();
+            stage_flush(p, stage, lane, row0, pc2, p.bias + pc2, 32, out_off, true, zero8);
+            __syncwarp();
             continue;
           }
-          if (!row_ok) continue;
+          // q / k thirds: x1 chunk and its RoPE partner chunk -> coalesced layout, then rotate
+          float4 xa[8], xb[8];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+          stage_put_row(stage, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xa[i] = stage[stage_idx(i * 4 + rsub, c4)];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
+          stage_put_row(stage, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xb[i] = stage[stage_idx(i * 4 + rsub, c4)];
+          __syncwarp();
           const int region = pc1 / p.hidden;              // 0 = q, 1 = k
           const int lp = pc1 - region * p.hidden;         // permuted column inside the region
           const int g = lp / (2 * p.rope_pd), w = lp - g * 2 * p.rope_pd;  // w < PD by construction
           const int e0 = g * p.rope_pd;                   // first "x1 element" index of this group
           const int head = e0 / p.rope_half;
-          const int j0 = e0 - head * p.rope_half + w;     // rotary frequency index of column 0 of the chunk
+          const int j0 = e0 - head * p.rope_half + w + c4 * 4;  // rotary frequency index of this lane's 4 columns
           const int dest1 = region * p.hidden + head * 2 * p.rope_half + j0;
-          const int pos = static_cast<int>(row % p.seq_T);
-          const float* cp = p.rope_cos + static_cast<long long>(pos) * p.rope_half + j0;
-          const float* sp = p.rope_sin + static_cast<long long>(pos) * p.rope_half + j0;
-          float o1[32], o2[32];
+          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + pc1 + c4 * 4);
+          const float4 b2 = *reinterpret_cast<const float4*>(p.bias + pc2 + c4 * 4);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 cs = *reinterpret_cast<const float4*>(cp + j);
-            const float4 sn = *reinterpret_cast<const float4*>(sp + j);
-            const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float x1 = __uint_as_float(r1[j + q]) + __ldg(p.bias + pc1 + j + q);
-              const float x2 = __uint_as_float(r2[j + q]) + __ldg(p.bias + pc2 + j + q);
-              o1[j + q] = x1 * cc[q] - x2 * ss[q];
-              o2[j + q] = x2 * cc[q] + x1 * ss[q];
-            }
+          for (int i = 0; i < 8; ++i) {
+            const long long row = row0 + i * 4 + rsub;
+            if (row >= p.M) break;
+            const int pos = static_cast<int>(row % p.seq_T);
+            const float4 cs = *reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * p.rope_half + j0);
+            const float4 sn = *reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * p.rope_half + j0);
+            const float x1x = xa[i].x + b1.x, x1y = xa[i].y + b1.y, x1z = xa[i].z + b1.z, x1w = xa[i].w + b1.w;
+            const float x2x = xb[i].x + b2.x, x2y = xb[i].y + b2.y, x2z = xb[i].z + b2.z, x2w = xb[i].w + b2.w;
+            bf16* dst = static_cast<bf16*>(p.out) + out_off + row * p.ldo + dest1;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x1x * cs.x - x2x * sn.x, x1y * cs.y - x2y * sn.y),
+                                                        pack_bf16x2(x1z * cs.z - x2z * sn.z, x1w * cs.w - x2w * sn.w));
+            *reinterpret_cast<uint2*>(dst + p.rope_half) =
+                make_uint2(pack_bf16x2(x2x * cs.x + x1x * sn.x, x2y * cs.y + x1y * sn.y),
+                           pack_bf16x2(x2z * cs.z + x1z * sn.z, x2w * cs.w + x1w * sn.w));
           }
-          bf16* dst = static_cast<bf16*>(p.out) + out_off + row * p.ldo + dest1;
-          store_bf16x32(dst, o1, 32);
-          store_bf16x32(dst + p.rope_half, o2, 32);
         }
       }
       tcgen05_fence_before();
@@ -422,7 +544,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.num_kb = static_cast<int>(ceil_div(q.K, BLOCK_K));
   p.a_bi = q.A.s_inner ? 1 : 0; p.a_bo = q.A.s_outer ? 1 : 0;
   p.b_bi = q.B.s_inner ? 1 : 0; p.b_bo = q.B.s_outer ? 1 : 0;
-  p.alpha = q.alpha; p.bias = q.bias;
+  p.alpha = q.alpha; p.bias = q.bias; p.sb_inner = q.sb_inner; p.sb_outer = q.sb_outer;
   p.out = q.out; p.out_bf16 = q.out_bf16 ? 1 : 0;
   p.ldo = q.ldo; p.so_inner = q.so_inner; p.so_outer = q.so_outer;
   p.resid = q.resid; p.ldr = q.ldr; p.sr_inner = q.sr_inner; p.sr_outer = q.sr_outer; p.resid_row_mod = q.resid_row_mod;

@@ -22,6 +22,8 @@ int launch_softmax(const float* s, int64_t lds, void* p, bool p_bf16, int64_t ld
 int launch_geglu_f32(const float* a, const float* g, float* out, int64_t n, cudaStream_t st);
 int launch_silu(float* x, int64_t n, cudaStream_t st);
 int launch_mean_silu(const float* text, float* out, int64_t n, int S, int D, cudaStream_t st);
+int launch_fold_bias(const bf16* kv, int64_t ld, const float* bq, float* sb, int64_t n, int S, int Sp, int heads, int d, float scale,
+                     cudaStream_t st);
 int launch_transpose_v(const bf16* v, int64_t ld, bf16* vt, int64_t n_seq, int T, int Tp, int heads, int d, cudaStream_t st);
 int launch_cfg_ddpm_update(const float* eps_c, const float* eps_u, const float* x, const float* z, const int64_t* t,
                            const float* coef, int steps, float w, float* out, int64_t B, int64_t elems_per_seq,
@@ -64,6 +66,7 @@ struct TcGemmParams {
   int tag = PC_TC_OTHER;                       // profiling class (call site)
   float alpha = 1.f;
   const float* bias = nullptr;                 // [N], indexed by GEMM column
+  int64_t sb_inner = 0, sb_outer = 0;          // optional per-batch-item bias (element strides)
   void* out = nullptr; bool out_bf16 = false;  // [M, ldo] per batch item
   int64_t ldo = 0, so_inner = 0, so_outer = 0;
   const float* resid = nullptr;                // fp32, added after bias

@@ -109,12 +109,14 @@ class DiTTO(nn.Module):
       * the NAC (HF EnCodec/GPT-2 + a checkpoint file, DiTTO.py:22-34) is not constructed: pass
         ``nac=<module>`` to attach one; ``nac.*`` keys of reference checkpoints are ignored on load;
       * extra keywords ``precision`` ("bf16" tensor-core path | "fp32" CUDA-core parity path),
-        ``max_seq_len`` (RoPE table rows) and ``fused_rope``.
+        ``max_seq_len`` (RoPE table rows), ``fused_rope`` (RoPE in the QKV GEMM epilogue) and ``fold_cross``
+        (cross-attention q/out projections folded into the per-utterance text K/V; single-head models only).
     """
 
     def __init__(self, hidden_dim=768, num_layers=12, num_heads=12, time_dim=256, text_dim=768,
                  diffusion_steps=1000, lambda_factor=0.1, nac_model_path=None, *, nac: Optional[nn.Module] = None,
-                 precision: str = "bf16", max_seq_len: int = 4096, fused_rope: bool = True):
+                 precision: str = "bf16", max_seq_len: int = 4096, fused_rope: bool = True,
+                 fold_cross: bool = True):
         super().__init__()
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -122,6 +124,7 @@ class DiTTO(nn.Module):
         self.time_dim, self.text_dim, self.diffusion_steps = time_dim, text_dim, diffusion_steps
         self.lambda_factor, self.nac_model_path = lambda_factor, nac_model_path
         self.precision, self.max_seq_len, self.fused_rope = precision, max_seq_len, fused_rope
+        self.fold_cross = fold_cross
         if nac is not None:
             self.nac = nac
         # construction order == reference (DiTTO.py:36-64): seeded default init gives the same weights
@@ -179,7 +182,8 @@ class DiTTO(nn.Module):
                                   diffusion_steps=self.diffusion_steps,
                                   precision=_lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32,
                                   max_seq_len=self.max_seq_len,
-                                  flags=_lib.F_FUSED_ROPE if self.fused_rope else 0)
+                                  flags=(_lib.F_FUSED_ROPE if self.fused_rope else 0) |
+                                  (_lib.F_FOLD_CROSS if self.fold_cross else 0))
                 h = C.c_void_p()
                 _lib.check(lib.ditto_engine_create(C.byref(cfg), C.byref(h)), "ditto_engine_create")
                 self._engine = h

@@ -31,7 +31,8 @@ def report(name, err, bar):
 
 def build_model(cfg, sd, precision, fused_rope=True):
     m = D.DiTTO(hidden_dim=cfg.hidden_dim, num_layers=cfg.num_layers, num_heads=cfg.num_heads, time_dim=cfg.time_dim,
-                text_dim=cfg.text_dim, diffusion_steps=cfg.diffusion_steps, precision=precision, fused_rope=fused_rope)
+                text_dim=cfg.text_dim, diffusion_steps=cfg.diffusion_steps, precision=precision, fused_rope=fused_rope,
+                fold_cross=fused_rope)
     m.load_state_dict(sd, strict=True)
     return m.to(dev)
 
