@@ -294,14 +294,57 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
   for (int c = cols + lane; c < ldp; c += 32) pr[c] = static_cast<OutT>(0.f);
 }
 
+// single-pass variant for rows of at most 32 * kMaxV columns: the row lives in registers (one HBM read, one write)
+template <typename OutT, bool kFast, int kMaxV>
+__global__ void __launch_bounds__(256) softmax_reg_kernel(const float* __restrict__ s, int64_t lds, OutT* __restrict__ p,
+                                                          int64_t ldp, int64_t rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* sr = s + row * lds;
+  OutT* pr = p + row * ldp;
+  float v[kMaxV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = c < cols ? sr[c] : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    v[i] = kFast ? __expf(v[i] - m) : expf(v[i] - m);  // exp(-inf) = 0 for the padding slots
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < ldp) pr[c] = static_cast<OutT>(c < cols ? v[i] * inv : 0.f);  // padding columns are zeroed
+  }
+}
+
 int launch_softmax(const float* s, int64_t lds, void* p, bool p_bf16, int64_t ldp, int64_t rows, int cols, cudaStream_t st) {
   if (rows <= 0) return 0;
   const unsigned blocks = static_cast<unsigned>(ceil_div(rows, 8));
   ProfScope prof(PC_SOFTMAX, st, 0.0, static_cast<double>(rows) * cols * (p_bf16 ? 6 : 8));
-  if (p_bf16)
-    softmax_kernel<bf16, true><<<blocks, 256, 0, st>>>(s, lds, static_cast<bf16*>(p), ldp, rows, cols);
-  else
-    softmax_kernel<float, false><<<blocks, 256, 0, st>>>(s, lds, static_cast<float*>(p), ldp, rows, cols);
+  const bool reg_ok = ldp <= 1024;
+  if (p_bf16) {
+    bf16* pp = static_cast<bf16*>(p);
+    if (reg_ok && ldp <= 128) softmax_reg_kernel<bf16, true, 4><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+    else if (reg_ok && ldp <= 256) softmax_reg_kernel<bf16, true, 8><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+    else if (reg_ok && ldp <= 768) softmax_reg_kernel<bf16, true, 24><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+    else if (reg_ok) softmax_reg_kernel<bf16, true, 32><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+    else softmax_kernel<bf16, true><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+  } else {
+    float* pp = static_cast<float*>(p);
+    if (reg_ok && ldp <= 256) softmax_reg_kernel<float, false, 8><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+    else if (reg_ok) softmax_reg_kernel<float, false, 32><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+    else softmax_kernel<float, false><<<blocks, 256, 0, st>>>(s, lds, pp, ldp, rows, cols);
+  }
   DITTO_LAUNCH_CHECK();
   return 0;
 }

@@ -8,6 +8,8 @@
 //   STORE     out = alpha*acc (+bias) (+fp32 residual), fp32 or bf16, optional extra bf16 copy
 //   GEGLU     columns interleaved [fc1(16) | gate(16)]: hid = GELU_erf(a+ba) * sigmoid(g+bg)          (DiT.py:153-155)
 //   QKV_ROPE  column-permuted q/k so that the RoPE partner (j, j+d/2) sits PD columns away in the tile  (DiT.py:52-72)
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace ditto {
@@ -45,6 +47,7 @@ struct DevParams {
   bf16* out2; long long ldo2;
   const float* rope_cos; const float* rope_sin;
   int rope_half, rope_pd, seq_T, hidden;
+  int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -106,7 +109,7 @@ __device__ __forceinline__ void resid_prefetch(const DevParams& p, int lane, lon
   for (int i = 0; i < 8; ++i) {
     const long long row = row0 + i * 4 + rsub;
     if (row >= p.M) break;
-    const long long rrow = p.resid_row_mod > 0 ? row % p.resid_row_mod : row;
+    const long long rrow = p.resid_row_mod > 0 ? static_cast<long long>(static_cast<unsigned>(row) % static_cast<unsigned>(p.resid_row_mod)) : row;
     const float* rp = p.resid + res_off + rrow * p.ldr + ocol0 + c;
     if (full) {
       rv[i] = *reinterpret_cast<const float4*>(rp);
@@ -178,6 +181,149 @@ __device__ __forceinline__ void stage_flush(const DevParams& p, const float4* st
   }
 }
 
+// One accumulator tile (this warp's 32 rows x 128 columns of it): TMEM -> registers -> swizzled smem -> coalesced global.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const DevParams& p, float4* stage, int lane, int half_sel, uint32_t t_row,
+                                              long long row0, int n_blk, long long out_off, long long res_off,
+                                              long long bias_off) {
+  float4 zero8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) zero8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool rows_live = row0 < p.M;  // warp-uniform: nothing to store for a fully out-of-range row group
+
+  if (EPI == TC_EPI_STORE) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int tcol = (half_sel * 4 + c) * 32;
+      const int col0 = n_blk * BLOCK_N + tcol;
+      if (col0 >= p.N || !rows_live) break;  // warp-uniform
+      const int ncols = min(32, p.N - col0);
+      float4 rv[8];
+      if (p.resid != nullptr) {
+        resid_prefetch(p, lane, row0, col0, ncols, res_off, rv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + tcol, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      stage_put_row(stage, lane, v);
+      __syncwarp();
+      stage_flush(p, stage, lane, row0, col0, p.bias ? p.bias + bias_off + col0 : nullptr, ncols, out_off, p.out_bf16 != 0, rv);
+      __syncwarp();
+    }
+  } else if (EPI == TC_EPI_GEGLU) {
+    // two 32-column accumulator chunks [a16|g16][a16|g16] -> 32 hidden values per row -> one staged tile
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int tcol = (half_sel * 4 + c * 2) * 32;
+      const int col0 = n_blk * BLOCK_N + tcol;
+      if (col0 >= p.N || !rows_live) break;
+      const bool second = col0 + 32 < p.N;  // N % 32 == 0, so the second chunk is all-or-nothing
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(t_row + tcol, r0);
+      if (second) tmem_ld_32x32(t_row + tcol + 32, r1);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        v[j] = geglu_fast(__uint_as_float(r0[j]) + __ldg(p.bias + col0 + j), __uint_as_float(r0[16 + j]) + __ldg(p.bias + col0 + 16 + j));
+      if (second) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[16 + j] = geglu_fast(__uint_as_float(r1[j]) + __ldg(p.bias + col0 + 32 + j),
+                                 __uint_as_float(r1[16 + j]) + __ldg(p.bias + col0 + 48 + j));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
+      }
+      stage_put_row(stage, lane, v);
+      __syncwarp();
+      stage_flush(p, stage, lane, row0, col0 >> 1, nullptr, second ? 32 : 16, out_off, true, zero8);
+      __syncwarp();
+    }
+  } else {  // TC_EPI_QKV_ROPE
+    const int cpp = p.rope_pd >> 5;  // 32-column chunks per PD block
+    const int c4 = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int pi = half_sel * 2 + c;
+      const int ch1 = (pi / cpp) * (2 * cpp) + (pi % cpp);
+      const int ch2 = ch1 + cpp;
+      const int pc1 = n_blk * BLOCK_N + ch1 * 32, pc2 = n_blk * BLOCK_N + ch2 * 32;
+      if (pc1 >= p.N || !rows_live) continue;  // warp-uniform
+      uint32_t r1[32], r2[32];
+      tmem_ld_32x32(t_row + ch1 * 32, r1);
+      tmem_ld_32x32(t_row + ch2 * 32, r2);
+      tmem_ld_wait();
+      float v[32];
+      if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store of both chunks
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+        stage_put_row(stage, lane, v);
+        __syncwarp();
+        stage_flush(p, stage, lane, row0, pc1, p.bias + pc1, 32, out_off, true, zero8);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
+        stage_put_row(stage, lane, v);
+        __syncwarp();
+        stage_flush(p, stage, lane, row0, pc2, p.bias + pc2, 32, out_off, true, zero8);
+        __syncwarp();
+        continue;
+      }
+      // q / k thirds: x1 chunk and its RoPE partner chunk -> coalesced layout, then rotate
+      float4 xa[8], xb[8];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
+      stage_put_row(stage, lane, v);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xa[i] = stage[stage_idx(i * 4 + rsub, c4)];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
+      stage_put_row(stage, lane, v);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xb[i] = stage[stage_idx(i * 4 + rsub, c4)];
+      __syncwarp();
+      const int region = pc1 / p.hidden;              // 0 = q, 1 = k
+      const int lp = pc1 - region * p.hidden;         // permuted column inside the region
+      const int g = lp / (2 * p.rope_pd), w = lp - g * 2 * p.rope_pd;  // w < PD by construction
+      const int e0 = g * p.rope_pd;                   // first "x1 element" index of this group
+      const int head = e0 / p.rope_half;
+      const int j0 = e0 - head * p.rope_half + w + c4 * 4;  // rotary frequency index of this lane's 4 columns
+      const int dest1 = region * p.hidden + head * 2 * p.rope_half + j0;
+      const float4 b1 = *reinterpret_cast<const float4*>(p.bias + pc1 + c4 * 4);
+      const float4 b2 = *reinterpret_cast<const float4*>(p.bias + pc2 + c4 * 4);
+      const unsigned pos_base = static_cast<unsigned>(row0) % static_cast<unsigned>(p.seq_T);  // M < 2^31 (host check)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long row = row0 + i * 4 + rsub;
+        if (row >= p.M) break;
+        unsigned pos_u = pos_base + static_cast<unsigned>(i * 4 + rsub);
+        if (pos_u >= static_cast<unsigned>(p.seq_T)) pos_u %= static_cast<unsigned>(p.seq_T);
+        const int pos = static_cast<int>(pos_u);
+        const float4 cs = *reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * p.rope_half + j0);
+        const float4 sn = *reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * p.rope_half + j0);
+        const float x1x = xa[i].x + b1.x, x1y = xa[i].y + b1.y, x1z = xa[i].z + b1.z, x1w = xa[i].w + b1.w;
+        const float x2x = xb[i].x + b2.x, x2y = xb[i].y + b2.y, x2z = xb[i].z + b2.z, x2w = xb[i].w + b2.w;
+        bf16* dst = static_cast<bf16*>(p.out) + out_off + row * p.ldo + dest1;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x1x * cs.x - x2x * sn.x, x1y * cs.y - x2y * sn.y),
+                                                    pack_bf16x2(x1z * cs.z - x2z * sn.z, x1w * cs.w - x2w * sn.w));
+        *reinterpret_cast<uint2*>(dst + p.rope_half) =
+            make_uint2(pack_bf16x2(x2x * cs.x + x1x * sn.x, x2y * cs.y + x1y * sn.y),
+                       pack_bf16x2(x2z * cs.z + x1z * sn.z, x2w * cs.w + x1w * sn.w));
+      }
+    }
+  }
+}
+
 template <int EPI, bool B_KN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
@@ -241,7 +387,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             for (int j = 0; j < BLOCK_N / 64; ++j)  // [64 k-rows x 64 n] boxes, N-contiguous (MN-major operand)
               tma_load_4d(&tmap_b, &full_bar[stage], sb + j * (BLOCK_K * 128), n_blk * BLOCK_N + j * 64, kb * BLOCK_K, bbi, bbo);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -270,7 +416,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -282,9 +428,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may touch
     const int half_sel = ew >> 2;  // which 4 of the 8 column chunks
     float4* stage = stage_base + ew * 256;
-    float4 zero8[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) zero8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -300,136 +443,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      const bool rows_live = row0 < p.M;  // warp-uniform: nothing to store for a fully out-of-range row group
-
-      if (EPI == TC_EPI_STORE) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int tcol = (half_sel * 4 + c) * 32;
-          const int col0 = n_blk * BLOCK_N + tcol;
-          if (col0 >= p.N || !rows_live) break;  // warp-uniform
-          const int ncols = min(32, p.N - col0);
-          float4 rv[8];
-          if (p.resid != nullptr) {
-            resid_prefetch(p, lane, row0, col0, ncols, res_off, rv);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + tcol, r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          stage_put_row(stage, lane, v);
-          __syncwarp();
-          stage_flush(p, stage, lane, row0, col0, p.bias ? p.bias + bias_off + col0 : nullptr, ncols, out_off, p.out_bf16 != 0, rv);
-          __syncwarp();
-        }
-      } else if (EPI == TC_EPI_GEGLU) {
-        // two 32-column accumulator chunks [a16|g16][a16|g16] -> 32 hidden values per row -> one staged tile
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int tcol = (half_sel * 4 + c * 2) * 32;
-          const int col0 = n_blk * BLOCK_N + tcol;
-          if (col0 >= p.N || !rows_live) break;
-          const bool second = col0 + 32 < p.N;  // N % 32 == 0, so the second chunk is all-or-nothing
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_row + tcol, r0);
-          if (second) tmem_ld_32x32(t_row + tcol + 32, r1);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = geglu_fast(__uint_as_float(r0[j]) + __ldg(p.bias + col0 + j), __uint_as_float(r0[16 + j]) + __ldg(p.bias + col0 + 16 + j));
-          if (second) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              v[16 + j] = geglu_fast(__uint_as_float(r1[j]) + __ldg(p.bias + col0 + 32 + j),
-                                     __uint_as_float(r1[16 + j]) + __ldg(p.bias + col0 + 48 + j));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
-          }
-          stage_put_row(stage, lane, v);
-          __syncwarp();
-          stage_flush(p, stage, lane, row0, col0 >> 1, nullptr, second ? 32 : 16, out_off, true, zero8);
-          __syncwarp();
-        }
-      } else {  // TC_EPI_QKV_ROPE
-        const int cpp = p.rope_pd >> 5;  // 32-column chunks per PD block
-        const int c4 = lane & 7, rsub = lane >> 3;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int pi = half_sel * 2 + c;
-          const int ch1 = (pi / cpp) * (2 * cpp) + (pi % cpp);
-          const int ch2 = ch1 + cpp;
-          const int pc1 = n_blk * BLOCK_N + ch1 * 32, pc2 = n_blk * BLOCK_N + ch2 * 32;
-          if (pc1 >= p.N || !rows_live) continue;  // warp-uniform
-          uint32_t r1[32], r2[32];
-          tmem_ld_32x32(t_row + ch1 * 32, r1);
-          tmem_ld_32x32(t_row + ch2 * 32, r2);
-          tmem_ld_wait();
-          float v[32];
-          if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store of both chunks
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
-            stage_put_row(stage, lane, v);
-            __syncwarp();
-            stage_flush(p, stage, lane, row0, pc1, p.bias + pc1, 32, out_off, true, zero8);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
-            stage_put_row(stage, lane, v);
-            __syncwarp();
-            stage_flush(p, stage, lane, row0, pc2, p.bias + pc2, 32, out_off, true, zero8);
-            __syncwarp();
-            continue;
-          }
-          // q / k thirds: x1 chunk and its RoPE partner chunk -> coalesced layout, then rotate
-          float4 xa[8], xb[8];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
-          stage_put_row(stage, lane, v);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xa[i] = stage[stage_idx(i * 4 + rsub, c4)];
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
-          stage_put_row(stage, lane, v);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xb[i] = stage[stage_idx(i * 4 + rsub, c4)];
-          __syncwarp();
-          const int region = pc1 / p.hidden;              // 0 = q, 1 = k
-          const int lp = pc1 - region * p.hidden;         // permuted column inside the region
-          const int g = lp / (2 * p.rope_pd), w = lp - g * 2 * p.rope_pd;  // w < PD by construction
-          const int e0 = g * p.rope_pd;                   // first "x1 element" index of this group
-          const int head = e0 / p.rope_half;
-          const int j0 = e0 - head * p.rope_half + w + c4 * 4;  // rotary frequency index of this lane's 4 columns
-          const int dest1 = region * p.hidden + head * 2 * p.rope_half + j0;
-          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + pc1 + c4 * 4);
-          const float4 b2 = *reinterpret_cast<const float4*>(p.bias + pc2 + c4 * 4);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const long long row = row0 + i * 4 + rsub;
-            if (row >= p.M) break;
-            const int pos = static_cast<int>(row % p.seq_T);
-            const float4 cs = *reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * p.rope_half + j0);
-            const float4 sn = *reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * p.rope_half + j0);
-            const float x1x = xa[i].x + b1.x, x1y = xa[i].y + b1.y, x1z = xa[i].z + b1.z, x1w = xa[i].w + b1.w;
-            const float x2x = xb[i].x + b2.x, x2y = xb[i].y + b2.y, x2z = xb[i].z + b2.z, x2w = xb[i].w + b2.w;
-            bf16* dst = static_cast<bf16*>(p.out) + out_off + row * p.ldo + dest1;
-            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x1x * cs.x - x2x * sn.x, x1y * cs.y - x2y * sn.y),
-                                                        pack_bf16x2(x1z * cs.z - x2z * sn.z, x1w * cs.w - x2w * sn.w));
-            *reinterpret_cast<uint2*>(dst + p.rope_half) =
-                make_uint2(pack_bf16x2(x2x * cs.x + x1x * sn.x, x2y * cs.y + x1y * sn.y),
-                           pack_bf16x2(x2z * cs.z + x1z * sn.z, x2w * cs.w + x1w * sn.w));
-          }
-        }
-      }
+      epilogue_tile<EPI>(p, stage, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -445,6 +459,178 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
 }
 
+// =====================================================================================================
+// cta_group::2 variant: a cluster of two CTAs (one SM pair) computes a 256 x 256 tile.  Each CTA loads its own 128 rows
+// of A and HALF of the B tile (128 of the 256 N-rows); the leader CTA issues tcgen05.mma.cta_group::2 (UMMA 256x256x16)
+// which reads both halves, so B is fetched into shared memory once per SM pair: 32 KiB per stage and CTA -> 6 stages.
+// Accumulators: each CTA's TMEM holds its own 128 rows.  K-major ("NK") B only, no batching (weight GEMMs).
+// =====================================================================================================
+constexpr int P_STAGES = 6;
+constexpr int P_B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KiB
+constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;  // 32 KiB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BARRIER_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024;
+static_assert(P_SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
+static_assert((2 * P_STAGES + 4) * 8 + 4 <= BARRIER_BYTES, "barrier block too small");
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive (once the issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tmem_full = empty_bar + P_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float4* stage_base = reinterpret_cast<float4*>(smem + P_STAGES * P_STAGE_BYTES + BARRIER_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_pairs = gridDim.x >> 1;
+  const int pair_id = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's copy is the one in use: 1 arrive (expect_tx) + bytes of both CTAs
+      mbar_init(&empty_bar[s], 1);  // one multicast commit per use, delivered to both CTAs
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS);  // leader's copy: epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();  // peer barriers initialised and TMEM allocated on both SMs before any remote arrive / MMA
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile = (m_pair, n_blk), n fastest; M is covered in 256-row pair tiles
+  const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_tiles = m_pairs * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+        const int m0 = m_pair * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * P_STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          tma_load_4d_2sm(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m0, 0, 0);
+          tma_load_4d_2sm(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n0, 0, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tmem_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    const int ew = warp - EPI_WARP0;
+    const int quarter = warp & 3;
+    const int half_sel = ew >> 2;
+    float4* stage = stage_base + ew * 256;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+      const long long row0 = static_cast<long long>(m_pair) * 2 * BLOCK_M + rank * BLOCK_M + quarter * 32;
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
+      epilogue_tile<EPI>(p, stage, lane, half_sel, t_row, row0, n_blk, 0, 0, 0);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer may still signal its barriers / read its shared memory
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -452,6 +638,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 bool g_init_done = false;
+bool g_use_pair = true;
+int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
 
 // 4-D bf16 map: dims (cols, rows, inner, outer), box (box_cols, box_rows, 1, 1), 128B swizzle, zero OOB fill.
 int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
@@ -476,6 +664,12 @@ int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_out
               std::to_string(op.cols) + " rows=" + std::to_string(op.rows) + " ld=" + std::to_string(op.ld) + ")");
     return DITTO_E_CUDA;
   }
+  return 0;
+}
+
+template <int EPI>
+int set_attr_pair() {
+  DITTO_CUDA(cudaFuncSetAttribute(tc_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
   return 0;
 }
 
@@ -504,6 +698,15 @@ int tc_gemm_init() {
   DITTO_TRY((set_attr<TC_EPI_STORE, true>()));
   DITTO_TRY((set_attr<TC_EPI_GEGLU, false>()));
   DITTO_TRY((set_attr<TC_EPI_QKV_ROPE, false>()));
+  DITTO_TRY((set_attr_pair<TC_EPI_STORE>()));
+  DITTO_TRY((set_attr_pair<TC_EPI_GEGLU>()));
+  DITTO_TRY((set_attr_pair<TC_EPI_QKV_ROPE>()));
+  {
+    const char* env = getenv("DITTO_NO_PAIR");
+    g_use_pair = !(env && env[0] == '1');
+    if (const char* e1 = getenv("DITTO_STAGES_1CTA")) g_stages_1cta = std::max(2, std::min(STAGES, atoi(e1)));
+    if (const char* e2 = getenv("DITTO_STAGES_PAIR")) g_stages_pair = std::max(2, std::min(P_STAGES, atoi(e2)));
+  }
   g_init_done = true;
   return 0;
 }
@@ -527,8 +730,12 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
 
   CUtensorMap ma, mb;
   TcOperand A = q.A, B = q.B;
+  // paired (cta_group::2) kernel for the large un-batched weight GEMMs
+  const bool pair = g_use_pair && !q.b_kn && q.batch_inner == 1 && q.batch_outer == 1 && q.M >= 2 * BLOCK_M && (g_num_sms % 2 == 0);
   DITTO_TRY(make_map(&ma, A, q.batch_inner, q.batch_outer, BLOCK_K, BLOCK_M));
-  if (!q.b_kn)
+  if (pair)
+    DITTO_TRY(make_map(&mb, B, 1, 1, BLOCK_K, BLOCK_N / 2));
+  else if (!q.b_kn)
     DITTO_TRY(make_map(&mb, B, q.batch_inner, q.batch_outer, BLOCK_K, BLOCK_N));
   else
     DITTO_TRY(make_map(&mb, B, q.batch_inner, q.batch_outer, 64, BLOCK_K));
@@ -552,8 +759,21 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin;
   p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
 
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
+  unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
+  p.stages = pair ? g_stages_pair : g_stages_1cta;
+  if (pair) {
+    const int64_t pair_tiles = ceil_div(q.M, 2 * BLOCK_M) * p.n_tiles;
+    grid = static_cast<unsigned>(2 * std::min<int64_t>(pair_tiles, g_num_sms / 2));
+    if (q.epilogue == TC_EPI_STORE)
+      tc_gemm_pair_kernel<TC_EPI_STORE><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p);
+    else if (q.epilogue == TC_EPI_GEGLU)
+      tc_gemm_pair_kernel<TC_EPI_GEGLU><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p);
+    else
+      tc_gemm_pair_kernel<TC_EPI_QKV_ROPE><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p);
+    DITTO_LAUNCH_CHECK();
+    return 0;
+  }
   if (q.epilogue == TC_EPI_STORE && !q.b_kn)
     tc_gemm_kernel<TC_EPI_STORE, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
   else if (q.epilogue == TC_EPI_STORE && q.b_kn)

@@ -18,7 +18,61 @@ from . import _lib
 from ._lib import DittoError
 from .model import DiTTO, _need_cuda_f32, _ptr, _stream
 
-__all__ = ["DiTTOSampler"]
+__all__ = ["DiTTOSampler", "StepGraph"]
+
+
+class StepGraph:
+    """One sampler iteration captured as a CUDA graph and replayed once per step.
+
+    The graph holds: (optional) the step's noise draw, the 2B-sequence forward, the fused CFG + DDPM update
+    (in place on ``x``) and the decrement of the device-resident step index ``t`` -- so the host issues ONE
+    launch per denoising step instead of ~70.  All buffers the graph touches are owned here (or pinned by
+    reference) so that the captured pointers stay valid."""
+
+    def __init__(self, sampler: "DiTTOSampler", B: int, T: int, S: int, guided: bool, w: float, ctx: torch.Tensor,
+                 draw_noise: bool, device):
+        m = sampler.model
+        H = m.hidden_dim
+        n = 2 * B if guided else B
+        self.B, self.T, self.S, self.guided, self.w, self.draw_noise = B, T, S, guided, w, draw_noise
+        self.x = torch.empty((B, T, H), dtype=torch.float32, device=device)
+        self.z = torch.empty((B, T, H), dtype=torch.float32, device=device)
+        self.eps = torch.empty((n, T, H), dtype=torch.float32, device=device)
+        self.t = torch.zeros((n,), dtype=torch.int64, device=device)
+        self.ctx = ctx
+        self.ws = m.workspace(n, T, S)
+        self.launches_per_step = 0
+        self.x.zero_()
+        self.z.zero_()
+        # eager warm-up (engine set-up, lazy initialisation) on a side stream, then capture
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            self._step(sampler)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._step(sampler)
+        self.launches_per_step = _lib.launch_count() - n0
+        self._keys = (self.ctx.data_ptr(), self.ws.data_ptr())
+
+    def _step(self, sampler):
+        if self.draw_noise:
+            self.z.normal_()                      # drawn every step incl. t = 0, like the reference's randn_like
+        sampler._p_sample_raw(self.x, self.ctx, self.t, self.z, self.guided, self.w, self.S, self.eps, self.x, ws=self.ws)
+        self.t.sub_(1)
+
+    def valid_for(self, ctx: torch.Tensor, ws: torch.Tensor) -> bool:
+        return self._keys == (ctx.data_ptr(), ws.data_ptr())
+
+    def reset(self, x_init: torch.Tensor, t_start: int):
+        self.x.copy_(x_init)
+        self.t.fill_(t_start)
+
+    def replay(self):
+        self.graph.replay()
 
 
 class DiTTOSampler:
@@ -43,12 +97,13 @@ class DiTTOSampler:
             text_emb = torch.cat([text_emb, null], dim=0)  # [cond(B); uncond(B)]
         return self.model.text_context(text_emb, name="sampler_ctx", T_hint=T)
 
-    def _p_sample_raw(self, x, ctx, t_n, z, guided, w, S, eps, x_out):
+    def _p_sample_raw(self, x, ctx, t_n, z, guided, w, S, eps, x_out, ws=None):
         m = self.model
         B, T, H = x.shape
         n = 2 * B if guided else B
         with torch.cuda.device(x.device):
-            ws = m.workspace(n, T, S)
+            if ws is None:
+                ws = m.workspace(n, T, S)
             _lib.check(_lib.load().ditto_p_sample(m.engine(), _ptr(x), _ptr(ctx), _ptr(t_n), _ptr(z), 1 if guided else 0,
                                                   float(w), B, T, S, _ptr(eps), _ptr(x_out), _ptr(ws), ws.numel(),
                                                   _stream()), "ditto_p_sample")
@@ -86,10 +141,20 @@ class DiTTOSampler:
         self._p_sample_raw(x, ctx, t_n, z, guided, w if guided else 0.0, text_emb.shape[1], eps, out)
         return out
 
+    def step_graph(self, B: int, T: int, S: int, guided: bool, w: float, ctx: torch.Tensor, draw_noise: bool, device):
+        """Cached CUDA graph of one sampler iteration for this shape (re-captured if the buffers moved)."""
+        key = (B, T, S, guided, float(w), draw_noise, str(device))
+        g = self._graphs.get(key)
+        n = 2 * B if guided else B
+        if g is None or not g.valid_for(ctx, self.model.workspace(n, T, S)):
+            g = StepGraph(self, B, T, S, guided, float(w), ctx, draw_noise, device)
+            self._graphs[key] = g
+        return g
+
     @torch.no_grad()
     def sample_latents(self, text_emb, audio_emb=None, *, x_init=None, noise=None, guidance_scale=None,
                        null_text_emb=None, cond_by_audio=False, record: Optional[List[torch.Tensor]] = None,
-                       generator: Optional[torch.Generator] = None):
+                       generator: Optional[torch.Generator] = None, use_graph: bool = True):
         """All reverse steps (reference: __sample_latents, SpeechGenerator.py:150-164).
 
         text_emb [B,S,text_dim]; ``audio_emb`` [B,T,H] gives the latent shape (and the start point when
@@ -113,6 +178,15 @@ class DiTTOSampler:
         steps = m.diffusion_steps
         ctx = self._context(text_emb, guided, null_text_emb, T)
         n = 2 * B if guided else B
+        if use_graph and record is None and generator is None:
+            # one CUDA-graph replay per denoising step (noise drawn inside the graph unless supplied)
+            g = self.step_graph(B, T, S, guided, w if guided else 0.0, ctx, noise is None, dev)
+            g.reset(x, steps - 1)
+            for i in range(steps):
+                if noise is not None:
+                    g.z.copy_(noise[steps - 1 - i], non_blocking=True)
+                g.replay()
+            return g.x.clone()
         # t for every step, all sequences share it (SpeechGenerator.py:162)
         t_all = torch.arange(steps - 1, -1, -1, device=dev, dtype=torch.int64).unsqueeze(1).repeat(1, n).contiguous()
         eps = torch.empty((n, T, H), dtype=torch.float32, device=dev)
