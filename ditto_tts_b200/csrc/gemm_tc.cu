@@ -30,7 +30,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int BARRIER_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BARRIER_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BARRIER_BYTES + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
 
 struct DevParams {
@@ -84,241 +84,196 @@ __device__ __forceinline__ float geglu_fast(float a, float g) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Epilogue staging: each epilogue warp owns a 32 x 32 fp32 tile in shared memory (4 KiB, 16-byte chunks XOR-swizzled
-// by row) used to turn the TMEM layout (thread = row) into a coalesced global layout (quarter-warp = 128 B of a row).
+// Epilogue, register-direct: tcgen05.ld.16x256b hands each warp a 16-row x 64-column block of the accumulator in the
+// classic mma-fragment layout -- thread t holds, for every 8-column block kb, columns kb*8 + (t%4)*2 + {0,1} of rows
+// t/4 and t/4 + 8.  Four neighbouring threads therefore cover 32 contiguous bytes (fp32) of a row, so plain st.global
+// writes whole 32-B sectors; no shared-memory staging (the UMMA operand reads own the smem bandwidth), the bias of a
+// column pair is loaded once for all rows, and RoPE / GLU partners (a multiple of 8 columns apart) sit in the same thread.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int stage_idx(int row, int chunk) { return row * 8 + (chunk ^ (row & 7)); }
-
-__device__ __forceinline__ void stage_put_row(float4* stage, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) stage[stage_idx(lane, j)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+__device__ __forceinline__ void tmem_ld_16x64(uint32_t taddr, uint32_t (&r)[32]) {  // 16 lanes x 64 fp32 columns
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
 }
 
-// Residual prefetch for one 32 x ncols chunk in the coalesced layout (lane -> 4 columns x 8 rows).  Issued BEFORE the
-// TMEM load / staging of the chunk so that the (HBM-latency) loads overlap them; out and resid alias for the in-place
-// residual update, so loads and stores of one chunk must not be interleaved.
-__device__ __forceinline__ void resid_prefetch(const DevParams& p, int lane, long long row0, int ocol0, int ncols,
-                                               long long res_off, float4 (&rv)[8]) {
-  const int c4 = lane & 7, rsub = lane >> 3;
-  const int c = c4 * 4;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c >= ncols) return;
-  const bool full = c + 3 < ncols;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long row = row0 + i * 4 + rsub;
-    if (row >= p.M) break;
-    const long long rrow = p.resid_row_mod > 0 ? static_cast<long long>(static_cast<unsigned>(row) % static_cast<unsigned>(p.resid_row_mod)) : row;
-    const float* rp = p.resid + res_off + rrow * p.ldr + ocol0 + c;
-    if (full) {
-      rv[i] = *reinterpret_cast<const float4*>(rp);
+// v = alpha * (a0, a1) (+bias) (+resid) for columns (col, col+1) of `row` -> out (+ bf16 copy)
+__device__ __forceinline__ void store_pair(const DevParams& p, long long row, int col, float a0, float a1, float2 bias2,
+                                           long long out_off, long long res_off) {
+  if (col >= p.N) return;
+  const bool both = col + 1 < p.N;
+  float v0 = fmaf(p.alpha, a0, bias2.x), v1 = fmaf(p.alpha, a1, bias2.y);
+  if (p.resid != nullptr) {
+    const long long rrow =
+        p.resid_row_mod > 0 ? static_cast<long long>(static_cast<unsigned>(row) % static_cast<unsigned>(p.resid_row_mod)) : row;
+    const float* rp = p.resid + res_off + rrow * p.ldr + col;
+    if (both) {
+      const float2 t = *reinterpret_cast<const float2*>(rp);
+      v0 += t.x;
+      v1 += t.y;
     } else {
-      rv[i].x = rp[0];
-      if (c + 1 < ncols) rv[i].y = rp[1];
-      if (c + 2 < ncols) rv[i].z = rp[2];
+      v0 += rp[0];
     }
+  }
+  const long long o = out_off + row * p.ldo + col;
+  if (p.out_bf16) {
+    bf16* dst = static_cast<bf16*>(p.out) + o;
+    if (both) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v0, v1);
+    else dst[0] = __float2bfloat16_rn(v0);
+  } else {
+    float* dst = static_cast<float*>(p.out) + o;
+    if (both) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+    else dst[0] = v0;
+  }
+  if (p.out2 != nullptr) {
+    bf16* d2 = p.out2 + out_off + row * p.ldo2 + col;
+    if (both) *reinterpret_cast<uint32_t*>(d2) = pack_bf16x2(v0, v1);
+    else d2[0] = __float2bfloat16_rn(v0);
   }
 }
 
-// Flush a staged 32 x ncols tile: v = alpha * staged (+bias) (+rv) -> out (fp32 or bf16) (+ bf16 copy).
-// Row r of the tile is global row row0 + r; column c is output column ocol0 + c (bias indexed by bias + c).
-__device__ __forceinline__ void stage_flush(const DevParams& p, const float4* stage, int lane, long long row0, int ocol0,
-                                            const float* bias, int ncols, long long out_off, bool out_bf16,
-                                            const float4 (&rv)[8]) {
-  const int c4 = lane & 7, rsub = lane >> 3;
-  const int c = c4 * 4;
-  if (c >= ncols) return;                      // after the caller's __syncwarp; no further warp-collectives inside
-  const bool full = c + 3 < ncols;
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias != nullptr) {
-    if (full) {
-      b4 = *reinterpret_cast<const float4*>(bias + c);
-    } else {
-      b4.x = bias[c];
-      if (c + 1 < ncols) b4.y = bias[c + 1];
-      if (c + 2 < ncols) b4.z = bias[c + 2];
-    }
+__device__ __forceinline__ float2 load_bias2(const float* bias, int col, int N) {
+  float2 b = make_float2(0.f, 0.f);
+  if (bias != nullptr && col < N) {
+    if (col + 1 < N) b = *reinterpret_cast<const float2*>(bias + col);
+    else b.x = bias[col];
   }
+  return b;
+}
+
+// plain store of a loaded 16 x 64 block whose first column is global column col0
+__device__ __forceinline__ void store_block64(const DevParams& p, const uint32_t (&r)[32], int lane, long long rowA, int col0,
+                                              const float* bias, long long out_off, long long res_off) {
+  const int q2 = (lane & 3) * 2;
+  const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    const long long row = row0 + r;
-    if (row >= p.M) break;
-    float4 v = stage[stage_idx(r, c4)];
-    v.x = fmaf(p.alpha, v.x, b4.x) + rv[i].x; v.y = fmaf(p.alpha, v.y, b4.y) + rv[i].y;
-    v.z = fmaf(p.alpha, v.z, b4.z) + rv[i].z; v.w = fmaf(p.alpha, v.w, b4.w) + rv[i].w;
-    const long long o = out_off + row * p.ldo + ocol0 + c;
-    if (out_bf16) {
-      bf16* dst = static_cast<bf16*>(p.out) + o;
-      if (full) {
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-      } else {
-        dst[0] = __float2bfloat16_rn(v.x);
-        if (c + 1 < ncols) dst[1] = __float2bfloat16_rn(v.y);
-        if (c + 2 < ncols) dst[2] = __float2bfloat16_rn(v.z);
-      }
-    } else {
-      float* dst = static_cast<float*>(p.out) + o;
-      if (full) {
-        *reinterpret_cast<float4*>(dst) = v;
-      } else {
-        dst[0] = v.x;
-        if (c + 1 < ncols) dst[1] = v.y;
-        if (c + 2 < ncols) dst[2] = v.z;
-      }
-    }
-    if (p.out2) {
-      bf16* d2 = p.out2 + out_off + row * p.ldo2 + ocol0 + c;
-      if (full) {
-        *reinterpret_cast<uint2*>(d2) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-      } else {
-        d2[0] = __float2bfloat16_rn(v.x);
-        if (c + 1 < ncols) d2[1] = __float2bfloat16_rn(v.y);
-        if (c + 2 < ncols) d2[2] = __float2bfloat16_rn(v.z);
-      }
-    }
+  for (int kb = 0; kb < 8; ++kb) {
+    const int col = col0 + kb * 8 + q2;
+    const float2 b2 = load_bias2(bias, col, p.N);
+    if (okA) store_pair(p, rowA, col, __uint_as_float(r[4 * kb]), __uint_as_float(r[4 * kb + 1]), b2, out_off, res_off);
+    if (okB) store_pair(p, rowA + 8, col, __uint_as_float(r[4 * kb + 2]), __uint_as_float(r[4 * kb + 3]), b2, out_off, res_off);
   }
 }
 
-// One accumulator tile (this warp's 32 rows x 128 columns of it): TMEM -> registers -> swizzled smem -> coalesced global.
+// One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const DevParams& p, float4* stage, int lane, int half_sel, uint32_t t_row,
-                                              long long row0, int n_blk, long long out_off, long long res_off,
-                                              long long bias_off) {
-  float4 zero8[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) zero8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool rows_live = row0 < p.M;  // warp-uniform: nothing to store for a fully out-of-range row group
+__device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
+                                              long long out_off, long long res_off, long long bias_off) {
+  if (row0 >= p.M) return;  // warp-uniform: nothing to store for a fully out-of-range row group
+  const int g = lane >> 2, q2 = (lane & 3) * 2;
+  const float* bias = p.bias ? p.bias + bias_off : nullptr;
 
   if (EPI == TC_EPI_STORE) {
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int tcol = (half_sel * 4 + c) * 32;
+    for (int it = 0; it < 4; ++it) {
+      const int hh = it & 1, cb = it >> 1;
+      const int tcol = half_sel * 128 + cb * 64;
       const int col0 = n_blk * BLOCK_N + tcol;
-      if (col0 >= p.N || !rows_live) break;  // warp-uniform
-      const int ncols = min(32, p.N - col0);
-      float4 rv[8];
-      if (p.resid != nullptr) {
-        resid_prefetch(p, lane, row0, col0, ncols, res_off, rv);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      if (col0 >= p.N) break;                       // warp-uniform
+      const long long rowA = row0 + hh * 16 + g;
+      if (row0 + hh * 16 >= p.M) continue;          // warp-uniform
       uint32_t r[32];
-      tmem_ld_32x32(t_row + tcol, r);
+      tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
       tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      stage_put_row(stage, lane, v);
-      __syncwarp();
-      stage_flush(p, stage, lane, row0, col0, p.bias ? p.bias + bias_off + col0 : nullptr, ncols, out_off, p.out_bf16 != 0, rv);
-      __syncwarp();
+      store_block64(p, r, lane, rowA, col0, bias, out_off, res_off);
     }
   } else if (EPI == TC_EPI_GEGLU) {
-    // two 32-column accumulator chunks [a16|g16][a16|g16] -> 32 hidden values per row -> one staged tile
+    // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int tcol = (half_sel * 4 + c * 2) * 32;
+    for (int it = 0; it < 4; ++it) {
+      const int hh = it & 1, cb = it >> 1;
+      const int tcol = half_sel * 128 + cb * 64;
       const int col0 = n_blk * BLOCK_N + tcol;
-      if (col0 >= p.N || !rows_live) break;
-      const bool second = col0 + 32 < p.N;  // N % 32 == 0, so the second chunk is all-or-nothing
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(t_row + tcol, r0);
-      if (second) tmem_ld_32x32(t_row + tcol + 32, r1);
+      if (col0 >= p.N) break;
+      const long long rowA = row0 + hh * 16 + g;
+      if (row0 + hh * 16 >= p.M) continue;
+      uint32_t r[32];
+      tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
       tmem_ld_wait();
-      float v[32];
+      const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+      bf16* outp = static_cast<bf16*>(p.out) + out_off;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        v[j] = geglu_fast(__uint_as_float(r0[j]) + __ldg(p.bias + col0 + j), __uint_as_float(r0[16 + j]) + __ldg(p.bias + col0 + 16 + j));
-      if (second) {
+      for (int gi = 0; gi < 2; ++gi) {
+        if (col0 + gi * 32 >= p.N) break;           // N % 32 == 0: a group is all-or-nothing
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[16 + j] = geglu_fast(__uint_as_float(r1[j]) + __ldg(p.bias + col0 + 32 + j),
-                                 __uint_as_float(r1[16 + j]) + __ldg(p.bias + col0 + 48 + j));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
+        for (int m = 0; m < 2; ++m) {
+          const int ka = gi * 4 + m, kg = ka + 2;   // 8-column blocks of the a and the g values
+          const int ca = col0 + gi * 32 + m * 8 + q2;
+          const float2 ba = *reinterpret_cast<const float2*>(bias + ca);
+          const float2 bg = *reinterpret_cast<const float2*>(bias + ca + 16);
+          const int oc = ((col0 + gi * 32) >> 1) + m * 8 + q2;
+          if (okA)
+            *reinterpret_cast<uint32_t*>(outp + rowA * p.ldo + oc) =
+                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka]) + ba.x, __uint_as_float(r[4 * kg]) + bg.x),
+                            geglu_fast(__uint_as_float(r[4 * ka + 1]) + ba.y, __uint_as_float(r[4 * kg + 1]) + bg.y));
+          if (okB)
+            *reinterpret_cast<uint32_t*>(outp + (rowA + 8) * p.ldo + oc) =
+                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka + 2]) + ba.x, __uint_as_float(r[4 * kg + 2]) + bg.x),
+                            geglu_fast(__uint_as_float(r[4 * ka + 3]) + ba.y, __uint_as_float(r[4 * kg + 3]) + bg.y));
+        }
       }
-      stage_put_row(stage, lane, v);
-      __syncwarp();
-      stage_flush(p, stage, lane, row0, col0 >> 1, nullptr, second ? 32 : 16, out_off, true, zero8);
-      __syncwarp();
     }
   } else {  // TC_EPI_QKV_ROPE
-    const int cpp = p.rope_pd >> 5;  // 32-column chunks per PD block
-    const int c4 = lane & 7, rsub = lane >> 3;
+    // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load
+    const int pd = p.rope_pd;
+    const int units = pd == 32 ? 2 : 1;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int pi = half_sel * 2 + c;
-      const int ch1 = (pi / cpp) * (2 * cpp) + (pi % cpp);
-      const int ch2 = ch1 + cpp;
-      const int pc1 = n_blk * BLOCK_N + ch1 * 32, pc2 = n_blk * BLOCK_N + ch2 * 32;
-      if (pc1 >= p.N || !rows_live) continue;  // warp-uniform
+    for (int it = 0; it < 2 * units; ++it) {
+      const int hh = it & 1, u = it >> 1;
+      const int b1 = pd == 128 ? half_sel * 64 : (pd == 64 ? half_sel * 128 : half_sel * 128 + u * 64);  // tile column of x1
+      const int pc1 = n_blk * BLOCK_N + b1;
+      if (pc1 >= p.N) break;
+      const long long rowA = row0 + hh * 16 + g;
+      if (row0 + hh * 16 >= p.M) continue;
+      const uint32_t tbase = t_row + (static_cast<uint32_t>(hh * 16) << 16);
       uint32_t r1[32], r2[32];
-      tmem_ld_32x32(t_row + ch1 * 32, r1);
-      tmem_ld_32x32(t_row + ch2 * 32, r2);
+      tmem_ld_16x64(tbase + b1, r1);
+      if (pd != 32) tmem_ld_16x64(tbase + b1 + pd, r2);
       tmem_ld_wait();
-      float v[32];
-      if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store of both chunks
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
-        stage_put_row(stage, lane, v);
-        __syncwarp();
-        stage_flush(p, stage, lane, row0, pc1, p.bias + pc1, 32, out_off, true, zero8);
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
-        stage_put_row(stage, lane, v);
-        __syncwarp();
-        stage_flush(p, stage, lane, row0, pc2, p.bias + pc2, 32, out_off, true, zero8);
-        __syncwarp();
+      if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store
+        store_block64(p, r1, lane, rowA, pc1, bias, out_off, res_off);
+        if (pd != 32) store_block64(p, r2, lane, rowA, pc1 + pd, bias, out_off, res_off);
         continue;
       }
-      // q / k thirds: x1 chunk and its RoPE partner chunk -> coalesced layout, then rotate
-      float4 xa[8], xb[8];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]);
-      stage_put_row(stage, lane, v);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xa[i] = stage[stage_idx(i * 4 + rsub, c4)];
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[j]);
-      stage_put_row(stage, lane, v);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xb[i] = stage[stage_idx(i * 4 + rsub, c4)];
-      __syncwarp();
       const int region = pc1 / p.hidden;              // 0 = q, 1 = k
       const int lp = pc1 - region * p.hidden;         // permuted column inside the region
-      const int g = lp / (2 * p.rope_pd), w = lp - g * 2 * p.rope_pd;  // w < PD by construction
-      const int e0 = g * p.rope_pd;                   // first "x1 element" index of this group
+      const int grp = lp / (2 * pd), w = lp - grp * 2 * pd;  // w < PD by construction
+      const int e0 = grp * pd;                        // first "x1 element" index of this group
       const int head = e0 / p.rope_half;
-      const int j0 = e0 - head * p.rope_half + w + c4 * 4;  // rotary frequency index of this lane's 4 columns
-      const int dest1 = region * p.hidden + head * 2 * p.rope_half + j0;
-      const float4 b1 = *reinterpret_cast<const float4*>(p.bias + pc1 + c4 * 4);
-      const float4 b2 = *reinterpret_cast<const float4*>(p.bias + pc2 + c4 * 4);
-      const unsigned pos_base = static_cast<unsigned>(row0) % static_cast<unsigned>(p.seq_T);  // M < 2^31 (host check)
+      const int jbase = e0 - head * p.rope_half + w;  // rotary frequency index of the block's first column
+      const int dbase = region * p.hidden + head * 2 * p.rope_half + jbase;
+      const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+      const unsigned seqT = static_cast<unsigned>(p.seq_T);
+      const unsigned posA = static_cast<unsigned>(rowA) % seqT, posB = static_cast<unsigned>(rowA + 8) % seqT;
+      bf16* outp = static_cast<bf16*>(p.out) + out_off;
+      const int nkb = pd == 32 ? 4 : 8;               // 8-column blocks of x1 values in this unit
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const long long row = row0 + i * 4 + rsub;
-        if (row >= p.M) break;
-        unsigned pos_u = pos_base + static_cast<unsigned>(i * 4 + rsub);
-        if (pos_u >= static_cast<unsigned>(p.seq_T)) pos_u %= static_cast<unsigned>(p.seq_T);
-        const int pos = static_cast<int>(pos_u);
-        const float4 cs = *reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * p.rope_half + j0);
-        const float4 sn = *reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * p.rope_half + j0);
-        const float x1x = xa[i].x + b1.x, x1y = xa[i].y + b1.y, x1z = xa[i].z + b1.z, x1w = xa[i].w + b1.w;
-        const float x2x = xb[i].x + b2.x, x2y = xb[i].y + b2.y, x2z = xb[i].z + b2.z, x2w = xb[i].w + b2.w;
-        bf16* dst = static_cast<bf16*>(p.out) + out_off + row * p.ldo + dest1;
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x1x * cs.x - x2x * sn.x, x1y * cs.y - x2y * sn.y),
-                                                    pack_bf16x2(x1z * cs.z - x2z * sn.z, x1w * cs.w - x2w * sn.w));
-        *reinterpret_cast<uint2*>(dst + p.rope_half) =
-            make_uint2(pack_bf16x2(x2x * cs.x + x1x * sn.x, x2y * cs.y + x1y * sn.y),
-                       pack_bf16x2(x2z * cs.z + x1z * sn.z, x2w * cs.w + x1w * sn.w));
+      for (int kb = 0; kb < 8; ++kb) {
+        if (kb >= nkb) break;
+        const int cofs = kb * 8 + q2;
+        const float2 bx1 = *reinterpret_cast<const float2*>(bias + pc1 + cofs);
+        const float2 bx2 = *reinterpret_cast<const float2*>(bias + pc1 + pd + cofs);
+        const int k2 = (kb + 4) & 7;  // partner block inside r1 when PD == 32
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          if (rr == 0 ? !okA : !okB) continue;
+          const long long row = rowA + rr * 8;
+          const unsigned pos = rr == 0 ? posA : posB;
+          const float2 cs = *reinterpret_cast<const float2*>(p.rope_cos + static_cast<long long>(pos) * p.rope_half + jbase + cofs);
+          const float2 sn = *reinterpret_cast<const float2*>(p.rope_sin + static_cast<long long>(pos) * p.rope_half + jbase + cofs);
+          const float x1a = __uint_as_float(r1[4 * kb + 2 * rr]) + bx1.x, x1b = __uint_as_float(r1[4 * kb + 2 * rr + 1]) + bx1.y;
+          const float x2a = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]) + bx2.x;
+          const float x2b = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]) + bx2.y;
+          bf16* dst = outp + row * p.ldo + dbase + cofs;
+          *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * cs.x - x2a * sn.x, x1b * cs.y - x2b * sn.y);
+          *reinterpret_cast<uint32_t*>(dst + p.rope_half) = pack_bf16x2(x2a * cs.x + x1a * sn.x, x2b * cs.y + x1b * sn.y);
+        }
       }
     }
   }
@@ -335,7 +290,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float4* stage_base = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + BARRIER_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -427,7 +381,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may touch
     const int half_sel = ew >> 2;  // which 4 of the 8 column chunks
-    float4* stage = stage_base + ew * 256;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -443,7 +396,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, stage, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -468,7 +421,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 constexpr int P_STAGES = 6;
 constexpr int P_B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KiB
 constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;  // 32 KiB
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BARRIER_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BARRIER_BYTES + 1024;
 static_assert(P_SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
 static_assert((2 * P_STAGES + 4) * 8 + 4 <= BARRIER_BYTES, "barrier block too small");
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
@@ -516,7 +469,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tmem_full = empty_bar + P_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float4* stage_base = reinterpret_cast<float4*>(smem + P_STAGES * P_STAGE_BYTES + BARRIER_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -605,7 +557,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;
     const int half_sel = ew >> 2;
-    float4* stage = stage_base + ew * 256;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
@@ -614,7 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, stage, lane, half_sel, t_row, row0, n_blk, 0, 0, 0);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
