@@ -103,24 +103,49 @@ __device__ __forceinline__ void tmem_ld_16x64(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
-// v = alpha * (a0, a1) (+bias) (+resid) for columns (col, col+1) of `row` -> out (+ bf16 copy)
-__device__ __forceinline__ void store_pair(const DevParams& p, long long row, int col, float a0, float a1, float2 bias2,
-                                           long long out_off, long long res_off) {
-  if (col >= p.N) return;
-  const bool both = col + 1 < p.N;
-  float v0 = fmaf(p.alpha, a0, bias2.x), v1 = fmaf(p.alpha, a1, bias2.y);
-  if (p.resid != nullptr) {
+// Residual fragment of one 16 x 64 block in the accumulator-fragment layout: v[2*kb + rr] = columns
+// (col0 + kb*8 + q2, +1) of row rowA + 8*rr.  Loaded BEFORE the matching TMEM load is waited for (and one block ahead of
+// the stores), so that the global-load latency overlaps the MMA / the previous block's stores.  The residual may alias
+// the output (in-place h += ...): every element is read and written by the same thread exactly once, so reading a later
+// block early is safe.
+struct ResFrag { float2 v[16]; };
+
+__device__ __forceinline__ void load_resid_block(const DevParams& p, int lane, long long rowA, int col0, long long res_off,
+                                                 ResFrag& f) {
+  const int q2 = (lane & 3) * 2;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const long long row = rowA + rr * 8;
+    const bool row_ok = row < p.M;
     const long long rrow =
         p.resid_row_mod > 0 ? static_cast<long long>(static_cast<unsigned>(row) % static_cast<unsigned>(p.resid_row_mod)) : row;
-    const float* rp = p.resid + res_off + rrow * p.ldr + col;
-    if (both) {
-      const float2 t = *reinterpret_cast<const float2*>(rp);
-      v0 += t.x;
-      v1 += t.y;
-    } else {
-      v0 += rp[0];
+    const float* rp = p.resid + res_off + rrow * p.ldr + col0 + q2;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const int col = col0 + kb * 8 + q2;
+      float2 t = make_float2(0.f, 0.f);
+      if (row_ok && col + 1 < p.N) t = *reinterpret_cast<const float2*>(rp + kb * 8);
+      else if (row_ok && col < p.N) t.x = rp[kb * 8];
+      f.v[2 * kb + rr] = t;
     }
   }
+}
+
+__device__ __forceinline__ float2 load_bias2(const float* bias, int col, int N) {
+  float2 b = make_float2(0.f, 0.f);
+  if (bias != nullptr && col < N) {
+    if (col + 1 < N) b = __ldg(reinterpret_cast<const float2*>(bias + col));  // read-only path: hoistable above stores
+    else b.x = __ldg(bias + col);
+  }
+  return b;
+}
+
+// v = alpha * (a0, a1) + bias + resid for columns (col, col+1) of `row` -> out (+ bf16 copy)
+__device__ __forceinline__ void store_pair(const DevParams& p, long long row, int col, float a0, float a1, float2 bias2, float2 res2,
+                                           long long out_off) {
+  if (col >= p.N) return;
+  const bool both = col + 1 < p.N;
+  const float v0 = fmaf(p.alpha, a0, bias2.x) + res2.x, v1 = fmaf(p.alpha, a1, bias2.y) + res2.y;
   const long long o = out_off + row * p.ldo + col;
   if (p.out_bf16) {
     bf16* dst = static_cast<bf16*>(p.out) + o;
@@ -138,53 +163,66 @@ __device__ __forceinline__ void store_pair(const DevParams& p, long long row, in
   }
 }
 
-__device__ __forceinline__ float2 load_bias2(const float* bias, int col, int N) {
-  float2 b = make_float2(0.f, 0.f);
-  if (bias != nullptr && col < N) {
-    if (col + 1 < N) b = *reinterpret_cast<const float2*>(bias + col);
-    else b.x = bias[col];
-  }
-  return b;
-}
-
 // plain store of a loaded 16 x 64 block whose first column is global column col0
 __device__ __forceinline__ void store_block64(const DevParams& p, const uint32_t (&r)[32], int lane, long long rowA, int col0,
-                                              const float* bias, long long out_off, long long res_off) {
+                                              const float* bias, long long out_off, const ResFrag& res) {
   const int q2 = (lane & 3) * 2;
   const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+  float2 b2[8];
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) b2[kb] = load_bias2(bias, col0 + kb * 8 + q2, p.N);
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
     const int col = col0 + kb * 8 + q2;
-    const float2 b2 = load_bias2(bias, col, p.N);
-    if (okA) store_pair(p, rowA, col, __uint_as_float(r[4 * kb]), __uint_as_float(r[4 * kb + 1]), b2, out_off, res_off);
-    if (okB) store_pair(p, rowA + 8, col, __uint_as_float(r[4 * kb + 2]), __uint_as_float(r[4 * kb + 3]), b2, out_off, res_off);
+    if (okA) store_pair(p, rowA, col, __uint_as_float(r[4 * kb]), __uint_as_float(r[4 * kb + 1]), b2[kb], res.v[2 * kb], out_off);
+    if (okB)
+      store_pair(p, rowA + 8, col, __uint_as_float(r[4 * kb + 2]), __uint_as_float(r[4 * kb + 3]), b2[kb], res.v[2 * kb + 1], out_off);
   }
 }
 
-// One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.
+// One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.  Waits for the
+// accumulator itself (after the first residual block has been requested).
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
-                                              long long out_off, long long res_off, long long bias_off) {
-  if (row0 >= p.M) return;  // warp-uniform: nothing to store for a fully out-of-range row group
+                                              long long out_off, long long res_off, long long bias_off, uint64_t* full_bar,
+                                              uint32_t full_parity) {
   const int g = lane >> 2, q2 = (lane & 3) * 2;
   const float* bias = p.bias ? p.bias + bias_off : nullptr;
 
   if (EPI == TC_EPI_STORE) {
-#pragma unroll 1
+    // block `it` of this warp: rows row0 + (it&1)*16 .. +16, tile columns half_sel*128 + (it>>1)*64 .. +64
+    const bool has_res = p.resid != nullptr;
+    ResFrag rf[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rf[0].v[i] = rf[1].v[i] = make_float2(0.f, 0.f);
+    const int colbase = n_blk * BLOCK_N + half_sel * 128;
+    if (has_res && row0 < p.M && colbase < p.N) load_resid_block(p, lane, row0 + g, colbase, res_off, rf[0]);
+    mbar_wait(full_bar, full_parity);
+    tcgen05_fence_after();
+    if (row0 >= p.M) return;  // warp-uniform: nothing to store for a fully out-of-range row group
+#pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int hh = it & 1, cb = it >> 1;
       const int tcol = half_sel * 128 + cb * 64;
       const int col0 = n_blk * BLOCK_N + tcol;
-      if (col0 >= p.N) break;                       // warp-uniform
-      const long long rowA = row0 + hh * 16 + g;
-      if (row0 + hh * 16 >= p.M) continue;          // warp-uniform
+      const bool valid = col0 < p.N && row0 + hh * 16 < p.M;  // warp-uniform
       uint32_t r[32];
-      tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
-      tmem_ld_wait();
-      store_block64(p, r, lane, rowA, col0, bias, out_off, res_off);
+      if (valid) tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
+      if (it + 1 < 4 && has_res) {  // request the next block's residual before this block's stores
+        const int nh = (it + 1) & 1, ncb = (it + 1) >> 1;
+        const int ncol0 = n_blk * BLOCK_N + half_sel * 128 + ncb * 64;
+        if (ncol0 < p.N && row0 + nh * 16 < p.M) load_resid_block(p, lane, row0 + nh * 16 + g, ncol0, res_off, rf[(it + 1) & 1]);
+      }
+      if (valid) {
+        tmem_ld_wait();
+        store_block64(p, r, lane, row0 + hh * 16 + g, col0, bias, out_off, rf[it & 1]);
+      }
     }
   } else if (EPI == TC_EPI_GEGLU) {
     // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread
+    mbar_wait(full_bar, full_parity);
+    tcgen05_fence_after();
+    if (row0 >= p.M) return;
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
       const int hh = it & 1, cb = it >> 1;
@@ -195,6 +233,14 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       if (row0 + hh * 16 >= p.M) continue;
       uint32_t r[32];
       tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
+      float2 ba[4], bg[4];  // biases of this thread's column pairs (read-only path, issued under the TMEM load)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ca = col0 + (j >> 1) * 32 + (j & 1) * 8 + q2;
+        const bool ok = col0 + (j >> 1) * 32 < p.N;
+        ba[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca)) : make_float2(0.f, 0.f);
+        bg[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca + 16)) : make_float2(0.f, 0.f);
+      }
       tmem_ld_wait();
       const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
       bf16* outp = static_cast<bf16*>(p.out) + out_off;
@@ -204,23 +250,27 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
           const int ka = gi * 4 + m, kg = ka + 2;   // 8-column blocks of the a and the g values
-          const int ca = col0 + gi * 32 + m * 8 + q2;
-          const float2 ba = *reinterpret_cast<const float2*>(bias + ca);
-          const float2 bg = *reinterpret_cast<const float2*>(bias + ca + 16);
+          const float2 b_a = ba[gi * 2 + m], b_g = bg[gi * 2 + m];
           const int oc = ((col0 + gi * 32) >> 1) + m * 8 + q2;
           if (okA)
             *reinterpret_cast<uint32_t*>(outp + rowA * p.ldo + oc) =
-                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka]) + ba.x, __uint_as_float(r[4 * kg]) + bg.x),
-                            geglu_fast(__uint_as_float(r[4 * ka + 1]) + ba.y, __uint_as_float(r[4 * kg + 1]) + bg.y));
+                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka]) + b_a.x, __uint_as_float(r[4 * kg]) + b_g.x),
+                            geglu_fast(__uint_as_float(r[4 * ka + 1]) + b_a.y, __uint_as_float(r[4 * kg + 1]) + b_g.y));
           if (okB)
             *reinterpret_cast<uint32_t*>(outp + (rowA + 8) * p.ldo + oc) =
-                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka + 2]) + ba.x, __uint_as_float(r[4 * kg + 2]) + bg.x),
-                            geglu_fast(__uint_as_float(r[4 * ka + 3]) + ba.y, __uint_as_float(r[4 * kg + 3]) + bg.y));
+                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka + 2]) + b_a.x, __uint_as_float(r[4 * kg + 2]) + b_g.x),
+                            geglu_fast(__uint_as_float(r[4 * ka + 3]) + b_a.y, __uint_as_float(r[4 * kg + 3]) + b_g.y));
         }
       }
     }
   } else {  // TC_EPI_QKV_ROPE
     // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load
+    mbar_wait(full_bar, full_parity);
+    tcgen05_fence_after();
+    if (row0 >= p.M) return;
+    ResFrag nores;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) nores.v[i] = make_float2(0.f, 0.f);
     const int pd = p.rope_pd;
     const int units = pd == 32 ? 2 : 1;
 #pragma unroll 1
@@ -235,10 +285,10 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       uint32_t r1[32], r2[32];
       tmem_ld_16x64(tbase + b1, r1);
       if (pd != 32) tmem_ld_16x64(tbase + b1 + pd, r2);
-      tmem_ld_wait();
       if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store
-        store_block64(p, r1, lane, rowA, pc1, bias, out_off, res_off);
-        if (pd != 32) store_block64(p, r2, lane, rowA, pc1 + pd, bias, out_off, res_off);
+        tmem_ld_wait();
+        store_block64(p, r1, lane, rowA, pc1, bias, out_off, nores);
+        if (pd != 32) store_block64(p, r2, lane, rowA, pc1 + pd, bias, out_off, nores);
         continue;
       }
       const int region = pc1 / p.hidden;              // 0 = q, 1 = k
@@ -253,26 +303,43 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       const unsigned posA = static_cast<unsigned>(rowA) % seqT, posB = static_cast<unsigned>(rowA + 8) % seqT;
       bf16* outp = static_cast<bf16*>(p.out) + out_off;
       const int nkb = pd == 32 ? 4 : 8;               // 8-column blocks of x1 values in this unit
+      const float* cosA = p.rope_cos + static_cast<long long>(posA) * p.rope_half + jbase + q2;
+      const float* sinA = p.rope_sin + static_cast<long long>(posA) * p.rope_half + jbase + q2;
+      const float* cosB = p.rope_cos + static_cast<long long>(posB) * p.rope_half + jbase + q2;
+      const float* sinB = p.rope_sin + static_cast<long long>(posB) * p.rope_half + jbase + q2;
+      bool waited = false;
 #pragma unroll
-      for (int kb = 0; kb < 8; ++kb) {
-        if (kb >= nkb) break;
-        const int cofs = kb * 8 + q2;
-        const float2 bx1 = *reinterpret_cast<const float2*>(bias + pc1 + cofs);
-        const float2 bx2 = *reinterpret_cast<const float2*>(bias + pc1 + pd + cofs);
-        const int k2 = (kb + 4) & 7;  // partner block inside r1 when PD == 32
+      for (int k0 = 0; k0 < 8; k0 += 4) {             // two halves of 4 column blocks: tables first, then math + stores
+        if (k0 >= nkb) break;
+        float2 cs[8], sn[8], bx1[4], bx2[4];
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          if (rr == 0 ? !okA : !okB) continue;
-          const long long row = rowA + rr * 8;
-          const unsigned pos = rr == 0 ? posA : posB;
-          const float2 cs = *reinterpret_cast<const float2*>(p.rope_cos + static_cast<long long>(pos) * p.rope_half + jbase + cofs);
-          const float2 sn = *reinterpret_cast<const float2*>(p.rope_sin + static_cast<long long>(pos) * p.rope_half + jbase + cofs);
-          const float x1a = __uint_as_float(r1[4 * kb + 2 * rr]) + bx1.x, x1b = __uint_as_float(r1[4 * kb + 2 * rr + 1]) + bx1.y;
-          const float x2a = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]) + bx2.x;
-          const float x2b = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]) + bx2.y;
-          bf16* dst = outp + row * p.ldo + dbase + cofs;
-          *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * cs.x - x2a * sn.x, x1b * cs.y - x2b * sn.y);
-          *reinterpret_cast<uint32_t*>(dst + p.rope_half) = pack_bf16x2(x2a * cs.x + x1a * sn.x, x2b * cs.y + x1b * sn.y);
+        for (int j = 0; j < 4; ++j) {
+          const int cofs = (k0 + j) * 8;
+          cs[2 * j] = __ldg(reinterpret_cast<const float2*>(cosA + cofs));
+          sn[2 * j] = __ldg(reinterpret_cast<const float2*>(sinA + cofs));
+          cs[2 * j + 1] = __ldg(reinterpret_cast<const float2*>(cosB + cofs));
+          sn[2 * j + 1] = __ldg(reinterpret_cast<const float2*>(sinB + cofs));
+          bx1[j] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + cofs + q2));
+          bx2[j] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + cofs + q2));
+        }
+        if (!waited) { tmem_ld_wait(); waited = true; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kb = k0 + j;
+          const int cofs = kb * 8 + q2;
+          const int k2 = (kb + 4) & 7;  // partner block inside r1 when PD == 32
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            if (rr == 0 ? !okA : !okB) continue;
+            const long long row = rowA + rr * 8;
+            const float2 c2 = cs[2 * j + rr], s2 = sn[2 * j + rr];
+            const float x1a = __uint_as_float(r1[4 * kb + 2 * rr]) + bx1[j].x, x1b = __uint_as_float(r1[4 * kb + 2 * rr + 1]) + bx1[j].y;
+            const float x2a = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]) + bx2[j].x;
+            const float x2b = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]) + bx2[j].y;
+            bf16* dst = outp + row * p.ldo + dbase + cofs;
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * c2.x - x2a * s2.x, x1b * c2.y - x2b * s2.y);
+            *reinterpret_cast<uint32_t*>(dst + p.rope_half) = pack_bf16x2(x2a * c2.x + x1a * s2.x, x2b * c2.y + x1b * s2.y);
+          }
         }
       }
     }
@@ -393,10 +460,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const long long res_off = bo * p.sr_outer + bi * p.sr_inner;
       const long long bias_off = bo * p.sb_outer + bi * p.sb_inner;
       const long long row0 = static_cast<long long>(m_blk) * BLOCK_M + quarter * 32;
-      mbar_wait(&tmem_full[as], aphase);
-      tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -562,10 +627,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
       const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
       const long long row0 = static_cast<long long>(m_pair) * 2 * BLOCK_M + rank * BLOCK_M + quarter * 32;
-      mbar_wait(&tmem_full[as], aphase);
-      tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0, &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);

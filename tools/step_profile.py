@@ -1,0 +1,68 @@
+"""Per-kernel-class timing of a few eager CFG sampler steps (library profiler: CUDA events on the launching stream)
+plus the graph-replayed step time.   python tools/step_profile.py [--batch 16] [--frames 750] [--text 64] [--layers 5]
+[--heads 1] [--steps 10]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ditto_tts_b200 as D  # noqa: E402
+from ditto_tts_b200 import _lib  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--frames", type=int, default=750)
+ap.add_argument("--text", type=int, default=64)
+ap.add_argument("--layers", type=int, default=5)
+ap.add_argument("--heads", type=int, default=1)
+ap.add_argument("--hidden", type=int, default=768)
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--precision", default="bf16")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+B, T, S, H, K = a.batch, a.frames, a.text, a.hidden, a.steps
+torch.manual_seed(0)
+m = D.DiTTO(hidden_dim=H, num_layers=a.layers, num_heads=a.heads, time_dim=256, text_dim=H, diffusion_steps=K,
+            precision=a.precision).to(dev)
+s = D.DiTTOSampler(m, guidance_scale=3.0)
+g = torch.Generator().manual_seed(1)
+text = torch.randn(B, S, H, generator=g).to(dev)
+x0 = torch.randn(B, T, H, generator=g).to(dev)
+ctx = s._context(text, True, None, T)
+n = 2 * B
+graph = s.step_graph(B, T, S, True, 3.0, ctx, True, dev)
+graph.reset(x0, K - 1)
+for _ in range(3):
+    graph.replay()
+graph.reset(x0, K - 1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(K):
+    graph.replay()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+flops = n * (a.layers * (34.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * S * H) + 4.0 * T * H * H)
+print(f"graph step: {ms:.3f} ms  -> {B * T / ms * 1e3:.0f} frames/s/step, {flops / ms / 1e9:.0f} algorithmic TFLOP/s "
+      f"({graph.launches_per_step} launches/step)")
+t_all = torch.arange(K - 1, -1, -1, device=dev, dtype=torch.int64).unsqueeze(1).repeat(1, n).contiguous()
+eps = torch.empty((n, T, H), dtype=torch.float32, device=dev)
+xe, z = x0.clone(), torch.empty_like(x0)
+_lib.profile_start()
+P = min(K, 3)
+for i in range(P):
+    z.normal_()
+    s._p_sample_raw(xe, ctx, t_all[i], z, True, 3.0, S, eps, xe)
+prof = _lib.profile_stop()
+tot = sum(v["ms"] for v in prof.values())
+print(f"{'class':<24s}{'launches/step':>14s}{'ms/step':>10s}{'us/launch':>11s}{'TFLOP/s':>9s}{'GB/s':>8s}{'share':>7s}")
+for k_, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+    tf = v["flops"] / v["ms"] / 1e9 if v["flops"] else 0.0
+    gb = v["bytes"] / v["ms"] / 1e6 if v["bytes"] else 0.0
+    print(f"{k_:<24s}{v['launches'] / P:>14.0f}{v['ms'] / P:>10.4f}{v['ms'] / v['launches'] * 1e3:>11.1f}{tf:>9.0f}{gb:>8.0f}"
+          f"{v['ms'] / tot:>7.1%}")
+print(f"{'sum (eager, profiled)':<24s}{'':>14s}{tot / P:>10.4f}")
+print("finite:", bool(torch.isfinite(graph.x).all()))
