@@ -33,6 +33,16 @@ constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BARRIER_BYTES + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
 
+// kernel variants (template parameter EPI of the kernels); the public TcEpilogue maps onto them in launch_tc_gemm
+enum KernelEpi {
+  K_STORE_F32 = 0,        // fp32 out = alpha*acc + bias                      (N even)
+  K_STORE_F32_RESID = 1,  // fp32 out = alpha*acc + bias + fp32 residual (+ bf16 copy), in place allowed   (N even)
+  K_STORE_BF16 = 2,       // bf16 out = alpha*acc + bias                      (N even)
+  K_STORE_GENERIC = 3,    // any combination / odd N: fully predicated slow path
+  K_GEGLU = 4,
+  K_QKV_ROPE = 5
+};
+
 struct DevParams {
   int M, N, K;
   int batch_inner, batch_outer;
@@ -63,24 +73,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// GELU_erf(a) * sigmoid(g) with 3 MUFU ops (2x ex2, 1x rcp shared by both factors).
-//   Phi(a) = 0.5 (1 + erf(a / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), exact-erf semantics of nn.GELU()
+// GELU_erf(a) * sigmoid(g) with 3 MUFU ops (2x ex2, 1x rcp shared by both factors) and ~12 FP32 ops.
+//   Phi(a) = 0.5 (1 + erf(a / sqrt 2)) ~= sigmoid(2 a s(a^2)), s = odd-polynomial fit of atanh(erf)/a on |a| <= 6
+//   (|GELU error| <= 1.3e-5, 150x below the bf16 rounding of the result; the fp32 path uses erff).
+//   out = a / ((1 + exp(-2 a s)) (1 + exp(-g)));  an overflowing exponential gives 1/inf = 0, never inf * 0.
 __device__ __forceinline__ float geglu_fast(float a, float g) {
-  const float z = fabsf(a) * 0.70710678118654752440f;
-  const float e1 = ex2_approx(-z * z * 1.4426950408889634f);                 // exp(-z^2)
-  const float e2 = ex2_approx(fminf(-g * 1.4426950408889634f, 80.f));        // exp(-g), clamped: no inf * 0
-  const float da = fmaf(0.3275911f, z, 1.0f);                                // 1 + p z
-  const float db = 1.0f + e2;                                                // 1 + exp(-g)
-  const float r = rcp_approx(da * db);
-  const float t = db * r;                                                    // 1 / (1 + p z)
-  const float sig = da * r;                                                  // sigmoid(g)
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float half_erfc = 0.5f * t * poly * e1;                              // 0.5 erfc(z)
-  const float phi = a >= 0.f ? 1.0f - half_erfc : half_erfc;
-  return a * phi * sig;
+  const float ac = fminf(fmaxf(a, -6.0f), 6.0f);
+  const float a2 = ac * ac;
+  float sp = fmaf(a2, 2.377971153e-05f, 7.501817227e-04f);   // coefficients pre-multiplied by -2 log2(e)
+  sp = fmaf(a2, sp, -1.060307563e-01f);
+  sp = fmaf(a2, sp, -2.301608248e+00f);
+  const float e1 = ex2_approx(ac * sp);                       // exp(-2 a s)
+  const float e2 = ex2_approx(g * -1.4426950408889634f);      // exp(-g)
+  return a * rcp_approx((1.0f + e1) * (1.0f + e2));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -180,16 +185,145 @@ __device__ __forceinline__ void store_block64(const DevParams& p, const uint32_t
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast STORE epilogues (N even; fp32 / fp32+residual / bf16): compile-time output type, 64-bit vector accesses only, two
+// row predicates + one column predicate per 8-column group, immediate address offsets.  ~5x fewer instructions than
+// the generic path, which made every K <= 3072 GEMM epilogue-bound (ncu: issue-slot and instruction-cache limited).
+// Block order per warp: column half cb (64 columns) outer, 16-row half hh inner; the residual of block i+1 is
+// requested before block i is stored.
+// ---------------------------------------------------------------------------------------------------
+template <bool RESID>
+__device__ __forceinline__ void load_resid_fast(const DevParams& p, const float* rpA, const float* rpB, bool okA, bool okB, int col0t,
+                                                float2 (&f)[16]) {
+  if (!RESID) return;
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    const bool cok = col0t + kb * 8 < p.N;
+    f[2 * kb] = (okA && cok) ? *reinterpret_cast<const float2*>(rpA + kb * 8) : make_float2(0.f, 0.f);
+    f[2 * kb + 1] = (okB && cok) ? *reinterpret_cast<const float2*>(rpB + kb * 8) : make_float2(0.f, 0.f);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void store_blk_fast(const DevParams& p, const uint32_t (&r)[32], const float2 (&b2)[8], const float2 (&f)[16],
+                                               long long rowA, bool okA, bool okB, int col0t, long long out_off) {
+  constexpr bool RESID = EPI == K_STORE_F32_RESID;
+  constexpr bool OBF = EPI == K_STORE_BF16;
+  const long long oA = out_off + rowA * p.ldo + col0t;
+  const long long oB = oA + 8 * p.ldo;
+  const float alpha = p.alpha;
+  float2 vA[8], vB[8];
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    vA[kb].x = fmaf(alpha, __uint_as_float(r[4 * kb]), b2[kb].x);
+    vA[kb].y = fmaf(alpha, __uint_as_float(r[4 * kb + 1]), b2[kb].y);
+    vB[kb].x = fmaf(alpha, __uint_as_float(r[4 * kb + 2]), b2[kb].x);
+    vB[kb].y = fmaf(alpha, __uint_as_float(r[4 * kb + 3]), b2[kb].y);
+    if (RESID) {
+      vA[kb].x += f[2 * kb].x; vA[kb].y += f[2 * kb].y;
+      vB[kb].x += f[2 * kb + 1].x; vB[kb].y += f[2 * kb + 1].y;
+    }
+  }
+  if (OBF) {
+    bf16* out = static_cast<bf16*>(p.out);
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const bool cok = col0t + kb * 8 < p.N;
+      if (okA && cok) *reinterpret_cast<uint32_t*>(out + oA + kb * 8) = pack_bf16x2(vA[kb].x, vA[kb].y);
+      if (okB && cok) *reinterpret_cast<uint32_t*>(out + oB + kb * 8) = pack_bf16x2(vB[kb].x, vB[kb].y);
+    }
+  } else {
+    float* out = static_cast<float*>(p.out);
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const bool cok = col0t + kb * 8 < p.N;
+      if (okA && cok) *reinterpret_cast<float2*>(out + oA + kb * 8) = vA[kb];
+      if (okB && cok) *reinterpret_cast<float2*>(out + oB + kb * 8) = vB[kb];
+    }
+    if (RESID && p.out2 != nullptr) {  // bf16 copy of the updated residual stream (operand of the next GEMM)
+      bf16* o2 = p.out2 + out_off + rowA * p.ldo2 + col0t;
+      bf16* o2B = o2 + 8 * p.ldo2;
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {
+        const bool cok = col0t + kb * 8 < p.N;
+        if (okA && cok) *reinterpret_cast<uint32_t*>(o2 + kb * 8) = pack_bf16x2(vA[kb].x, vA[kb].y);
+        if (okB && cok) *reinterpret_cast<uint32_t*>(o2B + kb * 8) = pack_bf16x2(vB[kb].x, vB[kb].y);
+      }
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0,
+                                                    int n_blk, long long out_off, long long res_off, long long bias_off,
+                                                    uint64_t* full_bar, uint32_t full_parity) {
+  constexpr bool RESID = EPI == K_STORE_F32_RESID;
+  const int g = lane >> 2, q2 = (lane & 3) * 2;
+  const int colt = n_blk * BLOCK_N + half_sel * 128 + q2;  // this thread's first column of the tile
+  // rows of this thread: row0 + hh*16 + rr*8 + g
+  const long long r00 = row0 + g;
+  const bool ok00 = r00 < p.M, ok01 = r00 + 8 < p.M, ok10 = r00 + 16 < p.M, ok11 = r00 + 24 < p.M;
+  const float *rp00 = nullptr, *rp01 = nullptr, *rp10 = nullptr, *rp11 = nullptr;
+  if (RESID) {
+    const float* rb = p.resid + res_off + colt;
+    if (p.resid_row_mod > 0) {
+      const unsigned md = static_cast<unsigned>(p.resid_row_mod);
+      rp00 = rb + static_cast<long long>(static_cast<unsigned>(r00) % md) * p.ldr;
+      rp01 = rb + static_cast<long long>(static_cast<unsigned>(r00 + 8) % md) * p.ldr;
+      rp10 = rb + static_cast<long long>(static_cast<unsigned>(r00 + 16) % md) * p.ldr;
+      rp11 = rb + static_cast<long long>(static_cast<unsigned>(r00 + 24) % md) * p.ldr;
+    } else {
+      rp00 = rb + r00 * p.ldr;
+      rp01 = rp00 + 8 * p.ldr;
+      rp10 = rp00 + 16 * p.ldr;
+      rp11 = rp00 + 24 * p.ldr;
+    }
+  }
+  float2 f0[16], f1[16];
+  load_resid_fast<RESID>(p, rp00, rp01, ok00, ok01, colt, f0);
+  mbar_wait(full_bar, full_parity);
+  tcgen05_fence_after();
+  if (row0 >= p.M) return;  // warp-uniform
+  const float* bias = p.bias ? p.bias + bias_off : nullptr;
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    const int col0t = colt + cb * 64;
+    if (col0t - q2 >= p.N) break;  // warp-uniform
+    float2 b2[8];
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb)
+      b2[kb] = (bias != nullptr && col0t + kb * 8 < p.N) ? __ldg(reinterpret_cast<const float2*>(bias + col0t + kb * 8))
+                                                         : make_float2(0.f, 0.f);
+    uint32_t r[32];
+    // ---- hh = 0
+    tmem_ld_16x64(t_row + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
+    if (row0 + 16 < p.M) load_resid_fast<RESID>(p, rp10 + cb * 64, rp11 + cb * 64, ok10, ok11, col0t, f1);
+    tmem_ld_wait();
+    store_blk_fast<EPI>(p, r, b2, f0, r00, ok00, ok01, col0t, out_off);
+    // ---- hh = 1
+    if (row0 + 16 < p.M) tmem_ld_16x64(t_row + (16u << 16) + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
+    if (cb == 0 && col0t - q2 + 64 < p.N) load_resid_fast<RESID>(p, rp00 + 64, rp01 + 64, ok00, ok01, col0t + 64, f0);
+    if (row0 + 16 < p.M) {
+      tmem_ld_wait();
+      store_blk_fast<EPI>(p, r, b2, f1, r00 + 16, ok10, ok11, col0t, out_off);
+    }
+  }
+}
+
 // One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.  Waits for the
 // accumulator itself (after the first residual block has been requested).
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
                                               long long out_off, long long res_off, long long bias_off, uint64_t* full_bar,
                                               uint32_t full_parity) {
+  if (EPI == K_STORE_F32 || EPI == K_STORE_F32_RESID || EPI == K_STORE_BF16) {
+    epilogue_store_fast<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, full_bar, full_parity);
+    return;
+  }
   const int g = lane >> 2, q2 = (lane & 3) * 2;
   const float* bias = p.bias ? p.bias + bias_off : nullptr;
 
-  if (EPI == TC_EPI_STORE) {
+  if (EPI == K_STORE_GENERIC) {
     // block `it` of this warp: rows row0 + (it&1)*16 .. +16, tile columns half_sel*128 + (it>>1)*64 .. +64
     const bool has_res = p.resid != nullptr;
     ResFrag rf[2];
@@ -218,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         store_block64(p, r, lane, row0 + hh * 16 + g, col0, bias, out_off, rf[it & 1]);
       }
     }
-  } else if (EPI == TC_EPI_GEGLU) {
+  } else if (EPI == K_GEGLU) {
     // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread
     mbar_wait(full_bar, full_parity);
     tcgen05_fence_after();
@@ -263,7 +397,7 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         }
       }
     }
-  } else {  // TC_EPI_QKV_ROPE
+  } else {  // K_QKV_ROPE
     // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load
     mbar_wait(full_bar, full_parity);
     tcgen05_fence_after();
@@ -285,10 +419,17 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       uint32_t r1[32], r2[32];
       tmem_ld_16x64(tbase + b1, r1);
       if (pd != 32) tmem_ld_16x64(tbase + b1 + pd, r2);
-      if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store
+      if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store (lean bf16 block store; N = 3H is even)
+        float2 bv[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) bv[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
         tmem_ld_wait();
-        store_block64(p, r1, lane, rowA, pc1, bias, out_off, nores);
-        if (pd != 32) store_block64(p, r2, lane, rowA, pc1 + pd, bias, out_off, nores);
+        store_blk_fast<K_STORE_BF16>(p, r1, bv, nores.v, rowA, rowA < p.M, rowA + 8 < p.M, pc1 + q2, out_off);
+        if (pd != 32) {
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) bv[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
+          store_blk_fast<K_STORE_BF16>(p, r2, bv, nores.v, rowA, rowA < p.M, rowA + 8 < p.M, pc1 + pd + q2, out_off);
+        }
         continue;
       }
       const int region = pc1 / p.hidden;              // 0 = q, 1 = k
@@ -653,6 +794,7 @@ EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 bool g_init_done = false;
 bool g_use_pair = true;
+bool g_force_generic = false;  // DITTO_GENERIC_EPI=1: route every STORE epilogue through the generic path (tests)
 int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
 
 // 4-D bf16 map: dims (cols, rows, inner, outer), box (box_cols, box_rows, 1, 1), 128B swizzle, zero OOB fill.
@@ -708,16 +850,27 @@ int tc_gemm_init() {
   DITTO_CUDA(cudaGetDeviceProperties(&prop, dev));
   DITTO_REQUIRE(prop.major == 10, DITTO_E_UNSUPPORTED, "libditto_b200 needs an sm_100a device (B200)");
   g_num_sms = prop.multiProcessorCount;
-  DITTO_TRY((set_attr<TC_EPI_STORE, false>()));
-  DITTO_TRY((set_attr<TC_EPI_STORE, true>()));
-  DITTO_TRY((set_attr<TC_EPI_GEGLU, false>()));
-  DITTO_TRY((set_attr<TC_EPI_QKV_ROPE, false>()));
-  DITTO_TRY((set_attr_pair<TC_EPI_STORE>()));
-  DITTO_TRY((set_attr_pair<TC_EPI_GEGLU>()));
-  DITTO_TRY((set_attr_pair<TC_EPI_QKV_ROPE>()));
+  DITTO_TRY((set_attr<K_STORE_F32, false>()));
+  DITTO_TRY((set_attr<K_STORE_F32, true>()));
+  DITTO_TRY((set_attr<K_STORE_F32_RESID, false>()));
+  DITTO_TRY((set_attr<K_STORE_F32_RESID, true>()));
+  DITTO_TRY((set_attr<K_STORE_BF16, false>()));
+  DITTO_TRY((set_attr<K_STORE_BF16, true>()));
+  DITTO_TRY((set_attr<K_STORE_GENERIC, false>()));
+  DITTO_TRY((set_attr<K_STORE_GENERIC, true>()));
+  DITTO_TRY((set_attr<K_GEGLU, false>()));
+  DITTO_TRY((set_attr<K_QKV_ROPE, false>()));
+  DITTO_TRY((set_attr_pair<K_STORE_F32>()));
+  DITTO_TRY((set_attr_pair<K_STORE_F32_RESID>()));
+  DITTO_TRY((set_attr_pair<K_STORE_BF16>()));
+  DITTO_TRY((set_attr_pair<K_STORE_GENERIC>()));
+  DITTO_TRY((set_attr_pair<K_GEGLU>()));
+  DITTO_TRY((set_attr_pair<K_QKV_ROPE>()));
   {
     const char* env = getenv("DITTO_NO_PAIR");
     g_use_pair = !(env && env[0] == '1');
+    const char* eg = getenv("DITTO_GENERIC_EPI");
+    g_force_generic = eg && eg[0] == '1';
     if (const char* e1 = getenv("DITTO_STAGES_1CTA")) g_stages_1cta = std::max(2, std::min(STAGES, atoi(e1)));
     if (const char* e2 = getenv("DITTO_STAGES_PAIR")) g_stages_pair = std::max(2, std::min(P_STAGES, atoi(e2)));
   }
@@ -776,30 +929,49 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
   p.stages = pair ? g_stages_pair : g_stages_1cta;
+  // kernel variant: the lean compile-time epilogues cover the hot cases, anything else takes the generic one
+  int ke;
+  if (q.epilogue == TC_EPI_GEGLU) ke = K_GEGLU;
+  else if (q.epilogue == TC_EPI_QKV_ROPE) ke = K_QKV_ROPE;
+  else if (q.epilogue != TC_EPI_STORE) {
+    set_error("tc_gemm: unknown epilogue");
+    return DITTO_E_BADARG;
+  } else if (q.N % 2 != 0) ke = K_STORE_GENERIC;
+  else if (!q.out_bf16) ke = q.resid ? K_STORE_F32_RESID : (q.out2 ? K_STORE_GENERIC : K_STORE_F32);
+  else ke = (q.resid || q.out2) ? K_STORE_GENERIC : K_STORE_BF16;
+  if (g_force_generic && q.epilogue == TC_EPI_STORE) ke = K_STORE_GENERIC;
+#define DITTO_LAUNCH_PAIR(E) tc_gemm_pair_kernel<E><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p)
+#define DITTO_LAUNCH_1CTA(E, KN) tc_gemm_kernel<E, KN><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p)
   if (pair) {
     const int64_t pair_tiles = ceil_div(q.M, 2 * BLOCK_M) * p.n_tiles;
     grid = static_cast<unsigned>(2 * std::min<int64_t>(pair_tiles, g_num_sms / 2));
-    if (q.epilogue == TC_EPI_STORE)
-      tc_gemm_pair_kernel<TC_EPI_STORE><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p);
-    else if (q.epilogue == TC_EPI_GEGLU)
-      tc_gemm_pair_kernel<TC_EPI_GEGLU><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p);
-    else
-      tc_gemm_pair_kernel<TC_EPI_QKV_ROPE><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p);
-    DITTO_LAUNCH_CHECK();
-    return 0;
+    switch (ke) {
+      case K_STORE_F32: DITTO_LAUNCH_PAIR(K_STORE_F32); break;
+      case K_STORE_F32_RESID: DITTO_LAUNCH_PAIR(K_STORE_F32_RESID); break;
+      case K_STORE_BF16: DITTO_LAUNCH_PAIR(K_STORE_BF16); break;
+      case K_STORE_GENERIC: DITTO_LAUNCH_PAIR(K_STORE_GENERIC); break;
+      case K_GEGLU: DITTO_LAUNCH_PAIR(K_GEGLU); break;
+      default: DITTO_LAUNCH_PAIR(K_QKV_ROPE); break;
+    }
+  } else if (q.b_kn) {
+    switch (ke) {
+      case K_STORE_F32: DITTO_LAUNCH_1CTA(K_STORE_F32, true); break;
+      case K_STORE_F32_RESID: DITTO_LAUNCH_1CTA(K_STORE_F32_RESID, true); break;
+      case K_STORE_BF16: DITTO_LAUNCH_1CTA(K_STORE_BF16, true); break;
+      default: DITTO_LAUNCH_1CTA(K_STORE_GENERIC, true); break;  // GEGLU / ROPE with b_kn were rejected above
+    }
+  } else {
+    switch (ke) {
+      case K_STORE_F32: DITTO_LAUNCH_1CTA(K_STORE_F32, false); break;
+      case K_STORE_F32_RESID: DITTO_LAUNCH_1CTA(K_STORE_F32_RESID, false); break;
+      case K_STORE_BF16: DITTO_LAUNCH_1CTA(K_STORE_BF16, false); break;
+      case K_STORE_GENERIC: DITTO_LAUNCH_1CTA(K_STORE_GENERIC, false); break;
+      case K_GEGLU: DITTO_LAUNCH_1CTA(K_GEGLU, false); break;
+      default: DITTO_LAUNCH_1CTA(K_QKV_ROPE, false); break;
+    }
   }
-  if (q.epilogue == TC_EPI_STORE && !q.b_kn)
-    tc_gemm_kernel<TC_EPI_STORE, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
-  else if (q.epilogue == TC_EPI_STORE && q.b_kn)
-    tc_gemm_kernel<TC_EPI_STORE, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
-  else if (q.epilogue == TC_EPI_GEGLU)
-    tc_gemm_kernel<TC_EPI_GEGLU, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
-  else if (q.epilogue == TC_EPI_QKV_ROPE)
-    tc_gemm_kernel<TC_EPI_QKV_ROPE, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
-  else {
-    set_error("tc_gemm: unknown epilogue");
-    return DITTO_E_BADARG;
-  }
+#undef DITTO_LAUNCH_PAIR
+#undef DITTO_LAUNCH_1CTA
   DITTO_LAUNCH_CHECK();
   return 0;
 }

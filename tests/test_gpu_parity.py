@@ -83,10 +83,11 @@ def test_gemm_f32(dev, M, N, K, batch, nk):
     assert rel(Cd, ref) <= 2e-6
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 8, 8), (300, 200, 136), (1000, 768, 768), (750, 750, 768),
-                                   (4096, 768, 3072), (24000, 2304, 768)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1, 8, 8), (300, 200, 136), (300, 201, 136), (1000, 768, 768),
+                                   (750, 750, 768), (4096, 768, 3072), (24000, 2304, 768)])
 def test_gemm_bf16_tcgen05(dev, M, N, K):
-    """tcgen05 GEMM == fp32 matmul of the same bf16 operands up to accumulation order (fp32 accumulators in TMEM)."""
+    """tcgen05 GEMM == fp32 matmul of the same bf16 operands up to accumulation order (fp32 accumulators in TMEM).
+    Covers every STORE-epilogue variant: fp32 / bf16 output, with / without residual, residual in place, odd N."""
     lib = _lib.load()
     g = torch.Generator().manual_seed(2)
     A = torch.randn(M, K, generator=g).bfloat16().to(dev)
@@ -94,13 +95,23 @@ def test_gemm_bf16_tcgen05(dev, M, N, K):
     bias = torch.randn(N, generator=g).to(dev)
     ldc = (N + 7) // 8 * 8
     R = torch.randn(M, ldc, generator=g).to(dev)
-    ref = 0.25 * (A.float() @ W.float().T) + bias + R[:, :N]
+    R[:, N:] = 0
+    base = 0.25 * (A.float() @ W.float().T) + bias
     for out_bf16 in (0, 1):
-        Cd = torch.zeros(M, ldc, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
-        _lib.check(lib.ditto_gemm_bf16(P(A), K, P(W), K, P(Cd), ldc, out_bf16, P(bias), P(R), ldc, 0.25, M, N, K, ST()))
-        assert rel(Cd[:, :N], ref) <= (4e-3 if out_bf16 else 2e-5)
-        if ldc > N:
-            assert float(Cd[:, N:].abs().max()) == 0.0   # padding columns untouched
+        for use_resid in (True, False):
+            ref = base + R[:, :N] if use_resid else base
+            Cd = torch.zeros(M, ldc, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+            _lib.check(lib.ditto_gemm_bf16(P(A), K, P(W), K, P(Cd), ldc, out_bf16, P(bias), P(R) if use_resid else None, ldc,
+                                           0.25, M, N, K, ST()))
+            assert rel(Cd[:, :N], ref) <= (4e-3 if out_bf16 else 2e-5), (out_bf16, use_resid)
+            if ldc > N:
+                assert float(Cd[:, N:].abs().max()) == 0.0   # padding columns untouched
+    # residual updated in place (how the engine keeps the fp32 residual stream h)
+    Cd = R.clone()
+    _lib.check(lib.ditto_gemm_bf16(P(A), K, P(W), K, P(Cd), ldc, 0, P(bias), P(Cd), ldc, 0.25, M, N, K, ST()))
+    assert rel(Cd[:, :N], base + R[:, :N]) <= 2e-5
+    if ldc > N:
+        assert float(Cd[:, N:].abs().max()) == 0.0
 
 
 def test_gemm_bf16_rejects_misaligned(dev):
