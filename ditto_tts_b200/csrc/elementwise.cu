@@ -94,34 +94,36 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, OutT* __restrict__ y,
                                                         int64_t rows, int H) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int nvec = H >> 2;                            // float4 per row
   const int nv_lane = (nvec - lane + 31) >> 5;        // slots of this lane
-  const float* xr = x + row * H;
-  float4 v[LN_MAXV];
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  // grid-stride over rows (grid = a whole number of resident blocks per SM: no partial last wave)
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const float* xr = x + row * H;
+    float4 v[LN_MAXV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv_lane) v[i] = *reinterpret_cast<const float4*>(xr + ((i << 5) + lane) * 4);
-  float mean, rstd;
-  row_stats(v, nv_lane, H, mean, rstd);
-  OutT* yr = y + row * H;
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv_lane) v[i] = *reinterpret_cast<const float4*>(xr + ((i << 5) + lane) * 4);
+    float mean, rstd;
+    row_stats(v, nv_lane, H, mean, rstd);
+    OutT* yr = y + row * H;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv_lane) {
-      const int c = ((i << 5) + lane) * 4;
-      float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-      float4 b = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      store4<OutT>(yr + c, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
-                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-    }
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv_lane) {
+        const int c = ((i << 5) + lane) * 4;
+        float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        store4<OutT>(yr + c, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      }
+  }
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* y, bool out_bf16, int64_t rows, int H,
                      cudaStream_t st) {
   DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128 && H > 0, DITTO_E_UNSUPPORTED, "layernorm: need H % 4 == 0 and H <= 1024");
   if (rows <= 0) return 0;
-  const unsigned blocks = static_cast<unsigned>(ceil_div(rows, 8));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(rows, 8), 148 * 8));
   ProfScope prof(PC_LAYERNORM, st, 0.0, static_cast<double>(rows) * H * (out_bf16 ? 6 : 8));
   if (out_bf16)
     layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x, gamma, beta, static_cast<bf16*>(y), rows, H);
@@ -215,19 +217,21 @@ int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const 
 // RoPE tables and application (DiT.py:46-72): angle[p][j] = float(p) * inv_freq[j] (fp32 product, as einsum)
 // =====================================================================================================
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cos_t, float* __restrict__ sin_t,
-                                  int max_T, int half, int head_dim) {
+                                  float* __restrict__ freq_out, int max_T, int half, int head_dim) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(max_T) * half) return;
   const int p = static_cast<int>(i / half), j = static_cast<int>(i % half);
   const float f = inv_freq ? inv_freq[j] : 1.0f / powf(10000.f, static_cast<float>(2 * j) / static_cast<float>(head_dim));
   const float a = static_cast<float>(p) * f;
+  if (p == 0 && freq_out != nullptr) freq_out[j] = f;  // the frequencies the fused QKV epilogue multiplies positions with
   cos_t[i] = cosf(a);  // accurate (non fast-math) range reduction: angles reach ~2.2e3 rad
   sin_t[i] = sinf(a);
 }
 
-int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, int max_T, int half, int head_dim, cudaStream_t st) {
+int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, float* freq_out, int max_T, int half, int head_dim,
+                      cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(max_T) * half;
-  rope_table_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(inv_freq, cos_t, sin_t, max_T, half, head_dim);
+  rope_table_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(inv_freq, cos_t, sin_t, freq_out, max_T, half, head_dim);
   DITTO_LAUNCH_CHECK();
   return 0;
 }

@@ -81,10 +81,11 @@ struct ditto_engine {
   int rope_pd = 0;
   bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
   int pv_transpose = 0;  // debug: use the transposed-V operand instead of the MN-major descriptor
+  bool rope_table_in_epilogue = false;  // debug (DITTO_ROPE_TABLE=1): fused RoPE reads the cos/sin tables instead of computing them
   std::map<std::string, int64_t> expected;  // key -> numel
   std::map<std::string, float*> w;          // device fp32 copies (owned)
   std::vector<void*> owned;                 // everything else cudaMalloc'ed by the engine
-  float *time_table = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *coef = nullptr, *qs_buf = nullptr;
+  float *time_table = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *rope_freq = nullptr, *coef = nullptr, *qs_buf = nullptr;
   bf16 *w_in16 = nullptr, *w_out16 = nullptr;
   std::vector<LayerPack> layers;
 
@@ -340,6 +341,7 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         g.tag = PC_TC_QKV;
         if (e->fused_rope) {
           g.epilogue = TC_EPI_QKV_ROPE; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_half = e->half;
+          g.rope_freq = e->rope_table_in_epilogue ? nullptr : e->rope_freq;
           g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(T); g.hidden = H;
         }
         DITTO_TRY(launch_tc_gemm(g, st));
@@ -518,6 +520,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     e->fold_cross = (cfg->flags & DITTO_F_FOLD_CROSS) != 0;
     const char* env = getenv("DITTO_PV_TRANSPOSE");
     e->pv_transpose = env && env[0] == '1';
+    const char* env2 = getenv("DITTO_ROPE_TABLE");
+    e->rope_table_in_epilogue = env2 && env2[0] == '1';
   }
   build_expected(e);
   e->layers.resize(e->L);
@@ -602,8 +606,9 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
   if (!e->rope_cos) {
     DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->rope_cos), sizeof(float) * e->maxT * e->half));
     DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->rope_sin), sizeof(float) * e->maxT * e->half));
+    DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->rope_freq), sizeof(float) * e->half));
   }
-  DITTO_TRY(launch_rope_table(e->W("rotary.inv_freq"), e->rope_cos, e->rope_sin, e->maxT, e->half, e->d, st));
+  DITTO_TRY(launch_rope_table(e->W("rotary.inv_freq"), e->rope_cos, e->rope_sin, e->rope_freq, e->maxT, e->half, e->d, st));
 
   // ---- bf16 packing
   if (e->bf16_mode) {

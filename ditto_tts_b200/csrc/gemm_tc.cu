@@ -55,7 +55,7 @@ struct DevParams {
   const float* resid;
   long long ldr, sr_inner, sr_outer, resid_row_mod;
   bf16* out2; long long ldo2;
-  const float* rope_cos; const float* rope_sin;
+  const float* rope_cos; const float* rope_sin; const float* rope_freq;
   int rope_half, rope_pd, seq_T, hidden;
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
 };
@@ -73,6 +73,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// cos/sin of a = float(pos) * inv_freq (the reference's fp32 angle, DiT.py:56-59) for |a| up to a few thousand radians:
+// two-constant Cody-Waite reduction to [-pi, pi] (k * 6.28125 is exact), then the MUFU approximations (abs. error ~5e-7).
+__device__ __forceinline__ void sincos_reduced(float a, float& s, float& c) {
+  const float k = rintf(a * 0.15915494309189535f);
+  float r = fmaf(k, -6.28125f, a);
+  r = fmaf(k, -1.9353071795864769e-3f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
 // GELU_erf(a) * sigmoid(g) with 3 MUFU ops (2x ex2, 1x rcp shared by both factors) and ~12 FP32 ops.
 //   Phi(a) = 0.5 (1 + erf(a / sqrt 2)) ~= sigmoid(2 a s(a^2)), s = odd-polynomial fit of atanh(erf)/a on |a| <= 6
 //   (|GELU error| <= 1.3e-5, 150x below the bf16 rounding of the result; the fp32 path uses erff).
@@ -281,19 +291,25 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
   }
   float2 f0[16], f1[16];
   load_resid_fast<RESID>(p, rp00, rp01, ok00, ok01, colt, f0);
+  // biases of both column halves, requested before the accumulator wait (no dependent global load after it)
+  const float* bias = p.bias ? p.bias + bias_off : nullptr;
+  float2 bA[8], bB[8];
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    bA[kb] = (bias != nullptr && colt + kb * 8 < p.N) ? __ldg(reinterpret_cast<const float2*>(bias + colt + kb * 8)) : make_float2(0.f, 0.f);
+    bB[kb] = (bias != nullptr && colt + 64 + kb * 8 < p.N) ? __ldg(reinterpret_cast<const float2*>(bias + colt + 64 + kb * 8))
+                                                           : make_float2(0.f, 0.f);
+  }
   mbar_wait(full_bar, full_parity);
   tcgen05_fence_after();
   if (row0 >= p.M) return;  // warp-uniform
-  const float* bias = p.bias ? p.bias + bias_off : nullptr;
 #pragma unroll 1
   for (int cb = 0; cb < 2; ++cb) {
     const int col0t = colt + cb * 64;
     if (col0t - q2 >= p.N) break;  // warp-uniform
     float2 b2[8];
 #pragma unroll
-    for (int kb = 0; kb < 8; ++kb)
-      b2[kb] = (bias != nullptr && col0t + kb * 8 < p.N) ? __ldg(reinterpret_cast<const float2*>(bias + col0t + kb * 8))
-                                                         : make_float2(0.f, 0.f);
+    for (int kb = 0; kb < 8; ++kb) b2[kb] = cb == 0 ? bA[kb] : bB[kb];
     uint32_t r[32];
     // ---- hh = 0
     tmem_ld_16x64(t_row + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
@@ -353,136 +369,156 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       }
     }
   } else if (EPI == K_GEGLU) {
-    // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread
+    // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread.
+    // Biases of this thread's column pairs for both 64-column halves are requested before the accumulator wait.
+    float2 ba[8], bg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // j = cb*4 + gi*2 + m
+      const int cg0 = n_blk * BLOCK_N + half_sel * 128 + (j >> 2) * 64 + ((j >> 1) & 1) * 32;  // first column of the group
+      const int ca = cg0 + (j & 1) * 8 + q2;
+      const bool ok = cg0 < p.N;
+      ba[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca)) : make_float2(0.f, 0.f);
+      bg[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca + 16)) : make_float2(0.f, 0.f);
+    }
     mbar_wait(full_bar, full_parity);
     tcgen05_fence_after();
     if (row0 >= p.M) return;
-#pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-      const int hh = it & 1, cb = it >> 1;
+    bf16* outp = static_cast<bf16*>(p.out) + out_off;
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
       const int tcol = half_sel * 128 + cb * 64;
       const int col0 = n_blk * BLOCK_N + tcol;
       if (col0 >= p.N) break;
-      const long long rowA = row0 + hh * 16 + g;
-      if (row0 + hh * 16 >= p.M) continue;
-      uint32_t r[32];
-      tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
-      float2 ba[4], bg[4];  // biases of this thread's column pairs (read-only path, issued under the TMEM load)
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        if (row0 + hh * 16 >= p.M) break;
+        const long long rowA = row0 + hh * 16 + g;
+        uint32_t r[32];
+        tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
+        tmem_ld_wait();
+        const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ca = col0 + (j >> 1) * 32 + (j & 1) * 8 + q2;
-        const bool ok = col0 + (j >> 1) * 32 < p.N;
-        ba[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca)) : make_float2(0.f, 0.f);
-        bg[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca + 16)) : make_float2(0.f, 0.f);
-      }
-      tmem_ld_wait();
-      const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
-      bf16* outp = static_cast<bf16*>(p.out) + out_off;
+        for (int gi = 0; gi < 2; ++gi) {
+          if (col0 + gi * 32 >= p.N) break;           // N % 32 == 0: a group is all-or-nothing
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        if (col0 + gi * 32 >= p.N) break;           // N % 32 == 0: a group is all-or-nothing
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const int ka = gi * 4 + m, kg = ka + 2;   // 8-column blocks of the a and the g values
-          const float2 b_a = ba[gi * 2 + m], b_g = bg[gi * 2 + m];
-          const int oc = ((col0 + gi * 32) >> 1) + m * 8 + q2;
-          if (okA)
-            *reinterpret_cast<uint32_t*>(outp + rowA * p.ldo + oc) =
-                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka]) + b_a.x, __uint_as_float(r[4 * kg]) + b_g.x),
-                            geglu_fast(__uint_as_float(r[4 * ka + 1]) + b_a.y, __uint_as_float(r[4 * kg + 1]) + b_g.y));
-          if (okB)
-            *reinterpret_cast<uint32_t*>(outp + (rowA + 8) * p.ldo + oc) =
-                pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka + 2]) + b_a.x, __uint_as_float(r[4 * kg + 2]) + b_g.x),
-                            geglu_fast(__uint_as_float(r[4 * ka + 3]) + b_a.y, __uint_as_float(r[4 * kg + 3]) + b_g.y));
+          for (int m = 0; m < 2; ++m) {
+            const int ka = gi * 4 + m, kg = ka + 2;   // 8-column blocks of the a and the g values
+            const float2 b_a = ba[cb * 4 + gi * 2 + m], b_g = bg[cb * 4 + gi * 2 + m];
+            const int oc = ((col0 + gi * 32) >> 1) + m * 8 + q2;
+            if (okA)
+              *reinterpret_cast<uint32_t*>(outp + rowA * p.ldo + oc) =
+                  pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka]) + b_a.x, __uint_as_float(r[4 * kg]) + b_g.x),
+                              geglu_fast(__uint_as_float(r[4 * ka + 1]) + b_a.y, __uint_as_float(r[4 * kg + 1]) + b_g.y));
+            if (okB)
+              *reinterpret_cast<uint32_t*>(outp + (rowA + 8) * p.ldo + oc) =
+                  pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka + 2]) + b_a.x, __uint_as_float(r[4 * kg + 2]) + b_g.x),
+                              geglu_fast(__uint_as_float(r[4 * ka + 3]) + b_a.y, __uint_as_float(r[4 * kg + 3]) + b_g.y));
+          }
         }
       }
     }
   } else {  // K_QKV_ROPE
-    // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load
-    mbar_wait(full_bar, full_parity);
-    tcgen05_fence_after();
-    if (row0 >= p.M) return;
-    ResFrag nores;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) nores.v[i] = make_float2(0.f, 0.f);
+    // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load.  Everything that
+    // is read from global memory (rotary frequencies, biases) is requested BEFORE the accumulator wait: with the L2 busy
+    // feeding the operand ring, a dependent load after the wait costs ~1 us and made this epilogue the bottleneck (ncu).
     const int pd = p.rope_pd;
     const int units = pd == 32 ? 2 : 1;
+    const bool on_the_fly = p.rope_freq != nullptr;  // warp-uniform
+    bool waited = false;
 #pragma unroll 1
-    for (int it = 0; it < 2 * units; ++it) {
-      const int hh = it & 1, u = it >> 1;
+    for (int u = 0; u < units; ++u) {
       const int b1 = pd == 128 ? half_sel * 64 : (pd == 64 ? half_sel * 128 : half_sel * 128 + u * 64);  // tile column of x1
       const int pc1 = n_blk * BLOCK_N + b1;
-      if (pc1 >= p.N) break;
-      const long long rowA = row0 + hh * 16 + g;
-      if (row0 + hh * 16 >= p.M) continue;
-      const uint32_t tbase = t_row + (static_cast<uint32_t>(hh * 16) << 16);
-      uint32_t r1[32], r2[32];
-      tmem_ld_16x64(tbase + b1, r1);
-      if (pd != 32) tmem_ld_16x64(tbase + b1 + pd, r2);
-      if (pc1 >= 2 * p.hidden) {  // v third: identity layout, plain bias store (lean bf16 block store; N = 3H is even)
-        float2 bv[8];
-#pragma unroll
-        for (int kb = 0; kb < 8; ++kb) bv[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
-        tmem_ld_wait();
-        store_blk_fast<K_STORE_BF16>(p, r1, bv, nores.v, rowA, rowA < p.M, rowA + 8 < p.M, pc1 + q2, out_off);
-        if (pd != 32) {
-#pragma unroll
-          for (int kb = 0; kb < 8; ++kb) bv[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
-          store_blk_fast<K_STORE_BF16>(p, r2, bv, nores.v, rowA, rowA < p.M, rowA + 8 < p.M, pc1 + pd + q2, out_off);
-        }
-        continue;
+      const bool in_range = pc1 < p.N;                  // warp-uniform
+      const bool is_v = pc1 >= 2 * p.hidden;            // v third: identity layout, plain bias store
+      const int nkb = pd == 32 ? 4 : 8;                 // 8-column blocks of x1 values in this unit
+      int jbase = 0, dbase = 0;
+      if (in_range && !is_v) {
+        const int region = pc1 / p.hidden;              // 0 = q, 1 = k
+        const int lp = pc1 - region * p.hidden;         // permuted column inside the region
+        const int grp = lp / (2 * pd), w = lp - grp * 2 * pd;  // w < PD by construction
+        const int e0 = grp * pd;                        // first "x1 element" index of this group
+        const int head = e0 / p.rope_half;
+        jbase = e0 - head * p.rope_half + w;            // rotary frequency index of the block's first column
+        dbase = region * p.hidden + head * 2 * p.rope_half + jbase;
       }
-      const int region = pc1 / p.hidden;              // 0 = q, 1 = k
-      const int lp = pc1 - region * p.hidden;         // permuted column inside the region
-      const int grp = lp / (2 * pd), w = lp - grp * 2 * pd;  // w < PD by construction
-      const int e0 = grp * pd;                        // first "x1 element" index of this group
-      const int head = e0 / p.rope_half;
-      const int jbase = e0 - head * p.rope_half + w;  // rotary frequency index of the block's first column
-      const int dbase = region * p.hidden + head * 2 * p.rope_half + jbase;
-      const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
-      const unsigned seqT = static_cast<unsigned>(p.seq_T);
-      const unsigned posA = static_cast<unsigned>(rowA) % seqT, posB = static_cast<unsigned>(rowA + 8) % seqT;
-      bf16* outp = static_cast<bf16*>(p.out) + out_off;
-      const int nkb = pd == 32 ? 4 : 8;               // 8-column blocks of x1 values in this unit
-      const float* cosA = p.rope_cos + static_cast<long long>(posA) * p.rope_half + jbase + q2;
-      const float* sinA = p.rope_sin + static_cast<long long>(posA) * p.rope_half + jbase + q2;
-      const float* cosB = p.rope_cos + static_cast<long long>(posB) * p.rope_half + jbase + q2;
-      const float* sinB = p.rope_sin + static_cast<long long>(posB) * p.rope_half + jbase + q2;
-      bool waited = false;
+      float2 fr[8], bx1[8], bx2[8];
 #pragma unroll
-      for (int k0 = 0; k0 < 8; k0 += 4) {             // two halves of 4 column blocks: tables first, then math + stores
-        if (k0 >= nkb) break;
-        float2 cs[8], sn[8], bx1[4], bx2[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cofs = (k0 + j) * 8;
-          cs[2 * j] = __ldg(reinterpret_cast<const float2*>(cosA + cofs));
-          sn[2 * j] = __ldg(reinterpret_cast<const float2*>(sinA + cofs));
-          cs[2 * j + 1] = __ldg(reinterpret_cast<const float2*>(cosB + cofs));
-          sn[2 * j + 1] = __ldg(reinterpret_cast<const float2*>(sinB + cofs));
-          bx1[j] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + cofs + q2));
-          bx2[j] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + cofs + q2));
+      for (int kb = 0; kb < 8; ++kb) {
+        fr[kb] = bx1[kb] = bx2[kb] = make_float2(0.f, 0.f);
+        if (!in_range) continue;
+        if (is_v) {  // plain blocks at pc1 and (PD != 32) pc1 + PD
+          bx1[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
+          if (pd != 32) bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
+        } else if (kb < nkb) {
+          if (on_the_fly) fr[kb] = __ldg(reinterpret_cast<const float2*>(p.rope_freq + jbase + q2 + kb * 8));
+          bx1[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
+          bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
         }
-        if (!waited) { tmem_ld_wait(); waited = true; }
+      }
+      if (!waited) {
+        mbar_wait(full_bar, full_parity);
+        tcgen05_fence_after();
+        waited = true;
+      }
+      if (row0 >= p.M || !in_range) continue;           // warp-uniform
+      ResFrag nores;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kb = k0 + j;
-          const int cofs = kb * 8 + q2;
+      for (int i = 0; i < 16; ++i) nores.v[i] = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        if (row0 + hh * 16 >= p.M) break;
+        const long long rowA = row0 + hh * 16 + g;
+        const uint32_t tbase = t_row + (static_cast<uint32_t>(hh * 16) << 16);
+        uint32_t r1[32], r2[32];
+        tmem_ld_16x64(tbase + b1, r1);
+        if (pd != 32) tmem_ld_16x64(tbase + b1 + pd, r2);
+        const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+        if (is_v) {
+          tmem_ld_wait();
+          store_blk_fast<K_STORE_BF16>(p, r1, bx1, nores.v, rowA, okA, okB, pc1 + q2, out_off);
+          if (pd != 32) store_blk_fast<K_STORE_BF16>(p, r2, bx2, nores.v, rowA, okA, okB, pc1 + pd + q2, out_off);
+          continue;
+        }
+        const unsigned seqT = static_cast<unsigned>(p.seq_T);
+        const unsigned posA = static_cast<unsigned>(rowA) % seqT, posB = static_cast<unsigned>(rowA + 8) % seqT;
+        const float fposA = static_cast<float>(posA), fposB = static_cast<float>(posB);
+        const float* cosA = p.rope_cos + static_cast<long long>(posA) * p.rope_half + jbase + q2;
+        const float* sinA = p.rope_sin + static_cast<long long>(posA) * p.rope_half + jbase + q2;
+        const float* cosB = p.rope_cos + static_cast<long long>(posB) * p.rope_half + jbase + q2;
+        const float* sinB = p.rope_sin + static_cast<long long>(posB) * p.rope_half + jbase + q2;
+        bf16* outp = static_cast<bf16*>(p.out) + out_off + rowA * p.ldo + dbase + q2;
+        tmem_ld_wait();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          if (kb >= nkb) break;
           const int k2 = (kb + 4) & 7;  // partner block inside r1 when PD == 32
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
-            if (rr == 0 ? !okA : !okB) continue;
-            const long long row = rowA + rr * 8;
-            const float2 c2 = cs[2 * j + rr], s2 = sn[2 * j + rr];
-            const float x1a = __uint_as_float(r1[4 * kb + 2 * rr]) + bx1[j].x, x1b = __uint_as_float(r1[4 * kb + 2 * rr + 1]) + bx1[j].y;
-            const float x2a = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]) + bx2[j].x;
-            const float x2b = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]) + bx2[j].y;
-            bf16* dst = outp + row * p.ldo + dbase + cofs;
-            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * c2.x - x2a * s2.x, x1b * c2.y - x2b * s2.y);
-            *reinterpret_cast<uint32_t*>(dst + p.rope_half) = pack_bf16x2(x2a * c2.x + x1a * s2.x, x2b * c2.y + x1b * s2.y);
+            float2 c2, s2;
+            if (on_the_fly) {  // angle = float(pos) * inv_freq[j] exactly as the reference forms it
+              const float fp = rr == 0 ? fposA : fposB;
+              sincos_reduced(fp * fr[kb].x, s2.x, c2.x);
+              sincos_reduced(fp * fr[kb].y, s2.y, c2.y);
+            } else {
+              c2 = __ldg(reinterpret_cast<const float2*>((rr == 0 ? cosA : cosB) + kb * 8));
+              s2 = __ldg(reinterpret_cast<const float2*>((rr == 0 ? sinA : sinB) + kb * 8));
+            }
+            const float x1a = __uint_as_float(r1[4 * kb + 2 * rr]) + bx1[kb].x, x1b = __uint_as_float(r1[4 * kb + 2 * rr + 1]) + bx1[kb].y;
+            const float x2a = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]) + bx2[kb].x;
+            const float x2b = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]) + bx2[kb].y;
+            if (rr == 0 ? okA : okB) {
+              bf16* dst = outp + rr * 8 * p.ldo + kb * 8;
+              *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * c2.x - x2a * s2.x, x1b * c2.y - x2b * s2.y);
+              *reinterpret_cast<uint32_t*>(dst + p.rope_half) = pack_bf16x2(x2a * c2.x + x1a * s2.x, x2b * c2.y + x1b * s2.y);
+            }
           }
         }
       }
+    }
+    if (!waited) {  // not reachable (units >= 1), kept so that the accumulator wait is provably on every path
+      mbar_wait(full_bar, full_parity);
+      tcgen05_fence_after();
     }
   }
 }
@@ -923,7 +959,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.ldo = q.ldo; p.so_inner = q.so_inner; p.so_outer = q.so_outer;
   p.resid = q.resid; p.ldr = q.ldr; p.sr_inner = q.sr_inner; p.sr_outer = q.sr_outer; p.resid_row_mod = q.resid_row_mod;
   p.out2 = q.out2; p.ldo2 = q.ldo2;
-  p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin;
+  p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
   p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
 
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));

@@ -15,7 +15,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
 int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
                     int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
                     int64_t n_seq, int T, int H, cudaStream_t st);
-int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, int max_T, int half, int head_dim, cudaStream_t st);
+int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, float* freq_out, int max_T, int half, int head_dim,
+                      cudaStream_t st);
 int launch_rope(void* qkv, bool is_bf16, int64_t ld, const float* cos_t, const float* sin_t, int64_t rows, int seq_T,
                 int H, int head_dim, cudaStream_t st);
 int launch_softmax(const float* s, int64_t lds, void* p, bool p_bf16, int64_t ldp, int64_t rows, int cols, cudaStream_t st);
@@ -75,6 +76,7 @@ struct TcGemmParams {
   bf16* out2 = nullptr; int64_t ldo2 = 0;      // optional bf16 copy of the (fp32) result, batch strides as `out`
   // TC_EPI_QKV_ROPE
   const float* rope_cos = nullptr; const float* rope_sin = nullptr;
+  const float* rope_freq = nullptr;            // [d/2] inv_freq: when set, cos/sin are computed in the epilogue (no table reads)
   int rope_half = 0, rope_pd = 0, seq_T = 0, hidden = 0;
 };
 int launch_tc_gemm(const TcGemmParams& p, cudaStream_t st);
