@@ -79,6 +79,7 @@ struct ditto_engine {
   int H = 0, L = 0, heads = 0, d = 0, half = 0, Td = 0, Xd = 0, steps = 0, maxT = 0;
   bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
   int rope_pd = 0;
+  bool fused_attn = false;  // scores + softmax fused (cluster kernel); falls back per call when a row needs > 16 tiles
   bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
   int pv_transpose = 0;  // debug: use the transposed-V operand instead of the MN-major descriptor
   bool rope_table_in_epilogue = false;  // debug (DITTO_ROPE_TABLE=1): fused RoPE reads the cos/sin tables instead of computing them
@@ -202,6 +203,7 @@ struct Workspace {
   void *u = nullptr, *qkv = nullptr, *P = nullptr, *qc = nullptr, *oc = nullptr, *hid = nullptr, *xb16 = nullptr;
   float *fc1 = nullptr, *gate = nullptr;  // fp32 path only
   bf16* vt = nullptr;                     // transposed-V fallback
+  float* lpart = nullptr;                 // [n*heads, T, ceil(Tp/256)] partial softmax denominators (fused attention)
   float* tmp_small = nullptr;             // [n, Xd] pooled text
   bf16* text16 = nullptr;                 // [n*S, Xd]
   int64_t Tp = 0, Sp = 0, ldp = 0;
@@ -231,6 +233,7 @@ static Workspace ws_layout(const ditto_engine* e, void* base, int64_t n, int64_t
   } else if (e->pv_transpose) {
     w.vt = a.take<bf16>(n * e->heads * e->d * w.ldp);
   }
+  if (e->bf16_mode) w.lpart = a.take<float>(n * e->heads * T * ceil_div(w.ldp, 256));
   w.tmp_small = a.take<float>(n * e->Xd);
   w.text16 = a.take<bf16>(n * S * e->Xd);
   w.total = a.off + 256;
@@ -251,15 +254,30 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
                           cudaStream_t st, bool cross) {
   const int d = e->d, heads = e->heads;
   const int64_t ldp = round_up(Tk, 8);
-  TcGemmParams g;
-  g.A.ptr = q; g.A.rows = Tq; g.A.cols = d; g.A.ld = ldq; g.A.s_inner = d; g.A.s_outer = q_seq_stride;
-  g.B.ptr = k; g.B.rows = Tk; g.B.cols = d; g.B.ld = ldk; g.B.s_inner = d; g.B.s_outer = k_seq_stride;
-  g.M = Tq; g.N = Tk; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
-  g.alpha = alpha; g.out = w.scores; g.out_bf16 = false; g.ldo = ldp; g.so_inner = static_cast<int64_t>(Tq) * ldp;
-  g.so_outer = static_cast<int64_t>(heads) * Tq * ldp;
-  g.tag = cross ? PC_TC_CROSS_SCORES : PC_TC_SELF_SCORES;
-  DITTO_TRY(launch_tc_gemm(g, st));
-  DITTO_TRY(launch_softmax(w.scores, ldp, w.P, true, ldp, n * heads * Tq, Tk, st));
+  const int csize = e->fused_attn ? tc_scores_softmax_csize(Tk) : 0;
+  if (csize > 0) {
+    // flash-style: P = exp(s - rowmax) straight from TMEM (normalised in the kernel when one tile holds the row)
+    TcScoresSoftmaxParams f;
+    f.Q.ptr = q; f.Q.rows = Tq; f.Q.cols = d; f.Q.ld = ldq; f.Q.s_inner = d; f.Q.s_outer = q_seq_stride;
+    f.Km.ptr = k; f.Km.rows = Tk; f.Km.cols = d; f.Km.ld = ldk; f.Km.s_inner = d; f.Km.s_outer = k_seq_stride;
+    f.M = Tq; f.N = Tk; f.K = d; f.batch_inner = heads; f.batch_outer = static_cast<int>(n);
+    f.alpha = alpha;
+    f.P = static_cast<bf16*>(w.P); f.ldp = ldp; f.sp_inner = static_cast<int64_t>(Tq) * ldp;
+    f.sp_outer = static_cast<int64_t>(heads) * Tq * ldp; f.npad = static_cast<int>(ldp);
+    f.lpart = w.lpart; f.sl_inner = static_cast<int64_t>(Tq) * csize; f.sl_outer = static_cast<int64_t>(heads) * Tq * csize;
+    f.tag = cross ? PC_TC_CROSS_SCORES : PC_TC_SELF_SCORES;
+    DITTO_TRY(launch_tc_scores_softmax(f, st));
+  } else {
+    TcGemmParams g;
+    g.A.ptr = q; g.A.rows = Tq; g.A.cols = d; g.A.ld = ldq; g.A.s_inner = d; g.A.s_outer = q_seq_stride;
+    g.B.ptr = k; g.B.rows = Tk; g.B.cols = d; g.B.ld = ldk; g.B.s_inner = d; g.B.s_outer = k_seq_stride;
+    g.M = Tq; g.N = Tk; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+    g.alpha = alpha; g.out = w.scores; g.out_bf16 = false; g.ldo = ldp; g.so_inner = static_cast<int64_t>(Tq) * ldp;
+    g.so_outer = static_cast<int64_t>(heads) * Tq * ldp;
+    g.tag = cross ? PC_TC_CROSS_SCORES : PC_TC_SELF_SCORES;
+    DITTO_TRY(launch_tc_gemm(g, st));
+    DITTO_TRY(launch_softmax(w.scores, ldp, w.P, true, ldp, n * heads * Tq, Tk, st));
+  }
   TcGemmParams o;
   o.A.ptr = static_cast<const bf16*>(w.P); o.A.rows = Tq; o.A.cols = Tk; o.A.ld = ldp; o.A.s_inner = static_cast<int64_t>(Tq) * ldp;
   o.A.s_outer = static_cast<int64_t>(heads) * Tq * ldp;
@@ -275,6 +293,10 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
   o.M = Tq; o.N = d; o.K = Tk; o.batch_inner = heads; o.batch_outer = static_cast<int>(n);
   o.out = out; o.out_bf16 = out_bf16; o.ldo = ldo; o.so_inner = d; o.so_outer = o_seq_stride;
   o.resid = resid; o.ldr = ldo; o.sr_inner = d; o.sr_outer = o_seq_stride;
+  if (csize > 1) {  // P is unnormalised: divide by the summed partial denominators in the epilogue
+    o.row_lsum = w.lpart; o.row_lparts = csize; o.sl_inner = static_cast<int64_t>(Tq) * csize;
+    o.sl_outer = static_cast<int64_t>(heads) * Tq * csize;
+  }
   o.tag = cross ? PC_TC_CROSS_PV : PC_TC_SELF_PV;
   DITTO_TRY(launch_tc_gemm(o, st));
   return 0;
@@ -355,16 +377,28 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
         const int heads = e->heads;
         const int64_t Sp = w.Sp;
-        TcGemmParams g;
-        g.A.ptr = u; g.A.rows = T; g.A.cols = H; g.A.ld = H; g.A.s_inner = 0; g.A.s_outer = T * H;
-        g.B.ptr = c.kfold0 + c.kfold_stride * i; g.B.rows = S; g.B.cols = H; g.B.ld = H; g.B.s_inner = S * H;
-        g.B.s_outer = static_cast<int64_t>(heads) * S * H;
-        g.M = static_cast<int>(T); g.N = static_cast<int>(S); g.K = H; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
-        g.alpha = sqrt_inv_d; g.bias = c.sbias0 + c.sbias_stride * i; g.sb_inner = Sp; g.sb_outer = heads * Sp;
-        g.out = w.scores; g.out_bf16 = false; g.ldo = heads * Sp; g.so_inner = Sp; g.so_outer = T * heads * Sp;
-        g.tag = PC_TC_CROSS_SCORES;
-        DITTO_TRY(launch_tc_gemm(g, st));
-        DITTO_TRY(launch_softmax(w.scores, Sp, w.P, true, Sp, n * T * heads, static_cast<int>(S), st));
+        if (e->fused_attn && tc_scores_softmax_csize(static_cast<int>(S)) == 1) {
+          TcScoresSoftmaxParams f;
+          f.Q.ptr = u; f.Q.rows = T; f.Q.cols = H; f.Q.ld = H; f.Q.s_inner = 0; f.Q.s_outer = T * H;
+          f.Km.ptr = c.kfold0 + c.kfold_stride * i; f.Km.rows = S; f.Km.cols = H; f.Km.ld = H; f.Km.s_inner = S * H;
+          f.Km.s_outer = static_cast<int64_t>(heads) * S * H;
+          f.M = static_cast<int>(T); f.N = static_cast<int>(S); f.K = H; f.batch_inner = heads; f.batch_outer = static_cast<int>(n);
+          f.alpha = sqrt_inv_d; f.bias = c.sbias0 + c.sbias_stride * i; f.sb_inner = Sp; f.sb_outer = heads * Sp;
+          f.P = static_cast<bf16*>(w.P); f.ldp = heads * Sp; f.sp_inner = Sp; f.sp_outer = T * heads * Sp; f.npad = static_cast<int>(Sp);
+          f.tag = PC_TC_CROSS_SCORES;
+          DITTO_TRY(launch_tc_scores_softmax(f, st));
+        } else {
+          TcGemmParams g;
+          g.A.ptr = u; g.A.rows = T; g.A.cols = H; g.A.ld = H; g.A.s_inner = 0; g.A.s_outer = T * H;
+          g.B.ptr = c.kfold0 + c.kfold_stride * i; g.B.rows = S; g.B.cols = H; g.B.ld = H; g.B.s_inner = S * H;
+          g.B.s_outer = static_cast<int64_t>(heads) * S * H;
+          g.M = static_cast<int>(T); g.N = static_cast<int>(S); g.K = H; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+          g.alpha = sqrt_inv_d; g.bias = c.sbias0 + c.sbias_stride * i; g.sb_inner = Sp; g.sb_outer = heads * Sp;
+          g.out = w.scores; g.out_bf16 = false; g.ldo = heads * Sp; g.so_inner = Sp; g.so_outer = T * heads * Sp;
+          g.tag = PC_TC_CROSS_SCORES;
+          DITTO_TRY(launch_tc_gemm(g, st));
+          DITTO_TRY(launch_softmax(w.scores, Sp, w.P, true, Sp, n * T * heads, static_cast<int>(S), st));
+        }
         TcGemmParams o;
         o.A.ptr = static_cast<const bf16*>(w.P); o.A.rows = T; o.A.cols = heads * Sp; o.A.ld = heads * Sp; o.A.s_outer = T * heads * Sp;
         o.B.ptr = c.vfold0 + c.vfold_stride * i; o.B.rows = heads * Sp; o.B.cols = H; o.B.ld = H; o.B.s_outer = heads * Sp * H;
@@ -518,6 +552,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
       if (e->half % pd == 0 && e->H % (2 * pd) == 0) { e->rope_pd = pd; break; }
     e->fused_rope = (cfg->flags & DITTO_F_FUSED_ROPE) && e->rope_pd != 0;
     e->fold_cross = (cfg->flags & DITTO_F_FOLD_CROSS) != 0;
+    e->fused_attn = (cfg->flags & DITTO_F_FUSED_ATTN) != 0;
+    if (const char* ef = getenv("DITTO_NO_FUSED_ATTN")) if (ef[0] == '1') e->fused_attn = false;
     const char* env = getenv("DITTO_PV_TRANSPOSE");
     e->pv_transpose = env && env[0] == '1';
     const char* env2 = getenv("DITTO_ROPE_TABLE");

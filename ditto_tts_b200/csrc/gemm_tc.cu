@@ -58,6 +58,7 @@ struct DevParams {
   const float* rope_cos; const float* rope_sin; const float* rope_freq;
   int rope_half, rope_pd, seq_T, hidden;
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
+  const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -216,19 +217,19 @@ __device__ __forceinline__ void load_resid_fast(const DevParams& p, const float*
 
 template <int EPI>
 __device__ __forceinline__ void store_blk_fast(const DevParams& p, const uint32_t (&r)[32], const float2 (&b2)[8], const float2 (&f)[16],
-                                               long long rowA, bool okA, bool okB, int col0t, long long out_off) {
+                                               long long rowA, bool okA, bool okB, int col0t, long long out_off, float alphaA,
+                                               float alphaB) {
   constexpr bool RESID = EPI == K_STORE_F32_RESID;
   constexpr bool OBF = EPI == K_STORE_BF16;
   const long long oA = out_off + rowA * p.ldo + col0t;
   const long long oB = oA + 8 * p.ldo;
-  const float alpha = p.alpha;
   float2 vA[8], vB[8];
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
-    vA[kb].x = fmaf(alpha, __uint_as_float(r[4 * kb]), b2[kb].x);
-    vA[kb].y = fmaf(alpha, __uint_as_float(r[4 * kb + 1]), b2[kb].y);
-    vB[kb].x = fmaf(alpha, __uint_as_float(r[4 * kb + 2]), b2[kb].x);
-    vB[kb].y = fmaf(alpha, __uint_as_float(r[4 * kb + 3]), b2[kb].y);
+    vA[kb].x = fmaf(alphaA, __uint_as_float(r[4 * kb]), b2[kb].x);
+    vA[kb].y = fmaf(alphaA, __uint_as_float(r[4 * kb + 1]), b2[kb].y);
+    vB[kb].x = fmaf(alphaB, __uint_as_float(r[4 * kb + 2]), b2[kb].x);
+    vB[kb].y = fmaf(alphaB, __uint_as_float(r[4 * kb + 3]), b2[kb].y);
     if (RESID) {
       vA[kb].x += f[2 * kb].x; vA[kb].y += f[2 * kb].y;
       vB[kb].x += f[2 * kb + 1].x; vB[kb].y += f[2 * kb + 1].y;
@@ -266,7 +267,7 @@ __device__ __forceinline__ void store_blk_fast(const DevParams& p, const uint32_
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0,
                                                     int n_blk, long long out_off, long long res_off, long long bias_off,
-                                                    uint64_t* full_bar, uint32_t full_parity) {
+                                                    long long ls_off, uint64_t* full_bar, uint32_t full_parity) {
   constexpr bool RESID = EPI == K_STORE_F32_RESID;
   const int g = lane >> 2, q2 = (lane & 3) * 2;
   const int colt = n_blk * BLOCK_N + half_sel * 128 + q2;  // this thread's first column of the tile
@@ -288,6 +289,20 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
       rp10 = rp00 + 16 * p.ldr;
       rp11 = rp00 + 24 * p.ldr;
     }
+  }
+  // per-row accumulator scale: alpha, or alpha / (sum of the row's partial softmax denominators)
+  float a00 = p.alpha, a01 = p.alpha, a10 = p.alpha, a11 = p.alpha;
+  if (p.row_lsum != nullptr) {
+    const float* lp = p.row_lsum + ls_off + r00 * p.row_lparts;
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+    for (int c = 0; c < p.row_lparts; ++c) {
+      if (ok00) s00 += __ldg(lp + c);
+      if (ok01) s01 += __ldg(lp + 8 * p.row_lparts + c);
+      if (ok10) s10 += __ldg(lp + 16 * p.row_lparts + c);
+      if (ok11) s11 += __ldg(lp + 24 * p.row_lparts + c);
+    }
+    a00 = ok00 ? p.alpha / s00 : 0.f; a01 = ok01 ? p.alpha / s01 : 0.f;
+    a10 = ok10 ? p.alpha / s10 : 0.f; a11 = ok11 ? p.alpha / s11 : 0.f;
   }
   float2 f0[16], f1[16];
   load_resid_fast<RESID>(p, rp00, rp01, ok00, ok01, colt, f0);
@@ -315,13 +330,13 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
     tmem_ld_16x64(t_row + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
     if (row0 + 16 < p.M) load_resid_fast<RESID>(p, rp10 + cb * 64, rp11 + cb * 64, ok10, ok11, col0t, f1);
     tmem_ld_wait();
-    store_blk_fast<EPI>(p, r, b2, f0, r00, ok00, ok01, col0t, out_off);
+    store_blk_fast<EPI>(p, r, b2, f0, r00, ok00, ok01, col0t, out_off, a00, a01);
     // ---- hh = 1
     if (row0 + 16 < p.M) tmem_ld_16x64(t_row + (16u << 16) + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
     if (cb == 0 && col0t - q2 + 64 < p.N) load_resid_fast<RESID>(p, rp00 + 64, rp01 + 64, ok00, ok01, col0t + 64, f0);
     if (row0 + 16 < p.M) {
       tmem_ld_wait();
-      store_blk_fast<EPI>(p, r, b2, f1, r00 + 16, ok10, ok11, col0t, out_off);
+      store_blk_fast<EPI>(p, r, b2, f1, r00 + 16, ok10, ok11, col0t, out_off, a10, a11);
     }
   }
 }
@@ -330,10 +345,10 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
 // accumulator itself (after the first residual block has been requested).
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
-                                              long long out_off, long long res_off, long long bias_off, uint64_t* full_bar,
-                                              uint32_t full_parity) {
+                                              long long out_off, long long res_off, long long bias_off, long long ls_off,
+                                              uint64_t* full_bar, uint32_t full_parity) {
   if (EPI == K_STORE_F32 || EPI == K_STORE_F32_RESID || EPI == K_STORE_BF16) {
-    epilogue_store_fast<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, full_bar, full_parity);
+    epilogue_store_fast<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, ls_off, full_bar, full_parity);
     return;
   }
   const int g = lane >> 2, q2 = (lane & 3) * 2;
@@ -476,8 +491,8 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
         if (is_v) {
           tmem_ld_wait();
-          store_blk_fast<K_STORE_BF16>(p, r1, bx1, nores.v, rowA, okA, okB, pc1 + q2, out_off);
-          if (pd != 32) store_blk_fast<K_STORE_BF16>(p, r2, bx2, nores.v, rowA, okA, okB, pc1 + pd + q2, out_off);
+          store_blk_fast<K_STORE_BF16>(p, r1, bx1, nores.v, rowA, okA, okB, pc1 + q2, out_off, 1.f, 1.f);
+          if (pd != 32) store_blk_fast<K_STORE_BF16>(p, r2, bx2, nores.v, rowA, okA, okB, pc1 + pd + q2, out_off, 1.f, 1.f);
           continue;
         }
         const unsigned seqT = static_cast<unsigned>(p.seq_T);
@@ -638,7 +653,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const long long bias_off = bo * p.sb_outer + bi * p.sb_inner;
       const long long row0 = static_cast<long long>(m_blk) * BLOCK_M + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, &tmem_full[as], aphase);
+      const long long ls_off = bo * p.sl_outer + bi * p.sl_inner;
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, ls_off, &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -805,7 +821,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
       const long long row0 = static_cast<long long>(m_pair) * 2 * BLOCK_M + rank * BLOCK_M + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0, &tmem_full[as], aphase);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0, 0, &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
@@ -819,6 +835,336 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// =====================================================================================================
+// Fused attention scores + softmax (flash-style: the fp32 score tile lives in TMEM only).
+//   One cluster of `csize` CTAs per work item (batch item, 128 query rows); CTA `rank` computes the 128 x 256 score tile
+//   of key columns [256 rank, +256) with the same TMA ring / tcgen05 main loop as the GEMM above (K = head dim), then
+//     pass 1  row maxima of the tile (accumulator fragments -> quad shuffles), written into EVERY peer's shared memory
+//             (st.shared::cluster) and announced on the peer's mbarrier (remote arrive, release.cluster);
+//     pass 2  p = 2^(s' - max') in log2 domain, bf16 store of P, row sums.
+//   csize == 1: a third pass stores the normalised probabilities.  csize > 1: P stays unnormalised (values in (0, 1]) and
+//   the partial sums go to lpart[row][rank]; the P.V GEMM applies 1 / sum in its epilogue (DevParams::row_lsum).
+//   Persistent over work items with double-buffered TMEM, so the exchange of item i overlaps the MMAs of item i + 1.
+// =====================================================================================================
+constexpr int SM_MAX_CLUSTER = 16;
+constexpr int SM_STAT_BYTES = 2 * SM_MAX_CLUSTER * BLOCK_M * 4;  // [acc stage][peer rank][row] row maxima
+constexpr int SM_SMEM_BYTES = STAGES * STAGE_BYTES + BARRIER_BYTES + SM_STAT_BYTES + 1024;
+static_assert(SM_SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
+
+struct SmDev {
+  int M, N, K;
+  int batch_inner, batch_outer;
+  int m_tiles, num_items, num_kb;
+  int a_bi, a_bo, b_bi, b_bo;
+  float alpha2;                 // alpha * log2(e)
+  const float* bias; long long sb_inner, sb_outer;
+  bf16* P; long long ldp, sp_inner, sp_outer;
+  int npad;
+  float* lpart; long long sl_inner, sl_outer;
+  int csize, stages;
+};
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// remote shared-memory store that signals the destination CTA's mbarrier with complete_tx (4 bytes): data and
+// notification travel together through the async proxy, so the sender needs no release fence (a release-scoped arrive
+// would first have to drain this thread's outstanding global stores of P).
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    tc_scores_softmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const SmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* stat_bar = tmem_empty + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stat_bar + 2);
+  float* stat = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BARRIER_BYTES);  // [2][SM_MAX_CLUSTER][BLOCK_M]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int csize = p.csize;
+  const int rank = csize > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int num_clusters = gridDim.x / csize;
+  const int cluster_id = blockIdx.x / csize;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+      mbar_init(&stat_bar[s], 1);  // one local arrive.expect_tx per use; the row maxima arrive as st.async transactions
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();  // every peer's barriers are initialised before the first remote arrive
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        const int m_blk = item % p.m_tiles;
+        const int b = item / p.m_tiles;
+        const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
+        const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
+        const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_4d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo);
+          tma_load_4d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, rank * BLOCK_N, bbi, bbo);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =========================== softmax epilogue ===========================
+    // warp -> TMEM lanes [32 (warp & 3), +32); its 16-row half hsel = (warp - EPI_WARP0) >> 2; all 256 tile columns
+    const int ew = warp - EPI_WARP0;
+    const int quarter = warp & 3, hsel = ew >> 2;
+    const int g = lane >> 2, q2 = (lane & 3) * 2;
+    const int trow = quarter * 32 + hsel * 16;  // first tile row of this warp
+    const int col_base = rank * BLOCK_N;        // first key column of this CTA
+    const bool writer = (lane & 3) == 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+      const int m_blk = item % p.m_tiles;
+      const int b = item / p.m_tiles;
+      const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
+      const long long rowA = static_cast<long long>(m_blk) * BLOCK_M + trow + g;  // second row: rowA + 8
+      const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+      const float* bias = HAS_BIAS ? p.bias + bo * p.sb_outer + bi * p.sb_inner : nullptr;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(trow) << 16) + static_cast<uint32_t>(as * BLOCK_N);
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+
+      // ---- pass 1: row maxima of this tile (log2 domain: s' = (alpha acc + bias) log2 e)
+      float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll 1
+      for (int cbk = 0; cbk < 4; ++cbk) {
+        const int col0 = col_base + cbk * 64 + q2;
+        if (col0 - q2 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_16x64(t_row + cbk * 64, r);
+        float2 bb[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          bb[kb] = make_float2(0.f, 0.f);
+          if (HAS_BIAS) {
+            const int c = col0 + kb * 8;
+            if (c < p.N) bb[kb].x = __ldg(bias + c) * 1.4426950408889634f;
+            if (c + 1 < p.N) bb[kb].y = __ldg(bias + c + 1) * 1.4426950408889634f;
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const int c = col0 + kb * 8;
+          if (c < p.N) {
+            mA = fmaxf(mA, fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x));
+            mB = fmaxf(mB, fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x));
+          }
+          if (c + 1 < p.N) {
+            mA = fmaxf(mA, fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y));
+            mB = fmaxf(mB, fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y));
+          }
+        }
+      }
+      mA = quad_max(mA);
+      mB = quad_max(mB);
+
+      // ---- exchange through distributed shared memory: every writer lane sends its two row maxima to every CTA of the
+      //      cluster (own CTA included); each CTA expects csize * 64 lanes * 8 bytes per work item
+      if (csize > 1) {
+        if (ew == 0 && lane == 0) mbar_expect_tx(&stat_bar[as], static_cast<uint32_t>(csize * NUM_EPI_WARPS * 8 * 8));
+        if (writer) {
+          const uint32_t slotA = smem_u32(stat + (as * SM_MAX_CLUSTER + rank) * BLOCK_M + trow + g);
+          const uint32_t barl = smem_u32(&stat_bar[as]);
+          for (int c = 0; c < csize; ++c) {
+            const uint32_t ra = mapa_shared(slotA, static_cast<uint32_t>(c));
+            const uint32_t rb = mapa_shared(barl, static_cast<uint32_t>(c));
+            st_async_f32(ra, mA, rb);
+            st_async_f32(ra + 8 * 4, mB, rb);
+          }
+        }
+        mbar_wait(&stat_bar[as], aphase);
+        const float* sp = stat + as * SM_MAX_CLUSTER * BLOCK_M + trow + g;
+        for (int c = 0; c < csize; ++c) {
+          mA = fmaxf(mA, sp[c * BLOCK_M]);
+          mB = fmaxf(mB, sp[c * BLOCK_M + 8]);
+        }
+        __syncwarp();
+      }
+
+      // ---- pass 2: exponentials, row sums; csize > 1: store the unnormalised P
+      bf16* Pb = p.P + bo * p.sp_outer + bi * p.sp_inner;
+      bf16* pA = Pb + rowA * p.ldp;
+      bf16* pB = pA + 8 * p.ldp;
+      float sumA = 0.f, sumB = 0.f;
+      const bool store2 = csize > 1;
+#pragma unroll 1
+      for (int cbk = 0; cbk < 4; ++cbk) {
+        const int col0 = col_base + cbk * 64 + q2;
+        if (col0 - q2 >= p.npad) break;  // warp-uniform (npad >= N)
+        uint32_t r[32];
+        tmem_ld_16x64(t_row + cbk * 64, r);
+        float2 bb[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          bb[kb] = make_float2(0.f, 0.f);
+          if (HAS_BIAS) {
+            const int c = col0 + kb * 8;
+            if (c < p.N) bb[kb].x = __ldg(bias + c) * 1.4426950408889634f;
+            if (c + 1 < p.N) bb[kb].y = __ldg(bias + c + 1) * 1.4426950408889634f;
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const int c = col0 + kb * 8;
+          const bool v0 = c < p.N, v1 = c + 1 < p.N;
+          const float a0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) - mA) : 0.f;
+          const float a1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) - mA) : 0.f;
+          const float b0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) - mB) : 0.f;
+          const float b1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) - mB) : 0.f;
+          sumA += a0 + a1;
+          sumB += b0 + b1;
+          if (store2 && c < p.npad) {  // npad is even: the pair (c, c + 1) is inside the row
+            if (okA) *reinterpret_cast<uint32_t*>(pA + c) = pack_bf16x2(a0, a1);
+            if (okB) *reinterpret_cast<uint32_t*>(pB + c) = pack_bf16x2(b0, b1);
+          }
+        }
+      }
+      sumA = quad_sum(sumA);
+      sumB = quad_sum(sumB);
+      if (csize > 1) {
+        if (writer) {
+          float* lp = p.lpart + bo * p.sl_outer + bi * p.sl_inner + rowA * csize + rank;
+          if (okA) lp[0] = sumA;
+          if (okB) lp[8 * csize] = sumB;
+        }
+      } else {
+        // ---- pass 3 (single tile): normalised probabilities
+        const float iA = 1.0f / sumA, iB = 1.0f / sumB;
+#pragma unroll 1
+        for (int cbk = 0; cbk < 4; ++cbk) {
+          const int col0 = col_base + cbk * 64 + q2;
+          if (col0 - q2 >= p.npad) break;
+          uint32_t r[32];
+          tmem_ld_16x64(t_row + cbk * 64, r);
+          float2 bb[8];
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            bb[kb] = make_float2(0.f, 0.f);
+            if (HAS_BIAS) {
+              const int c = col0 + kb * 8;
+              if (c < p.N) bb[kb].x = __ldg(bias + c) * 1.4426950408889634f;
+              if (c + 1 < p.N) bb[kb].y = __ldg(bias + c + 1) * 1.4426950408889634f;
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const int c = col0 + kb * 8;
+            if (c >= p.npad) continue;
+            const bool v0 = c < p.N, v1 = c + 1 < p.N;
+            const float a0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) - mA) * iA : 0.f;
+            const float a1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) - mA) * iA : 0.f;
+            const float b0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) - mB) * iB : 0.f;
+            const float b1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) - mB) * iB : 0.f;
+            if (okA) *reinterpret_cast<uint32_t*>(pA + c) = pack_bf16x2(a0, a1);
+            if (okB) *reinterpret_cast<uint32_t*>(pB + c) = pack_bf16x2(b0, b1);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();  // nobody leaves while a peer may still write its row maxima into this CTA
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -902,6 +1248,10 @@ int tc_gemm_init() {
   DITTO_TRY((set_attr_pair<K_STORE_GENERIC>()));
   DITTO_TRY((set_attr_pair<K_GEGLU>()));
   DITTO_TRY((set_attr_pair<K_QKV_ROPE>()));
+  DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
+  DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
+  DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   {
     const char* env = getenv("DITTO_NO_PAIR");
     g_use_pair = !(env && env[0] == '1');
@@ -961,6 +1311,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.out2 = q.out2; p.ldo2 = q.ldo2;
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
   p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
+  p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
 
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
@@ -976,6 +1327,9 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   else if (!q.out_bf16) ke = q.resid ? K_STORE_F32_RESID : (q.out2 ? K_STORE_GENERIC : K_STORE_F32);
   else ke = (q.resid || q.out2) ? K_STORE_GENERIC : K_STORE_BF16;
   if (g_force_generic && q.epilogue == TC_EPI_STORE) ke = K_STORE_GENERIC;
+  if (q.row_lsum != nullptr)
+    DITTO_REQUIRE(ke == K_STORE_F32 || ke == K_STORE_F32_RESID || ke == K_STORE_BF16, DITTO_E_UNSUPPORTED,
+                  "tc_gemm: row_lsum needs a fast STORE epilogue (even N)");
 #define DITTO_LAUNCH_PAIR(E) tc_gemm_pair_kernel<E><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p)
 #define DITTO_LAUNCH_1CTA(E, KN) tc_gemm_kernel<E, KN><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p)
   if (pair) {
@@ -1010,6 +1364,87 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
 #undef DITTO_LAUNCH_1CTA
   DITTO_LAUNCH_CHECK();
   return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// fused scores + softmax launcher
+// ---------------------------------------------------------------------------------------------------
+namespace {
+int g_sm_max_clusters[2][SM_MAX_CLUSTER + 1];  // [has_bias][csize]: co-resident clusters (0 = not queried, -1 = cannot launch)
+
+template <bool HAS_BIAS>
+int scores_softmax_launch(const CUtensorMap& ma, const CUtensorMap& mb, const SmDev& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SM_SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  int clusters = g_num_sms;
+  if (p.csize > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(p.csize);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+    int& cached = g_sm_max_clusters[HAS_BIAS ? 1 : 0][p.csize];
+    if (cached == 0) {
+      cfg.gridDim = dim3(static_cast<unsigned>(p.csize * g_num_sms), 1, 1);
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_scores_softmax_kernel<HAS_BIAS>, &cfg);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+      cached = n > 0 ? n : -1;
+    }
+    DITTO_REQUIRE(cached > 0, DITTO_E_UNSUPPORTED, "tc_scores_softmax: this cluster size cannot be scheduled on the device");
+    clusters = cached;
+  }
+  clusters = std::min(clusters, p.num_items);
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * p.csize), 1, 1);
+  DITTO_CUDA(cudaLaunchKernelEx(&cfg, tc_scores_softmax_kernel<HAS_BIAS>, ma, mb, p));
+  count_launch();
+  return 0;
+}
+}  // namespace
+
+int tc_scores_softmax_csize(int N) {
+  const int64_t c = ceil_div(N, BLOCK_N);
+  return (N > 0 && c <= SM_MAX_CLUSTER) ? static_cast<int>(c) : 0;
+}
+
+int launch_tc_scores_softmax(const TcScoresSoftmaxParams& q, cudaStream_t st) {
+  DITTO_TRY(tc_gemm_init());
+  DITTO_REQUIRE(q.M > 0 && q.N > 0 && q.K > 0 && q.batch_inner >= 1 && q.batch_outer >= 1, DITTO_E_BADARG, "tc_scores_softmax: bad sizes");
+  DITTO_REQUIRE(q.Q.ptr && q.Km.ptr && q.P, DITTO_E_BADARG, "tc_scores_softmax: null operand");
+  const int csize = tc_scores_softmax_csize(q.N);
+  DITTO_REQUIRE(csize > 0, DITTO_E_UNSUPPORTED, "tc_scores_softmax: too many key columns for one cluster");
+  DITTO_REQUIRE(q.npad >= q.N && q.npad % 2 == 0 && q.npad <= q.ldp, DITTO_E_BADARG, "tc_scores_softmax: npad");
+  DITTO_REQUIRE(q.ldp % 8 == 0 && q.sp_inner % 8 == 0 && q.sp_outer % 8 == 0, DITTO_E_UNSUPPORTED, "tc_scores_softmax: P strides");
+  DITTO_REQUIRE(csize == 1 || q.lpart != nullptr, DITTO_E_BADARG, "tc_scores_softmax: lpart required for multi-tile rows");
+  CUtensorMap ma, mb;
+  DITTO_TRY(make_map(&ma, q.Q, q.batch_inner, q.batch_outer, BLOCK_K, BLOCK_M));
+  DITTO_TRY(make_map(&mb, q.Km, q.batch_inner, q.batch_outer, BLOCK_K, BLOCK_N));
+  SmDev p;
+  p.M = q.M; p.N = q.N; p.K = q.K;
+  p.batch_inner = q.batch_inner; p.batch_outer = q.batch_outer;
+  p.m_tiles = static_cast<int>(ceil_div(q.M, BLOCK_M));
+  const int64_t items = static_cast<int64_t>(p.m_tiles) * q.batch_inner * q.batch_outer;
+  DITTO_REQUIRE(items < (1ll << 31), DITTO_E_UNSUPPORTED, "tc_scores_softmax: too many work items");
+  p.num_items = static_cast<int>(items);
+  p.num_kb = static_cast<int>(ceil_div(q.K, BLOCK_K));
+  p.a_bi = q.Q.s_inner ? 1 : 0; p.a_bo = q.Q.s_outer ? 1 : 0;
+  p.b_bi = q.Km.s_inner ? 1 : 0; p.b_bo = q.Km.s_outer ? 1 : 0;
+  p.alpha2 = q.alpha * 1.4426950408889634f;
+  p.bias = q.bias; p.sb_inner = q.sb_inner; p.sb_outer = q.sb_outer;
+  p.P = q.P; p.ldp = q.ldp; p.sp_inner = q.sp_inner; p.sp_outer = q.sp_outer;
+  p.npad = q.npad;
+  p.lpart = q.lpart; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
+  p.csize = csize; p.stages = g_stages_1cta;
+  // flops: the contraction; bytes: nothing (the fused softmax saves 12 B per score of HBM round trips)
+  ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
+  if (q.bias != nullptr) return scores_softmax_launch<true>(ma, mb, p, st);
+  return scores_softmax_launch<false>(ma, mb, p, st);
 }
 
 }  // namespace ditto

@@ -78,8 +78,30 @@ struct TcGemmParams {
   const float* rope_cos = nullptr; const float* rope_sin = nullptr;
   const float* rope_freq = nullptr;            // [d/2] inv_freq: when set, cos/sin are computed in the epilogue (no table reads)
   int rope_half = 0, rope_pd = 0, seq_T = 0, hidden = 0;
+  // optional per-row scale 1 / sum_c row_lsum[row*row_lparts + c] applied to the accumulator (softmax normalisation of an
+  // unnormalised P operand, see launch_tc_scores_softmax); batch strides in elements
+  const float* row_lsum = nullptr; int row_lparts = 0; int64_t sl_inner = 0, sl_outer = 0;
 };
 int launch_tc_gemm(const TcGemmParams& p, cudaStream_t st);
+
+// Fused attention scores + softmax: P[b] = softmax_rows(alpha * Q[b] K[b]^T + bias[b]) written as bf16, the fp32 scores
+// never leave the SM (TMEM).  One thread-block CLUSTER per 128 query rows: CTA r owns key columns [256 r, 256 r + 256)
+// and the row maxima are exchanged through distributed shared memory.  Cluster size 1: P is normalised in the kernel.
+// Cluster size > 1: P holds exp(s - rowmax) (in (0, 1]) and lpart[row][r] the partial row sums; the P.V GEMM divides by
+// their sum through TcGemmParams::row_lsum.  Columns [N, npad) of P are zero-filled.
+struct TcScoresSoftmaxParams {
+  TcOperand Q, Km;                              // [M, K] and [N, K] per batch item, K contiguous
+  int M = 0, N = 0, K = 0;
+  int batch_inner = 1, batch_outer = 1;
+  float alpha = 1.f;
+  const float* bias = nullptr; int64_t sb_inner = 0, sb_outer = 0;  // optional additive score bias per key column
+  bf16* P = nullptr; int64_t ldp = 0, sp_inner = 0, sp_outer = 0;
+  int npad = 0;                                 // zero-fill bound (multiple of 2, >= N)
+  float* lpart = nullptr; int64_t sl_inner = 0, sl_outer = 0;  // [M, csize] per batch item; required when csize > 1
+  int tag = PC_TC_OTHER;
+};
+int tc_scores_softmax_csize(int N);             // cluster size the kernel will use for N key columns (0: unsupported)
+int launch_tc_scores_softmax(const TcScoresSoftmaxParams& p, cudaStream_t st);
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 
 }  // namespace ditto

@@ -116,7 +116,7 @@ class DiTTO(nn.Module):
     def __init__(self, hidden_dim=768, num_layers=12, num_heads=12, time_dim=256, text_dim=768,
                  diffusion_steps=1000, lambda_factor=0.1, nac_model_path=None, *, nac: Optional[nn.Module] = None,
                  precision: str = "bf16", max_seq_len: int = 4096, fused_rope: bool = True,
-                 fold_cross: bool = True):
+                 fold_cross: bool = True, fused_attn: bool = True):
         super().__init__()
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -125,6 +125,7 @@ class DiTTO(nn.Module):
         self.lambda_factor, self.nac_model_path = lambda_factor, nac_model_path
         self.precision, self.max_seq_len, self.fused_rope = precision, max_seq_len, fused_rope
         self.fold_cross = fold_cross
+        self.fused_attn = fused_attn
         if nac is not None:
             self.nac = nac
         # construction order == reference (DiTTO.py:36-64): seeded default init gives the same weights
@@ -183,7 +184,8 @@ class DiTTO(nn.Module):
                                   precision=_lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32,
                                   max_seq_len=self.max_seq_len,
                                   flags=(_lib.F_FUSED_ROPE if self.fused_rope else 0) |
-                                  (_lib.F_FOLD_CROSS if self.fold_cross else 0))
+                                  (_lib.F_FOLD_CROSS if self.fold_cross else 0) |
+                                  (_lib.F_FUSED_ATTN if self.fused_attn else 0))
                 h = C.c_void_p()
                 _lib.check(lib.ditto_engine_create(C.byref(cfg), C.byref(h)), "ditto_engine_create")
                 self._engine = h

@@ -47,7 +47,8 @@ enum {
 /* optional features of the bf16 path (bit mask in ditto_config_t.flags); 0 = the plain composition */
 enum {
   DITTO_F_FUSED_ROPE = 1 << 0, /* RoPE fused into the QKV GEMM epilogue (column-permuted weights) */
-  DITTO_F_FOLD_CROSS = 1 << 1  /* fold cross-attn q/out projections into the per-utterance text K/V */
+  DITTO_F_FOLD_CROSS = 1 << 1, /* fold cross-attn q/out projections into the per-utterance text K/V */
+  DITTO_F_FUSED_ATTN = 1 << 2  /* scores + softmax in one cluster kernel (fp32 scores never leave TMEM)   */
 };
 
 /* Shapes of one DiTTO instance == ctor arguments of the reference, src/model/DiTTO.py:10-19
