@@ -8,7 +8,10 @@
 //   STORE     out = alpha*acc (+bias) (+fp32 residual), fp32 or bf16, optional extra bf16 copy
 //   GEGLU     columns interleaved [fc1(16) | gate(16)]: hid = GELU_erf(a+ba) * sigmoid(g+bg)          (DiT.py:153-155)
 //   QKV_ROPE  column-permuted q/k so that the RoPE partner (j, j+d/2) sits PD columns away in the tile  (DiT.py:52-72)
+#include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -58,6 +61,7 @@ struct DevParams {
   const float* rope_cos; const float* rope_sin; const float* rope_freq;
   int rope_half, rope_pd, seq_T, hidden;
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
+  int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
 };
 
@@ -203,77 +207,71 @@ __device__ __forceinline__ void store_block64(const DevParams& p, const uint32_t
 // Block order per warp: column half cb (64 columns) outer, 16-row half hh inner; the residual of block i+1 is
 // requested before block i is stored.
 // ---------------------------------------------------------------------------------------------------
-template <bool RESID>
-__device__ __forceinline__ void load_resid_fast(const DevParams& p, const float* rpA, const float* rpB, bool okA, bool okB, int col0t,
-                                                float2 (&f)[16]) {
+// FULL: the warp's whole 32 x 128 slab is inside the matrix -> no predicates at all (the common case; the edge variant
+// costs ~3x the instructions, mostly branches around predicated loads and 64-bit compares).
+template <bool RESID, bool FULL>
+__device__ __forceinline__ void load_resid_fast(const float* rpA, const float* rpB, bool okA, bool okB, int col0t, int N, float2 (&f)[16]) {
   if (!RESID) return;
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
-    const bool cok = col0t + kb * 8 < p.N;
-    f[2 * kb] = (okA && cok) ? *reinterpret_cast<const float2*>(rpA + kb * 8) : make_float2(0.f, 0.f);
-    f[2 * kb + 1] = (okB && cok) ? *reinterpret_cast<const float2*>(rpB + kb * 8) : make_float2(0.f, 0.f);
+    if (FULL) {
+      f[2 * kb] = *reinterpret_cast<const float2*>(rpA + kb * 8);
+      f[2 * kb + 1] = *reinterpret_cast<const float2*>(rpB + kb * 8);
+    } else {
+      const bool cok = col0t + kb * 8 < N;
+      f[2 * kb] = (okA && cok) ? *reinterpret_cast<const float2*>(rpA + kb * 8) : make_float2(0.f, 0.f);
+      f[2 * kb + 1] = (okB && cok) ? *reinterpret_cast<const float2*>(rpB + kb * 8) : make_float2(0.f, 0.f);
+    }
   }
 }
 
-template <int EPI>
-__device__ __forceinline__ void store_blk_fast(const DevParams& p, const uint32_t (&r)[32], const float2 (&b2)[8], const float2 (&f)[16],
-                                               long long rowA, bool okA, bool okB, int col0t, long long out_off, float alphaA,
-                                               float alphaB) {
+// outA / outB (and o2A / o2B): this thread's element (row, col0t) of the two rows it owns in the block
+template <int EPI, bool FULL, typename OutT>
+__device__ __forceinline__ void store_blk_fast(const uint32_t (&r)[32], const float2 (&b2)[8], const float2 (&f)[16], OutT* outA, OutT* outB,
+                                               bf16* o2A, bf16* o2B, bool okA, bool okB, int col0t, int N, float alphaA, float alphaB) {
   constexpr bool RESID = EPI == K_STORE_F32_RESID;
   constexpr bool OBF = EPI == K_STORE_BF16;
-  const long long oA = out_off + rowA * p.ldo + col0t;
-  const long long oB = oA + 8 * p.ldo;
-  float2 vA[8], vB[8];
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
-    vA[kb].x = fmaf(alphaA, __uint_as_float(r[4 * kb]), b2[kb].x);
-    vA[kb].y = fmaf(alphaA, __uint_as_float(r[4 * kb + 1]), b2[kb].y);
-    vB[kb].x = fmaf(alphaB, __uint_as_float(r[4 * kb + 2]), b2[kb].x);
-    vB[kb].y = fmaf(alphaB, __uint_as_float(r[4 * kb + 3]), b2[kb].y);
+    float2 vA, vB;
+    vA.x = fmaf(alphaA, __uint_as_float(r[4 * kb]), b2[kb].x);
+    vA.y = fmaf(alphaA, __uint_as_float(r[4 * kb + 1]), b2[kb].y);
+    vB.x = fmaf(alphaB, __uint_as_float(r[4 * kb + 2]), b2[kb].x);
+    vB.y = fmaf(alphaB, __uint_as_float(r[4 * kb + 3]), b2[kb].y);
     if (RESID) {
-      vA[kb].x += f[2 * kb].x; vA[kb].y += f[2 * kb].y;
-      vB[kb].x += f[2 * kb + 1].x; vB[kb].y += f[2 * kb + 1].y;
+      vA.x += f[2 * kb].x; vA.y += f[2 * kb].y;
+      vB.x += f[2 * kb + 1].x; vB.y += f[2 * kb + 1].y;
     }
-  }
-  if (OBF) {
-    bf16* out = static_cast<bf16*>(p.out);
-#pragma unroll
-    for (int kb = 0; kb < 8; ++kb) {
-      const bool cok = col0t + kb * 8 < p.N;
-      if (okA && cok) *reinterpret_cast<uint32_t*>(out + oA + kb * 8) = pack_bf16x2(vA[kb].x, vA[kb].y);
-      if (okB && cok) *reinterpret_cast<uint32_t*>(out + oB + kb * 8) = pack_bf16x2(vB[kb].x, vB[kb].y);
-    }
-  } else {
-    float* out = static_cast<float*>(p.out);
-#pragma unroll
-    for (int kb = 0; kb < 8; ++kb) {
-      const bool cok = col0t + kb * 8 < p.N;
-      if (okA && cok) *reinterpret_cast<float2*>(out + oA + kb * 8) = vA[kb];
-      if (okB && cok) *reinterpret_cast<float2*>(out + oB + kb * 8) = vB[kb];
-    }
-    if (RESID && p.out2 != nullptr) {  // bf16 copy of the updated residual stream (operand of the next GEMM)
-      bf16* o2 = p.out2 + out_off + rowA * p.ldo2 + col0t;
-      bf16* o2B = o2 + 8 * p.ldo2;
-#pragma unroll
-      for (int kb = 0; kb < 8; ++kb) {
-        const bool cok = col0t + kb * 8 < p.N;
-        if (okA && cok) *reinterpret_cast<uint32_t*>(o2 + kb * 8) = pack_bf16x2(vA[kb].x, vA[kb].y);
-        if (okB && cok) *reinterpret_cast<uint32_t*>(o2B + kb * 8) = pack_bf16x2(vB[kb].x, vB[kb].y);
+    const bool cok = FULL || col0t + kb * 8 < N;
+    const bool sA = FULL || (okA && cok), sB = FULL || (okB && cok);
+    if (OBF) {
+      if (sA) *reinterpret_cast<uint32_t*>(outA + kb * 8) = pack_bf16x2(vA.x, vA.y);
+      if (sB) *reinterpret_cast<uint32_t*>(outB + kb * 8) = pack_bf16x2(vB.x, vB.y);
+    } else {
+      if (sA) *reinterpret_cast<float2*>(outA + kb * 8) = vA;
+      if (sB) *reinterpret_cast<float2*>(outB + kb * 8) = vB;
+      if (RESID && o2A != nullptr) {  // bf16 copy of the updated residual stream (operand of the next GEMM)
+        if (sA) *reinterpret_cast<uint32_t*>(o2A + kb * 8) = pack_bf16x2(vA.x, vA.y);
+        if (sB) *reinterpret_cast<uint32_t*>(o2B + kb * 8) = pack_bf16x2(vB.x, vB.y);
       }
     }
   }
 }
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0,
-                                                    int n_blk, long long out_off, long long res_off, long long bias_off,
-                                                    long long ls_off, uint64_t* full_bar, uint32_t full_parity) {
+template <int EPI, bool FULL>
+__device__ __forceinline__ void epilogue_store_fast_impl(const DevParams& p, int lane, int half_sel, uint32_t t_row, int row0, int n_blk,
+                                                         long long out_off, long long res_off, long long bias_off, long long ls_off,
+                                                         uint64_t* full_bar, uint32_t full_parity) {
   constexpr bool RESID = EPI == K_STORE_F32_RESID;
+  constexpr bool OBF = EPI == K_STORE_BF16;
+  typedef typename std::conditional<OBF, bf16, float>::type OutT;
   const int g = lane >> 2, q2 = (lane & 3) * 2;
   const int colt = n_blk * BLOCK_N + half_sel * 128 + q2;  // this thread's first column of the tile
+  const int N = p.N, M = p.M;
   // rows of this thread: row0 + hh*16 + rr*8 + g
-  const long long r00 = row0 + g;
-  const bool ok00 = r00 < p.M, ok01 = r00 + 8 < p.M, ok10 = r00 + 16 < p.M, ok11 = r00 + 24 < p.M;
+  const int r00 = row0 + g;
+  const bool ok00 = FULL || r00 < M, ok01 = FULL || r00 + 8 < M, ok10 = FULL || r00 + 16 < M, ok11 = FULL || r00 + 24 < M;
+  const bool half1 = FULL || row0 + 16 < M;  // warp-uniform: the second 16-row block has rows inside the matrix
   const float *rp00 = nullptr, *rp01 = nullptr, *rp10 = nullptr, *rp11 = nullptr;
   if (RESID) {
     const float* rb = p.resid + res_off + colt;
@@ -284,7 +282,7 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
       rp10 = rb + static_cast<long long>(static_cast<unsigned>(r00 + 16) % md) * p.ldr;
       rp11 = rb + static_cast<long long>(static_cast<unsigned>(r00 + 24) % md) * p.ldr;
     } else {
-      rp00 = rb + r00 * p.ldr;
+      rp00 = rb + static_cast<long long>(r00) * p.ldr;
       rp01 = rp00 + 8 * p.ldr;
       rp10 = rp00 + 16 * p.ldr;
       rp11 = rp00 + 24 * p.ldr;
@@ -293,7 +291,7 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
   // per-row accumulator scale: alpha, or alpha / (sum of the row's partial softmax denominators)
   float a00 = p.alpha, a01 = p.alpha, a10 = p.alpha, a11 = p.alpha;
   if (p.row_lsum != nullptr) {
-    const float* lp = p.row_lsum + ls_off + r00 * p.row_lparts;
+    const float* lp = p.row_lsum + ls_off + static_cast<long long>(r00) * p.row_lparts;
     float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
     for (int c = 0; c < p.row_lparts; ++c) {
       if (ok00) s00 += __ldg(lp + c);
@@ -305,40 +303,58 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
     a10 = ok10 ? p.alpha / s10 : 0.f; a11 = ok11 ? p.alpha / s11 : 0.f;
   }
   float2 f0[16], f1[16];
-  load_resid_fast<RESID>(p, rp00, rp01, ok00, ok01, colt, f0);
-  // biases of both column halves, requested before the accumulator wait (no dependent global load after it)
+  load_resid_fast<RESID, FULL>(rp00, rp01, ok00, ok01, colt, N, f0);
+  // bias of the first column half, requested before the accumulator wait; the second half is requested while the
+  // first is being stored
   const float* bias = p.bias ? p.bias + bias_off : nullptr;
-  float2 bA[8], bB[8];
+  float2 b2[8];
 #pragma unroll
-  for (int kb = 0; kb < 8; ++kb) {
-    bA[kb] = (bias != nullptr && colt + kb * 8 < p.N) ? __ldg(reinterpret_cast<const float2*>(bias + colt + kb * 8)) : make_float2(0.f, 0.f);
-    bB[kb] = (bias != nullptr && colt + 64 + kb * 8 < p.N) ? __ldg(reinterpret_cast<const float2*>(bias + colt + 64 + kb * 8))
-                                                           : make_float2(0.f, 0.f);
-  }
+  for (int kb = 0; kb < 8; ++kb)
+    b2[kb] = (bias != nullptr && (FULL || colt + kb * 8 < N)) ? __ldg(reinterpret_cast<const float2*>(bias + colt + kb * 8)) : make_float2(0.f, 0.f);
+  // output pointers of row r00 (the other rows are 8 / 16 / 24 rows further)
+  OutT* o00 = static_cast<OutT*>(p.out) + out_off + static_cast<long long>(r00) * p.ldo + colt;
+  const long long o8 = 8 * p.ldo;
+  bf16* q00 = (RESID && p.out2 != nullptr) ? p.out2 + out_off + static_cast<long long>(r00) * p.ldo2 + colt : nullptr;
+  const long long q8 = 8 * p.ldo2;
   mbar_wait(full_bar, full_parity);
   tcgen05_fence_after();
-  if (row0 >= p.M) return;  // warp-uniform
+  if (row0 >= M) return;  // warp-uniform (cluster padding tile or fully out-of-range row group)
 #pragma unroll 1
   for (int cb = 0; cb < 2; ++cb) {
     const int col0t = colt + cb * 64;
-    if (col0t - q2 >= p.N) break;  // warp-uniform
-    float2 b2[8];
-#pragma unroll
-    for (int kb = 0; kb < 8; ++kb) b2[kb] = cb == 0 ? bA[kb] : bB[kb];
+    if (!FULL && col0t - q2 >= N) break;  // warp-uniform
     uint32_t r[32];
     // ---- hh = 0
     tmem_ld_16x64(t_row + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
-    if (row0 + 16 < p.M) load_resid_fast<RESID>(p, rp10 + cb * 64, rp11 + cb * 64, ok10, ok11, col0t, f1);
+    if (half1) load_resid_fast<RESID, FULL>(rp10 + cb * 64, rp11 + cb * 64, ok10, ok11, col0t, N, f1);
     tmem_ld_wait();
-    store_blk_fast<EPI>(p, r, b2, f0, r00, ok00, ok01, col0t, out_off, a00, a01);
+    store_blk_fast<EPI, FULL, OutT>(r, b2, f0, o00 + cb * 64, o00 + o8 + cb * 64, q00 ? q00 + cb * 64 : nullptr,
+                                    q00 ? q00 + q8 + cb * 64 : nullptr, ok00, ok01, col0t, N, a00, a01);
     // ---- hh = 1
-    if (row0 + 16 < p.M) tmem_ld_16x64(t_row + (16u << 16) + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
-    if (cb == 0 && col0t - q2 + 64 < p.N) load_resid_fast<RESID>(p, rp00 + 64, rp01 + 64, ok00, ok01, col0t + 64, f0);
-    if (row0 + 16 < p.M) {
+    if (half1) tmem_ld_16x64(t_row + (16u << 16) + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
+    if (cb == 0 && (FULL || col0t - q2 + 64 < N)) load_resid_fast<RESID, FULL>(rp00 + 64, rp01 + 64, ok00, ok01, col0t + 64, N, f0);
+    if (half1) {
       tmem_ld_wait();
-      store_blk_fast<EPI>(p, r, b2, f1, r00 + 16, ok10, ok11, col0t, out_off, a10, a11);
+      store_blk_fast<EPI, FULL, OutT>(r, b2, f1, o00 + 2 * o8 + cb * 64, o00 + 3 * o8 + cb * 64, q00 ? q00 + 2 * q8 + cb * 64 : nullptr,
+                                      q00 ? q00 + 3 * q8 + cb * 64 : nullptr, ok10, ok11, col0t, N, a10, a11);
+    }
+    if (cb == 0) {
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb)
+        b2[kb] = (bias != nullptr && (FULL || colt + 64 + kb * 8 < N)) ? __ldg(reinterpret_cast<const float2*>(bias + colt + 64 + kb * 8))
+                                                                       : make_float2(0.f, 0.f);
     }
   }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0,
+                                                    int n_blk, long long out_off, long long res_off, long long bias_off,
+                                                    long long ls_off, uint64_t* full_bar, uint32_t full_parity) {
+  const int r0 = static_cast<int>(row0);  // rows of one GEMM fit in 31 bits (checked at launch)
+  const bool full = r0 + 32 <= p.M && n_blk * BLOCK_N + half_sel * 128 + 128 <= p.N;  // warp-uniform
+  if (full) epilogue_store_fast_impl<EPI, true>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off, full_bar, full_parity);
+  else epilogue_store_fast_impl<EPI, false>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off, full_bar, full_parity);
 }
 
 // One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.  Waits for the
@@ -491,8 +507,11 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
         if (is_v) {
           tmem_ld_wait();
-          store_blk_fast<K_STORE_BF16>(p, r1, bx1, nores.v, rowA, okA, okB, pc1 + q2, out_off, 1.f, 1.f);
-          if (pd != 32) store_blk_fast<K_STORE_BF16>(p, r2, bx2, nores.v, rowA, okA, okB, pc1 + pd + q2, out_off, 1.f, 1.f);
+          bf16* vo = static_cast<bf16*>(p.out) + out_off + rowA * p.ldo + pc1 + q2;
+          store_blk_fast<K_STORE_BF16, false, bf16>(r1, bx1, nores.v, vo, vo + 8 * p.ldo, nullptr, nullptr, okA, okB, pc1 + q2, p.N, 1.f, 1.f);
+          if (pd != 32)
+            store_blk_fast<K_STORE_BF16, false, bf16>(r2, bx2, nores.v, vo + pd, vo + 8 * p.ldo + pd, nullptr, nullptr, okA, okB,
+                                                      pc1 + pd + q2, p.N, 1.f, 1.f);
           continue;
         }
         const unsigned seqT = static_cast<unsigned>(p.seq_T);
@@ -538,6 +557,48 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster multicast (1-CTA kernels).  The L2 -> SM operand feed, not the tensor pipe, bounds these GEMMs (ncu: a
+// 128 x 256 tile pulls 48 KiB per k-block, ~2.5x what the L2 can deliver at full MMA rate), so a cluster of cm x cn CTAs
+// computing adjacent tiles shares its operands: the A k-block of a tile row is loaded ONCE and multicast to the cn CTAs
+// of that row, the B k-block once for the cm CTAs of a tile column.  The loader rotates with the k-block index
+// (kb % cn, kb % cm), so every CTA issues an equal share and no tensor-map box has to be split.
+// A shared-memory slot may only be overwritten once every CTA that receives the multicast has consumed it: the MMA
+// issuer's commit is multicast to the empty barriers of its whole row and column group (cm + cn - 1 arrivals per phase).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], %7;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank();
+__device__ __forceinline__ void cluster_sync_all();
+
+struct ClusterPos {
+  int csize, rm, rn;          // cluster size, this CTA's tile-row / tile-column inside the cluster
+  uint16_t row_mask, col_mask;  // CTAs sharing this CTA's A block / B block (both include the CTA itself)
+};
+__device__ __forceinline__ ClusterPos cluster_pos(int cm, int cn) {
+  ClusterPos c;
+  c.csize = cm * cn;
+  const int rank = c.csize > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  c.rm = rank / cn;
+  c.rn = rank - c.rm * cn;
+  c.row_mask = static_cast<uint16_t>(((1u << cn) - 1u) << (c.rm * cn));
+  uint32_t cmask = 0;
+  for (int j = 0; j < cm; ++j) cmask |= 1u << (j * cn + c.rn);
+  c.col_mask = static_cast<uint16_t>(cmask);
+  return c;
+}
+
 template <int EPI, bool B_KN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
@@ -552,6 +613,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const ClusterPos cp = cluster_pos(p.cm, p.cn);
+  const int num_clusters = gridDim.x / cp.csize;
+  const int cluster_id = blockIdx.x / cp.csize;
+  // super tile st = (batch item, sm, sn), sn fastest; this CTA's tile: (sm * cm + rm, sn * cn + rn)
+  const int n_super = (p.n_tiles + p.cn - 1) / p.cn, m_super = (p.m_tiles + p.cm - 1) / p.cm;
+  const int num_super = n_super * m_super * p.batch_inner * p.batch_outer;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -560,7 +627,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.cm + p.cn - 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -571,6 +638,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tcgen05_fence_before();
   __syncthreads();
+  if (cp.csize > 1) cluster_sync_all();  // peers' barriers exist before the first multicast load / commit reaches them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -579,11 +647,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles;
-        const int rest = tile / p.n_tiles;
-        const int m_blk = rest % p.m_tiles;
-        const int b = rest / p.m_tiles;
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
+        const int sn = st % n_super;
+        const int rest = st / n_super;
+        const int smi = rest % m_super;
+        const int b = rest / m_super;
+        const int m_blk = smi * p.cm + cp.rm, n_blk = sn * p.cn + cp.rn;  // may lie past the edge: TMA zero-fills
         const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
         const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
         const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
@@ -592,13 +661,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_4d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo);
-          if (!B_KN) {
-            tma_load_4d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N, bbi, bbo);
-          } else {
+          if (cp.csize == 1) {
+            tma_load_4d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo);
+            if (!B_KN) {
+              tma_load_4d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N, bbi, bbo);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)  // [64 k-rows x 64 n] boxes, N-contiguous (MN-major operand)
-              tma_load_4d(&tmap_b, &full_bar[stage], sb + j * (BLOCK_K * 128), n_blk * BLOCK_N + j * 64, kb * BLOCK_K, bbi, bbo);
+              for (int j = 0; j < BLOCK_N / 64; ++j)  // [64 k-rows x 64 n] boxes, N-contiguous (MN-major operand)
+                tma_load_4d(&tmap_b, &full_bar[stage], sb + j * (BLOCK_K * 128), n_blk * BLOCK_N + j * 64, kb * BLOCK_K, bbi, bbo);
+            }
+          } else {
+            if (kb % p.cn == cp.rn)  // this CTA fetches the A block for its whole tile row
+              tma_load_4d_mc(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo, cp.row_mask);
+            if (kb % p.cm == cp.rm) {  // ... and the B block for its whole tile column
+              if (!B_KN) {
+                tma_load_4d_mc(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N, bbi, bbo, cp.col_mask);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                  tma_load_4d_mc(&tmap_b, &full_bar[stage], sb + j * (BLOCK_K * 128), n_blk * BLOCK_N + j * 64, kb * BLOCK_K, bbi, bbo,
+                                 cp.col_mask);
+              }
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -608,11 +692,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     // =========================== MMA issuer (single thread) ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, B_KN);
+      const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
         mbar_wait(&tmem_empty[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
@@ -628,7 +713,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                                      : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire -- announced to every CTA that may multicast into this slot
+          if (cp.csize == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], commit_mask);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
@@ -636,25 +723,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // =========================== epilogue: TMEM -> registers -> swizzled smem -> coalesced global ===========================
+    // =========================== epilogue: TMEM -> registers -> global ===========================
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may touch
     const int half_sel = ew >> 2;  // which 4 of the 8 column chunks
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_blk = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int m_blk = rest % p.m_tiles;
-      const int b = rest / p.m_tiles;
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int sn = st % n_super;
+      const int rest = st / n_super;
+      const int smi = rest % m_super;
+      const int b = rest / m_super;
+      const int m_blk = smi * p.cm + cp.rm, n_blk = sn * p.cn + cp.rn;
       const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
       const long long out_off = bo * p.so_outer + bi * p.so_inner;
       const long long res_off = bo * p.sr_outer + bi * p.sr_inner;
       const long long bias_off = bo * p.sb_outer + bi * p.sb_inner;
-      const long long row0 = static_cast<long long>(m_blk) * BLOCK_M + quarter * 32;
+      // a tile past the matrix edge (cluster padding) is computed on zero-filled operands and stores nothing:
+      // row0 >= M and column >= N make every store predicate false
+      const long long row0 = (m_blk < p.m_tiles && n_blk < p.n_tiles) ? static_cast<long long>(m_blk) * BLOCK_M + quarter * 32
+                                                                    : static_cast<long long>(p.M);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
       const long long ls_off = bo * p.sl_outer + bi * p.sl_inner;
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, ls_off, &tmem_full[as], aphase);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk < p.n_tiles ? n_blk : 0, out_off, res_off, bias_off, ls_off,
+                         &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -662,8 +754,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   }
 
+  __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
+  if (cp.csize > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into it / signal its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -864,7 +958,7 @@ struct SmDev {
   bf16* P; long long ldp, sp_inner, sp_outer;
   int npad;
   float* lpart; long long sl_inner, sl_outer;
-  int csize, stages;
+  int csize, cm, stages;  // csize key tiles per row (cluster columns), cm query blocks per cluster (cluster rows)
 };
 
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
@@ -910,10 +1004,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // cluster = cm tile rows x csize tile columns: CTA (rm, rank) computes query block mg * cm + rm against key tile `rank`;
+  // Q blocks are multicast along a row, K blocks along a column, row maxima are exchanged along a row
   const int csize = p.csize;
-  const int rank = csize > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int num_clusters = gridDim.x / csize;
-  const int cluster_id = blockIdx.x / csize;
+  const ClusterPos cp = cluster_pos(p.cm, csize);
+  const int rank = cp.rn;
+  const int num_clusters = gridDim.x / cp.csize;
+  const int cluster_id = blockIdx.x / cp.csize;
+  const int m_groups = (p.m_tiles + p.cm - 1) / p.cm;
+  const int num_items = m_groups * p.batch_inner * p.batch_outer;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -922,7 +1021,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.cm + csize - 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -934,7 +1033,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tcgen05_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // every peer's barriers are initialised before the first remote arrive
+  if (cp.csize > 1) cluster_sync_all();  // every peer's barriers are initialised before the first remote arrive / multicast
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -943,9 +1042,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
-        const int m_blk = item % p.m_tiles;
-        const int b = item / p.m_tiles;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int m_blk = (item % m_groups) * p.cm + cp.rm;  // may lie past the last block (cluster padding): zero-filled
+        const int b = item / m_groups;
         const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
         const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
         const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
@@ -954,8 +1053,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_4d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo);
-          tma_load_4d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, rank * BLOCK_N, bbi, bbo);
+          if (cp.csize == 1) {
+            tma_load_4d(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo);
+            tma_load_4d(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, rank * BLOCK_N, bbi, bbo);
+          } else {
+            if (kb % csize == rank)
+              tma_load_4d_mc(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M, abi, abo, cp.row_mask);
+            if (kb % p.cm == cp.rm)
+              tma_load_4d_mc(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, rank * BLOCK_N, bbi, bbo, cp.col_mask);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -968,7 +1074,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+      const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
@@ -983,7 +1090,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const uint64_t db = umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cp.csize == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], commit_mask);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[as]);
@@ -1001,11 +1109,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const bool writer = (lane & 3) == 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
-      const int m_blk = item % p.m_tiles;
-      const int b = item / p.m_tiles;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int m_blk = (item % m_groups) * p.cm + cp.rm;
+      const int b = item / m_groups;
       const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
-      const long long rowA = static_cast<long long>(m_blk) * BLOCK_M + trow + g;  // second row: rowA + 8
+      // second row: rowA + 8; a padding block (m_blk >= m_tiles) has every row >= M and stores nothing
+      const long long rowA = static_cast<long long>(m_blk) * BLOCK_M + trow + g;
       const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
       const float* bias = HAS_BIAS ? p.bias + bo * p.sb_outer + bi * p.sb_inner : nullptr;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(trow) << 16) + static_cast<uint32_t>(as * BLOCK_N);
@@ -1054,9 +1163,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (writer) {
           const uint32_t slotA = smem_u32(stat + (as * SM_MAX_CLUSTER + rank) * BLOCK_M + trow + g);
           const uint32_t barl = smem_u32(&stat_bar[as]);
-          for (int c = 0; c < csize; ++c) {
-            const uint32_t ra = mapa_shared(slotA, static_cast<uint32_t>(c));
-            const uint32_t rb = mapa_shared(barl, static_cast<uint32_t>(c));
+          for (int c = 0; c < csize; ++c) {  // the CTAs of this tile row: cluster ranks rm * csize + c
+            const uint32_t ra = mapa_shared(slotA, static_cast<uint32_t>(cp.rm * csize + c));
+            const uint32_t rb = mapa_shared(barl, static_cast<uint32_t>(cp.rm * csize + c));
             st_async_f32(ra, mA, rb);
             st_async_f32(ra + 8 * 4, mB, rb);
           }
@@ -1161,7 +1270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // nobody leaves while a peer may still write its row maxima into this CTA
+  if (cp.csize > 1) cluster_sync_all();  // nobody leaves while a peer may still write into this CTA / signal its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -1176,6 +1285,7 @@ EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 bool g_init_done = false;
 bool g_use_pair = true;
+int g_cluster_m = 0, g_cluster_n = 0;  // DITTO_CLUSTER="cm,cn": default cluster shape of the 1-CTA GEMM kernel (0 = heuristic)
 bool g_force_generic = false;  // DITTO_GENERIC_EPI=1: route every STORE epilogue through the generic path (tests)
 int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
 
@@ -1217,6 +1327,48 @@ int set_attr() {
   return 0;
 }
 
+
+// Launch a persistent 1-CTA kernel as clusters of `csize` CTAs (csize == 1: plain launch): grid = csize x min(work items,
+// co-resident clusters).  The co-residency query is cached per (kernel, cluster size).
+std::map<std::pair<const void*, int>, int> g_max_clusters;
+template <typename Params>
+int launch_clustered(const void* func, int csize, int smem_bytes, int64_t num_work, const CUtensorMap& ma, const CUtensorMap& mb,
+                     const Params& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  int clusters = g_num_sms;
+  if (csize > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+    auto key = std::make_pair(func, csize);
+    auto it = g_max_clusters.find(key);
+    if (it == g_max_clusters.end()) {
+      if (csize > 8) (void)cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cfg.gridDim = dim3(static_cast<unsigned>(csize * g_num_sms), 1, 1);
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, func, &cfg);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+      it = g_max_clusters.emplace(key, n > 0 ? n : -1).first;
+    }
+    DITTO_REQUIRE(it->second > 0, DITTO_E_UNSUPPORTED, "tc_gemm: this cluster size cannot be scheduled on the device");
+    clusters = it->second;
+  }
+  clusters = static_cast<int>(std::min<int64_t>(clusters, num_work));
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * csize), 1, 1);
+  void* args[3] = {const_cast<CUtensorMap*>(&ma), const_cast<CUtensorMap*>(&mb), const_cast<Params*>(&p)};
+  DITTO_CUDA(cudaLaunchKernelExC(&cfg, func, args));
+  count_launch();
+  return 0;
+}
+
 }  // namespace
 
 int tc_gemm_init() {
@@ -1255,6 +1407,10 @@ int tc_gemm_init() {
   {
     const char* env = getenv("DITTO_NO_PAIR");
     g_use_pair = !(env && env[0] == '1');
+    if (const char* ec = getenv("DITTO_CLUSTER")) {
+      int a = 0, b = 0;
+      if (sscanf(ec, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 16) { g_cluster_m = a; g_cluster_n = b; }
+    }
     const char* eg = getenv("DITTO_GENERIC_EPI");
     g_force_generic = eg && eg[0] == '1';
     if (const char* e1 = getenv("DITTO_STAGES_1CTA")) g_stages_1cta = std::max(2, std::min(STAGES, atoi(e1)));
@@ -1316,6 +1472,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
   p.stages = pair ? g_stages_pair : g_stages_1cta;
+  p.cm = 1; p.cn = 1;
   // kernel variant: the lean compile-time epilogues cover the hot cases, anything else takes the generic one
   int ke;
   if (q.epilogue == TC_EPI_GEGLU) ke = K_GEGLU;
@@ -1331,7 +1488,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
     DITTO_REQUIRE(ke == K_STORE_F32 || ke == K_STORE_F32_RESID || ke == K_STORE_BF16, DITTO_E_UNSUPPORTED,
                   "tc_gemm: row_lsum needs a fast STORE epilogue (even N)");
 #define DITTO_LAUNCH_PAIR(E) tc_gemm_pair_kernel<E><<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(ma, mb, p)
-#define DITTO_LAUNCH_1CTA(E, KN) tc_gemm_kernel<E, KN><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p)
+#define DITTO_FUNC_1CTA(E, KN) reinterpret_cast<const void*>(&tc_gemm_kernel<E, KN>)
   if (pair) {
     const int64_t pair_tiles = ceil_div(q.M, 2 * BLOCK_M) * p.n_tiles;
     grid = static_cast<unsigned>(2 * std::min<int64_t>(pair_tiles, g_num_sms / 2));
@@ -1343,70 +1500,51 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
       case K_GEGLU: DITTO_LAUNCH_PAIR(K_GEGLU); break;
       default: DITTO_LAUNCH_PAIR(K_QKV_ROPE); break;
     }
-  } else if (q.b_kn) {
+    DITTO_LAUNCH_CHECK();
+    return 0;
+  }
+  const void* func;
+  if (q.b_kn) {
     switch (ke) {
-      case K_STORE_F32: DITTO_LAUNCH_1CTA(K_STORE_F32, true); break;
-      case K_STORE_F32_RESID: DITTO_LAUNCH_1CTA(K_STORE_F32_RESID, true); break;
-      case K_STORE_BF16: DITTO_LAUNCH_1CTA(K_STORE_BF16, true); break;
-      default: DITTO_LAUNCH_1CTA(K_STORE_GENERIC, true); break;  // GEGLU / ROPE with b_kn were rejected above
+      case K_STORE_F32: func = DITTO_FUNC_1CTA(K_STORE_F32, true); break;
+      case K_STORE_F32_RESID: func = DITTO_FUNC_1CTA(K_STORE_F32_RESID, true); break;
+      case K_STORE_BF16: func = DITTO_FUNC_1CTA(K_STORE_BF16, true); break;
+      default: func = DITTO_FUNC_1CTA(K_STORE_GENERIC, true); break;  // GEGLU / ROPE with b_kn were rejected above
     }
   } else {
     switch (ke) {
-      case K_STORE_F32: DITTO_LAUNCH_1CTA(K_STORE_F32, false); break;
-      case K_STORE_F32_RESID: DITTO_LAUNCH_1CTA(K_STORE_F32_RESID, false); break;
-      case K_STORE_BF16: DITTO_LAUNCH_1CTA(K_STORE_BF16, false); break;
-      case K_STORE_GENERIC: DITTO_LAUNCH_1CTA(K_STORE_GENERIC, false); break;
-      case K_GEGLU: DITTO_LAUNCH_1CTA(K_GEGLU, false); break;
-      default: DITTO_LAUNCH_1CTA(K_QKV_ROPE, false); break;
+      case K_STORE_F32: func = DITTO_FUNC_1CTA(K_STORE_F32, false); break;
+      case K_STORE_F32_RESID: func = DITTO_FUNC_1CTA(K_STORE_F32_RESID, false); break;
+      case K_STORE_BF16: func = DITTO_FUNC_1CTA(K_STORE_BF16, false); break;
+      case K_STORE_GENERIC: func = DITTO_FUNC_1CTA(K_STORE_GENERIC, false); break;
+      case K_GEGLU: func = DITTO_FUNC_1CTA(K_GEGLU, false); break;
+      default: func = DITTO_FUNC_1CTA(K_QKV_ROPE, false); break;
     }
   }
-#undef DITTO_LAUNCH_PAIR
-#undef DITTO_LAUNCH_1CTA
-  DITTO_LAUNCH_CHECK();
+  {
+    // cluster shape: explicit > DITTO_CLUSTER > heuristic (share A across up to 3-4 tile columns, B across 2 tile rows,
+    // only shapes that tile the matrix without padding tiles)
+    int cm = q.cluster_m > 0 ? q.cluster_m : g_cluster_m, cn = q.cluster_n > 0 ? q.cluster_n : g_cluster_n;
+    if (cm <= 0 || cn <= 0) {
+      cn = p.n_tiles % 3 == 0 ? 3 : (p.n_tiles % 4 == 0 ? 4 : (p.n_tiles % 2 == 0 ? 2 : 1));
+      cm = (p.m_tiles % 2 == 0 && cn * 2 <= 8) ? 2 : 1;
+    }
+    cm = std::min(cm, p.m_tiles);
+    cn = std::min(cn, p.n_tiles);
+    p.cm = cm; p.cn = cn;
+    const int csize = cm * cn;
+    const int64_t num_super = ceil_div(p.m_tiles, cm) * ceil_div(p.n_tiles, cn) * q.batch_inner * q.batch_outer;
+    DITTO_TRY(launch_clustered(func, csize, SMEM_BYTES, num_super, ma, mb, p, st));
+  }
   return 0;
 }
+#undef DITTO_LAUNCH_PAIR
+#undef DITTO_FUNC_1CTA
 
 
 // ---------------------------------------------------------------------------------------------------
 // fused scores + softmax launcher
 // ---------------------------------------------------------------------------------------------------
-namespace {
-int g_sm_max_clusters[2][SM_MAX_CLUSTER + 1];  // [has_bias][csize]: co-resident clusters (0 = not queried, -1 = cannot launch)
-
-template <bool HAS_BIAS>
-int scores_softmax_launch(const CUtensorMap& ma, const CUtensorMap& mb, const SmDev& p, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = SM_SMEM_BYTES;
-  cfg.stream = st;
-  cfg.attrs = attr;
-  cfg.numAttrs = 0;
-  int clusters = g_num_sms;
-  if (p.csize > 1) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = static_cast<unsigned>(p.csize);
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.numAttrs = 1;
-    int& cached = g_sm_max_clusters[HAS_BIAS ? 1 : 0][p.csize];
-    if (cached == 0) {
-      cfg.gridDim = dim3(static_cast<unsigned>(p.csize * g_num_sms), 1, 1);
-      int n = 0;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_scores_softmax_kernel<HAS_BIAS>, &cfg);
-      if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
-      cached = n > 0 ? n : -1;
-    }
-    DITTO_REQUIRE(cached > 0, DITTO_E_UNSUPPORTED, "tc_scores_softmax: this cluster size cannot be scheduled on the device");
-    clusters = cached;
-  }
-  clusters = std::min(clusters, p.num_items);
-  cfg.gridDim = dim3(static_cast<unsigned>(clusters * p.csize), 1, 1);
-  DITTO_CUDA(cudaLaunchKernelEx(&cfg, tc_scores_softmax_kernel<HAS_BIAS>, ma, mb, p));
-  count_launch();
-  return 0;
-}
-}  // namespace
 
 int tc_scores_softmax_csize(int N) {
   const int64_t c = ceil_div(N, BLOCK_N);
@@ -1441,10 +1579,15 @@ int launch_tc_scores_softmax(const TcScoresSoftmaxParams& q, cudaStream_t st) {
   p.npad = q.npad;
   p.lpart = q.lpart; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.csize = csize; p.stages = g_stages_1cta;
+  int cm = q.cluster_m > 0 ? q.cluster_m : (g_cluster_m > 0 ? g_cluster_m : ((p.m_tiles % 2 == 0 && csize * 2 <= 8) ? 2 : 1));
+  cm = std::max(1, std::min(cm, std::min(p.m_tiles, SM_MAX_CLUSTER / csize)));
+  p.cm = cm;
   // flops: the contraction; bytes: nothing (the fused softmax saves 12 B per score of HBM round trips)
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
-  if (q.bias != nullptr) return scores_softmax_launch<true>(ma, mb, p, st);
-  return scores_softmax_launch<false>(ma, mb, p, st);
+  const int64_t work = ceil_div(p.m_tiles, cm) * q.batch_inner * q.batch_outer;
+  const void* func = q.bias != nullptr ? reinterpret_cast<const void*>(&tc_scores_softmax_kernel<true>)
+                                       : reinterpret_cast<const void*>(&tc_scores_softmax_kernel<false>);
+  return launch_clustered(func, csize * cm, SM_SMEM_BYTES, work, ma, mb, p, st);
 }
 
 }  // namespace ditto

@@ -81,6 +81,8 @@ struct TcGemmParams {
   // optional per-row scale 1 / sum_c row_lsum[row*row_lparts + c] applied to the accumulator (softmax normalisation of an
   // unnormalised P operand, see launch_tc_scores_softmax); batch strides in elements
   const float* row_lsum = nullptr; int row_lparts = 0; int64_t sl_inner = 0, sl_outer = 0;
+  // cluster shape in tiles for the 1-CTA kernel (operands shared by TMA multicast); 0 = library default
+  int cluster_m = 0, cluster_n = 0;
 };
 int launch_tc_gemm(const TcGemmParams& p, cudaStream_t st);
 
@@ -98,6 +100,7 @@ struct TcScoresSoftmaxParams {
   bf16* P = nullptr; int64_t ldp = 0, sp_inner = 0, sp_outer = 0;
   int npad = 0;                                 // zero-fill bound (multiple of 2, >= N)
   float* lpart = nullptr; int64_t sl_inner = 0, sl_outer = 0;  // [M, csize] per batch item; required when csize > 1
+  int cluster_m = 0;                            // query-row tiles per cluster (K blocks multicast across them); 0 = default
   int tag = PC_TC_OTHER;
 };
 int tc_scores_softmax_csize(int N);             // cluster size the kernel will use for N key columns (0: unsupported)
