@@ -1522,13 +1522,11 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
     }
   }
   {
-    // cluster shape: explicit > DITTO_CLUSTER > heuristic (share A across up to 3-4 tile columns, B across 2 tile rows,
-    // only shapes that tile the matrix without padding tiles)
+    // cluster shape: explicit > DITTO_CLUSTER > 1 x 1.  Measured on B200 (profiles/README.md): for the epilogue-heavy
+    // batched attention GEMMs the lock-step coupling of a multicast cluster costs more than the saved L2 traffic, so
+    // multicast stays opt-in here; the fused scores kernel always shares the Q block across its key-tile cluster.
     int cm = q.cluster_m > 0 ? q.cluster_m : g_cluster_m, cn = q.cluster_n > 0 ? q.cluster_n : g_cluster_n;
-    if (cm <= 0 || cn <= 0) {
-      cn = p.n_tiles % 3 == 0 ? 3 : (p.n_tiles % 4 == 0 ? 4 : (p.n_tiles % 2 == 0 ? 2 : 1));
-      cm = (p.m_tiles % 2 == 0 && cn * 2 <= 8) ? 2 : 1;
-    }
+    if (cm <= 0 || cn <= 0) cm = cn = 1;
     cm = std::min(cm, p.m_tiles);
     cn = std::min(cn, p.n_tiles);
     p.cm = cm; p.cn = cn;
@@ -1579,7 +1577,7 @@ int launch_tc_scores_softmax(const TcScoresSoftmaxParams& q, cudaStream_t st) {
   p.npad = q.npad;
   p.lpart = q.lpart; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.csize = csize; p.stages = g_stages_1cta;
-  int cm = q.cluster_m > 0 ? q.cluster_m : (g_cluster_m > 0 ? g_cluster_m : ((p.m_tiles % 2 == 0 && csize * 2 <= 8) ? 2 : 1));
+  int cm = q.cluster_m > 0 ? q.cluster_m : (g_cluster_m > 0 ? g_cluster_m : 1);
   cm = std::max(1, std::min(cm, std::min(p.m_tiles, SM_MAX_CLUSTER / csize)));
   p.cm = cm;
   // flops: the contraction; bytes: nothing (the fused softmax saves 12 B per score of HBM round trips)
