@@ -36,6 +36,7 @@ SIGNATURES = {
     "ditto_profile_class_name": (C.c_char_p, [_I32]),
     "ditto_profile_get": (_I32, [_I32, C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double)]),
+    "ditto_debug_set_counters": (_I32, [_P]),
     "ditto_engine_create": (_I32, [C.POINTER(Config), C.POINTER(_P)]),
     "ditto_engine_destroy": (_I32, [_P]),
     "ditto_engine_load_weight": (_I32, [_P, C.c_char_p, _P, _I64, _P]),

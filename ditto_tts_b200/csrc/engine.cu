@@ -519,6 +519,11 @@ int32_t ditto_profile_get(int32_t i, int64_t* launches, double* total_ms, double
   return 0;
 }
 
+int32_t ditto_debug_set_counters(uint64_t* counters) {
+  tc_gemm_set_debug_counters(reinterpret_cast<unsigned long long*>(counters));
+  return 0;
+}
+
 int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
   DITTO_REQUIRE(cfg && out, DITTO_E_BADARG, "engine_create: null argument");
   DITTO_REQUIRE(cfg->hidden_dim > 0 && cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->time_dim > 0 && cfg->diffusion_steps > 0,

@@ -63,6 +63,10 @@ struct DevParams {
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
+  // developer diagnostics (ditto_debug_set_counters): clock cycles, summed over CTAs, that the pair kernel's MMA issuer
+  // spent [0] waiting for operands, [1] waiting for a free accumulator, [2] in total; the TMA producer [3] waiting for a
+  // free ring slot, [4] in total.  nullptr = off.
+  unsigned long long* dbg;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -861,11 +865,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_slot = 0;
+      const long long t_begin = p.dbg ? clock64() : 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
         const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
         const int m0 = m_pair * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (p.dbg) {
+            const long long t0 = clock64();
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            w_slot += clock64() - t0;
+          } else
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -875,6 +886,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.dbg && rank == 0) {
+        atomicAdd(p.dbg + 3, static_cast<unsigned long long>(w_slot));
+        atomicAdd(p.dbg + 4, static_cast<unsigned long long>(clock64() - t_begin));
+      }
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
@@ -883,11 +898,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      long long w_ops = 0, w_acc = 0;
+      const long long t_begin = p.dbg ? clock64() : 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        if (p.dbg) {
+          const long long t0 = clock64();
+          mbar_wait(&tmem_empty[as], aphase ^ 1u);
+          w_acc += clock64() - t0;
+        } else
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (p.dbg) {
+            const long long t0 = clock64();
+            mbar_wait(&full_bar[stage], phase);
+            w_ops += clock64() - t0;
+          } else
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
@@ -903,6 +930,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         }
         umma_commit_2sm(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+      if (p.dbg) {
+        atomicAdd(p.dbg + 0, static_cast<unsigned long long>(w_ops));
+        atomicAdd(p.dbg + 1, static_cast<unsigned long long>(w_acc));
+        atomicAdd(p.dbg + 2, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -1288,6 +1320,7 @@ bool g_use_pair = true;
 int g_cluster_m = 0, g_cluster_n = 0;  // DITTO_CLUSTER="cm,cn": default cluster shape of the 1-CTA GEMM kernel (0 = heuristic)
 bool g_force_generic = false;  // DITTO_GENERIC_EPI=1: route every STORE epilogue through the generic path (tests)
 int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
+unsigned long long* g_dbg = nullptr;
 
 // 4-D bf16 map: dims (cols, rows, inner, outer), box (box_cols, box_rows, 1, 1), 128B swizzle, zero OOB fill.
 int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
@@ -1370,6 +1403,8 @@ int launch_clustered(const void* func, int csize, int smem_bytes, int64_t num_wo
 }
 
 }  // namespace
+
+void tc_gemm_set_debug_counters(unsigned long long* dev_ptr) { g_dbg = dev_ptr; }
 
 int tc_gemm_init() {
   if (g_init_done) return 0;
@@ -1468,6 +1503,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
   p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
   p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
+  p.dbg = g_dbg;
 
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);

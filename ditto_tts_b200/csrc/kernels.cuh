@@ -106,5 +106,6 @@ struct TcScoresSoftmaxParams {
 int tc_scores_softmax_csize(int N);             // cluster size the kernel will use for N key columns (0: unsupported)
 int launch_tc_scores_softmax(const TcScoresSoftmaxParams& p, cudaStream_t st);
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
+void tc_gemm_set_debug_counters(unsigned long long* dev_ptr);  // ditto_debug_set_counters
 
 }  // namespace ditto

@@ -82,6 +82,10 @@ int32_t ditto_profile_stop(void);
 int32_t ditto_profile_num_classes(void);
 const char* ditto_profile_class_name(int32_t i);
 int32_t ditto_profile_get(int32_t i, int64_t* launches, double* total_ms, double* flops, double* bytes);
+/* Developer diagnostics of the paired tcgen05 GEMM: `counters` = 5 zero-initialised device uint64 (NULL = off) that
+ * receive SM clock cycles summed over CTA pairs: [0] MMA issuer waiting for operands, [1] waiting for a drained
+ * accumulator, [2] MMA issuer total; [3] TMA producer waiting for a free ring slot, [4] TMA producer total. */
+int32_t ditto_debug_set_counters(uint64_t* counters);
 
 /* ---- engine life cycle == DiTTO.__init__ + load_state_dict (src/model/DiTTO.py:10-64) -------------- */
 int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out);
