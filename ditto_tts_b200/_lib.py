@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libditto_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
-F_FUSED_ROPE, F_FOLD_CROSS, F_FUSED_ATTN = 1, 2, 4
+F_FUSED_ROPE, F_FOLD_CROSS, F_FUSED_ATTN, F_DEFER_LN = 1, 2, 4, 8
 
 
 class DittoError(RuntimeError):

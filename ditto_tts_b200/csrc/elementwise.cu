@@ -33,22 +33,63 @@ int launch_cast_bf16(const float* x, bf16* y, int64_t n, cudaStream_t st) {
   return 0;
 }
 
-// rows [rows, K] fp32 -> bf16 with an output-row permutation: y[r] = x[perm(r)]
-//  mode 0: identity; mode 1: GLU interleave (16-row blocks: [fc1 16 | gate 16]); src = [fc1 (R/2 rows); gate (R/2)]
-//  mode 2: RoPE pairing for the q and k thirds of in_proj (see pack notes in engine.cu)
+// rows [rows, K] fp32 -> bf16 with an output-row permutation: y[r] = x[perm(r)]  (perm built on the host: GLU interleave
+// of [fc1 16 | gate 16] row blocks, RoPE pairing of the q and k thirds of in_proj -- see engine.cu)
+// With gamma / beta (deferred LayerNorm folded into the weight, see gemm_tc.cu DevParams):
+//   y[r][k] = bf16(x[src][k] gamma[k]),  csum[r] = sum_k float(y[r][k]),  bias_out[r] = bias_in[src] + sum_k x[src][k] beta[k]
 __global__ void pack_rows_kernel(const float* __restrict__ x, bf16* __restrict__ y, float* __restrict__ bias_out,
-                                 const float* __restrict__ bias_in, const int* __restrict__ perm, int rows, int K) {
+                                 const float* __restrict__ bias_in, const int* __restrict__ perm, int rows, int K,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ csum) {
   const int r = blockIdx.x;
   const int src = perm ? perm[r] : r;
   const float* xr = x + static_cast<int64_t>(src) * K;
   bf16* yr = y + static_cast<int64_t>(r) * K;
-  for (int c = threadIdx.x; c < K; c += blockDim.x) yr[c] = __float2bfloat16_rn(xr[c]);
-  if (bias_out && threadIdx.x == 0) bias_out[r] = bias_in[src];
+  float cs = 0.f, bs = 0.f;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    const float w = xr[c];
+    const bf16 q = __float2bfloat16_rn(gamma ? w * gamma[c] : w);
+    yr[c] = q;
+    cs += __bfloat162float(q);
+    if (beta) bs = fmaf(w, beta[c], bs);
+  }
+  __shared__ float red[2][8];
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cs; red[1][threadIdx.x >> 5] = bs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cs = bs = 0.f;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) { cs += red[0][i]; bs += red[1][i]; }
+    if (bias_out) bias_out[r] = bias_in[src] + bs;
+    if (csum) csum[r] = cs;
+  }
 }
 
 int launch_pack_rows(const float* x, bf16* y, float* bias_out, const float* bias_in, const int* perm, int rows, int K,
-                     cudaStream_t st) {
-  pack_rows_kernel<<<rows, 256, 0, st>>>(x, y, bias_out, bias_in, perm, rows, K);
+                     cudaStream_t st, const float* gamma, const float* beta, float* csum) {
+  pack_rows_kernel<<<rows, 256, 0, st>>>(x, y, bias_out, bias_in, perm, rows, K, gamma, beta, csum);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[g * Sp + s] = sum_k x[(g * S + s) * K + k] for s < S, 0 for S <= s < Sp  (row sums of the gamma-scaled folded keys)
+__global__ void rowsum_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t total, int S, int Sp, int K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= total) return;
+  const int s_idx = static_cast<int>(o % Sp);
+  const int64_t g = o / Sp;
+  float acc = 0.f;
+  if (s_idx < S) {
+    const bf16* row = x + (g * S + s_idx) * K;
+    for (int i = lane; i < K; i += 32) acc += __bfloat162float(row[i]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[o] = acc;
+}
+int launch_rowsum_bf16(const bf16* x, float* out, int64_t groups, int S, int Sp, int K, cudaStream_t st) {
+  const int64_t total = groups * Sp;
+  rowsum_bf16_kernel<<<static_cast<unsigned>(ceil_div(total, 8)), 256, 0, st>>>(x, out, total, S, Sp, K);
   DITTO_LAUNCH_CHECK();
   return 0;
 }
@@ -145,7 +186,7 @@ __global__ void __launch_bounds__(256)
     adaln_ln_kernel(const float* __restrict__ x, int64_t n_x, const float* __restrict__ time_table,
                     const float* __restrict__ text_mod, const int64_t* __restrict__ t, int steps,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ h,
-                    OutT* __restrict__ u, bf16* __restrict__ xcast, int64_t n_seq, int T, int H) {
+                    OutT* __restrict__ u, bf16* __restrict__ xcast, int64_t n_seq, int T, int H, float2* __restrict__ stat) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_seq * T) return;
@@ -185,6 +226,21 @@ __global__ void __launch_bounds__(256)
       v[i].w = (v[i].w - mean) * rstd * ((1.f + ts.w) + xs.w) + (tb.w + xb.w);
       *reinterpret_cast<float4*>(h + row * H + c) = v[i];
     }
+  if (stat != nullptr) {
+    // deferred LayerNorm: u = bf16(h) and the row's (sum, sum of squares); the consuming GEMM epilogue normalises
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv_lane) {
+        sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        store4<OutT>(u + row * H + ((i << 5) + lane) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
+      }
+    sm = warp_sum(sm);
+    sq = warp_sum(sq);
+    if (lane == 0) stat[row] = make_float2(sm, sq);
+    return;
+  }
   row_stats(v, nv_lane, H, mean, rstd);
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
@@ -199,16 +255,16 @@ __global__ void __launch_bounds__(256)
 
 int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
                     int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
-                    int64_t n_seq, int T, int H, cudaStream_t st) {
+                    int64_t n_seq, int T, int H, cudaStream_t st, float2* stat) {
   DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128, DITTO_E_UNSUPPORTED, "adaln: need H % 4 == 0 and H <= 1024");
   const unsigned blocks = static_cast<unsigned>(ceil_div(n_seq * T, 8));
   ProfScope prof(PC_ADALN, st, 0.0, static_cast<double>(n_seq) * T * H * (u_bf16 ? 10 + 2 : 12));
   if (u_bf16)
     adaln_ln_kernel<bf16><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
-                                                  static_cast<bf16*>(u), xcast, n_seq, T, H);
+                                                  static_cast<bf16*>(u), xcast, n_seq, T, H, stat);
   else
     adaln_ln_kernel<float><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
-                                                   static_cast<float*>(u), xcast, n_seq, T, H);
+                                                   static_cast<float*>(u), xcast, n_seq, T, H, stat);
   DITTO_LAUNCH_CHECK();
   return 0;
 }

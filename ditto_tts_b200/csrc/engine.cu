@@ -68,6 +68,10 @@ struct Arena {
 struct LayerPack {
   bf16 *w_qkv = nullptr, *wc_in = nullptr, *wc_o = nullptr, *w_glu = nullptr, *w_fc2 = nullptr;
   float *b_qkv = nullptr, *b_glu = nullptr;  // permuted / interleaved copies
+  // deferred LayerNorm (DITTO_F_DEFER_LN): w_qkv / w_glu carry gamma1 / gamma3, b_* carry W beta, c_* = row sums of the
+  // scaled bf16 weights; wq_g / bq_g = cross-attention query projection with gamma2 / beta2 folded in (folded cross path)
+  float *c_qkv = nullptr, *c_glu = nullptr, *bq_g = nullptr;
+  bf16* wq_g = nullptr;
 };
 
 }  // namespace ditto
@@ -81,6 +85,7 @@ struct ditto_engine {
   int rope_pd = 0;
   bool fused_attn = false;  // scores + softmax fused (cluster kernel); falls back per call when a row needs > 16 tiles
   bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
+  bool defer_ln = false;    // block LayerNorms folded into the neighbouring GEMM epilogues (no LayerNorm launches)
   int pv_transpose = 0;  // debug: use the transposed-V operand instead of the MN-major descriptor
   bool rope_table_in_epilogue = false;  // debug (DITTO_ROPE_TABLE=1): fused RoPE reads the cos/sin tables instead of computing them
   std::map<std::string, int64_t> expected;  // key -> numel
@@ -148,9 +153,10 @@ static int sgemm_nt(const float* A, int64_t lda, const float* Wt, int64_t ldw, f
 // bf16 tensor-core helper: out = alpha * A[M,K] @ W[N,K]^T (+bias) (+resid)
 static int tc_nt(const bf16* A, int64_t lda, const bf16* Wt, int64_t ldw, void* out, bool out_bf16, int64_t ldo,
                  const float* bias, const float* resid, int64_t ldr, int64_t resid_row_mod, bf16* out2, int64_t ldo2,
-                 int M, int N, int K, cudaStream_t st, int tag = PC_TC_OTHER) {
+                 int M, int N, int K, cudaStream_t st, int tag = PC_TC_OTHER, float2* stat_out = nullptr, int stat_parts = 0) {
   TcGemmParams p;
   p.tag = tag;
+  p.stat_out = stat_out; p.stat_parts = stat_parts;
   p.A.ptr = A; p.A.rows = M; p.A.cols = K; p.A.ld = lda;
   p.B.ptr = Wt; p.B.rows = N; p.B.cols = K; p.B.ld = ldw;
   p.M = M; p.N = N; p.K = K;
@@ -167,14 +173,19 @@ struct CtxLayout {
   //   kfold [n, heads, S, H]   = K_h Wq_h           (scores = u . kfold^T + sbias)
   //   vfold [n, heads*Sp, H]   = V_h Wo_h^T         (out = P . vfold + bo), zero rows for s >= S
   //   sbias [n, heads, Sp] f32 = sqrt(1/d) K_h bq_h
+  //   cvec  [n, heads, Sp] f32 = row sums of the gamma2-scaled kfold (deferred LayerNorm only), strided like sbias
   bf16 *kfold0 = nullptr, *vfold0 = nullptr;
-  float* sbias0 = nullptr;
+  float *sbias0 = nullptr, *cvec0 = nullptr;
   size_t kfold_stride = 0, vfold_stride = 0, sbias_stride = 0;  // elements between layers
   size_t total = 0;
 };
 static bool fold_active(const ditto_engine* e, int64_t S) {
   // folding trades the two M x H x H projections for (heads*S)-wide products: only worth it when heads*S << H
   return e->bf16_mode && e->fold_cross && e->heads * round_up(S, 8) * 2 <= e->H;
+}
+// LN2 is folded into the cross-attention scores only on the folded path with a single key tile (fused scores kernel)
+static bool fold_ln_active(const ditto_engine* e, int64_t S) {
+  return e->defer_ln && fold_active(e, S) && tc_scores_softmax_csize(static_cast<int>(S)) == 1;
 }
 static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_t S) {
   Arena a(base);
@@ -193,6 +204,7 @@ static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_
     c.kfold0 = a.take<bf16>(static_cast<int64_t>(c.kfold_stride) * e->L);
     c.vfold0 = a.take<bf16>(static_cast<int64_t>(c.vfold_stride) * e->L);
     c.sbias0 = a.take<float>(static_cast<int64_t>(c.sbias_stride) * e->L);
+    if (e->defer_ln) c.cvec0 = a.take<float>(static_cast<int64_t>(c.sbias_stride) * e->L);
   }
   c.total = a.off + 256;
   return c;
@@ -204,6 +216,8 @@ struct Workspace {
   float *fc1 = nullptr, *gate = nullptr;  // fp32 path only
   bf16* vt = nullptr;                     // transposed-V fallback
   float* lpart = nullptr;                 // [n*heads, T, ceil(Tp/256)] partial softmax denominators (fused attention)
+  float2* lnstat = nullptr;               // [M, ln_parts] per-row partial (sum, sum of squares) of h (deferred LayerNorm)
+  int ln_parts_h = 0, ln_parts_attn = 0;  // parts written by an N = H producer / by the per-head P.V producer
   float* tmp_small = nullptr;             // [n, Xd] pooled text
   bf16* text16 = nullptr;                 // [n*S, Xd]
   int64_t Tp = 0, Sp = 0, ldp = 0;
@@ -234,6 +248,9 @@ static Workspace ws_layout(const ditto_engine* e, void* base, int64_t n, int64_t
     w.vt = a.take<bf16>(n * e->heads * e->d * w.ldp);
   }
   if (e->bf16_mode) w.lpart = a.take<float>(n * e->heads * T * ceil_div(w.ldp, 256));
+  w.ln_parts_h = static_cast<int>(ceil_div(H, 128));
+  w.ln_parts_attn = static_cast<int>(e->heads * ceil_div(e->d, 128));
+  if (e->defer_ln) w.lnstat = a.take<float2>(M * std::max(w.ln_parts_h, w.ln_parts_attn));
   w.tmp_small = a.take<float>(n * e->Xd);
   w.text16 = a.take<bf16>(n * S * e->Xd);
   w.total = a.off + 256;
@@ -251,7 +268,7 @@ namespace ditto {
 static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, int64_t ldq, int64_t q_seq_stride, const bf16* k,
                           int64_t ldk, int64_t k_seq_stride, const bf16* v, int64_t ldv, int64_t v_seq_stride, int64_t n, int Tq,
                           int Tk, float alpha, void* out, bool out_bf16, int64_t ldo, int64_t o_seq_stride, const float* resid,
-                          cudaStream_t st, bool cross) {
+                          cudaStream_t st, bool cross, bf16* out2 = nullptr, float2* stat_out = nullptr) {
   const int d = e->d, heads = e->heads;
   const int64_t ldp = round_up(Tk, 8);
   const int csize = e->fused_attn ? tc_scores_softmax_csize(Tk) : 0;
@@ -298,6 +315,8 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
     o.sl_outer = static_cast<int64_t>(heads) * Tq * csize;
   }
   o.tag = cross ? PC_TC_CROSS_PV : PC_TC_SELF_PV;
+  if (out2 != nullptr) { o.out2 = out2; o.ldo2 = ldo; }
+  if (stat_out != nullptr) { o.stat_out = stat_out; o.stat_parts = w.ln_parts_attn; o.stat_rows_outer = Tq; }
   DITTO_TRY(launch_tc_gemm(o, st));
   return 0;
 }
@@ -336,9 +355,13 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
   const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(d));          // DiT.py:131-132: scores / sqrt(d)
   const float sqrt_inv_d = sqrtf(1.0f / static_cast<float>(d));          // torch MHA: q * sqrt(1/d)
 
+  // deferred LayerNorm: `u` holds bf16(h) and w.lnstat the row statistics; ln1_parts = parts written by the last producer
+  const bool dln = e->defer_ln;
+  const bool dln2 = fold_ln_active(e, S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
+  int ln1_parts = 1;
   // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
   DITTO_TRY(launch_adaln_ln(x, n_x, e->time_table, c.text_mod, t, e->steps, e->LW(0, "norm1.weight"), e->LW(0, "norm1.bias"), w.h, w.u,
-                            b16, b16 ? static_cast<bf16*>(w.xb16) : nullptr, n, static_cast<int>(T), H, st));
+                            b16, b16 ? static_cast<bf16*>(w.xb16) : nullptr, n, static_cast<int>(T), H, st, dln ? w.lnstat : nullptr));
   // x_skip = proj_in(x), once per distinct x                               DiTTO.py:83
   const int Mx = static_cast<int>(n_x * T);
   if (b16)
@@ -366,13 +389,15 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
           g.rope_freq = e->rope_table_in_epilogue ? nullptr : e->rope_freq;
           g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(T); g.hidden = H;
         }
+        if (dln) { g.ln_stat = w.lnstat; g.ln_parts = ln1_parts; g.ln_width = H; g.ln_c = lp.c_qkv; }
         DITTO_TRY(launch_tc_gemm(g, st));
         if (!e->fused_rope) DITTO_TRY(launch_rope(qkv, true, 3 * H, e->rope_cos, e->rope_sin, M, static_cast<int>(T), H, d, st));
       }
       DITTO_TRY(attention_bf16(e, w, qkv, 3 * H, T * 3 * H, qkv + H, 3 * H, T * 3 * H, qkv + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
-                               static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st, false));
+                               static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st, false, dln2 ? u : nullptr,
+                               dln2 ? w.lnstat : nullptr));
       // ---- cross-attention (torch MHA math path)                                                     DiT.py:141-148
-      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
+      if (!dln2) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
       if (fold_active(e, S)) {
         // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
         const int heads = e->heads;
@@ -386,8 +411,10 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
           f.alpha = sqrt_inv_d; f.bias = c.sbias0 + c.sbias_stride * i; f.sb_inner = Sp; f.sb_outer = heads * Sp;
           f.P = static_cast<bf16*>(w.P); f.ldp = heads * Sp; f.sp_inner = Sp; f.sp_outer = T * heads * Sp; f.npad = static_cast<int>(Sp);
           f.tag = PC_TC_CROSS_SCORES;
+          if (dln2) { f.ln_stat = w.lnstat; f.ln_parts = w.ln_parts_attn; f.ln_width = H; f.ln_c = c.cvec0 + c.sbias_stride * i; }
           DITTO_TRY(launch_tc_scores_softmax(f, st));
         } else {
+          DITTO_REQUIRE(!dln2, DITTO_E_UNSUPPORTED, "forward: deferred LayerNorm needs the fused scores kernel on the folded cross path");
           TcGemmParams g;
           g.A.ptr = u; g.A.rows = T; g.A.cols = H; g.A.ld = H; g.A.s_inner = 0; g.A.s_outer = T * H;
           g.B.ptr = c.kfold0 + c.kfold_stride * i; g.B.rows = S; g.B.cols = H; g.B.ld = H; g.B.s_inner = S * H;
@@ -407,6 +434,7 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         o.bias = e->LW(i, "cross_attn.out_proj.bias");
         o.out = w.h; o.out_bf16 = false; o.ldo = H; o.so_outer = T * H; o.resid = w.h; o.ldr = H; o.sr_outer = T * H;
         o.tag = PC_TC_CROSS_PV;
+        if (dln) { o.out2 = u; o.ldo2 = H; o.stat_out = w.lnstat; o.stat_parts = w.ln_parts_h; o.stat_rows_outer = T; }
         DITTO_TRY(launch_tc_gemm(o, st));
       } else {
         bf16* qc = static_cast<bf16*>(w.qc);
@@ -416,23 +444,26 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         const bf16* kc = static_cast<const bf16*>(kv);
         DITTO_TRY(attention_bf16(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
                                  sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
-        DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, nullptr, 0, static_cast<int>(M), H,
-                        H, st, PC_TC_CROSS_OUT));
+        DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, dln ? u : nullptr, H,
+                        static_cast<int>(M), H, H, st, PC_TC_CROSS_OUT, dln ? w.lnstat : nullptr, w.ln_parts_h));
       }
       // ---- gated MLP                                                                                  DiT.py:150-155
-      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
+      if (!dln) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
       {
         TcGemmParams g;
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
         g.B.ptr = lp.w_glu; g.B.rows = 8 * H; g.B.cols = H; g.B.ld = H;
         g.M = static_cast<int>(M); g.N = 8 * H; g.K = H; g.bias = lp.b_glu; g.out = w.hid; g.out_bf16 = true; g.ldo = 4 * H;
         g.epilogue = TC_EPI_GEGLU;
+        if (dln) { g.ln_stat = w.lnstat; g.ln_parts = w.ln_parts_h; g.ln_width = H; g.ln_c = lp.c_glu; }
         g.tag = PC_TC_GLU;
         DITTO_TRY(launch_tc_gemm(g, st));
       }
       DITTO_TRY(tc_nt(static_cast<bf16*>(w.hid), 4 * H, lp.w_fc2, 4 * H, w.h, false, H, e->LW(i, "mlp_fc2.bias"), w.h, H, 0,
-                      last ? static_cast<bf16*>(w.xb16) : nullptr, H, static_cast<int>(M), H, 4 * H, st, PC_TC_FC2));
-      if (!last)
+                      last ? static_cast<bf16*>(w.xb16) : (dln ? u : nullptr), H, static_cast<int>(M), H, 4 * H, st, PC_TC_FC2,
+                      (dln && !last) ? w.lnstat : nullptr, w.ln_parts_h));
+      ln1_parts = w.ln_parts_h;
+      if (!last && !dln)
         DITTO_TRY(launch_layernorm(w.h, e->LW(i + 1, "norm1.weight"), e->LW(i + 1, "norm1.bias"), u, true, M, H, st));
     } else {
       float* u = static_cast<float*>(w.u);
@@ -558,6 +589,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     e->fused_rope = (cfg->flags & DITTO_F_FUSED_ROPE) && e->rope_pd != 0;
     e->fold_cross = (cfg->flags & DITTO_F_FOLD_CROSS) != 0;
     e->fused_attn = (cfg->flags & DITTO_F_FUSED_ATTN) != 0;
+    e->defer_ln = (cfg->flags & DITTO_F_DEFER_LN) != 0 && e->fused_rope && e->fused_attn;
+    if (const char* ed = getenv("DITTO_NO_DEFER_LN")) if (ed[0] == '1') e->defer_ln = false;
     if (const char* ef = getenv("DITTO_NO_FUSED_ATTN")) if (ef[0] == '1') e->fused_attn = false;
     const char* env = getenv("DITTO_PV_TRANSPOSE");
     e->pv_transpose = env && env[0] == '1';
@@ -692,9 +725,18 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
         if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.b_qkv), sizeof(float) * 3 * H);
         if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.w_glu), sizeof(bf16) * 8ll * H * H);
         if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.b_glu), sizeof(float) * 8 * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.c_qkv), sizeof(float) * 3 * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.c_glu), sizeof(float) * 8 * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.wq_g), sizeof(bf16) * static_cast<int64_t>(H) * H);
+        if (!rc) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.bq_g), sizeof(float) * H);
         if (rc) break;
       }
-      rc = launch_pack_rows(e->LW(i, "attn.in_proj_weight"), lp.w_qkv, lp.b_qkv, e->LW(i, "attn.in_proj_bias"), d_qkv, 3 * H, H, st);
+      const bool dl = e->defer_ln;
+      rc = launch_pack_rows(e->LW(i, "attn.in_proj_weight"), lp.w_qkv, lp.b_qkv, e->LW(i, "attn.in_proj_bias"), d_qkv, 3 * H, H, st,
+                            dl ? e->LW(i, "norm1.weight") : nullptr, dl ? e->LW(i, "norm1.bias") : nullptr, lp.c_qkv);
+      if (!rc && dl)
+        rc = launch_pack_rows(e->LW(i, "cross_attn.in_proj_weight"), lp.wq_g, lp.bq_g, e->LW(i, "cross_attn.in_proj_bias"), nullptr, H, H, st,
+                              e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), nullptr);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.in_proj_weight"), 3ll * H * H, &lp.wc_in);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.out_proj.weight"), static_cast<int64_t>(H) * H, &lp.wc_o);
       if (!rc) rc = cast_new(e->LW(i, "mlp_fc2.weight"), 4ll * H * H, &lp.w_fc2);
@@ -703,7 +745,8 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
       cudaMemcpyAsync(cat + 4ll * H * H, e->LW(i, "gate.weight"), sizeof(float) * 4ll * H * H, cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(cat_bias, e->LW(i, "mlp_fc1.bias"), sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(cat_bias + 4 * H, e->LW(i, "gate.bias"), sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
-      rc = launch_pack_rows(cat, lp.w_glu, lp.b_glu, cat_bias, d_glu, 8 * H, H, st);
+      rc = launch_pack_rows(cat, lp.w_glu, lp.b_glu, cat_bias, d_glu, 8 * H, H, st, dl ? e->LW(i, "norm3.weight") : nullptr,
+                            dl ? e->LW(i, "norm3.bias") : nullptr, lp.c_glu);
     }
     se = cudaStreamSynchronize(st);
     cudaFree(d_glu);
@@ -760,7 +803,10 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
         // kfold[seq, h] (S x H) = K[seq][:, h*d:(h+1)*d] (S x d) @ Wq[h*d:(h+1)*d, :] (d x H, "KN" operand)
         TcGemmParams g;
         g.A.ptr = kvb; g.A.rows = S; g.A.cols = d; g.A.ld = 2 * H; g.A.s_inner = d; g.A.s_outer = S * 2 * H;
-        g.B.ptr = e->layers[i].wc_in; g.B.rows = d; g.B.cols = H; g.B.ld = H; g.B.s_inner = static_cast<int64_t>(d) * H; g.B.s_outer = 0;
+        // deferred LayerNorm: Wq diag(gamma2) instead of Wq, bq + Wq beta2 instead of bq, plus the row sums of the result
+        const bool fln = fold_ln_active(e, S);
+        g.B.ptr = fln ? e->layers[i].wq_g : e->layers[i].wc_in;
+        g.B.rows = d; g.B.cols = H; g.B.ld = H; g.B.s_inner = static_cast<int64_t>(d) * H; g.B.s_outer = 0;
         g.b_kn = true;
         g.M = static_cast<int>(S); g.N = H; g.K = d; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
         g.out = kf; g.out_bf16 = true; g.ldo = H; g.so_inner = S * H; g.so_outer = static_cast<int64_t>(heads) * S * H;
@@ -774,8 +820,10 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
         v.out = vf; v.out_bf16 = true; v.ldo = H; v.so_inner = Sp * H; v.so_outer = static_cast<int64_t>(heads) * Sp * H;
         v.tag = PC_TC_TEXT_KV;
         DITTO_TRY(launch_tc_gemm(v, st));
-        DITTO_TRY(launch_fold_bias(kvb, 2 * H, e->LW(i, "cross_attn.in_proj_bias"), sb, n, static_cast<int>(S), static_cast<int>(Sp), heads, d,
-                                   sqrtf(1.0f / static_cast<float>(d)), st));
+        DITTO_TRY(launch_fold_bias(kvb, 2 * H, fln ? e->layers[i].bq_g : e->LW(i, "cross_attn.in_proj_bias"), sb, n,
+                                   static_cast<int>(S), static_cast<int>(Sp), heads, d, sqrtf(1.0f / static_cast<float>(d)), st));
+        if (fln)
+          DITTO_TRY(launch_rowsum_bf16(kf, c.cvec0 + c.sbias_stride * i, n * heads, static_cast<int>(S), static_cast<int>(Sp), H, st));
       }
     } else {
       DITTO_TRY(sgemm_nt(text_emb, Xd, e->LW(i, "cross_attn.in_proj_weight") + static_cast<int64_t>(H) * H, H, static_cast<float*>(kv),

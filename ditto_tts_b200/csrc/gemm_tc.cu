@@ -19,6 +19,13 @@ namespace ditto {
 
 namespace {
 
+// ditto_debug_set_counters(): the wait-cycle counters of the paired kernel cost registers in the 56-register control
+// warps, so they are compiled in only with -DDITTO_DBG_COUNTERS=1 (the entry point stays, the counters read 0 otherwise)
+#ifndef DITTO_DBG_COUNTERS
+#define DITTO_DBG_COUNTERS 0
+#endif
+constexpr bool kDbgCounters = DITTO_DBG_COUNTERS != 0;
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle span
@@ -63,6 +70,13 @@ struct DevParams {
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
+  // Deferred LayerNorm (DiT.py:105,143,151 without a LayerNorm pass over HBM).
+  //  producer (STORE_F32_RESID): besides the fp32 result and its bf16 copy (out2), every epilogue warp writes the
+  //    (sum, sum of squares) of its 128-column slab of each row to stat_out[row][part]  (deterministic: no atomics);
+  //  consumer (QKV_ROPE / GEGLU): A is the raw bf16 residual stream, the weights carry gamma (W' = W diag(gamma)), and
+  //    LN(h) W^T + b = rstd (h W'^T) - rstd mean c + b',  c_n = sum_k W'_nk,  b' = b + W beta,  applied per row here.
+  float2* stat_out; int stat_parts; long long stat_rows_outer; int stat_parts_item;
+  const float2* ln_stat; int ln_parts; float ln_inv_h; const float* ln_c;
   // developer diagnostics (ditto_debug_set_counters): clock cycles, summed over CTAs, that the pair kernel's MMA issuer
   // spent [0] waiting for operands, [1] waiting for a free accumulator, [2] in total; the TMA producer [3] waiting for a
   // free ring slot, [4] in total.  nullptr = off.
@@ -72,6 +86,14 @@ struct DevParams {
 // ---------------------------------------------------------------------------------------------------
 // epilogue math
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -82,6 +104,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// per-row LayerNorm coefficients from the producer's partial statistics: LN(h)_k = a h_k + nm  (before gamma / beta);
+// eps 1e-5, biased variance (nn.LayerNorm).  stat == nullptr: identity (a = 1, nm = 0).
+__device__ __forceinline__ void ln_row_coef(const float2* stat, int parts, long long row, bool ok, float inv_h, float& a, float& nm) {
+  a = 1.f; nm = 0.f;
+  if (stat == nullptr || !ok) return;
+  const float2* sp = stat + row * parts;
+  float s = 0.f, q = 0.f;
+  for (int c = 0; c < parts; ++c) {
+    const float2 v = __ldg(sp + c);
+    s += v.x; q += v.y;
+  }
+  const float mean = s * inv_h;
+  const float var = fmaxf(fmaf(-mean, mean, q * inv_h), 0.f);
+  a = rsqrtf(var + 1e-5f);
+  nm = -mean * a;
+}
+
 // cos/sin of a = float(pos) * inv_freq (the reference's fp32 angle, DiT.py:56-59) for |a| up to a few thousand radians:
 // two-constant Cody-Waite reduction to [-pi, pi] (k * 6.28125 is exact), then the MUFU approximations (abs. error ~5e-7).
 __device__ __forceinline__ void sincos_reduced(float a, float& s, float& c) {
@@ -230,9 +269,11 @@ __device__ __forceinline__ void load_resid_fast(const float* rpA, const float* r
 }
 
 // outA / outB (and o2A / o2B): this thread's element (row, col0t) of the two rows it owns in the block
-template <int EPI, bool FULL, typename OutT>
+// STATS: st = {sum A, sumsq A, sum B, sumsq B} of the stored values of this thread's two rows (deferred LayerNorm)
+template <int EPI, bool FULL, typename OutT, bool STATS = false>
 __device__ __forceinline__ void store_blk_fast(const uint32_t (&r)[32], const float2 (&b2)[8], const float2 (&f)[16], OutT* outA, OutT* outB,
-                                               bf16* o2A, bf16* o2B, bool okA, bool okB, int col0t, int N, float alphaA, float alphaB) {
+                                               bf16* o2A, bf16* o2B, bool okA, bool okB, int col0t, int N, float alphaA, float alphaB,
+                                               float* st = nullptr) {
   constexpr bool RESID = EPI == K_STORE_F32_RESID;
   constexpr bool OBF = EPI == K_STORE_BF16;
 #pragma unroll
@@ -248,6 +289,10 @@ __device__ __forceinline__ void store_blk_fast(const uint32_t (&r)[32], const fl
     }
     const bool cok = FULL || col0t + kb * 8 < N;
     const bool sA = FULL || (okA && cok), sB = FULL || (okB && cok);
+    if (STATS && cok) {
+      st[0] += vA.x + vA.y; st[1] = fmaf(vA.x, vA.x, fmaf(vA.y, vA.y, st[1]));
+      st[2] += vB.x + vB.y; st[3] = fmaf(vB.x, vB.x, fmaf(vB.y, vB.y, st[3]));
+    }
     if (OBF) {
       if (sA) *reinterpret_cast<uint32_t*>(outA + kb * 8) = pack_bf16x2(vA.x, vA.y);
       if (sB) *reinterpret_cast<uint32_t*>(outB + kb * 8) = pack_bf16x2(vB.x, vB.y);
@@ -262,10 +307,10 @@ __device__ __forceinline__ void store_blk_fast(const uint32_t (&r)[32], const fl
   }
 }
 
-template <int EPI, bool FULL>
+template <int EPI, bool FULL, bool STATS>
 __device__ __forceinline__ void epilogue_store_fast_impl(const DevParams& p, int lane, int half_sel, uint32_t t_row, int row0, int n_blk,
                                                          long long out_off, long long res_off, long long bias_off, long long ls_off,
-                                                         uint64_t* full_bar, uint32_t full_parity) {
+                                                         long long st_off, uint64_t* full_bar, uint32_t full_parity) {
   constexpr bool RESID = EPI == K_STORE_F32_RESID;
   constexpr bool OBF = EPI == K_STORE_BF16;
   typedef typename std::conditional<OBF, bf16, float>::type OutT;
@@ -323,6 +368,7 @@ __device__ __forceinline__ void epilogue_store_fast_impl(const DevParams& p, int
   mbar_wait(full_bar, full_parity);
   tcgen05_fence_after();
   if (row0 >= M) return;  // warp-uniform (cluster padding tile or fully out-of-range row group)
+  float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};  // STATS: rows (r00, r00+8) and (r00+16, r00+24)
 #pragma unroll 1
   for (int cb = 0; cb < 2; ++cb) {
     const int col0t = colt + cb * 64;
@@ -332,15 +378,16 @@ __device__ __forceinline__ void epilogue_store_fast_impl(const DevParams& p, int
     tmem_ld_16x64(t_row + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
     if (half1) load_resid_fast<RESID, FULL>(rp10 + cb * 64, rp11 + cb * 64, ok10, ok11, col0t, N, f1);
     tmem_ld_wait();
-    store_blk_fast<EPI, FULL, OutT>(r, b2, f0, o00 + cb * 64, o00 + o8 + cb * 64, q00 ? q00 + cb * 64 : nullptr,
-                                    q00 ? q00 + q8 + cb * 64 : nullptr, ok00, ok01, col0t, N, a00, a01);
+    store_blk_fast<EPI, FULL, OutT, STATS>(r, b2, f0, o00 + cb * 64, o00 + o8 + cb * 64, q00 ? q00 + cb * 64 : nullptr,
+                                           q00 ? q00 + q8 + cb * 64 : nullptr, ok00, ok01, col0t, N, a00, a01, st0);
     // ---- hh = 1
     if (half1) tmem_ld_16x64(t_row + (16u << 16) + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
     if (cb == 0 && (FULL || col0t - q2 + 64 < N)) load_resid_fast<RESID, FULL>(rp00 + 64, rp01 + 64, ok00, ok01, col0t + 64, N, f0);
     if (half1) {
       tmem_ld_wait();
-      store_blk_fast<EPI, FULL, OutT>(r, b2, f1, o00 + 2 * o8 + cb * 64, o00 + 3 * o8 + cb * 64, q00 ? q00 + 2 * q8 + cb * 64 : nullptr,
-                                      q00 ? q00 + 3 * q8 + cb * 64 : nullptr, ok10, ok11, col0t, N, a10, a11);
+      store_blk_fast<EPI, FULL, OutT, STATS>(r, b2, f1, o00 + 2 * o8 + cb * 64, o00 + 3 * o8 + cb * 64,
+                                             q00 ? q00 + 2 * q8 + cb * 64 : nullptr, q00 ? q00 + 3 * q8 + cb * 64 : nullptr, ok10, ok11,
+                                             col0t, N, a10, a11, st1);
     }
     if (cb == 0) {
 #pragma unroll
@@ -349,16 +396,63 @@ __device__ __forceinline__ void epilogue_store_fast_impl(const DevParams& p, int
                                                                        : make_float2(0.f, 0.f);
     }
   }
+  if (STATS) {
+    // this warp's slab = part (2 n_blk + half_sel) of the row; a slab without any column inside the matrix writes nothing
+    // (its part index is >= stat_parts_item and does not exist)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      st0[i] = quad_sum(st0[i]);
+      st1[i] = quad_sum(st1[i]);
+    }
+    if ((lane & 3) == 0 && (FULL || colt - q2 < N)) {
+      float2* sp = p.stat_out + st_off + static_cast<long long>(r00) * p.stat_parts + (n_blk * 2 + half_sel);
+      const long long s8 = 8ll * p.stat_parts;
+      if (ok00) sp[0] = make_float2(st0[0], st0[1]);
+      if (ok01) sp[s8] = make_float2(st0[2], st0[3]);
+      if (ok10) sp[2 * s8] = make_float2(st1[0], st1[1]);
+      if (ok11) sp[3 * s8] = make_float2(st1[2], st1[3]);
+    }
+  }
 }
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0,
                                                     int n_blk, long long out_off, long long res_off, long long bias_off,
-                                                    long long ls_off, uint64_t* full_bar, uint32_t full_parity) {
+                                                    long long ls_off, long long st_off, uint64_t* full_bar, uint32_t full_parity) {
   const int r0 = static_cast<int>(row0);  // rows of one GEMM fit in 31 bits (checked at launch)
   const bool full = r0 + 32 <= p.M && n_blk * BLOCK_N + half_sel * 128 + 128 <= p.N;  // warp-uniform
-  if (full) epilogue_store_fast_impl<EPI, true>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off, full_bar, full_parity);
-  else epilogue_store_fast_impl<EPI, false>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off, full_bar, full_parity);
+  if (EPI == K_STORE_F32_RESID && p.stat_out != nullptr) {  // warp-uniform
+    if (full)
+      epilogue_store_fast_impl<EPI, true, EPI == K_STORE_F32_RESID>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off,
+                                                                    st_off, full_bar, full_parity);
+    else
+      epilogue_store_fast_impl<EPI, false, EPI == K_STORE_F32_RESID>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off,
+                                                                     st_off, full_bar, full_parity);
+    return;
+  }
+  if (full)
+    epilogue_store_fast_impl<EPI, true, false>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off, st_off, full_bar,
+                                               full_parity);
+  else
+    epilogue_store_fast_impl<EPI, false, false>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off, st_off, full_bar,
+                                                full_parity);
+}
+
+// bf16 store of one 16 x 64 block: v = a_row acc + (n_row c + b)  (plain bias store when the row coefficients are (1, 0))
+__device__ __forceinline__ void store_blk_bf16_ln(const uint32_t (&r)[32], const float2 (&b2)[8], const float2 (&c2)[8], bf16* outA, bf16* outB,
+                                                  bool okA, bool okB, int col0t, int N, float aA, float nA, float aB, float nB) {
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    const bool cok = col0t + kb * 8 < N;
+    const float tAx = fmaf(nA, c2[kb].x, b2[kb].x), tAy = fmaf(nA, c2[kb].y, b2[kb].y);
+    const float tBx = fmaf(nB, c2[kb].x, b2[kb].x), tBy = fmaf(nB, c2[kb].y, b2[kb].y);
+    if (okA && cok)
+      *reinterpret_cast<uint32_t*>(outA + kb * 8) =
+          pack_bf16x2(fmaf(aA, __uint_as_float(r[4 * kb]), tAx), fmaf(aA, __uint_as_float(r[4 * kb + 1]), tAy));
+    if (okB && cok)
+      *reinterpret_cast<uint32_t*>(outB + kb * 8) =
+          pack_bf16x2(fmaf(aB, __uint_as_float(r[4 * kb + 2]), tBx), fmaf(aB, __uint_as_float(r[4 * kb + 3]), tBy));
+  }
 }
 
 // One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.  Waits for the
@@ -366,9 +460,9 @@ __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
                                               long long out_off, long long res_off, long long bias_off, long long ls_off,
-                                              uint64_t* full_bar, uint32_t full_parity) {
+                                              long long st_off, uint64_t* full_bar, uint32_t full_parity) {
   if (EPI == K_STORE_F32 || EPI == K_STORE_F32_RESID || EPI == K_STORE_BF16) {
-    epilogue_store_fast<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, ls_off, full_bar, full_parity);
+    epilogue_store_fast<EPI>(p, lane, half_sel, t_row, row0, n_blk, out_off, res_off, bias_off, ls_off, st_off, full_bar, full_parity);
     return;
   }
   const int g = lane >> 2, q2 = (lane & 3) * 2;
@@ -406,7 +500,10 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
   } else if (EPI == K_GEGLU) {
     // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread.
     // Biases of this thread's column pairs for both 64-column halves are requested before the accumulator wait.
-    float2 ba[8], bg[8];
+    // Deferred LayerNorm (ln_stat != nullptr): a = rstd acc + (nm c + b') per row -- one extra FMA per element; without
+    // it the row coefficients are (1, 0) and the expression reduces to acc + b.
+    float2 ba[8], bg[8], ca2[8], cg2[8];
+    const bool dln = p.ln_stat != nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {  // j = cb*4 + gi*2 + m
       const int cg0 = n_blk * BLOCK_N + half_sel * 128 + (j >> 2) * 64 + ((j >> 1) & 1) * 32;  // first column of the group
@@ -414,7 +511,14 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       const bool ok = cg0 < p.N;
       ba[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca)) : make_float2(0.f, 0.f);
       bg[j] = ok ? __ldg(reinterpret_cast<const float2*>(bias + ca + 16)) : make_float2(0.f, 0.f);
+      ca2[j] = (ok && dln) ? __ldg(reinterpret_cast<const float2*>(p.ln_c + ca)) : make_float2(0.f, 0.f);
+      cg2[j] = (ok && dln) ? __ldg(reinterpret_cast<const float2*>(p.ln_c + ca + 16)) : make_float2(0.f, 0.f);
     }
+    float lnA0, lnN0, lnA1, lnN1, lnA2, lnN2, lnA3, lnN3;  // rows row0 + g + {0, 8, 16, 24}
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g, row0 + g < p.M, p.ln_inv_h, lnA0, lnN0);
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 8, row0 + g + 8 < p.M, p.ln_inv_h, lnA1, lnN1);
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 16, row0 + g + 16 < p.M, p.ln_inv_h, lnA2, lnN2);
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 24, row0 + g + 24 < p.M, p.ln_inv_h, lnA3, lnN3);
     mbar_wait(full_bar, full_parity);
     tcgen05_fence_after();
     if (row0 >= p.M) return;
@@ -432,6 +536,7 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + tcol, r);
         tmem_ld_wait();
         const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+        const float aA = hh ? lnA2 : lnA0, nA = hh ? lnN2 : lnN0, aB = hh ? lnA3 : lnA1, nB = hh ? lnN3 : lnN1;
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
           if (col0 + gi * 32 >= p.N) break;           // N % 32 == 0: a group is all-or-nothing
@@ -439,15 +544,20 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
           for (int m = 0; m < 2; ++m) {
             const int ka = gi * 4 + m, kg = ka + 2;   // 8-column blocks of the a and the g values
             const float2 b_a = ba[cb * 4 + gi * 2 + m], b_g = bg[cb * 4 + gi * 2 + m];
+            const float2 c_a = ca2[cb * 4 + gi * 2 + m], c_g = cg2[cb * 4 + gi * 2 + m];
             const int oc = ((col0 + gi * 32) >> 1) + m * 8 + q2;
             if (okA)
               *reinterpret_cast<uint32_t*>(outp + rowA * p.ldo + oc) =
-                  pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka]) + b_a.x, __uint_as_float(r[4 * kg]) + b_g.x),
-                              geglu_fast(__uint_as_float(r[4 * ka + 1]) + b_a.y, __uint_as_float(r[4 * kg + 1]) + b_g.y));
+                  pack_bf16x2(geglu_fast(fmaf(aA, __uint_as_float(r[4 * ka]), fmaf(nA, c_a.x, b_a.x)),
+                                         fmaf(aA, __uint_as_float(r[4 * kg]), fmaf(nA, c_g.x, b_g.x))),
+                              geglu_fast(fmaf(aA, __uint_as_float(r[4 * ka + 1]), fmaf(nA, c_a.y, b_a.y)),
+                                         fmaf(aA, __uint_as_float(r[4 * kg + 1]), fmaf(nA, c_g.y, b_g.y))));
             if (okB)
               *reinterpret_cast<uint32_t*>(outp + (rowA + 8) * p.ldo + oc) =
-                  pack_bf16x2(geglu_fast(__uint_as_float(r[4 * ka + 2]) + b_a.x, __uint_as_float(r[4 * kg + 2]) + b_g.x),
-                              geglu_fast(__uint_as_float(r[4 * ka + 3]) + b_a.y, __uint_as_float(r[4 * kg + 3]) + b_g.y));
+                  pack_bf16x2(geglu_fast(fmaf(aB, __uint_as_float(r[4 * ka + 2]), fmaf(nB, c_a.x, b_a.x)),
+                                         fmaf(aB, __uint_as_float(r[4 * kg + 2]), fmaf(nB, c_g.x, b_g.x))),
+                              geglu_fast(fmaf(aB, __uint_as_float(r[4 * ka + 3]), fmaf(nB, c_a.y, b_a.y)),
+                                         fmaf(aB, __uint_as_float(r[4 * kg + 3]), fmaf(nB, c_g.y, b_g.y))));
           }
         }
       }
@@ -459,6 +569,12 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
     const int pd = p.rope_pd;
     const int units = pd == 32 ? 2 : 1;
     const bool on_the_fly = p.rope_freq != nullptr;  // warp-uniform
+    const bool dln = p.ln_stat != nullptr;           // deferred LayerNorm: x = rstd acc + (nm c + b') before the rotation
+    float lnA0, lnN0, lnA1, lnN1, lnA2, lnN2, lnA3, lnN3;  // rows row0 + g + {0, 8, 16, 24}
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g, row0 + g < p.M, p.ln_inv_h, lnA0, lnN0);
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 8, row0 + g + 8 < p.M, p.ln_inv_h, lnA1, lnN1);
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 16, row0 + g + 16 < p.M, p.ln_inv_h, lnA2, lnN2);
+    ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 24, row0 + g + 24 < p.M, p.ln_inv_h, lnA3, lnN3);
     bool waited = false;
 #pragma unroll 1
     for (int u = 0; u < units; ++u) {
@@ -477,18 +593,26 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         jbase = e0 - head * p.rope_half + w;            // rotary frequency index of the block's first column
         dbase = region * p.hidden + head * 2 * p.rope_half + jbase;
       }
-      float2 fr[8], bx1[8], bx2[8];
+      float2 fr[8], bx1[8], bx2[8], cx1[8], cx2[8];
 #pragma unroll
       for (int kb = 0; kb < 8; ++kb) {
-        fr[kb] = bx1[kb] = bx2[kb] = make_float2(0.f, 0.f);
+        fr[kb] = bx1[kb] = bx2[kb] = cx1[kb] = cx2[kb] = make_float2(0.f, 0.f);
         if (!in_range) continue;
         if (is_v) {  // plain blocks at pc1 and (PD != 32) pc1 + PD
           bx1[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
-          if (pd != 32) bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
+          if (dln) cx1[kb] = __ldg(reinterpret_cast<const float2*>(p.ln_c + pc1 + q2 + kb * 8));
+          if (pd != 32) {
+            bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
+            if (dln) cx2[kb] = __ldg(reinterpret_cast<const float2*>(p.ln_c + pc1 + pd + q2 + kb * 8));
+          }
         } else if (kb < nkb) {
           if (on_the_fly) fr[kb] = __ldg(reinterpret_cast<const float2*>(p.rope_freq + jbase + q2 + kb * 8));
           bx1[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
           bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + pd + q2 + kb * 8));
+          if (dln) {
+            cx1[kb] = __ldg(reinterpret_cast<const float2*>(p.ln_c + pc1 + q2 + kb * 8));
+            cx2[kb] = __ldg(reinterpret_cast<const float2*>(p.ln_c + pc1 + pd + q2 + kb * 8));
+          }
         }
       }
       if (!waited) {
@@ -497,9 +621,6 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         waited = true;
       }
       if (row0 >= p.M || !in_range) continue;           // warp-uniform
-      ResFrag nores;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) nores.v[i] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         if (row0 + hh * 16 >= p.M) break;
@@ -509,13 +630,12 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
         tmem_ld_16x64(tbase + b1, r1);
         if (pd != 32) tmem_ld_16x64(tbase + b1 + pd, r2);
         const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
+        const float aA = hh ? lnA2 : lnA0, nA = hh ? lnN2 : lnN0, aB = hh ? lnA3 : lnA1, nB = hh ? lnN3 : lnN1;
         if (is_v) {
           tmem_ld_wait();
           bf16* vo = static_cast<bf16*>(p.out) + out_off + rowA * p.ldo + pc1 + q2;
-          store_blk_fast<K_STORE_BF16, false, bf16>(r1, bx1, nores.v, vo, vo + 8 * p.ldo, nullptr, nullptr, okA, okB, pc1 + q2, p.N, 1.f, 1.f);
-          if (pd != 32)
-            store_blk_fast<K_STORE_BF16, false, bf16>(r2, bx2, nores.v, vo + pd, vo + 8 * p.ldo + pd, nullptr, nullptr, okA, okB,
-                                                      pc1 + pd + q2, p.N, 1.f, 1.f);
+          store_blk_bf16_ln(r1, bx1, cx1, vo, vo + 8 * p.ldo, okA, okB, pc1 + q2, p.N, aA, nA, aB, nB);
+          if (pd != 32) store_blk_bf16_ln(r2, bx2, cx2, vo + pd, vo + 8 * p.ldo + pd, okA, okB, pc1 + pd + q2, p.N, aA, nA, aB, nB);
           continue;
         }
         const unsigned seqT = static_cast<unsigned>(p.seq_T);
@@ -542,9 +662,12 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
               c2 = __ldg(reinterpret_cast<const float2*>((rr == 0 ? cosA : cosB) + kb * 8));
               s2 = __ldg(reinterpret_cast<const float2*>((rr == 0 ? sinA : sinB) + kb * 8));
             }
-            const float x1a = __uint_as_float(r1[4 * kb + 2 * rr]) + bx1[kb].x, x1b = __uint_as_float(r1[4 * kb + 2 * rr + 1]) + bx1[kb].y;
-            const float x2a = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]) + bx2[kb].x;
-            const float x2b = __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]) + bx2[kb].y;
+            const float ar = rr == 0 ? aA : aB, nr = rr == 0 ? nA : nB;
+            const float x1a = fmaf(ar, __uint_as_float(r1[4 * kb + 2 * rr]), fmaf(nr, cx1[kb].x, bx1[kb].x));
+            const float x1b = fmaf(ar, __uint_as_float(r1[4 * kb + 2 * rr + 1]), fmaf(nr, cx1[kb].y, bx1[kb].y));
+            const float x2a = fmaf(ar, __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr] : r2[4 * kb + 2 * rr]), fmaf(nr, cx2[kb].x, bx2[kb].x));
+            const float x2b =
+                fmaf(ar, __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]), fmaf(nr, cx2[kb].y, bx2[kb].y));
             if (rr == 0 ? okA : okB) {
               bf16* dst = outp + rr * 8 * p.ldo + kb * 8;
               *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * c2.x - x2a * s2.x, x1b * c2.y - x2b * s2.y);
@@ -603,6 +726,15 @@ __device__ __forceinline__ ClusterPos cluster_pos(int cm, int cn) {
   return c;
 }
 
+// Register re-distribution between the warp roles (setmaxnreg, one instruction per warpgroup): warps 0-3 (TMA producer,
+// MMA issuer, TMEM allocator, idle) shrink to 56 registers, the two epilogue warpgroups grow from the launch-bound limit
+// of 168 to 224 -- the fused epilogues (RoPE, GLU, residual + statistics) keep two accumulator blocks, their constants and
+// the prefetched residual live at once and spilled at 168.
+constexpr int REGS_CTRL = 56, REGS_EPI = 224;
+static_assert(128 * REGS_CTRL + 256 * REGS_EPI <= 65536, "register re-distribution exceeds the register file");
+__device__ __forceinline__ void regs_shrink_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL)); }
+__device__ __forceinline__ void regs_grow_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI)); }
+
 template <int EPI, bool B_KN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
@@ -648,6 +780,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    regs_shrink_ctrl();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -694,6 +827,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (single thread) ===========================
+    regs_shrink_ctrl();
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, B_KN);
       const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
@@ -728,6 +862,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp >= EPI_WARP0) {
     // =========================== epilogue: TMEM -> registers -> global ===========================
+    regs_grow_epi();
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may touch
     const int half_sel = ew >> 2;  // which 4 of the 8 column chunks
@@ -749,13 +884,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                                                                     : static_cast<long long>(p.M);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
       const long long ls_off = bo * p.sl_outer + bi * p.sl_inner;
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk < p.n_tiles ? n_blk : 0, out_off, res_off, bias_off, ls_off,
+      const long long st_off = (bo * p.stat_rows_outer) * p.stat_parts + static_cast<long long>(bi) * p.stat_parts_item;
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk < p.n_tiles ? n_blk : 0, out_off, res_off, bias_off, ls_off, st_off,
                          &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+  } else {
+    regs_shrink_ctrl();  // warps 2 and 3 idle; the whole warpgroup has to execute the setmaxnreg
   }
 
   __syncwarp();
@@ -862,17 +1000,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   const int num_tiles = m_pairs * p.n_tiles;
 
   if (warp == 0) {
+    regs_shrink_ctrl();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       long long w_slot = 0;
-      const long long t_begin = p.dbg ? clock64() : 0;
+      const long long t_begin = (kDbgCounters && p.dbg) ? clock64() : 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
         const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
         const int m0 = m_pair * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (p.dbg) {
+          if (kDbgCounters && p.dbg) {
             const long long t0 = clock64();
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             w_slot += clock64() - t0;
@@ -886,12 +1025,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
-      if (p.dbg && rank == 0) {
+      if (kDbgCounters && p.dbg && rank == 0) {
         atomicAdd(p.dbg + 3, static_cast<unsigned long long>(w_slot));
         atomicAdd(p.dbg + 4, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
   } else if (warp == 1) {
+    regs_shrink_ctrl();
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, false, false);
       int stage = 0;
@@ -899,9 +1039,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       int as = 0;
       uint32_t aphase = 0;
       long long w_ops = 0, w_acc = 0;
-      const long long t_begin = p.dbg ? clock64() : 0;
+      const long long t_begin = (kDbgCounters && p.dbg) ? clock64() : 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-        if (p.dbg) {
+        if (kDbgCounters && p.dbg) {
           const long long t0 = clock64();
           mbar_wait(&tmem_empty[as], aphase ^ 1u);
           w_acc += clock64() - t0;
@@ -910,7 +1050,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (p.dbg) {
+          if (kDbgCounters && p.dbg) {
             const long long t0 = clock64();
             mbar_wait(&full_bar[stage], phase);
             w_ops += clock64() - t0;
@@ -931,13 +1071,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         umma_commit_2sm(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      if (p.dbg) {
+      if (kDbgCounters && p.dbg) {
         atomicAdd(p.dbg + 0, static_cast<unsigned long long>(w_ops));
         atomicAdd(p.dbg + 1, static_cast<unsigned long long>(w_acc));
         atomicAdd(p.dbg + 2, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
   } else if (warp >= EPI_WARP0) {
+    regs_grow_epi();
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;
     const int half_sel = ew >> 2;
@@ -947,12 +1088,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
       const long long row0 = static_cast<long long>(m_pair) * 2 * BLOCK_M + rank * BLOCK_M + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N);
-      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0, 0, &tmem_full[as], aphase);
+      epilogue_tile<EPI>(p, lane, half_sel, t_row, row0, n_blk, 0, 0, 0, 0, 0, &tmem_full[as], aphase);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+  } else {
+    regs_shrink_ctrl();  // warps 2 and 3 idle; the whole warpgroup has to execute the setmaxnreg
   }
 
   __syncwarp();
@@ -991,6 +1134,9 @@ struct SmDev {
   int npad;
   float* lpart; long long sl_inner, sl_outer;
   int csize, cm, stages;  // csize key tiles per row (cluster columns), cm query blocks per cluster (cluster rows)
+  // deferred LayerNorm of the query operand (HAS_BIAS variant): s = alpha (rstd acc - rstd mean c[col]) + bias[col];
+  // statistics row = outer batch index * M + query row; c has the layout / strides of bias
+  const float2* ln_stat; int ln_parts; float ln_inv_h; const float* ln_c;
 };
 
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
@@ -1011,15 +1157,6 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ float quad_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-}
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v + __shfl_xor_sync(0xffffffffu, v, 2);
-}
-
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     tc_scores_softmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const SmDev p) {
@@ -1071,6 +1208,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    regs_shrink_ctrl();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -1100,6 +1238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    regs_shrink_ctrl();
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
       int stage = 0;
@@ -1132,6 +1271,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp >= EPI_WARP0) {
     // =========================== softmax epilogue ===========================
+    regs_grow_epi();
     // warp -> TMEM lanes [32 (warp & 3), +32); its 16-row half hsel = (warp - EPI_WARP0) >> 2; all 256 tile columns
     const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3, hsel = ew >> 2;
@@ -1149,7 +1289,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const long long rowA = static_cast<long long>(m_blk) * BLOCK_M + trow + g;
       const bool okA = rowA < p.M, okB = rowA + 8 < p.M;
       const float* bias = HAS_BIAS ? p.bias + bo * p.sb_outer + bi * p.sb_inner : nullptr;
+      const float* lnc = (HAS_BIAS && p.ln_stat != nullptr) ? p.ln_c + bo * p.sb_outer + bi * p.sb_inner : nullptr;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(trow) << 16) + static_cast<uint32_t>(as * BLOCK_N);
+      // s' = aX acc + (nX c + bias log2e): (alpha2, 0) without the deferred LayerNorm
+      float aA = p.alpha2, nA = 0.f, aB = p.alpha2, nB = 0.f;
+      if (HAS_BIAS && lnc != nullptr) {
+        const long long srow = static_cast<long long>(bo) * p.M + rowA;
+        ln_row_coef(p.ln_stat, p.ln_parts, srow, okA, p.ln_inv_h, aA, nA);
+        ln_row_coef(p.ln_stat, p.ln_parts, srow + 8, okB, p.ln_inv_h, aB, nB);
+        aA *= p.alpha2; nA *= p.alpha2; aB *= p.alpha2; nB *= p.alpha2;
+      }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
 
@@ -1161,14 +1310,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (col0 - q2 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_16x64(t_row + cbk * 64, r);
-        float2 bb[8];
+        float2 bb[8], cc[8];
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
-          bb[kb] = make_float2(0.f, 0.f);
+          bb[kb] = cc[kb] = make_float2(0.f, 0.f);
           if (HAS_BIAS) {
             const int c = col0 + kb * 8;
             if (c < p.N) bb[kb].x = __ldg(bias + c) * 1.4426950408889634f;
             if (c + 1 < p.N) bb[kb].y = __ldg(bias + c + 1) * 1.4426950408889634f;
+            if (lnc != nullptr) {
+              if (c < p.N) cc[kb].x = __ldg(lnc + c);
+              if (c + 1 < p.N) cc[kb].y = __ldg(lnc + c + 1);
+            }
           }
         }
         tmem_ld_wait();
@@ -1176,12 +1329,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         for (int kb = 0; kb < 8; ++kb) {
           const int c = col0 + kb * 8;
           if (c < p.N) {
-            mA = fmaxf(mA, fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x));
-            mB = fmaxf(mB, fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x));
+            mA = fmaxf(mA, fmaf(aA, __uint_as_float(r[4 * kb]), fmaf(nA, cc[kb].x, bb[kb].x)));
+            mB = fmaxf(mB, fmaf(aB, __uint_as_float(r[4 * kb + 2]), fmaf(nB, cc[kb].x, bb[kb].x)));
           }
           if (c + 1 < p.N) {
-            mA = fmaxf(mA, fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y));
-            mB = fmaxf(mB, fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y));
+            mA = fmaxf(mA, fmaf(aA, __uint_as_float(r[4 * kb + 1]), fmaf(nA, cc[kb].y, bb[kb].y)));
+            mB = fmaxf(mB, fmaf(aB, __uint_as_float(r[4 * kb + 3]), fmaf(nB, cc[kb].y, bb[kb].y)));
           }
         }
       }
@@ -1223,14 +1376,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (col0 - q2 >= p.npad) break;  // warp-uniform (npad >= N)
         uint32_t r[32];
         tmem_ld_16x64(t_row + cbk * 64, r);
-        float2 bb[8];
+        float2 bb[8], cc[8];
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
-          bb[kb] = make_float2(0.f, 0.f);
+          bb[kb] = cc[kb] = make_float2(0.f, 0.f);
           if (HAS_BIAS) {
             const int c = col0 + kb * 8;
             if (c < p.N) bb[kb].x = __ldg(bias + c) * 1.4426950408889634f;
             if (c + 1 < p.N) bb[kb].y = __ldg(bias + c + 1) * 1.4426950408889634f;
+            if (lnc != nullptr) {
+              if (c < p.N) cc[kb].x = __ldg(lnc + c);
+              if (c + 1 < p.N) cc[kb].y = __ldg(lnc + c + 1);
+            }
           }
         }
         tmem_ld_wait();
@@ -1238,10 +1395,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         for (int kb = 0; kb < 8; ++kb) {
           const int c = col0 + kb * 8;
           const bool v0 = c < p.N, v1 = c + 1 < p.N;
-          const float a0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) - mA) : 0.f;
-          const float a1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) - mA) : 0.f;
-          const float b0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) - mB) : 0.f;
-          const float b1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) - mB) : 0.f;
+          const float a0 = v0 ? ex2_approx(fmaf(aA, __uint_as_float(r[4 * kb]), fmaf(nA, cc[kb].x, bb[kb].x)) - mA) : 0.f;
+          const float a1 = v1 ? ex2_approx(fmaf(aA, __uint_as_float(r[4 * kb + 1]), fmaf(nA, cc[kb].y, bb[kb].y)) - mA) : 0.f;
+          const float b0 = v0 ? ex2_approx(fmaf(aB, __uint_as_float(r[4 * kb + 2]), fmaf(nB, cc[kb].x, bb[kb].x)) - mB) : 0.f;
+          const float b1 = v1 ? ex2_approx(fmaf(aB, __uint_as_float(r[4 * kb + 3]), fmaf(nB, cc[kb].y, bb[kb].y)) - mB) : 0.f;
           sumA += a0 + a1;
           sumB += b0 + b1;
           if (store2 && c < p.npad) {  // npad is even: the pair (c, c + 1) is inside the row
@@ -1267,14 +1424,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if (col0 - q2 >= p.npad) break;
           uint32_t r[32];
           tmem_ld_16x64(t_row + cbk * 64, r);
-          float2 bb[8];
+          float2 bb[8], cc[8];
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {
-            bb[kb] = make_float2(0.f, 0.f);
+            bb[kb] = cc[kb] = make_float2(0.f, 0.f);
             if (HAS_BIAS) {
               const int c = col0 + kb * 8;
               if (c < p.N) bb[kb].x = __ldg(bias + c) * 1.4426950408889634f;
               if (c + 1 < p.N) bb[kb].y = __ldg(bias + c + 1) * 1.4426950408889634f;
+              if (lnc != nullptr) {
+                if (c < p.N) cc[kb].x = __ldg(lnc + c);
+                if (c + 1 < p.N) cc[kb].y = __ldg(lnc + c + 1);
+              }
             }
           }
           tmem_ld_wait();
@@ -1283,10 +1444,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const int c = col0 + kb * 8;
             if (c >= p.npad) continue;
             const bool v0 = c < p.N, v1 = c + 1 < p.N;
-            const float a0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) - mA) * iA : 0.f;
-            const float a1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) - mA) * iA : 0.f;
-            const float b0 = v0 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) - mB) * iB : 0.f;
-            const float b1 = v1 ? ex2_approx(fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) - mB) * iB : 0.f;
+            const float a0 = v0 ? ex2_approx(fmaf(aA, __uint_as_float(r[4 * kb]), fmaf(nA, cc[kb].x, bb[kb].x)) - mA) * iA : 0.f;
+            const float a1 = v1 ? ex2_approx(fmaf(aA, __uint_as_float(r[4 * kb + 1]), fmaf(nA, cc[kb].y, bb[kb].y)) - mA) * iA : 0.f;
+            const float b0 = v0 ? ex2_approx(fmaf(aB, __uint_as_float(r[4 * kb + 2]), fmaf(nB, cc[kb].x, bb[kb].x)) - mB) * iB : 0.f;
+            const float b1 = v1 ? ex2_approx(fmaf(aB, __uint_as_float(r[4 * kb + 3]), fmaf(nB, cc[kb].y, bb[kb].y)) - mB) * iB : 0.f;
             if (okA) *reinterpret_cast<uint32_t*>(pA + c) = pack_bf16x2(a0, a1);
             if (okB) *reinterpret_cast<uint32_t*>(pB + c) = pack_bf16x2(b0, b1);
           }
@@ -1297,6 +1458,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+  } else {
+    regs_shrink_ctrl();  // warps 2 and 3 idle; the whole warpgroup has to execute the setmaxnreg
   }
 
   __syncwarp();
@@ -1503,6 +1666,18 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
   p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
   p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
+  p.stat_out = q.stat_out; p.stat_parts = q.stat_parts; p.stat_rows_outer = q.stat_rows_outer;
+  p.stat_parts_item = static_cast<int>(ceil_div(q.N, 128));
+  p.ln_stat = q.ln_stat; p.ln_parts = q.ln_parts; p.ln_inv_h = q.ln_width > 0 ? 1.0f / static_cast<float>(q.ln_width) : 0.f;
+  p.ln_c = q.ln_c;
+  if (q.stat_out != nullptr)
+    DITTO_REQUIRE(q.epilogue == TC_EPI_STORE && q.resid && !q.out_bf16 && q.N % 2 == 0 && !g_force_generic &&
+                      q.stat_parts == q.batch_inner * p.stat_parts_item && (q.batch_outer == 1 || q.stat_rows_outer >= q.M),
+                  DITTO_E_UNSUPPORTED, "tc_gemm: row statistics need the fp32 + residual STORE epilogue and matching stat_parts");
+  if (q.ln_stat != nullptr)
+    DITTO_REQUIRE((q.epilogue == TC_EPI_GEGLU || q.epilogue == TC_EPI_QKV_ROPE) && q.ln_c && q.ln_parts > 0 && q.ln_width > 0 &&
+                      q.batch_inner == 1 && q.batch_outer == 1,
+                  DITTO_E_UNSUPPORTED, "tc_gemm: deferred LayerNorm is implemented in the GEGLU / QKV_ROPE epilogues only");
   p.dbg = g_dbg;
 
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
@@ -1613,6 +1788,10 @@ int launch_tc_scores_softmax(const TcScoresSoftmaxParams& q, cudaStream_t st) {
   p.npad = q.npad;
   p.lpart = q.lpart; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.csize = csize; p.stages = g_stages_1cta;
+  p.ln_stat = q.ln_stat; p.ln_parts = q.ln_parts; p.ln_inv_h = q.ln_width > 0 ? 1.0f / static_cast<float>(q.ln_width) : 0.f;
+  p.ln_c = q.ln_c;
+  if (q.ln_stat != nullptr)
+    DITTO_REQUIRE(q.bias && q.ln_c && q.ln_parts > 0 && q.ln_width > 0, DITTO_E_BADARG, "tc_scores_softmax: deferred LayerNorm arguments");
   int cm = q.cluster_m > 0 ? q.cluster_m : (g_cluster_m > 0 ? g_cluster_m : 1);
   cm = std::max(1, std::min(cm, std::min(p.m_tiles, SM_MAX_CLUSTER / csize)));
   p.cm = cm;

@@ -9,12 +9,13 @@ namespace ditto {
 // ---- elementwise.cu ----------------------------------------------------------------------------------
 int launch_cast_bf16(const float* x, bf16* y, int64_t n, cudaStream_t st);
 int launch_pack_rows(const float* x, bf16* y, float* bias_out, const float* bias_in, const int* perm, int rows, int K,
-                     cudaStream_t st);
+                     cudaStream_t st, const float* gamma = nullptr, const float* beta = nullptr, float* csum = nullptr);
+int launch_rowsum_bf16(const bf16* x, float* out, int64_t groups, int S, int Sp, int K, cudaStream_t st);
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* y, bool out_bf16, int64_t rows, int H,
                      cudaStream_t st);
 int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
                     int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
-                    int64_t n_seq, int T, int H, cudaStream_t st);
+                    int64_t n_seq, int T, int H, cudaStream_t st, float2* stat = nullptr);
 int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, float* freq_out, int max_T, int half, int head_dim,
                       cudaStream_t st);
 int launch_rope(void* qkv, bool is_bf16, int64_t ld, const float* cos_t, const float* sin_t, int64_t rows, int seq_T,
@@ -83,6 +84,14 @@ struct TcGemmParams {
   const float* row_lsum = nullptr; int row_lparts = 0; int64_t sl_inner = 0, sl_outer = 0;
   // cluster shape in tiles for the 1-CTA kernel (operands shared by TMA multicast); 0 = library default
   int cluster_m = 0, cluster_n = 0;
+  // Deferred LayerNorm (see DevParams in gemm_tc.cu).
+  //  producer (STORE with fp32 residual, even N): stat_out[(outer * stat_rows_outer + row) * stat_parts + inner *
+  //    ceil(N / 128) + slab] = (sum, sum of squares) of the 128-column slab of the stored row; stat_parts must equal
+  //    batch_inner * ceil(N / 128)
+  //  consumer (QKV_ROPE / GEGLU, unbatched): ln_stat [M, ln_parts] as written by a producer over rows of width ln_width;
+  //    ln_c [N] = row sums of the gamma-scaled weight; `bias` must already contain W beta
+  float2* stat_out = nullptr; int stat_parts = 0; int64_t stat_rows_outer = 0;
+  const float2* ln_stat = nullptr; int ln_parts = 0; int ln_width = 0; const float* ln_c = nullptr;
 };
 int launch_tc_gemm(const TcGemmParams& p, cudaStream_t st);
 
@@ -101,6 +110,8 @@ struct TcScoresSoftmaxParams {
   int npad = 0;                                 // zero-fill bound (multiple of 2, >= N)
   float* lpart = nullptr; int64_t sl_inner = 0, sl_outer = 0;  // [M, csize] per batch item; required when csize > 1
   int cluster_m = 0;                            // query-row tiles per cluster (K blocks multicast across them); 0 = default
+  // deferred LayerNorm of Q (needs bias): statistics row = outer batch index * M + query row; ln_c strided like bias
+  const float2* ln_stat = nullptr; int ln_parts = 0; int ln_width = 0; const float* ln_c = nullptr;
   int tag = PC_TC_OTHER;
 };
 int tc_scores_softmax_csize(int N);             // cluster size the kernel will use for N key columns (0: unsupported)

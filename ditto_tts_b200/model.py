@@ -110,13 +110,16 @@ class DiTTO(nn.Module):
         ``nac=<module>`` to attach one; ``nac.*`` keys of reference checkpoints are ignored on load;
       * extra keywords ``precision`` ("bf16" tensor-core path | "fp32" CUDA-core parity path),
         ``max_seq_len`` (RoPE table rows), ``fused_rope`` (RoPE in the QKV GEMM epilogue) and ``fold_cross``
-        (cross-attention q/out projections folded into the per-utterance text K/V; single-head models only).
+        (cross-attention q/out projections folded into the per-utterance text K/V; single-head models only),
+        ``fused_attn`` (scores + softmax in one kernel) and ``defer_ln`` (block LayerNorms folded into the GEMMs
+        on either side: no LayerNorm pass over HBM; parity-tested, off by default -- on B200 the heavier GEMM
+        epilogues cost more than the 14 LayerNorm launches they replace, see profiles/README.md).
     """
 
     def __init__(self, hidden_dim=768, num_layers=12, num_heads=12, time_dim=256, text_dim=768,
                  diffusion_steps=1000, lambda_factor=0.1, nac_model_path=None, *, nac: Optional[nn.Module] = None,
                  precision: str = "bf16", max_seq_len: int = 4096, fused_rope: bool = True,
-                 fold_cross: bool = True, fused_attn: bool = True):
+                 fold_cross: bool = True, fused_attn: bool = True, defer_ln: bool = False):
         super().__init__()
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -126,6 +129,7 @@ class DiTTO(nn.Module):
         self.precision, self.max_seq_len, self.fused_rope = precision, max_seq_len, fused_rope
         self.fold_cross = fold_cross
         self.fused_attn = fused_attn
+        self.defer_ln = defer_ln and fused_rope
         if nac is not None:
             self.nac = nac
         # construction order == reference (DiTTO.py:36-64): seeded default init gives the same weights
@@ -185,7 +189,8 @@ class DiTTO(nn.Module):
                                   max_seq_len=self.max_seq_len,
                                   flags=(_lib.F_FUSED_ROPE if self.fused_rope else 0) |
                                   (_lib.F_FOLD_CROSS if self.fold_cross else 0) |
-                                  (_lib.F_FUSED_ATTN if self.fused_attn else 0))
+                                  (_lib.F_FUSED_ATTN if self.fused_attn else 0) |
+                                  (_lib.F_DEFER_LN if self.defer_ln else 0))
                 h = C.c_void_p()
                 _lib.check(lib.ditto_engine_create(C.byref(cfg), C.byref(h)), "ditto_engine_create")
                 self._engine = h

@@ -48,7 +48,10 @@ enum {
 enum {
   DITTO_F_FUSED_ROPE = 1 << 0, /* RoPE fused into the QKV GEMM epilogue (column-permuted weights) */
   DITTO_F_FOLD_CROSS = 1 << 1, /* fold cross-attn q/out projections into the per-utterance text K/V */
-  DITTO_F_FUSED_ATTN = 1 << 2  /* scores + softmax in one cluster kernel (fp32 scores never leave TMEM)   */
+  DITTO_F_FUSED_ATTN = 1 << 2, /* scores + softmax in one cluster kernel (fp32 scores never leave TMEM)   */
+  DITTO_F_DEFER_LN = 1 << 3    /* block LayerNorms (DiT.py:105,143,151) folded into the neighbouring GEMMs: the producer
+                                  epilogue emits bf16(h) + per-row partial (sum, sum of squares), gamma/beta live in the
+                                  consumer's weights/bias and its epilogue applies rstd / mean (needs DITTO_F_FUSED_ROPE)  */
 };
 
 /* Shapes of one DiTTO instance == ctor arguments of the reference, src/model/DiTTO.py:10-19

@@ -28,11 +28,15 @@ def dev():
     return torch.device("cuda:0")
 
 
-def build_model(cfg, sd, precision, dev, fused_rope=True, fold_cross=None):
-    fold_cross = fused_rope if fold_cross is None else fold_cross   # 'fused=False' runs the plain composition
+def build_model(cfg, sd, precision, dev, fused_rope=True, fold_cross=None, defer_ln=False):
+    """fused_rope=False runs the plain composition (separate RoPE / LayerNorm / projection kernels);
+    fused_rope="defer_ln" adds the LayerNorm folding (DITTO_F_DEFER_LN) to the default fusions."""
+    if fused_rope == "defer_ln":
+        fused_rope, defer_ln = True, True
+    fold_cross = fused_rope if fold_cross is None else fold_cross
     m = D.DiTTO(hidden_dim=cfg.hidden_dim, num_layers=cfg.num_layers, num_heads=cfg.num_heads, time_dim=cfg.time_dim,
                 text_dim=cfg.text_dim, diffusion_steps=cfg.diffusion_steps, precision=precision, fused_rope=fused_rope,
-                fold_cross=fold_cross)
+                fold_cross=fold_cross, defer_ln=defer_ln)
     m.load_state_dict(sd, strict=True)
     return m.to(dev)
 
@@ -160,7 +164,7 @@ def test_tiny_forward_vs_reference_golden(dev, golden, precision):
     assert rel(out, torch.from_numpy(g["out"])) <= BAR[precision]
 
 
-@pytest.mark.parametrize("precision,fused", [("fp32", True), ("bf16", True), ("bf16", False)])
+@pytest.mark.parametrize("precision,fused", [("fp32", True), ("bf16", True), ("bf16", "defer_ln"), ("bf16", False)])
 @pytest.mark.parametrize("name", ["c1_default", "ctor_default", "ragged"])
 def test_full_size_forward_vs_reference_golden(dev, golden, name, precision, fused):
     """C1 (B=1, T=750, S=64, repo-default 5 layers x 1 head of 768), the constructor-default model
@@ -199,6 +203,22 @@ def test_forward_vs_oracle_odd_shapes(dev, precision):
     out = m.forward_with_context(x.to(dev), ctx, t.to(dev), 4, S)
     ref = O.ditto_forward(sd, cfg, torch.cat([x, x]), both, t)
     assert rel(out, ref) <= BAR[precision]
+
+
+@pytest.mark.parametrize("fused", [True, "defer_ln"])
+def test_layernorm_folding_with_offset_rows(dev, fused):
+    """Deferred LayerNorm consumes bf16(h) and per-row (sum, sum of squares) instead of LN(h): rows whose mean is several
+    standard deviations away from zero (AdaLN shift biased by +4) and a multi-head model (per-head statistics parts,
+    materialised LN2) must still meet the bf16 bar."""
+    for heads, (B, T, S) in ((1, (2, 300, 33)), (4, (2, 131, 40))):
+        cfg = O.OracleConfig(256, 2, heads, 64, 256, 20)
+        sd = O.make_state_dict(cfg, 41)
+        sd["ada_ln.time_mlp.1.bias"][cfg.hidden_dim:] += 4.0
+        x, text, _ = O.make_inputs(B, T, S, cfg, 42)
+        t = torch.tensor([0, 19])
+        ref = O.ditto_forward(sd, cfg, x, text, t)
+        out = build_model(cfg, sd, "bf16", dev, fused)(x.to(dev), text.to(dev), t.to(dev))
+        assert rel(out, ref) <= BAR["bf16"], (heads, rel(out, ref))
 
 
 def test_long_sequence_bf16_vs_oracle(dev):
