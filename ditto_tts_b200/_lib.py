@@ -23,6 +23,11 @@ class Config(C.Structure):
                 ("reserved", C.c_int32 * 7)]
 
 
+class SeqGroup(C.Structure):
+    """ditto_seq_group_t: one group of equal-length sequences of a ragged batch."""
+    _fields_ = [("n_seq", C.c_int64), ("n_x", C.c_int64), ("T", C.c_int64), ("S", C.c_int64), ("ctx", C.c_void_p)]
+
+
 _P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
 # name -> (restype, argtypes); mirrors include/ditto_b200.h one to one
@@ -49,6 +54,9 @@ SIGNATURES = {
     "ditto_cfg_ddpm_update": (_I32, [_P, _P, _P, _P, _P, _P, _F, _P, _I64, _I64, _P]),
     "ditto_p_sample": (_I32, [_P, _P, _P, _P, _P, _I32, _F, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
     "ditto_q_sample": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "ditto_workspace_bytes_ragged": (_I64, [_P, C.POINTER(SeqGroup), _I64]),
+    "ditto_forward_ragged": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _P, _I64, _P]),
+    "ditto_p_sample_ragged": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _I32, _F, _P, _P, _P, _I64, _P]),
     "ditto_layernorm": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _P]),
     "ditto_gemm_f32": (_I32, [_P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64, _I64, _P, _P, _F, _I64, _I64, _I64,
                               _I64, _P]),

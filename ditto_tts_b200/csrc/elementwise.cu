@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256)
     adaln_ln_kernel(const float* __restrict__ x, int64_t n_x, const float* __restrict__ time_table,
                     const float* __restrict__ text_mod, const int64_t* __restrict__ t, int steps,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ h,
-                    OutT* __restrict__ u, bf16* __restrict__ xcast, int64_t n_seq, int T, int H, float2* __restrict__ stat) {
+                    OutT* __restrict__ u, bf16* __restrict__ xcast, int64_t n_seq, int T, int H, float2* __restrict__ stat,
+                    bool xcast_all, int* __restrict__ row_pos) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_seq * T) return;
@@ -204,11 +205,13 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
     if (i < nv_lane) v[i] = *reinterpret_cast<const float4*>(xr + ((i << 5) + lane) * 4);
-  if (xcast != nullptr && seq < n_x) {
+  if (xcast != nullptr && (xcast_all || seq < n_x)) {  // bf16 copy of x: once per distinct x, or per sequence (ragged batches)
+    bf16* xc = xcast + (xcast_all ? row : xrow) * H;
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i)
-      if (i < nv_lane) store4<bf16>(xcast + xrow * H + ((i << 5) + lane) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
+      if (i < nv_lane) store4<bf16>(xc + ((i << 5) + lane) * 4, v[i].x, v[i].y, v[i].z, v[i].w);
   }
+  if (row_pos != nullptr && lane == 0) row_pos[row] = static_cast<int>(pos);  // RoPE position table of a ragged batch
   float mean, rstd;
   row_stats(v, nv_lane, H, mean, rstd);
 #pragma unroll
@@ -255,16 +258,16 @@ __global__ void __launch_bounds__(256)
 
 int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
                     int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
-                    int64_t n_seq, int T, int H, cudaStream_t st, float2* stat) {
+                    int64_t n_seq, int T, int H, cudaStream_t st, float2* stat, bool xcast_all, int* row_pos) {
   DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128, DITTO_E_UNSUPPORTED, "adaln: need H % 4 == 0 and H <= 1024");
   const unsigned blocks = static_cast<unsigned>(ceil_div(n_seq * T, 8));
   ProfScope prof(PC_ADALN, st, 0.0, static_cast<double>(n_seq) * T * H * (u_bf16 ? 10 + 2 : 12));
   if (u_bf16)
     adaln_ln_kernel<bf16><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
-                                                  static_cast<bf16*>(u), xcast, n_seq, T, H, stat);
+                                                  static_cast<bf16*>(u), xcast, n_seq, T, H, stat, xcast_all, row_pos);
   else
     adaln_ln_kernel<float><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
-                                                   static_cast<float*>(u), xcast, n_seq, T, H, stat);
+                                                   static_cast<float*>(u), xcast, n_seq, T, H, stat, xcast_all, row_pos);
   DITTO_LAUNCH_CHECK();
   return 0;
 }

@@ -210,6 +210,18 @@ static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_
   return c;
 }
 
+// One group of equal-length sequences of a (possibly ragged) batch, with its offsets into the packed buffers.
+struct SeqGroup {
+  int64_t n = 0, n_x = 0, T = 0, S = 0;
+  const void* ctx = nullptr;
+  int64_t row0 = 0;    // first row of the group in the packed [M, *] activations (sequence layout)
+  int64_t xrow0 = 0;   // first row of the group's latents in the packed x / z / x_out buffers
+  int64_t seq0 = 0;    // index of the group's first sequence (t, per-sequence tables)
+  int64_t p_off = 0;   // element offset of the group's score / P scratch
+  int64_t l_off = 0;   // element offset of the group's partial-denominator scratch
+  int64_t vt_off = 0;  // element offset of the transposed-V scratch (debug fallback)
+};
+
 struct Workspace {
   float *h = nullptr, *xskip = nullptr, *scores = nullptr;
   void *u = nullptr, *qkv = nullptr, *P = nullptr, *qc = nullptr, *oc = nullptr, *hid = nullptr, *xb16 = nullptr;
@@ -220,24 +232,37 @@ struct Workspace {
   int ln_parts_h = 0, ln_parts_attn = 0;  // parts written by an N = H producer / by the per-head P.V producer
   float* tmp_small = nullptr;             // [n, Xd] pooled text
   bf16* text16 = nullptr;                 // [n*S, Xd]
-  int64_t Tp = 0, Sp = 0, ldp = 0;
+  int* row_pos = nullptr;                 // [M] position of each packed row inside its sequence (ragged batches: RoPE)
+  int64_t M = 0;                          // packed rows: sum over groups of n * T
   size_t total = 0;
 };
-static Workspace ws_layout(const ditto_engine* e, void* base, int64_t n, int64_t T, int64_t S) {
+// Lays the workspace out for `ng` groups and fills in the groups' offsets.  Token-wise buffers are sized by the packed
+// row count; the attention scratch is the sum over groups (so groups may run concurrently).
+static Workspace ws_layout(const ditto_engine* e, void* base, SeqGroup* gs, int ng) {
   Arena a(base);
   Workspace w;
-  const int64_t H = e->H, M = n * T;
+  const int64_t H = e->H;
   const int es = e->bf16_mode ? 2 : 4;
-  w.Tp = round_up(T, 8);
-  w.Sp = round_up(S, 8);
-  w.ldp = std::max(w.Tp, w.Sp);
+  int64_t M = 0, Mx = 0, seqs = 0, p_el = 0, l_el = 0, vt_el = 0, n_tot = 0, text_el = 0;
+  for (int i = 0; i < ng; ++i) {
+    SeqGroup& g = gs[i];
+    const int64_t ldp = std::max(round_up(g.T, 8), round_up(g.S, 8));
+    g.row0 = M; g.xrow0 = Mx; g.seq0 = seqs; g.p_off = p_el; g.l_off = l_el; g.vt_off = vt_el;
+    M += g.n * g.T; Mx += g.n_x * g.T; seqs += g.n;
+    p_el += round_up(g.n * e->heads * g.T * ldp, 128);
+    l_el += round_up(g.n * e->heads * g.T * ceil_div(ldp, 256), 64);
+    vt_el += round_up(g.n * e->heads * e->d * ldp, 128);
+    n_tot = std::max(n_tot, g.n);
+    text_el = std::max(text_el, g.n * g.S);
+  }
+  w.M = M;
   w.h = a.take<float>(M * H);
   w.xskip = a.take<float>(M * H);
   w.u = a.take<char>(M * H * es);
   w.xb16 = a.take<char>(M * H * 2);
   w.qkv = a.take<char>(M * 3 * H * es);
-  w.scores = a.take<float>(n * e->heads * T * w.ldp);
-  w.P = e->bf16_mode ? static_cast<void*>(a.take<bf16>(n * e->heads * T * w.ldp)) : static_cast<void*>(w.scores);
+  w.scores = a.take<float>(p_el);
+  w.P = e->bf16_mode ? static_cast<void*>(a.take<bf16>(p_el)) : static_cast<void*>(w.scores);
   w.qc = a.take<char>(M * H * es);
   w.oc = a.take<char>(M * H * es);
   w.hid = a.take<char>(M * 4 * H * es);
@@ -245,16 +270,22 @@ static Workspace ws_layout(const ditto_engine* e, void* base, int64_t n, int64_t
     w.fc1 = a.take<float>(M * 4 * H);
     w.gate = a.take<float>(M * 4 * H);
   } else if (e->pv_transpose) {
-    w.vt = a.take<bf16>(n * e->heads * e->d * w.ldp);
+    w.vt = a.take<bf16>(vt_el);
   }
-  if (e->bf16_mode) w.lpart = a.take<float>(n * e->heads * T * ceil_div(w.ldp, 256));
+  if (e->bf16_mode) w.lpart = a.take<float>(l_el);
   w.ln_parts_h = static_cast<int>(ceil_div(H, 128));
   w.ln_parts_attn = static_cast<int>(e->heads * ceil_div(e->d, 128));
   if (e->defer_ln) w.lnstat = a.take<float2>(M * std::max(w.ln_parts_h, w.ln_parts_attn));
-  w.tmp_small = a.take<float>(n * e->Xd);
-  w.text16 = a.take<bf16>(n * S * e->Xd);
+  w.tmp_small = a.take<float>(n_tot * e->Xd);
+  w.text16 = a.take<bf16>(text_el * e->Xd);
+  if (ng > 1) w.row_pos = a.take<int>(M);
   w.total = a.off + 256;
   return w;
+}
+static Workspace ws_layout(const ditto_engine* e, void* base, int64_t n, int64_t T, int64_t S) {
+  SeqGroup g;
+  g.n = n; g.n_x = n; g.T = T; g.S = S;
+  return ws_layout(e, base, &g, 1);
 }
 
 }  // namespace ditto
@@ -343,37 +374,63 @@ static int attention_f32(ditto_engine* e, const Workspace& w, const float* q, in
   return 0;
 }
 
-static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void* ctx, const int64_t* t, int64_t n, int64_t T,
-                        int64_t S, float* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+// Workspace view of one group: the attention scratch pointers moved to the group's slice.
+static Workspace group_view(const ditto_engine* e, const Workspace& w, const SeqGroup& g) {
+  Workspace v = w;
+  v.scores = w.scores ? w.scores + g.p_off : nullptr;
+  v.P = e->bf16_mode ? static_cast<void*>(static_cast<bf16*>(w.P) + g.p_off) : static_cast<void*>(v.scores);
+  v.lpart = w.lpart ? w.lpart + g.l_off : nullptr;
+  v.vt = w.vt ? w.vt + g.vt_off : nullptr;
+  return v;
+}
+
+// One DiTTO forward over `ng` groups of equal-length sequences packed back to back (group-major, sequences of a group
+// contiguous).  Everything that works on single rows (LayerNorm, the QKV / GLU / fc2 / projection GEMMs) runs ONCE over
+// all packed rows; only what depends on sequence boundaries (AdaLN modulation, attention, RoPE positions) runs per group.
+// ng == 1 is the uniform batch of ditto_forward (x shared between CFG branches through n_x).
+static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGroup* gs, int ng, float* out, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t st) {
   const int H = e->H, d = e->d;
-  const int64_t M = n * T;
+  Workspace w = ws_layout(e, workspace, gs, ng);
+  const int64_t M = w.M;
   DITTO_REQUIRE(M < (1ll << 31) / 8, DITTO_E_UNSUPPORTED, "forward: batch too large for one call (split it)");
-  Workspace w = ws_layout(e, workspace, n, T, S);
   DITTO_REQUIRE(static_cast<int64_t>(w.total) <= workspace_bytes, DITTO_E_WORKSPACE, "forward: workspace too small");
-  CtxLayout c = ctx_layout(e, const_cast<void*>(ctx), n, S);
+  const bool ragged = ng > 1;
   const bool b16 = e->bf16_mode;
   const float inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(d));          // DiT.py:131-132: scores / sqrt(d)
   const float sqrt_inv_d = sqrtf(1.0f / static_cast<float>(d));          // torch MHA: q * sqrt(1/d)
+  DITTO_REQUIRE(!(ragged && e->defer_ln), DITTO_E_UNSUPPORTED, "forward: ragged batches do not support DITTO_F_DEFER_LN");
+  const SeqGroup& g0 = gs[0];
 
   // deferred LayerNorm: `u` holds bf16(h) and w.lnstat the row statistics; ln1_parts = parts written by the last producer
   const bool dln = e->defer_ln;
-  const bool dln2 = fold_ln_active(e, S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
+  const bool dln2 = dln && fold_ln_active(e, g0.S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
   int ln1_parts = 1;
   // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
-  DITTO_TRY(launch_adaln_ln(x, n_x, e->time_table, c.text_mod, t, e->steps, e->LW(0, "norm1.weight"), e->LW(0, "norm1.bias"), w.h, w.u,
-                            b16, b16 ? static_cast<bf16*>(w.xb16) : nullptr, n, static_cast<int>(T), H, st, dln ? w.lnstat : nullptr));
-  // x_skip = proj_in(x), once per distinct x                               DiTTO.py:83
-  const int Mx = static_cast<int>(n_x * T);
-  if (b16)
-    DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_in16, H, w.xskip, false, H, e->W("proj_in.bias"), nullptr, 0, 0, nullptr, 0, Mx, H,
+  for (int gi = 0; gi < ng; ++gi) {
+    const SeqGroup& g = gs[gi];
+    CtxLayout c = ctx_layout(e, const_cast<void*>(g.ctx), g.n, g.S);
+    const int es = b16 ? 2 : 4;
+    // ragged: the bf16 copy of x is written for EVERY sequence (sequence layout) so that proj_in / proj_out stay single GEMMs
+    bf16* xc = b16 ? static_cast<bf16*>(w.xb16) + (ragged ? g.row0 : g.xrow0) * H : nullptr;
+    DITTO_TRY(launch_adaln_ln(x + g.xrow0 * H, g.n_x, e->time_table, c.text_mod, t + g.seq0, e->steps, e->LW(0, "norm1.weight"),
+                              e->LW(0, "norm1.bias"), w.h + g.row0 * H, static_cast<char*>(w.u) + g.row0 * H * es, b16, xc, g.n,
+                              static_cast<int>(g.T), H, st, dln ? w.lnstat : nullptr, ragged, ragged ? w.row_pos + g.row0 : nullptr));
+  }
+  // x_skip = proj_in(x): once per distinct x (uniform batch) / per packed row (ragged)      DiTTO.py:83
+  if (b16) {
+    const int Mp = static_cast<int>(ragged ? M : g0.n_x * g0.T);
+    DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_in16, H, w.xskip, false, H, e->W("proj_in.bias"), nullptr, 0, 0, nullptr, 0, Mp, H,
                     H, st, PC_TC_PROJ_IN));
-  else
-    DITTO_TRY(sgemm_nt(x, H, e->W("proj_in.weight"), H, w.xskip, H, e->W("proj_in.bias"), nullptr, 0, 1.f, Mx, H, H, st));
+  } else {
+    for (int gi = 0; gi < ng; ++gi)  // fp32: x-layout rows, group by group
+      DITTO_TRY(sgemm_nt(x + gs[gi].xrow0 * H, H, e->W("proj_in.weight"), H, w.xskip + gs[gi].xrow0 * H, H, e->W("proj_in.bias"), nullptr, 0,
+                         1.f, static_cast<int>(gs[gi].n_x * gs[gi].T), H, H, st));
+  }
 
   for (int i = 0; i < e->L; ++i) {
     const LayerPack& lp = e->layers[i];
     const bool last = (i == e->L - 1);
-    void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
     if (b16) {
       bf16* u = static_cast<bf16*>(w.u);
       bf16* qkv = static_cast<bf16*>(w.qkv);
@@ -387,65 +444,85 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
         if (e->fused_rope) {
           g.epilogue = TC_EPI_QKV_ROPE; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_half = e->half;
           g.rope_freq = e->rope_table_in_epilogue ? nullptr : e->rope_freq;
-          g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(T); g.hidden = H;
+          g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(g0.T); g.hidden = H;
+          g.rope_pos = ragged ? w.row_pos : nullptr;
         }
         if (dln) { g.ln_stat = w.lnstat; g.ln_parts = ln1_parts; g.ln_width = H; g.ln_c = lp.c_qkv; }
         DITTO_TRY(launch_tc_gemm(g, st));
-        if (!e->fused_rope) DITTO_TRY(launch_rope(qkv, true, 3 * H, e->rope_cos, e->rope_sin, M, static_cast<int>(T), H, d, st));
+        if (!e->fused_rope)
+          for (int gi = 0; gi < ng; ++gi)
+            DITTO_TRY(launch_rope(qkv + gs[gi].row0 * 3 * H, true, 3 * H, e->rope_cos, e->rope_sin, gs[gi].n * gs[gi].T,
+                                  static_cast<int>(gs[gi].T), H, d, st));
       }
-      DITTO_TRY(attention_bf16(e, w, qkv, 3 * H, T * 3 * H, qkv + H, 3 * H, T * 3 * H, qkv + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
-                               static_cast<int>(T), inv_sqrt_d, w.h, false, H, T * H, w.h, st, false, dln2 ? u : nullptr,
-                               dln2 ? w.lnstat : nullptr));
+      for (int gi = 0; gi < ng; ++gi) {
+        const SeqGroup& g = gs[gi];
+        const Workspace wg = group_view(e, w, g);
+        bf16* q = qkv + g.row0 * 3 * H;
+        float* hg = w.h + g.row0 * H;
+        const int64_t T = g.T;
+        DITTO_TRY(attention_bf16(e, wg, q, 3 * H, T * 3 * H, q + H, 3 * H, T * 3 * H, q + 2 * H, 3 * H, T * 3 * H, g.n, static_cast<int>(T),
+                                 static_cast<int>(T), inv_sqrt_d, hg, false, H, T * H, hg, st, false, dln2 ? u : nullptr,
+                                 dln2 ? w.lnstat : nullptr));
+      }
       // ---- cross-attention (torch MHA math path)                                                     DiT.py:141-148
       if (!dln2) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
-      if (fold_active(e, S)) {
-        // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
-        const int heads = e->heads;
-        const int64_t Sp = w.Sp;
-        if (e->fused_attn && tc_scores_softmax_csize(static_cast<int>(S)) == 1) {
-          TcScoresSoftmaxParams f;
-          f.Q.ptr = u; f.Q.rows = T; f.Q.cols = H; f.Q.ld = H; f.Q.s_inner = 0; f.Q.s_outer = T * H;
-          f.Km.ptr = c.kfold0 + c.kfold_stride * i; f.Km.rows = S; f.Km.cols = H; f.Km.ld = H; f.Km.s_inner = S * H;
-          f.Km.s_outer = static_cast<int64_t>(heads) * S * H;
-          f.M = static_cast<int>(T); f.N = static_cast<int>(S); f.K = H; f.batch_inner = heads; f.batch_outer = static_cast<int>(n);
-          f.alpha = sqrt_inv_d; f.bias = c.sbias0 + c.sbias_stride * i; f.sb_inner = Sp; f.sb_outer = heads * Sp;
-          f.P = static_cast<bf16*>(w.P); f.ldp = heads * Sp; f.sp_inner = Sp; f.sp_outer = T * heads * Sp; f.npad = static_cast<int>(Sp);
-          f.tag = PC_TC_CROSS_SCORES;
-          if (dln2) { f.ln_stat = w.lnstat; f.ln_parts = w.ln_parts_attn; f.ln_width = H; f.ln_c = c.cvec0 + c.sbias_stride * i; }
-          DITTO_TRY(launch_tc_scores_softmax(f, st));
+      for (int gi = 0; gi < ng; ++gi) {
+        const SeqGroup& grp = gs[gi];
+        const Workspace wg = group_view(e, w, grp);
+        const CtxLayout c = ctx_layout(e, const_cast<void*>(grp.ctx), grp.n, grp.S);
+        const int64_t n = grp.n, T = grp.T, S = grp.S, Mg = n * T;
+        bf16* ug = u + grp.row0 * H;
+        float* hg = w.h + grp.row0 * H;
+        void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
+        if (fold_active(e, S)) {
+          // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
+          const int heads = e->heads;
+          const int64_t Sp = round_up(S, 8);
+          if (e->fused_attn && tc_scores_softmax_csize(static_cast<int>(S)) == 1) {
+            TcScoresSoftmaxParams f;
+            f.Q.ptr = ug; f.Q.rows = T; f.Q.cols = H; f.Q.ld = H; f.Q.s_inner = 0; f.Q.s_outer = T * H;
+            f.Km.ptr = c.kfold0 + c.kfold_stride * i; f.Km.rows = S; f.Km.cols = H; f.Km.ld = H; f.Km.s_inner = S * H;
+            f.Km.s_outer = static_cast<int64_t>(heads) * S * H;
+            f.M = static_cast<int>(T); f.N = static_cast<int>(S); f.K = H; f.batch_inner = heads; f.batch_outer = static_cast<int>(n);
+            f.alpha = sqrt_inv_d; f.bias = c.sbias0 + c.sbias_stride * i; f.sb_inner = Sp; f.sb_outer = heads * Sp;
+            f.P = static_cast<bf16*>(wg.P); f.ldp = heads * Sp; f.sp_inner = Sp; f.sp_outer = T * heads * Sp; f.npad = static_cast<int>(Sp);
+            f.tag = PC_TC_CROSS_SCORES;
+            if (dln2) { f.ln_stat = w.lnstat; f.ln_parts = w.ln_parts_attn; f.ln_width = H; f.ln_c = c.cvec0 + c.sbias_stride * i; }
+            DITTO_TRY(launch_tc_scores_softmax(f, st));
+          } else {
+            DITTO_REQUIRE(!dln2, DITTO_E_UNSUPPORTED, "forward: deferred LayerNorm needs the fused scores kernel on the folded cross path");
+            TcGemmParams g;
+            g.A.ptr = ug; g.A.rows = T; g.A.cols = H; g.A.ld = H; g.A.s_inner = 0; g.A.s_outer = T * H;
+            g.B.ptr = c.kfold0 + c.kfold_stride * i; g.B.rows = S; g.B.cols = H; g.B.ld = H; g.B.s_inner = S * H;
+            g.B.s_outer = static_cast<int64_t>(heads) * S * H;
+            g.M = static_cast<int>(T); g.N = static_cast<int>(S); g.K = H; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
+            g.alpha = sqrt_inv_d; g.bias = c.sbias0 + c.sbias_stride * i; g.sb_inner = Sp; g.sb_outer = heads * Sp;
+            g.out = wg.scores; g.out_bf16 = false; g.ldo = heads * Sp; g.so_inner = Sp; g.so_outer = T * heads * Sp;
+            g.tag = PC_TC_CROSS_SCORES;
+            DITTO_TRY(launch_tc_gemm(g, st));
+            DITTO_TRY(launch_softmax(wg.scores, Sp, wg.P, true, Sp, n * T * heads, static_cast<int>(S), st));
+          }
+          TcGemmParams o;
+          o.A.ptr = static_cast<const bf16*>(wg.P); o.A.rows = T; o.A.cols = heads * Sp; o.A.ld = heads * Sp; o.A.s_outer = T * heads * Sp;
+          o.B.ptr = c.vfold0 + c.vfold_stride * i; o.B.rows = heads * Sp; o.B.cols = H; o.B.ld = H; o.B.s_outer = heads * Sp * H;
+          o.b_kn = true;
+          o.M = static_cast<int>(T); o.N = H; o.K = static_cast<int>(heads * Sp); o.batch_inner = 1; o.batch_outer = static_cast<int>(n);
+          o.bias = e->LW(i, "cross_attn.out_proj.bias");
+          o.out = hg; o.out_bf16 = false; o.ldo = H; o.so_outer = T * H; o.resid = hg; o.ldr = H; o.sr_outer = T * H;
+          o.tag = PC_TC_CROSS_PV;
+          if (dln) { o.out2 = u; o.ldo2 = H; o.stat_out = w.lnstat; o.stat_parts = w.ln_parts_h; o.stat_rows_outer = T; }
+          DITTO_TRY(launch_tc_gemm(o, st));
         } else {
-          DITTO_REQUIRE(!dln2, DITTO_E_UNSUPPORTED, "forward: deferred LayerNorm needs the fused scores kernel on the folded cross path");
-          TcGemmParams g;
-          g.A.ptr = u; g.A.rows = T; g.A.cols = H; g.A.ld = H; g.A.s_inner = 0; g.A.s_outer = T * H;
-          g.B.ptr = c.kfold0 + c.kfold_stride * i; g.B.rows = S; g.B.cols = H; g.B.ld = H; g.B.s_inner = S * H;
-          g.B.s_outer = static_cast<int64_t>(heads) * S * H;
-          g.M = static_cast<int>(T); g.N = static_cast<int>(S); g.K = H; g.batch_inner = heads; g.batch_outer = static_cast<int>(n);
-          g.alpha = sqrt_inv_d; g.bias = c.sbias0 + c.sbias_stride * i; g.sb_inner = Sp; g.sb_outer = heads * Sp;
-          g.out = w.scores; g.out_bf16 = false; g.ldo = heads * Sp; g.so_inner = Sp; g.so_outer = T * heads * Sp;
-          g.tag = PC_TC_CROSS_SCORES;
-          DITTO_TRY(launch_tc_gemm(g, st));
-          DITTO_TRY(launch_softmax(w.scores, Sp, w.P, true, Sp, n * T * heads, static_cast<int>(S), st));
+          bf16* qc = static_cast<bf16*>(w.qc) + grp.row0 * H;
+          bf16* oc = static_cast<bf16*>(w.oc) + grp.row0 * H;
+          DITTO_TRY(tc_nt(ug, H, lp.wc_in, H, qc, true, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 0, nullptr, 0, static_cast<int>(Mg),
+                          H, H, st, PC_TC_CROSS_Q));
+          const bf16* kc = static_cast<const bf16*>(kv);
+          DITTO_TRY(attention_bf16(e, wg, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T),
+                                   static_cast<int>(S), sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
+          DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, hg, false, H, e->LW(i, "cross_attn.out_proj.bias"), hg, H, 0, dln ? u : nullptr, H,
+                          static_cast<int>(Mg), H, H, st, PC_TC_CROSS_OUT, dln ? w.lnstat : nullptr, w.ln_parts_h));
         }
-        TcGemmParams o;
-        o.A.ptr = static_cast<const bf16*>(w.P); o.A.rows = T; o.A.cols = heads * Sp; o.A.ld = heads * Sp; o.A.s_outer = T * heads * Sp;
-        o.B.ptr = c.vfold0 + c.vfold_stride * i; o.B.rows = heads * Sp; o.B.cols = H; o.B.ld = H; o.B.s_outer = heads * Sp * H;
-        o.b_kn = true;
-        o.M = static_cast<int>(T); o.N = H; o.K = static_cast<int>(heads * Sp); o.batch_inner = 1; o.batch_outer = static_cast<int>(n);
-        o.bias = e->LW(i, "cross_attn.out_proj.bias");
-        o.out = w.h; o.out_bf16 = false; o.ldo = H; o.so_outer = T * H; o.resid = w.h; o.ldr = H; o.sr_outer = T * H;
-        o.tag = PC_TC_CROSS_PV;
-        if (dln) { o.out2 = u; o.ldo2 = H; o.stat_out = w.lnstat; o.stat_parts = w.ln_parts_h; o.stat_rows_outer = T; }
-        DITTO_TRY(launch_tc_gemm(o, st));
-      } else {
-        bf16* qc = static_cast<bf16*>(w.qc);
-        bf16* oc = static_cast<bf16*>(w.oc);
-        DITTO_TRY(tc_nt(u, H, lp.wc_in, H, qc, true, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 0, nullptr, 0, static_cast<int>(M), H,
-                        H, st, PC_TC_CROSS_Q));
-        const bf16* kc = static_cast<const bf16*>(kv);
-        DITTO_TRY(attention_bf16(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
-                                 sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
-        DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, w.h, false, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 0, dln ? u : nullptr, H,
-                        static_cast<int>(M), H, H, st, PC_TC_CROSS_OUT, dln ? w.lnstat : nullptr, w.ln_parts_h));
       }
       // ---- gated MLP                                                                                  DiT.py:150-155
       if (!dln) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
@@ -468,19 +545,32 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
     } else {
       float* u = static_cast<float*>(w.u);
       float* qkv = static_cast<float*>(w.qkv);
-      DITTO_TRY(sgemm_nt(u, H, e->LW(i, "attn.in_proj_weight"), H, qkv, 3 * H, e->LW(i, "attn.in_proj_bias"), nullptr, 0, 1.f,
-                         static_cast<int>(M), 3 * H, H, st));
-      DITTO_TRY(launch_rope(qkv, false, 3 * H, e->rope_cos, e->rope_sin, M, static_cast<int>(T), H, d, st));
-      DITTO_TRY(attention_f32(e, w, qkv, 3 * H, T * 3 * H, qkv + H, 3 * H, T * 3 * H, qkv + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
-                              static_cast<int>(T), inv_sqrt_d, w.h, H, T * H, w.h, st));
-      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, false, M, H, st));
       float* qc = static_cast<float*>(w.qc);
       float* oc = static_cast<float*>(w.oc);
+      DITTO_TRY(sgemm_nt(u, H, e->LW(i, "attn.in_proj_weight"), H, qkv, 3 * H, e->LW(i, "attn.in_proj_bias"), nullptr, 0, 1.f,
+                         static_cast<int>(M), 3 * H, H, st));
+      for (int gi = 0; gi < ng; ++gi) {
+        const SeqGroup& g = gs[gi];
+        const Workspace wg = group_view(e, w, g);
+        float* q = qkv + g.row0 * 3 * H;
+        float* hg = w.h + g.row0 * H;
+        const int64_t T = g.T;
+        DITTO_TRY(launch_rope(q, false, 3 * H, e->rope_cos, e->rope_sin, g.n * T, static_cast<int>(T), H, d, st));
+        DITTO_TRY(attention_f32(e, wg, q, 3 * H, T * 3 * H, q + H, 3 * H, T * 3 * H, q + 2 * H, 3 * H, T * 3 * H, g.n, static_cast<int>(T),
+                                static_cast<int>(T), inv_sqrt_d, hg, H, T * H, hg, st));
+      }
+      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, false, M, H, st));
       DITTO_TRY(sgemm_nt(u, H, e->LW(i, "cross_attn.in_proj_weight"), H, qc, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 1.f,
                          static_cast<int>(M), H, H, st));
-      const float* kc = static_cast<const float*>(kv);
-      DITTO_TRY(attention_f32(e, w, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T), static_cast<int>(S),
-                              sqrt_inv_d, oc, H, T * H, nullptr, st));
+      for (int gi = 0; gi < ng; ++gi) {
+        const SeqGroup& g = gs[gi];
+        const Workspace wg = group_view(e, w, g);
+        const CtxLayout c = ctx_layout(e, const_cast<void*>(g.ctx), g.n, g.S);
+        const float* kc = reinterpret_cast<const float*>(static_cast<const char*>(c.kv0) + c.kv_stride * i);
+        const int64_t T = g.T, S = g.S;
+        DITTO_TRY(attention_f32(e, wg, qc + g.row0 * H, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, g.n, static_cast<int>(T),
+                                static_cast<int>(S), sqrt_inv_d, oc + g.row0 * H, H, T * H, nullptr, st));
+      }
       DITTO_TRY(sgemm_nt(oc, H, e->LW(i, "cross_attn.out_proj.weight"), H, w.h, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 1.f,
                          static_cast<int>(M), H, H, st));
       DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, false, M, H, st));
@@ -497,15 +587,28 @@ static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void
   }
   // eps = x_skip + proj_out(h)                                              DiTTO.py:93-94
   if (b16) {
-    DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_out16, H, out, false, H, e->W("proj_out.bias"), w.xskip, H, n_x * T, nullptr, 0,
-                    static_cast<int>(M), H, H, st, PC_TC_PROJ_OUT));
+    DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_out16, H, out, false, H, e->W("proj_out.bias"), w.xskip, H,
+                    ragged ? 0 : g0.n_x * g0.T, nullptr, 0, static_cast<int>(M), H, H, st, PC_TC_PROJ_OUT));
   } else {
-    // residual rows repeat with period n_x*T: one GEMM per group of n_x sequences
-    for (int64_t g0 = 0; g0 < n; g0 += n_x)
-      DITTO_TRY(sgemm_nt(w.h + g0 * T * H, H, e->W("proj_out.weight"), H, out + g0 * T * H, H, e->W("proj_out.bias"), w.xskip, H, 1.f, Mx,
-                         H, H, st));
+    // residual rows repeat with period n_x*T inside a group: one GEMM per run of n_x sequences
+    for (int gi = 0; gi < ng; ++gi) {
+      const SeqGroup& g = gs[gi];
+      for (int64_t s0 = 0; s0 < g.n; s0 += g.n_x) {
+        const int64_t r = g.row0 + s0 * g.T;
+        DITTO_TRY(sgemm_nt(w.h + r * H, H, e->W("proj_out.weight"), H, out + r * H, H, e->W("proj_out.bias"), w.xskip + g.xrow0 * H, H, 1.f,
+                           static_cast<int>(g.n_x * g.T), H, H, st));
+      }
+    }
   }
   return 0;
+}
+
+// uniform batch: one group
+static int forward_impl(ditto_engine* e, const float* x, int64_t n_x, const void* ctx, const int64_t* t, int64_t n, int64_t T,
+                        int64_t S, float* out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  SeqGroup g;
+  g.n = n; g.n_x = n_x; g.T = T; g.S = S; g.ctx = ctx;
+  return forward_impl(e, x, t, &g, 1, out, workspace, workspace_bytes, st);
 }
 
 }  // namespace ditto
@@ -870,6 +973,58 @@ int32_t ditto_q_sample(ditto_engine_t* e, const float* x_start, const float* noi
   DITTO_REQUIRE(e && x_start && noise && t && out, DITTO_E_BADARG, "q_sample: null argument");
   DITTO_REQUIRE(e->have_schedule, DITTO_E_STATE, "q_sample: schedule not loaded");
   return launch_q_sample(x_start, noise, t, e->qs_buf, e->steps, out, B, elems_per_seq, static_cast<cudaStream_t>(stream));
+}
+
+// ---- ragged batches ------------------------------------------------------------------------------------
+static int parse_groups(const ditto_engine_t* e, const ditto_seq_group_t* groups, int64_t n_groups, bool need_ctx,
+                        std::vector<SeqGroup>& gs) {
+  DITTO_REQUIRE(e && groups && n_groups > 0 && n_groups <= 4096, DITTO_E_BADARG, "ragged: bad group list");
+  gs.resize(static_cast<size_t>(n_groups));
+  for (int64_t i = 0; i < n_groups; ++i) {
+    const ditto_seq_group_t& q = groups[i];
+    DITTO_REQUIRE(q.n_seq > 0 && q.T > 0 && q.S > 0 && q.n_x > 0 && q.n_seq % q.n_x == 0, DITTO_E_BADARG, "ragged: bad group sizes");
+    DITTO_REQUIRE(q.T <= e->maxT, DITTO_E_UNSUPPORTED, "ragged: T exceeds max_seq_len of the engine");
+    DITTO_REQUIRE(!need_ctx || q.ctx != nullptr, DITTO_E_BADARG, "ragged: group without a text context");
+    SeqGroup& g = gs[static_cast<size_t>(i)];
+    g.n = q.n_seq; g.n_x = q.n_x; g.T = q.T; g.S = q.S; g.ctx = q.ctx;
+  }
+  return 0;
+}
+
+int64_t ditto_workspace_bytes_ragged(const ditto_engine_t* e, const ditto_seq_group_t* groups, int64_t n_groups) {
+  std::vector<SeqGroup> gs;
+  if (parse_groups(e, groups, n_groups, false, gs) != 0) return -1;
+  return static_cast<int64_t>(ws_layout(e, nullptr, gs.data(), static_cast<int>(gs.size())).total);
+}
+
+int32_t ditto_forward_ragged(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups, const int64_t* t,
+                             float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && x && t && out && workspace, DITTO_E_BADARG, "forward_ragged: null argument");
+  DITTO_REQUIRE(e->finalized, DITTO_E_STATE, "forward_ragged: engine not finalized");
+  std::vector<SeqGroup> gs;
+  DITTO_TRY(parse_groups(e, groups, n_groups, true, gs));
+  return forward_impl(e, x, t, gs.data(), static_cast<int>(gs.size()), out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_p_sample_ragged(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups, const int64_t* t,
+                              const float* z, int32_t guided, float guidance_scale, float* eps_scratch, float* x_out, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && x && t && eps_scratch && x_out && workspace, DITTO_E_BADARG, "p_sample_ragged: null argument");
+  DITTO_REQUIRE(e->finalized && e->have_schedule, DITTO_E_STATE, "p_sample_ragged: engine not finalized / schedule not loaded");
+  std::vector<SeqGroup> gs;
+  DITTO_TRY(parse_groups(e, groups, n_groups, true, gs));
+  for (const SeqGroup& g : gs)
+    DITTO_REQUIRE(g.n == (guided ? 2 : 1) * g.n_x, DITTO_E_BADARG, "p_sample_ragged: n_seq must be n_x (unguided) or 2 n_x (guided)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DITTO_TRY(forward_impl(e, x, t, gs.data(), static_cast<int>(gs.size()), eps_scratch, workspace, workspace_bytes, st));
+  const int64_t H = e->H;
+  for (const SeqGroup& g : gs) {  // offsets were filled in by the layout pass of forward_impl
+    const int64_t per = g.T * H;
+    const float* ec = eps_scratch + g.row0 * H;
+    DITTO_TRY(launch_cfg_ddpm_update(ec, guided ? ec + g.n_x * per : nullptr, x + g.xrow0 * H, z ? z + g.xrow0 * H : nullptr, t + g.seq0,
+                                     e->coef, e->steps, guidance_scale, x_out + g.xrow0 * H, g.n_x, per, st));
+  }
+  return 0;
 }
 
 // ---- single operators ---------------------------------------------------------------------------------

@@ -67,6 +67,7 @@ struct DevParams {
   bf16* out2; long long ldo2;
   const float* rope_cos; const float* rope_sin; const float* rope_freq;
   int rope_half, rope_pd, seq_T, hidden;
+  const int* rope_pos;  // optional [M] row -> position table (ragged batches); nullptr: position = row % seq_T
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
@@ -575,6 +576,14 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
     ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 8, row0 + g + 8 < p.M, p.ln_inv_h, lnA1, lnN1);
     ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 16, row0 + g + 16 < p.M, p.ln_inv_h, lnA2, lnN2);
     ln_row_coef(p.ln_stat, p.ln_parts, row0 + g + 24, row0 + g + 24 < p.M, p.ln_inv_h, lnA3, lnN3);
+    // sequence positions of the thread's four rows (requested before the accumulator wait, like every other global read)
+    unsigned pos4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long rr = row0 + g + 8 * i;
+      pos4[i] = p.rope_pos != nullptr ? (rr < p.M ? static_cast<unsigned>(__ldg(p.rope_pos + rr)) : 0u)
+                                      : static_cast<unsigned>(rr) % static_cast<unsigned>(p.seq_T);
+    }
     bool waited = false;
 #pragma unroll 1
     for (int u = 0; u < units; ++u) {
@@ -638,8 +647,7 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
           if (pd != 32) store_blk_bf16_ln(r2, bx2, cx2, vo + pd, vo + 8 * p.ldo + pd, okA, okB, pc1 + pd + q2, p.N, aA, nA, aB, nB);
           continue;
         }
-        const unsigned seqT = static_cast<unsigned>(p.seq_T);
-        const unsigned posA = static_cast<unsigned>(rowA) % seqT, posB = static_cast<unsigned>(rowA + 8) % seqT;
+        const unsigned posA = hh ? pos4[2] : pos4[0], posB = hh ? pos4[3] : pos4[1];
         const float fposA = static_cast<float>(posA), fposB = static_cast<float>(posB);
         const float* cosA = p.rope_cos + static_cast<long long>(posA) * p.rope_half + jbase + q2;
         const float* sinA = p.rope_sin + static_cast<long long>(posA) * p.rope_half + jbase + q2;
@@ -1664,7 +1672,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.resid = q.resid; p.ldr = q.ldr; p.sr_inner = q.sr_inner; p.sr_outer = q.sr_outer; p.resid_row_mod = q.resid_row_mod;
   p.out2 = q.out2; p.ldo2 = q.ldo2;
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
-  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden;
+  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos;
   p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.stat_out = q.stat_out; p.stat_parts = q.stat_parts; p.stat_rows_outer = q.stat_rows_outer;
   p.stat_parts_item = static_cast<int>(ceil_div(q.N, 128));

@@ -15,7 +15,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
                      cudaStream_t st);
 int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
                     int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
-                    int64_t n_seq, int T, int H, cudaStream_t st, float2* stat = nullptr);
+                    int64_t n_seq, int T, int H, cudaStream_t st, float2* stat = nullptr, bool xcast_all = false,
+                    int* row_pos = nullptr);
 int launch_rope_table(const float* inv_freq, float* cos_t, float* sin_t, float* freq_out, int max_T, int half, int head_dim,
                       cudaStream_t st);
 int launch_rope(void* qkv, bool is_bf16, int64_t ld, const float* cos_t, const float* sin_t, int64_t rows, int seq_T,
@@ -79,6 +80,7 @@ struct TcGemmParams {
   const float* rope_cos = nullptr; const float* rope_sin = nullptr;
   const float* rope_freq = nullptr;            // [d/2] inv_freq: when set, cos/sin are computed in the epilogue (no table reads)
   int rope_half = 0, rope_pd = 0, seq_T = 0, hidden = 0;
+  const int* rope_pos = nullptr;               // optional [M] row -> position table (ragged batches) instead of row % seq_T
   // optional per-row scale 1 / sum_c row_lsum[row*row_lparts + c] applied to the accumulator (softmax normalisation of an
   // unnormalised P operand, see launch_tc_scores_softmax); batch strides in elements
   const float* row_lsum = nullptr; int row_lparts = 0; int64_t sl_inner = 0, sl_outer = 0;

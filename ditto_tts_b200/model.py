@@ -275,6 +275,16 @@ class DiTTO(nn.Module):
         return self.forward_with_context(x, ctx, t, x.shape[0], text_emb.shape[1])
 
     @torch.no_grad()
+    def forward_ragged(self, xs, texts, t):
+        """``DiTTO.forward`` on a mixed-length batch, every utterance at its own length (no padding, no masks -- the
+        reference has none): xs[i] [T_i,H], texts[i] [S_i,text_dim], t [B] -> list of eps_hat [T_i,H].
+        Equals ``[forward(x[None], text[None], t[i:i+1])[0] for ...]`` of the reference (DiTTO.py:66-94)."""
+        from .ragged import RaggedBatch
+        rb = RaggedBatch(self, texts, [int(x.shape[0]) for x in xs], guided=False)
+        out = rb.forward(rb.pack(xs), rb.seq_t(t))
+        return rb.unpack(out)
+
+    @torch.no_grad()
     def q_sample(self, x_start, t, noise=None):
         """Forward diffusion (reference: DiTTO.py:106-126, incl. its betas-as-alphas_cumprod buffer)."""
         x_start = _need_cuda_f32("x_start", x_start)

@@ -206,3 +206,48 @@ class DiTTOSampler:
                 record.append((eps[B:] + w * (eps[:B] - eps[B:])).clone() if guided else eps.clone())
             x, x_next = x_next, x
         return x
+
+    # ------------------------------------------------------------------------------------------ ragged batches
+    @torch.no_grad()
+    def sample_latents_ragged(self, texts, lengths, *, x_init=None, noise=None, guidance_scale=None, null_texts=None,
+                              record: Optional[List[List[torch.Tensor]]] = None, use_graph: bool = True):
+        """``__sample_latents`` (SpeechGenerator.py:150-164) for a mixed-length batch: utterance i has ``lengths[i]`` latent
+        frames (what the speech-length predictor returns x 75 fps, SpeechGenerator.py:157-158) and text ``texts[i]``
+        [S_i, text_dim].  Every utterance is sampled at its own length, unpadded (see ragged.py).  ``x_init`` /
+        ``noise`` are per-utterance lists ([T_i,H] / [steps,T_i,H]) for parity runs.  Returns a list of [T_i,H]."""
+        from .ragged import RaggedBatch, RaggedStepGraph
+        m = self.model
+        w = self.guidance_scale if guidance_scale is None else guidance_scale
+        guided = w is not None
+        rb = RaggedBatch(m, texts, lengths, guided=guided, null_texts=null_texts)
+        dev, H, steps = rb.device, m.hidden_dim, m.diffusion_steps
+        if x_init is not None:
+            x = rb.pack(x_init)
+        else:
+            x = torch.randn((rb.x_rows, H), dtype=torch.float32, device=dev)
+        zs = None
+        if noise is not None:   # [steps, sum T, H] packed once
+            zs = torch.empty((steps, rb.x_rows, H), dtype=torch.float32, device=dev)
+            for i, z in enumerate(noise):
+                z = _need_cuda_f32(f"noise[{i}]", z)
+                zs[:, rb.x_offset[i]:rb.x_offset[i] + rb.lengths[i]] = z
+        if use_graph and record is None:
+            g = RaggedStepGraph(rb, w if guided else 0.0, zs is None)
+            g.reset(x, steps - 1)
+            for i in range(steps):
+                if zs is not None:
+                    g.z.copy_(zs[steps - 1 - i], non_blocking=True)
+                g.replay()
+            return rb.unpack(g.x)
+        eps = torch.empty((rb.seq_rows, H), dtype=torch.float32, device=dev)
+        x_next = torch.empty_like(x)
+        z_buf = torch.empty_like(x)
+        for i in range(steps):
+            t_val = steps - 1 - i
+            t_seq = torch.full((rb.n_seq,), t_val, dtype=torch.int64, device=dev)
+            z = zs[t_val] if zs is not None else z_buf.normal_()
+            rb.p_sample(x, t_seq, z, w if guided else 0.0, eps, x_next)
+            if record is not None:
+                record.append(rb.unpack_eps(eps, w))
+            x, x_next = x_next, x
+        return rb.unpack(x)

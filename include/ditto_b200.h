@@ -144,6 +144,29 @@ int32_t ditto_p_sample(ditto_engine_t* e, const float* x, const void* ctx, const
 int32_t ditto_q_sample(ditto_engine_t* e, const float* x_start, const float* noise, const int64_t* t,
                        float* out, int64_t B, int64_t elems_per_seq, void* stream);
 
+/* ---- ragged (mixed-length) batches: BASELINE.json config 5 ------------------------------------------------
+ * The reference has no padding masks (DiT.py:131-148 attends over every frame it is given), so utterances of different
+ * length must run UNPADDED to match it.  A ragged batch is a list of groups of equal-length sequences; x, z, x_out are
+ * packed group after group ([sum n_x*T, H]), t/out/eps_scratch likewise in sequence order ([sum n_seq], [sum n_seq*T, H]).
+ * Row-wise work (LayerNorm, QKV/GLU/fc2/projection GEMMs) runs once over all packed rows; AdaLN modulation, RoPE
+ * positions and both attentions run per group.  Each group has its own text context (ditto_text_context on its n_seq
+ * sequences, S tokens each). */
+typedef struct ditto_seq_group {
+  int64_t n_seq;   /* sequences in the group; CFG: n_x conditional then n_x unconditional                 */
+  int64_t n_x;     /* distinct latents: sequence i reads the group's x[i % n_x]  (n_seq % n_x == 0)      */
+  int64_t T;       /* latent frames of every sequence of the group                                      */
+  int64_t S;       /* text tokens of every sequence of the group                                        */
+  const void* ctx; /* device buffer filled by ditto_text_context(e, text[n_seq,S,text_dim], n_seq, S, ...) */
+} ditto_seq_group_t;
+int64_t ditto_workspace_bytes_ragged(const ditto_engine_t* e, const ditto_seq_group_t* groups, int64_t n_groups);
+/* DiTTO.forward (DiTTO.py:66-94) on every sequence of the ragged batch, each at its own length. */
+int32_t ditto_forward_ragged(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups,
+                             const int64_t* t, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* __p_sample (SpeechGenerator.py:131-147) + CFG on a ragged batch; guided: every group has n_seq == 2 n_x. */
+int32_t ditto_p_sample_ragged(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups,
+                              const int64_t* t, const float* z, int32_t guided, float guidance_scale,
+                              float* eps_scratch, float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- single operators (unit-tested against the oracle; also usable on their own) --------------------- */
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5, biased variance; DiT.py:84,89,94).
  * gamma/beta may be NULL (no affine, DiT.py:23).  out_bf16 != 0: y is written as bf16. */
