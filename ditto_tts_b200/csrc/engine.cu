@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "kernels.cuh"
@@ -94,6 +95,14 @@ struct ditto_engine {
   float *time_table = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *rope_freq = nullptr, *coef = nullptr, *qs_buf = nullptr;
   bf16 *w_in16 = nullptr, *w_out16 = nullptr;
   std::vector<LayerPack> layers;
+  // ragged batches: the per-group launches (small attention kernels) are spread over side streams so that groups overlap
+  // on the GPU; fork/join with events, which CUDA-graph capture turns into parallel branches.  The mutex serialises the
+  // ENQUEUE of ragged forwards from different host threads (the fork event is re-recorded by every call).
+  static constexpr int kSide = 8;
+  cudaStream_t side[kSide] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
+  int n_side = 0;
+  std::recursive_mutex fork_mutex;
 
   const float* W(const std::string& k) const {
     auto it = w.find(k);
@@ -384,6 +393,28 @@ static Workspace group_view(const ditto_engine* e, const Workspace& w, const Seq
   return v;
 }
 
+// fork / join of the per-group launches over the engine's side streams (no-op for a single group)
+struct Fork {
+  ditto_engine* e; cudaStream_t st; int used = 0;
+  Fork(ditto_engine* e_, cudaStream_t st_) : e(e_), st(st_) {}
+  int begin(int ng) {
+    used = (ng > 1) ? std::min(ng, e->n_side) : 0;
+    if (used == 0) return 0;
+    DITTO_CUDA(cudaEventRecord(e->ev_fork, st));
+    for (int k = 0; k < used; ++k) DITTO_CUDA(cudaStreamWaitEvent(e->side[k], e->ev_fork, 0));
+    return 0;
+  }
+  cudaStream_t stream(int gi) const { return used ? e->side[gi % used] : st; }
+  int end() {
+    for (int k = 0; k < used; ++k) {
+      DITTO_CUDA(cudaEventRecord(e->ev_join[k], e->side[k]));
+      DITTO_CUDA(cudaStreamWaitEvent(st, e->ev_join[k], 0));
+    }
+    used = 0;
+    return 0;
+  }
+};
+
 // One DiTTO forward over `ng` groups of equal-length sequences packed back to back (group-major, sequences of a group
 // contiguous).  Everything that works on single rows (LayerNorm, the QKV / GLU / fc2 / projection GEMMs) runs ONCE over
 // all packed rows; only what depends on sequence boundaries (AdaLN modulation, attention, RoPE positions) runs per group.
@@ -401,12 +432,16 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
   const float sqrt_inv_d = sqrtf(1.0f / static_cast<float>(d));          // torch MHA: q * sqrt(1/d)
   DITTO_REQUIRE(!(ragged && e->defer_ln), DITTO_E_UNSUPPORTED, "forward: ragged batches do not support DITTO_F_DEFER_LN");
   const SeqGroup& g0 = gs[0];
+  std::unique_lock<std::recursive_mutex> fork_lock(e->fork_mutex, std::defer_lock);
+  if (ragged && e->n_side > 0) fork_lock.lock();
+  Fork fork(e, st);
 
   // deferred LayerNorm: `u` holds bf16(h) and w.lnstat the row statistics; ln1_parts = parts written by the last producer
   const bool dln = e->defer_ln;
   const bool dln2 = dln && fold_ln_active(e, g0.S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
   int ln1_parts = 1;
   // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
+  DITTO_TRY(fork.begin(ng));
   for (int gi = 0; gi < ng; ++gi) {
     const SeqGroup& g = gs[gi];
     CtxLayout c = ctx_layout(e, const_cast<void*>(g.ctx), g.n, g.S);
@@ -415,8 +450,10 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
     bf16* xc = b16 ? static_cast<bf16*>(w.xb16) + (ragged ? g.row0 : g.xrow0) * H : nullptr;
     DITTO_TRY(launch_adaln_ln(x + g.xrow0 * H, g.n_x, e->time_table, c.text_mod, t + g.seq0, e->steps, e->LW(0, "norm1.weight"),
                               e->LW(0, "norm1.bias"), w.h + g.row0 * H, static_cast<char*>(w.u) + g.row0 * H * es, b16, xc, g.n,
-                              static_cast<int>(g.T), H, st, dln ? w.lnstat : nullptr, ragged, ragged ? w.row_pos + g.row0 : nullptr));
+                              static_cast<int>(g.T), H, fork.stream(gi), dln ? w.lnstat : nullptr, ragged,
+                              ragged ? w.row_pos + g.row0 : nullptr));
   }
+  DITTO_TRY(fork.end());
   // x_skip = proj_in(x): once per distinct x (uniform batch) / per packed row (ragged)      DiTTO.py:83
   if (b16) {
     const int Mp = static_cast<int>(ragged ? M : g0.n_x * g0.T);
@@ -454,25 +491,22 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
             DITTO_TRY(launch_rope(qkv + gs[gi].row0 * 3 * H, true, 3 * H, e->rope_cos, e->rope_sin, gs[gi].n * gs[gi].T,
                                   static_cast<int>(gs[gi].T), H, d, st));
       }
-      for (int gi = 0; gi < ng; ++gi) {
-        const SeqGroup& g = gs[gi];
-        const Workspace wg = group_view(e, w, g);
-        bf16* q = qkv + g.row0 * 3 * H;
-        float* hg = w.h + g.row0 * H;
-        const int64_t T = g.T;
-        DITTO_TRY(attention_bf16(e, wg, q, 3 * H, T * 3 * H, q + H, 3 * H, T * 3 * H, q + 2 * H, 3 * H, T * 3 * H, g.n, static_cast<int>(T),
-                                 static_cast<int>(T), inv_sqrt_d, hg, false, H, T * H, hg, st, false, dln2 ? u : nullptr,
-                                 dln2 ? w.lnstat : nullptr));
-      }
-      // ---- cross-attention (torch MHA math path)                                                     DiT.py:141-148
-      if (!dln2) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, true, M, H, st));
+      // per group (each on its own side stream when the batch is ragged): self-attention, LN2, cross-attention
+      DITTO_TRY(fork.begin(ng));
       for (int gi = 0; gi < ng; ++gi) {
         const SeqGroup& grp = gs[gi];
         const Workspace wg = group_view(e, w, grp);
         const CtxLayout c = ctx_layout(e, const_cast<void*>(grp.ctx), grp.n, grp.S);
         const int64_t n = grp.n, T = grp.T, S = grp.S, Mg = n * T;
+        cudaStream_t st = fork.stream(gi);  // shadows the caller's stream inside the group section
+        bf16* q = qkv + grp.row0 * 3 * H;
         bf16* ug = u + grp.row0 * H;
         float* hg = w.h + grp.row0 * H;
+        DITTO_TRY(attention_bf16(e, wg, q, 3 * H, T * 3 * H, q + H, 3 * H, T * 3 * H, q + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
+                                 static_cast<int>(T), inv_sqrt_d, hg, false, H, T * H, hg, st, false, dln2 ? u : nullptr,
+                                 dln2 ? w.lnstat : nullptr));
+        // ---- cross-attention (torch MHA math path)                                                   DiT.py:141-148
+        if (!dln2) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), ug, true, Mg, H, st));
         void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
         if (fold_active(e, S)) {
           // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
@@ -524,6 +558,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
                           static_cast<int>(Mg), H, H, st, PC_TC_CROSS_OUT, dln ? w.lnstat : nullptr, w.ln_parts_h));
         }
       }
+      DITTO_TRY(fork.end());
       // ---- gated MLP                                                                                  DiT.py:150-155
       if (!dln) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
       {
@@ -702,12 +737,27 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
   }
   build_expected(e);
   e->layers.resize(e->L);
+  int want_side = ditto_engine::kSide;
+  if (const char* es = getenv("DITTO_SIDE_STREAMS")) want_side = std::max(0, std::min(ditto_engine::kSide, atoi(es)));
+  if (want_side > 0 && cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess) {
+    for (int k = 0; k < want_side; ++k) {
+      if (cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming) != cudaSuccess)
+        break;
+      e->n_side = k + 1;
+    }
+  }
   *out = e;
   return 0;
 }
 
 int32_t ditto_engine_destroy(ditto_engine_t* e) {
   if (!e) return 0;
+  for (int k = 0; k < ditto_engine::kSide; ++k) {
+    if (e->side[k]) cudaStreamDestroy(e->side[k]);
+    if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   for (auto& kv : e->w) cudaFree(kv.second);
   for (void* p : e->owned) cudaFree(p);
   delete e;
@@ -1018,12 +1068,18 @@ int32_t ditto_p_sample_ragged(ditto_engine_t* e, const float* x, const ditto_seq
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DITTO_TRY(forward_impl(e, x, t, gs.data(), static_cast<int>(gs.size()), eps_scratch, workspace, workspace_bytes, st));
   const int64_t H = e->H;
-  for (const SeqGroup& g : gs) {  // offsets were filled in by the layout pass of forward_impl
+  std::unique_lock<std::recursive_mutex> fork_lock(e->fork_mutex, std::defer_lock);
+  if (gs.size() > 1 && e->n_side > 0) fork_lock.lock();
+  Fork fork(e, st);
+  DITTO_TRY(fork.begin(static_cast<int>(gs.size())));
+  for (size_t gi = 0; gi < gs.size(); ++gi) {  // offsets were filled in by the layout pass of forward_impl
+    const SeqGroup& g = gs[gi];
     const int64_t per = g.T * H;
     const float* ec = eps_scratch + g.row0 * H;
     DITTO_TRY(launch_cfg_ddpm_update(ec, guided ? ec + g.n_x * per : nullptr, x + g.xrow0 * H, z ? z + g.xrow0 * H : nullptr, t + g.seq0,
-                                     e->coef, e->steps, guidance_scale, x_out + g.xrow0 * H, g.n_x, per, st));
+                                     e->coef, e->steps, guidance_scale, x_out + g.xrow0 * H, g.n_x, per, fork.stream(static_cast<int>(gi))));
   }
+  DITTO_TRY(fork.end());
   return 0;
 }
 

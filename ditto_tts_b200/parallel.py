@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_indices", "balance_by_cost", "utterance_cost", "gather_latents"]
+__all__ = ["shard_indices", "balance_by_cost", "utterance_cost", "gather_latents", "gather_ragged_latents", "c5_lengths"]
 
 
 def shard_indices(n_utts: int, world: int, rank: int) -> List[int]:
@@ -68,4 +68,57 @@ def gather_latents(local: torch.Tensor, indices: Sequence[int], n_total: int, gr
     keep = all_idx >= 0
     out = local.new_empty((n_total,) + tuple(local.shape[1:]))
     out[all_idx[keep]] = all_lat[keep]
+    return out
+
+
+def c5_lengths(n_utts: int = 256, seed: int = 0, fps: int = 75, tokens_per_second: float = 6.4):
+    """BASELINE.json config 5 / SURVEY.md 8d: durations ``random.seed(0); randint(2, 20)`` s -> T_i = 75 sec frames
+    (what the speech-length predictor's classes map to), S_i = round(6.4 sec) text tokens."""
+    import random
+    rnd = random.Random(seed)
+    secs = [rnd.randint(2, 20) for _ in range(n_utts)]
+    return [fps * s for s in secs], [int(round(tokens_per_second * s)) for s in secs]
+
+
+def gather_ragged_latents(local: Sequence[torch.Tensor], indices: Sequence[int], lengths: Sequence[int], group=None):
+    """Mixed-length counterpart of gather_latents: ``local[j]`` is the [T_i, H] latent of utterance ``indices[j]``;
+    ``lengths`` holds T_i of ALL utterances (known on every rank: it is what the shards were balanced with).
+    Returns the full list in utterance order on every rank.  One padded all_gather of the packed rows."""
+    n_total = len(lengths)
+    if len(local) != len(indices):
+        raise ValueError("one latent per local index expected")
+    for j, i in enumerate(indices):
+        if local[j].shape[0] != lengths[i]:
+            raise ValueError(f"utterance {i}: latent has {local[j].shape[0]} frames, expected {lengths[i]}")
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out = [None] * n_total
+        for j, i in enumerate(indices):
+            out[i] = local[j]
+        return out
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev, H = local[0].device, local[0].shape[1]
+    # every rank's index list (padded with -1) so that the packed rows can be cut apart again
+    cnt = torch.zeros(world, dtype=torch.int64, device=dev)
+    cnt[rank] = len(indices)
+    dist.all_reduce(cnt, group=group)
+    bmax = int(cnt.max())
+    idx = torch.full((bmax,), -1, dtype=torch.int64, device=dev)
+    idx[: len(indices)] = torch.as_tensor(list(indices), dtype=torch.int64, device=dev)
+    all_idx = torch.empty(world * bmax, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_idx, idx, group=group)
+    all_idx = all_idx.view(world, bmax).tolist()
+    rows = [sum(lengths[i] for i in r if i >= 0) for r in all_idx]
+    rmax = max(rows)
+    pack = local[0].new_zeros((rmax, H))
+    pack[: rows[rank]] = torch.cat(list(local), dim=0)
+    everything = local[0].new_empty((world * rmax, H))
+    dist.all_gather_into_tensor(everything, pack, group=group)
+    out = [None] * n_total
+    for r in range(world):
+        off = r * rmax
+        for i in all_idx[r]:
+            if i < 0:
+                continue
+            out[i] = everything[off: off + lengths[i]]
+            off += lengths[i]
     return out

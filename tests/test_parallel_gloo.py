@@ -46,3 +46,32 @@ def test_gather_single_process():
     x = torch.randn(3, 2, 4)
     out = parallel.gather_latents(x, [2, 0, 1], 3)
     assert torch.equal(out[2], x[0]) and torch.equal(out[0], x[1])
+
+
+def _ragged_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lengths, H = [3, 7, 2, 5, 4], 4
+    g = torch.Generator().manual_seed(0)
+    full = [torch.randn(T, H, generator=g) for T in lengths]
+    parts = parallel.balance_by_cost(lengths, world, [2] * len(lengths), hidden=H, layers=1)
+    idx = parts[rank]
+    out = parallel.gather_ragged_latents([full[i].clone() for i in idx], idx, lengths)
+    ret[rank] = all(torch.equal(a, b) for a, b in zip(out, full))
+    dist.destroy_process_group()
+
+
+def test_gather_ragged_latents_world2_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_ragged_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_c5_workload_matches_survey():
+    T, S = parallel.c5_lengths()
+    assert len(T) == 256 and sum(T) == 206025 and min(T) == 150 and max(T) == 1500
+    assert all(s == round(6.4 * t / 75) for t, s in zip(T, S))
+    out = parallel.gather_ragged_latents([torch.zeros(3, 2), torch.ones(1, 2)], [1, 0], [1, 3])
+    assert out[0].shape[0] == 1 and out[1].shape[0] == 3
