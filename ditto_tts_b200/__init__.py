@@ -7,6 +7,7 @@ from ._lib import DittoError, LIB_PATH, launch_count  # noqa: F401
 from .config import ConfigDiTTO  # noqa: F401
 from .model import DiT, DiTTO, GlobalAdaLN, RotaryEmbedding  # noqa: F401
 from .sampler import DiTTOSampler  # noqa: F401
+from .codec import VectorQuantizer, latents_to_codes, pool_latents, mse_loss, validation_step  # noqa: F401
 
 __all__ = ["DiTTO", "DiT", "GlobalAdaLN", "RotaryEmbedding", "DiTTOSampler", "ConfigDiTTO", "DittoError",
-           "launch_count", "LIB_PATH"]
+           "launch_count", "LIB_PATH", "VectorQuantizer", "latents_to_codes", "pool_latents", "mse_loss", "validation_step"]

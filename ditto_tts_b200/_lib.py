@@ -62,6 +62,11 @@ SIGNATURES = {
                               _I64, _P]),
     "ditto_gemm_bf16": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _I64, _F, _I64, _I64, _I64, _P]),
     "ditto_cast_bf16": (_I32, [_P, _P, _I64, _P]),
+    "ditto_vq_code_sqnorm": (_I32, [_P, _I64, _I64, _P, _P]),
+    "ditto_vq_encode": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P]),
+    "ditto_pool_latents": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "ditto_mse_workspace_bytes": (_I64, []),
+    "ditto_mse_loss": (_I32, [_P, _P, _I64, _P, _P, _I64, _P]),
 }
 
 _lib = None

@@ -186,6 +186,27 @@ int32_t ditto_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, 
 /* fp32 -> bf16 (round to nearest even) */
 int32_t ditto_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 
+/* ---- hand-off steps either side of the sampling loop (fp32, like the reference) ----------------------- */
+/* |c|^2 of every codebook row: torch.sum(self.codebook**2, dim=1), VectorQuantizer.py:37.  codebook [codes, dim] ->
+ * sqnorm [codes].  Step-invariant: compute once per codebook. */
+int32_t ditto_vq_code_sqnorm(const float* codebook, int64_t codes, int64_t dim, float* sqnorm, void* stream);
+/* VectorQuantizer.forward (VectorQuantizer.py:22-43): indices = argmin_k (|z|^2 - 2 z.c_k + |c_k|^2), fp32, lowest index
+ * on ties.  latents [batch, frames, dim]; indices int64 [batch, repeat_channels, frames]: repeat_channels > 1 writes the
+ * same index to every channel, which is what quantising latents.unsqueeze(1).repeat(1, C, 1, 1) gives
+ * (SpeechGenerator.py:117-118) without the C-fold work.  A general [B, C, T, dim] input is batch = B*C, repeat 1. */
+int32_t ditto_vq_encode(const float* latents, int64_t batch, int64_t frames, int64_t dim, const float* codebook,
+                        int64_t codes, const float* code_sqnorm, int64_t repeat_channels, int64_t* indices,
+                        void* stream);
+/* audio_latents[:, :, :max_frames].mean(dim=1) (TrainDiTTO.py:70-71, :113-114): latents [batch, channels, frames, dim]
+ * -> out [batch, min(frames, max_frames), dim].  dim % 4 == 0. */
+int32_t ditto_pool_latents(const float* latents, int64_t batch, int64_t channels, int64_t frames, int64_t dim,
+                           int64_t max_frames, float* out, void* stream);
+/* nn.MSELoss() (TrainDiTTO.py:51,87,126): loss[0] = mean((a - b)^2) over n elements; deterministic two-stage
+ * reduction, workspace of ditto_mse_workspace_bytes() (8-byte aligned). */
+int64_t ditto_mse_workspace_bytes(void);
+int32_t ditto_mse_loss(const float* a, const float* b, int64_t n, float* loss, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,68 @@ def make_inputs(B: int, T: int, S: int, cfg: OracleConfig, seed: int = 1, steps_
     return x, text, noise
 
 
+# --------------------------------------------------------------------------
+# hand-off steps either side of the loop
+# --------------------------------------------------------------------------
+def make_codebook(codebook_size: int, latent_dim: int, seed: int = 0) -> Tensor:
+    """A seeded codebook with the reference's init distribution (xavier_uniform_, VectorQuantizer.py:19-20),
+    drawn from a private CPU generator so that it regenerates identically on every box."""
+    g = torch.Generator().manual_seed(seed)
+    bound = math.sqrt(6.0 / (codebook_size + latent_dim))
+    return (torch.rand(codebook_size, latent_dim, generator=g) * 2 - 1) * bound
+
+
+def vq_distances(codebook: Tensor, latents_flat: Tensor) -> Tensor:
+    """|z|^2 - 2 z C^T + |c|^2, in the reference's association.  VectorQuantizer.py:34-38."""
+    return (
+        torch.sum(latents_flat ** 2, dim=1, keepdim=True)
+        - 2 * torch.matmul(latents_flat, codebook.T)
+        + torch.sum(codebook ** 2, dim=1)
+    )
+
+
+def vq_indices(codebook: Tensor, latents: Tensor) -> Tensor:
+    """VectorQuantizer.forward: latents [B,C,T,D] -> argmin indices int64 [B,C,T].  VectorQuantizer.py:22-43."""
+    batch_size, num_channels, num_frames, latent_dim = latents.shape
+    flat = latents.reshape(-1, latent_dim)                                     # :31
+    indices = torch.argmin(vq_distances(codebook, flat), dim=-1)               # :40
+    return indices.view(batch_size, num_channels, num_frames)                  # :41
+
+
+def latents_to_codes(codebook: Tensor, latents: Tensor, channels: int = 2) -> Tensor:
+    """The step right after the sampling loop.  SpeechGenerator.py:117-118."""
+    return vq_indices(codebook, latents.unsqueeze(1).repeat(1, channels, 1, 1))
+
+
+def vq_near_tie(codebook: Tensor, latents_flat: Tensor, got: Tensor, want: Tensor, rel_tol: float = 1e-5) -> Tensor:
+    """For rows where ``got`` != ``want``: True where the two candidates' distances (fp64) differ by less than
+    rel_tol * |distance| -- i.e. the disagreement is an fp32 re-association tie, not a wrong winner."""
+    d = vq_distances(codebook.double(), latents_flat.double())
+    dg = d.gather(1, got.reshape(-1, 1)).squeeze(1)
+    dw = d.gather(1, want.reshape(-1, 1)).squeeze(1)
+    return (dg - dw).abs() <= rel_tol * dw.abs().clamp_min(1e-30)
+
+
+def pool_latents(audio_latents: Tensor, max_length: int) -> Tensor:
+    """audio_latents[:, :, :max_length].mean(dim=1).  TrainDiTTO.py:70-71 (validation: :113-114)."""
+    return audio_latents[:, :, :max_length].mean(dim=1)
+
+
+def mse_loss(pred: Tensor, target: Tensor) -> Tensor:
+    """nn.MSELoss() (mean reduction).  TrainDiTTO.py:51,87,126."""
+    return F.mse_loss(pred, target)
+
+
+def validation_step(sd, cfg: OracleConfig, audio_latents: Tensor, text_embeddings: Tensor, t: Tensor, noise: Tensor,
+                    max_length: int = 1024):
+    """One iteration of the validation loop after the NAC encoder.  TrainDiTTO.py:113-127."""
+    lat = pool_latents(audio_latents, max_length)                              # :113-114
+    text = text_embeddings[:, :lat.size(1)]                                    # :115
+    noisy = q_sample(sd, lat, t, noise)                                        # :123
+    pred = ditto_forward(sd, cfg, noisy, text, t)                              # :124
+    return mse_loss(pred, noise), pred                                         # :126
+
+
 def rel_l2(a: Tensor, b: Tensor) -> float:
     """||a-b||_2 / ||b||_2 in fp64 (b = reference)."""
     a = a.detach().double().cpu()
