@@ -46,6 +46,7 @@ SIGNATURES = {
     "ditto_engine_destroy": (_I32, [_P]),
     "ditto_engine_load_weight": (_I32, [_P, C.c_char_p, _P, _I64, _P]),
     "ditto_engine_load_schedule": (_I32, [_P, _P, _P, _P, _I64, _P]),
+    "ditto_engine_load_update_table": (_I32, [_P, _P, _I64, _P]),
     "ditto_engine_finalize": (_I32, [_P, _P]),
     "ditto_text_context_bytes": (_I64, [_P, _I64, _I64]),
     "ditto_workspace_bytes": (_I64, [_P, _I64, _I64, _I64]),

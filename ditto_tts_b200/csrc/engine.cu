@@ -801,6 +801,14 @@ int32_t ditto_engine_load_schedule(ditto_engine_t* e, const float* betas, const 
   return 0;
 }
 
+int32_t ditto_engine_load_update_table(ditto_engine_t* e, const float* coef, int64_t steps, void* stream) {
+  DITTO_REQUIRE(e && coef, DITTO_E_BADARG, "load_update_table: null argument");
+  DITTO_REQUIRE(steps == e->steps, DITTO_E_BADARG, "load_update_table: steps != diffusion_steps");
+  DITTO_REQUIRE(e->have_schedule, DITTO_E_STATE, "load_update_table: call ditto_engine_load_schedule first (q_sample needs the betas)");
+  DITTO_CUDA(cudaMemcpyAsync(e->coef, coef, sizeof(float) * 3 * steps, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
   DITTO_REQUIRE(e, DITTO_E_BADARG, "finalize: null engine");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -204,8 +204,9 @@ class DiTTO(nn.Module):
         self._engine_key = key
         return self._engine
 
-    def load_schedule(self, betas: torch.Tensor, alphas: torch.Tensor, alphas_cumprod: torch.Tensor):
-        """Hand the sampler tables (SpeechGenerator.py:70-72) to the engine."""
+    def load_schedule(self, betas: torch.Tensor, alphas: torch.Tensor, alphas_cumprod: torch.Tensor, owner=None):
+        """Hand the sampler tables (SpeechGenerator.py:70-72) to the engine.  ``owner`` tags whose tables the engine
+        holds (a sampler with its own schedule / update rule re-loads them when another user replaced them)."""
         eng = self.engine()
         dev = self.proj_in.weight.device
         tabs = [z.detach().to(device=dev, dtype=torch.float32).contiguous() for z in (betas, alphas, alphas_cumprod)]
@@ -214,9 +215,23 @@ class DiTTO(nn.Module):
                                                              tabs[0].numel(), _stream()), "ditto_engine_load_schedule")
             torch.cuda.current_stream().synchronize()
         self._schedule_loaded = True
+        self._schedule_owner = owner
+
+    def load_update_table(self, coef: torch.Tensor):
+        """Replace the per-timestep update coefficients [diffusion_steps, 3] (sampler variants, schedules.py)."""
+        eng = self.engine()
+        dev = self.proj_in.weight.device
+        if tuple(coef.shape) != (self.diffusion_steps, 3):
+            raise DittoError(f"update table must be [{self.diffusion_steps}, 3]")
+        tab = coef.detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ditto_engine_load_update_table(eng, _ptr(tab), self.diffusion_steps, _stream()),
+                       "ditto_engine_load_update_table")
+            torch.cuda.current_stream().synchronize()
 
     def _ensure_schedule(self):
-        if not self._schedule_loaded:
+        """The module's own (reference) schedule: what q_sample reads (DiTTO.py:63-64,106-126)."""
+        if not self._schedule_loaded or getattr(self, "_schedule_owner", None) is not None:
             betas = self.cosine_beta_schedule(self.diffusion_steps)
             alphas = 1.0 - betas
             self.load_schedule(betas, alphas, torch.cumprod(alphas, dim=0))

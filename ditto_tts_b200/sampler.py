@@ -14,7 +14,7 @@ from typing import List, Optional
 
 import torch
 
-from . import _lib
+from . import _lib, schedules
 from ._lib import DittoError
 from .model import DiTTO, _need_cuda_f32, _ptr, _stream
 
@@ -76,16 +76,51 @@ class StepGraph:
 
 
 class DiTTOSampler:
-    def __init__(self, model: DiTTO, guidance_scale: Optional[float] = None):
+    """``method`` / ``num_steps`` / ``eta`` / ``schedule_scale`` select the sampler variants of SURVEY.md 8f row 4
+    (schedules.py); the defaults are the reference's sampler: DDPM over every timestep of the cosine schedule."""
+
+    def __init__(self, model: DiTTO, guidance_scale: Optional[float] = None, *, method: str = "ddpm",
+                 num_steps: Optional[int] = None, eta: float = 0.0, schedule_scale: Optional[float] = None):
+        if method not in ("ddpm", "ddim"):
+            raise ValueError("method must be 'ddpm' or 'ddim'")
         self.model = model
         self.guidance_scale = guidance_scale
+        self.method, self.eta, self.schedule_scale = method, float(eta), schedule_scale
         steps = model.diffusion_steps
         # SpeechGenerator.py:70-72 (host torch ops => bit-identical tables)
-        self.betas = model.cosine_beta_schedule(steps)
+        self.betas = model.cosine_beta_schedule(steps) if schedule_scale is None else \
+            schedules.shifted_cosine_betas(steps, schedule_scale)
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
-        model.load_schedule(self.betas, self.alphas, self.alphas_cumprod)
+        self.num_steps = steps if num_steps is None else int(num_steps)
+        # model timesteps visited, descending (the reference: reversed(range(DIFFUSION_STEPS)), SpeechGenerator.py:161)
+        self.timesteps = schedules.spaced_timesteps(steps, self.num_steps)
+        self.update_table = None
+        if method == "ddim" or self.num_steps != steps:
+            acp64 = torch.cumprod(1.0 - self.betas.to(torch.float64), dim=0)
+            taus = self.timesteps.tolist()
+            coef = schedules.ddim_coef(acp64, taus, eta) if method == "ddim" else schedules.ddpm_coef(acp64, taus)
+            self.update_table = schedules.coef_table(steps, taus, coef)
+        self._variant = self.update_table is not None or schedule_scale is not None
+        self._tau_dev = None
         self._graphs = {}
+        self._activate()
+
+    def _activate(self):
+        """Make the engine hold THIS sampler's schedule / update table (another sampler or q_sample may have replaced them)."""
+        m = self.model
+        owner = self if self._variant else None
+        if m._schedule_loaded and getattr(m, "_schedule_owner", None) is owner and getattr(m, "_schedule_engine", None) is m._engine:
+            return
+        m.load_schedule(self.betas, self.alphas, self.alphas_cumprod, owner=owner)
+        if self.update_table is not None:
+            m.load_update_table(self.update_table)
+        m._schedule_engine = m._engine
+
+    def _taus(self, device):
+        if self._tau_dev is None or self._tau_dev.device != device:
+            self._tau_dev = self.timesteps.to(device)
+        return self._tau_dev
 
     # ------------------------------------------------------------------------------------------
     def _context(self, text_emb: torch.Tensor, guided: bool, null_text_emb: Optional[torch.Tensor], T: int):
@@ -132,6 +167,7 @@ class DiTTOSampler:
         guided = w is not None
         x = _need_cuda_f32("x", x)
         B, T, H = x.shape
+        self._activate()
         ctx = self._context(text_emb, guided, null_text_emb, T)
         t = t.to(device=x.device, dtype=torch.int64)
         t_n = (torch.cat([t, t]) if guided else t).contiguous()
@@ -175,25 +211,28 @@ class DiTTOSampler:
             raise DittoError("sample_latents needs audio_emb (shape donor) or x_init")
         B, T, H = x.shape
         S = text_emb.shape[1]
-        steps = m.diffusion_steps
+        self._activate()
+        taus = self.timesteps.tolist()
+        consecutive = self.num_steps == m.diffusion_steps
         ctx = self._context(text_emb, guided, null_text_emb, T)
         n = 2 * B if guided else B
         if use_graph and record is None and generator is None:
             # one CUDA-graph replay per denoising step (noise drawn inside the graph unless supplied)
             g = self.step_graph(B, T, S, guided, w if guided else 0.0, ctx, noise is None, dev)
-            g.reset(x, steps - 1)
-            for i in range(steps):
+            g.reset(x, taus[0])
+            for t_val in taus:
                 if noise is not None:
-                    g.z.copy_(noise[steps - 1 - i], non_blocking=True)
+                    g.z.copy_(noise[t_val], non_blocking=True)
+                if not consecutive:
+                    g.t.fill_(t_val)      # the graph's own "t -= 1" only covers the reference's consecutive timesteps
                 g.replay()
             return g.x.clone()
         # t for every step, all sequences share it (SpeechGenerator.py:162)
-        t_all = torch.arange(steps - 1, -1, -1, device=dev, dtype=torch.int64).unsqueeze(1).repeat(1, n).contiguous()
+        t_all = self._taus(dev).unsqueeze(1).repeat(1, n).contiguous()
         eps = torch.empty((n, T, H), dtype=torch.float32, device=dev)
         x_next = torch.empty_like(x)
         z_buf = None if noise is not None else torch.empty_like(x)
-        for i in range(steps):
-            t_val = steps - 1 - i
+        for i, t_val in enumerate(taus):
             if noise is not None:
                 z = noise[t_val]
                 if not z.is_cuda:
@@ -221,6 +260,9 @@ class DiTTOSampler:
         guided = w is not None
         rb = RaggedBatch(m, texts, lengths, guided=guided, null_texts=null_texts)
         dev, H, steps = rb.device, m.hidden_dim, m.diffusion_steps
+        self._activate()
+        taus = self.timesteps.tolist()
+        consecutive = self.num_steps == steps
         if x_init is not None:
             x = rb.pack(x_init)
         else:
@@ -233,17 +275,18 @@ class DiTTOSampler:
                 zs[:, rb.x_offset[i]:rb.x_offset[i] + rb.lengths[i]] = z
         if use_graph and record is None:
             g = RaggedStepGraph(rb, w if guided else 0.0, zs is None)
-            g.reset(x, steps - 1)
-            for i in range(steps):
+            g.reset(x, taus[0])
+            for t_val in taus:
                 if zs is not None:
-                    g.z.copy_(zs[steps - 1 - i], non_blocking=True)
+                    g.z.copy_(zs[t_val], non_blocking=True)
+                if not consecutive:
+                    g.t.fill_(t_val)
                 g.replay()
             return rb.unpack(g.x)
         eps = torch.empty((rb.seq_rows, H), dtype=torch.float32, device=dev)
         x_next = torch.empty_like(x)
         z_buf = torch.empty_like(x)
-        for i in range(steps):
-            t_val = steps - 1 - i
+        for t_val in taus:
             t_seq = torch.full((rb.n_seq,), t_val, dtype=torch.int64, device=dev)
             z = zs[t_val] if zs is not None else z_buf.normal_()
             rb.p_sample(x, t_seq, z, w if guided else 0.0, eps, x_next)

@@ -101,6 +101,11 @@ int32_t ditto_engine_load_weight(ditto_engine_t* e, const char* key, const float
  * src/model/SpeechGenerator.py:70-72 does. */
 int32_t ditto_engine_load_schedule(ditto_engine_t* e, const float* betas, const float* alphas,
                                    const float* alphas_cumprod, int64_t steps, void* stream);
+/* Sampler variants: replace the update table the schedule produced.  coef [diffusion_steps, 3] fp32
+ * (device), row t = {c1, c2, c3} of   x_out = c1 (x - c2 eps) + c3 z   -- the form of SpeechGenerator.py:143-145, which
+ * also expresses DDIM(eta) and DDPM over a strided sub-sequence of timesteps (rows that are never visited may hold
+ * anything).  The host computes the rows (ditto_tts_b200/schedules.py); load_schedule restores the reference's table. */
+int32_t ditto_engine_load_update_table(ditto_engine_t* e, const float* coef, int64_t steps, void* stream);
 /* Pack weights (bf16 copies, interleaved [fc1;gate], permuted QKV), build the per-step modulation table
  * time_mlp(SiLU(time_embed(t_embedding))) [steps, 2H] (DiTTO.py:75-76 + DiT.py:30) and the RoPE cos/sin
  * tables (DiT.py:46-59).  Synchronises the stream. */

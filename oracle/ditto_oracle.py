@@ -260,6 +260,70 @@ def sample_latents(sd, cfg: OracleConfig, text_emb: Tensor, x_init: Tensor, nois
 
 
 # --------------------------------------------------------------------------
+# sampler variants.  EXTENSIONS: the reference has one sampler (above); these are the textbook
+# forms (DDIM: Song et al. 2021 eq. 12; sub-sequence DDPM: Nichol & Dhariwal 2021 sec. 4; SNR-shifted cosine schedule:
+# Hoogeboom et al. 2023 sec. 3.1), written step by step in float64 and NOT through the c1/c2/c3 rewrite the product uses.
+# "Parity unpinned" for these: there is no reference implementation to mint goldens from; the pin is that with all
+# timesteps / eta-free DDPM they reduce to p_sample_update above (tests/test_schedules.py).
+# --------------------------------------------------------------------------
+def spaced_timesteps(train_steps: int, num_steps: int) -> List[int]:
+    """num_steps timesteps from train_steps-1 down to 0, evenly spaced, rounded half up (integer arithmetic)."""
+    if num_steps == 1:
+        return [train_steps - 1]
+    d = num_steps - 1
+    return [(2 * (train_steps - 1) * (d - i) + d) // (2 * d) for i in range(num_steps)]
+
+
+def shifted_cosine_betas(timesteps: int, scale: float, s: float = 0.008) -> Tensor:
+    """cosine_beta_schedule with SNR(t) multiplied by scale^2; same clip as DiTTO.py:104."""
+    acp = [math.cos(((i / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2 for i in range(timesteps + 1)]
+    acp = [a / acp[0] for a in acp]
+    out = []
+    for a in acp:
+        snr_num = scale * scale * a
+        out.append(snr_num / (snr_num + (1.0 - a)))
+    betas = [min(max(1.0 - out[i + 1] / out[i], 0.0001), 0.9999) for i in range(timesteps)]
+    return torch.tensor(betas, dtype=torch.float64).to(torch.float32)
+
+
+def variant_update(x: Tensor, eps: Tensor, z: Tensor, acp_t: float, acp_prev: float, method: str, eta: float,
+                   last: bool) -> Tensor:
+    """One reverse step from abar_t to abar_prev in float64 (result cast back to x.dtype)."""
+    xd, ed, zd = x.double(), eps.double(), z.double()
+    if method == "ddim":
+        x0 = (xd - math.sqrt(1.0 - acp_t) * ed) / math.sqrt(acp_t)
+        sigma = eta * math.sqrt((1.0 - acp_prev) / (1.0 - acp_t)) * math.sqrt(max(1.0 - acp_t / acp_prev, 0.0))
+        out = math.sqrt(acp_prev) * x0 + math.sqrt(max(1.0 - acp_prev - sigma * sigma, 0.0)) * ed + sigma * zd
+    else:  # ancestral, sigma^2 = beta' (the reference's variance choice, SpeechGenerator.py:143-145)
+        alpha = acp_t / acp_prev
+        out = (xd - (1.0 - alpha) / math.sqrt(1.0 - acp_t) * ed) / math.sqrt(alpha)
+        if not last:
+            out = out + math.sqrt(1.0 - alpha) * zd
+    return out.to(x.dtype)
+
+
+def sample_latents_variant(sd, cfg: OracleConfig, text_emb: Tensor, x_init: Tensor, noise: Tensor,
+                           guidance_scale: Optional[float] = None, method: str = "ddpm", num_steps: Optional[int] = None,
+                           eta: float = 0.0, schedule_scale: Optional[float] = None,
+                           record: Optional[List[Tensor]] = None) -> Tensor:
+    """sample_latents over a sub-sequence of timesteps / with DDIM / with the shifted schedule.  noise index = t_val."""
+    steps = cfg.diffusion_steps
+    betas = cosine_beta_schedule(steps) if schedule_scale is None else shifted_cosine_betas(steps, schedule_scale)
+    acp = torch.cumprod(1.0 - betas.double(), dim=0).tolist()
+    taus = spaced_timesteps(steps, steps if num_steps is None else num_steps)
+    x = x_init
+    for i, t_val in enumerate(taus):
+        t = torch.full((x.shape[0],), t_val, dtype=torch.long)
+        eps = predict_noise(sd, cfg, x, text_emb, t, guidance_scale)
+        if record is not None:
+            record.append(eps)
+        last = i == len(taus) - 1
+        acp_prev = 1.0 if last else acp[taus[i + 1]]
+        x = variant_update(x, eps, noise[t_val], acp[t_val], acp_prev, method, eta, last)
+    return x
+
+
+# --------------------------------------------------------------------------
 # deterministic synthetic weights (used by tests, bench and the golden script alike)
 # --------------------------------------------------------------------------
 def state_dict_keys(cfg: OracleConfig):
