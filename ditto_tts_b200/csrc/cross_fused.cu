@@ -1,0 +1,586 @@
+// Fused cross-attention block of the folded single-head path (reference: src/components/DiT.py:141-151 -> torch
+// nn.MultiheadAttention math path, then norm3):
+//
+//     h   <- h + softmax(alpha * u (K Wq)^T + sbias) (V Wo^T) + bo          (one utterance's S <= 64 text tokens)
+//     u3  <- LayerNorm(h) * gamma3 + beta3                                     (bf16 operand of the gated-MLP GEMM)
+//
+// in ONE kernel per layer instead of scores+softmax -> P (HBM) -> P.V GEMM with residual epilogue -> LayerNorm: the scores
+// and the probabilities never leave the SM, and the residual stream is read once and written once per block instead of
+// being re-read by a separate LayerNorm launch.  The kernel is an HBM stream over u (bf16), h (fp32, in place) and u3
+// (bf16): 12 B per element of h -> 221 MB per launch at C2 (24 000 x 768).
+//
+// Per CTA (persistent over 128-row tiles; a tile never crosses an utterance):
+//   warp 0   TMA producer of the MMA operands: u tile [128 x H] and K-fold [64 x H] through a 2-stage ring (64-column
+//            k-blocks, 128-B swizzle), then per output chunk the V-fold rows [64 x 128] as an MN-major operand
+//   warp 1   MMA issuer:  scores S[128 x 64] = U Kf^T (tcgen05.mma, fp32 in TMEM, one tile AHEAD of the rest so the
+//            operand loads of tile i+1 overlap the epilogue of tile i);  O chunk c [128 x 128] = P[128 x 64] Vf[64 x 128c..]
+//            into a ring of three 128-column TMEM buffers
+//   warp 3   mover: the residual stream goes global <-> shared memory by TMA only (4 staging buffers of 128 rows x 64
+//            fp32 columns, 3 loads in flight): no LSU wavefronts are spent on HBM traffic -- the first version of this
+//            kernel moved h with 8-byte register accesses (8 wavefronts per warp instruction) and was LSU-bound at 117 us
+//   warps 4-11  softmax on the accumulator fragments (tcgen05.ld.16x256b), probabilities written as the bf16 K-major
+//            A operand into shared memory (128-B swizzle by hand);  pass 0: O + bias + residual in place in the staging
+//            buffer (-> TMA store to h) with running row sums;  row statistics exchanged through shared memory;  pass 1
+//            over the rows just written (TMA re-load, L2 hits): normalise, gamma/beta, bf16 in place (-> TMA store to u3)
+// TMEM: columns [0, 384) O ring, [384, 512) two score buffers.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ditto {
+namespace {
+
+constexpr int XF_THREADS = 384;
+constexpr int XF_EPI_WARP0 = 4;
+constexpr int XF_EPI_WARPS = 8;
+constexpr int XF_BM = 128;          // rows per tile
+constexpr int XF_BK = 64;           // k-block (one 128-B swizzle span of bf16)
+constexpr int XF_NS = 64;           // score columns (text tokens, padded)
+constexpr int XF_CH = 128;          // output columns per TMEM chunk
+constexpr int XF_HC = 64;           // output columns per staged half-chunk (two 32-column fp32 slabs)
+constexpr int XF_STAGES = 2;
+constexpr int XF_A_BYTES = XF_BM * XF_BK * 2;   // 16 KiB
+constexpr int XF_B_BYTES = XF_NS * XF_BK * 2;   //  8 KiB
+constexpr int XF_STAGE_BYTES = XF_A_BYTES + XF_B_BYTES;
+constexpr int XF_MAX_H = 768;
+constexpr int XF_P_BYTES = XF_BM * XF_NS * 2;   // 16 KiB
+constexpr int XF_VF_BYTES = XF_NS * XF_CH * 2;  // 16 KiB: V-fold rows of one output chunk
+constexpr int XF_NB = 4;                        // staging buffers for the residual stream
+constexpr int XF_SLAB_BYTES = XF_BM * 32 * 4;   // 16 KiB: 128 rows x 32 fp32 columns (one TMA box)
+constexpr int XF_HBUF_BYTES = 2 * XF_SLAB_BYTES;
+constexpr int XF_OFF_P = XF_STAGES * XF_STAGE_BYTES;
+constexpr int XF_OFF_VF = XF_OFF_P + XF_P_BYTES;
+constexpr int XF_OFF_HB = XF_OFF_VF + XF_VF_BYTES;
+constexpr int XF_OFF_BAR = XF_OFF_HB + XF_NB * XF_HBUF_BYTES;
+constexpr int XF_BAR_BYTES = 256;
+constexpr int XF_OFF_STAT = XF_OFF_BAR + XF_BAR_BYTES;
+constexpr int XF_STAT_BYTES = 2 * XF_BM * 2 * 8;  // [tile parity][row][column half] (sum, sum of squares)
+constexpr int XF_SMEM_BYTES = XF_OFF_STAT + XF_STAT_BYTES + 1024 /*align slack*/;
+static_assert(XF_SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
+static_assert(XF_OFF_P % 1024 == 0 && XF_OFF_VF % 1024 == 0 && XF_OFF_HB % 1024 == 0 && XF_STAGE_BYTES % 1024 == 0,
+              "swizzled operands need 1024-B alignment");
+constexpr int XF_TMEM_COLS = 512;
+constexpr int XF_O_BUFS = 3;
+constexpr int XF_S_COL0 = XF_O_BUFS * XF_CH;  // 384
+
+struct XfDev {
+  int n_seq, T, S, H;
+  int m_tiles, num_tiles, num_kb, num_ch, num_hc;
+  float alpha2;                               // alpha * log2(e)
+  const float* sbias; long long sb_seq;       // [n_seq, sb_seq] additive score bias
+  const float* out_bias;                      // [H]
+  const float* gamma; const float* beta;      // LayerNorm after the block
+  float inv_h;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_16x32(uint32_t taddr, uint32_t (&r)[16]) {  // 16 lanes x 32 fp32 columns, fragment layout
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// shared -> global tiled store (bulk async-group completion); out-of-range rows are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+template <int N>  // ... only until the sources have been READ (the shared-memory buffers may be reused)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(XF_THREADS, 1)
+    cross_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_kf,
+                       const __grid_constant__ CUtensorMap tmap_vf, const __grid_constant__ CUtensorMap tmap_h,
+                       const __grid_constant__ CUtensorMap tmap_uo, const XfDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* p_smem = smem + XF_OFF_P;
+  uint8_t* vf_smem = smem + XF_OFF_VF;
+  uint8_t* hbuf = smem + XF_OFF_HB;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XF_OFF_BAR);
+  uint64_t* empty_bar = full_bar + XF_STAGES;
+  uint64_t* s_full = empty_bar + XF_STAGES;   // [2] scores accumulator complete        (MMA -> epilogue)
+  uint64_t* s_empty = s_full + 2;             // [2] scores accumulator read            (epilogue -> MMA)
+  uint64_t* p_full = s_empty + 2;             //     probabilities in shared memory     (epilogue -> MMA)
+  uint64_t* vf_full = p_full + 1;             //     V-fold chunk landed                (TMA -> MMA)
+  uint64_t* vf_empty = vf_full + 1;           //     P.V chunk retired                  (MMA -> TMA)
+  uint64_t* o_full = vf_empty + 1;            // [3] output chunk complete              (MMA -> epilogue)
+  uint64_t* o_empty = o_full + XF_O_BUFS;     // [3] output chunk read                  (epilogue -> MMA)
+  uint64_t* hin_full = o_empty + XF_O_BUFS;   // [NB] residual half-chunk landed        (mover TMA -> epilogue)
+  uint64_t* hout_full = hin_full + XF_NB;     // [NB] result half-chunk in place        (epilogue -> mover)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hout_full + XF_NB);
+  float2* stat = reinterpret_cast<float2*>(smem + XF_OFF_STAT);
+  static_assert((2 * XF_STAGES + 2 + 2 + 3 + 2 * XF_O_BUFS + 2 * XF_NB) * 8 + 4 <= XF_BAR_BYTES, "barrier block too small");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_u);
+    tma_prefetch_desc(&tmap_kf);
+    tma_prefetch_desc(&tmap_vf);
+    tma_prefetch_desc(&tmap_h);
+    tma_prefetch_desc(&tmap_uo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < XF_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], XF_EPI_WARPS);
+    }
+    mbar_init(p_full, XF_EPI_WARPS);
+    mbar_init(vf_full, 1);
+    mbar_init(vf_empty, 1);
+    for (int s = 0; s < XF_O_BUFS; ++s) {
+      mbar_init(&o_full[s], 1);
+      mbar_init(&o_empty[s], XF_EPI_WARPS);
+    }
+    for (int s = 0; s < XF_NB; ++s) {
+      mbar_init(&hin_full[s], 1);
+      mbar_init(&hout_full[s], XF_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<XF_TMEM_COLS>(tmem_ptr);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0) {
+    // =========================== TMA producer: MMA operands ===========================
+    regs_shrink_ctrl();
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t vc = 0;  // V-fold chunks loaded so far
+      auto load_scores_operands = [&](int tile) {
+        const int seq = tile / p.m_tiles, mb = tile - seq * p.m_tiles;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * XF_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], XF_STAGE_BYTES);
+          tma_load_4d(&tmap_u, &full_bar[stage], sa, kb * XF_BK, mb * XF_BM, 0, seq);
+          tma_load_4d(&tmap_kf, &full_bar[stage], sa + XF_A_BYTES, kb * XF_BK, 0, 0, seq);  // rows >= S: zero-filled
+          if (++stage == XF_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      };
+      // same order as the MMA issuer consumes: scores(0), then per tile scores(next) before the tile's P.V chunks
+      if (first < p.num_tiles) load_scores_operands(first);
+      for (int tile = first; tile < p.num_tiles; tile += step) {
+        if (tile + step < p.num_tiles) load_scores_operands(tile + step);
+        const int seq = tile / p.m_tiles;
+        for (int c = 0; c < p.num_ch; ++c, ++vc) {
+          mbar_wait(vf_empty, (vc & 1u) ^ 1u);  // the previous chunk's MMAs have retired
+          mbar_expect_tx(vf_full, XF_VF_BYTES);
+          for (int j = 0; j < XF_CH / 64; ++j)  // [64 k-rows x 64 n] boxes, n contiguous (MN-major operand); rows >= Sp zero-filled
+            tma_load_4d(&tmap_vf, vf_full, vf_smem + j * (XF_NS * 128), c * XF_CH + j * 64, 0, 0, seq);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (single thread) ===========================
+    regs_shrink_ctrl();
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(XF_BM, XF_NS, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(XF_BM, XF_CH, false, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto issue_scores = [&](uint32_t j) {  // scores of this CTA's j-th tile into score buffer j & 1
+        const uint32_t sb = j & 1u;
+        mbar_wait(&s_empty[sb], ((j >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + XF_S_COL0 + sb * XF_NS;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * XF_STAGE_BYTES);
+          const uint32_t sbm = sa + XF_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < XF_BK / 16; ++k)
+            umma_bf16(d_tmem, umma_smem_desc(sa + k * 32, 16, 1024), umma_smem_desc(sbm + k * 32, 16, 1024), idesc_s, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == XF_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&s_full[sb]);
+      };
+      uint32_t it = 0, oc = 0;
+      if (first < p.num_tiles) issue_scores(0);
+      const uint32_t pa = smem_u32(p_smem), vb = smem_u32(vf_smem);
+      for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+        if (tile + step < p.num_tiles) issue_scores(it + 1);
+        mbar_wait(p_full, it & 1u);
+        for (int c = 0; c < p.num_ch; ++c, ++oc) {
+          const uint32_t ob = oc % XF_O_BUFS;
+          mbar_wait(vf_full, oc & 1u);
+          mbar_wait(&o_empty[ob], ((oc / XF_O_BUFS) & 1u) ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + ob * XF_CH;
+#pragma unroll
+          for (int k = 0; k < XF_NS / 16; ++k)
+            umma_bf16(d_tmem, umma_smem_desc(pa + k * 32, 16, 1024), umma_smem_desc(vb + k * (16 * 128), XF_NS * 128, 1024), idesc_o,
+                      k != 0 ? 1u : 0u);
+          umma_commit(&o_full[ob]);
+          umma_commit(vf_empty);  // the V-fold buffer (and, after the last chunk, P) may be overwritten once these MMAs retire
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== mover: residual stream global <-> shared by TMA ===========================
+    // job j = (tile, pass, half-chunk): pass 0 loads h (fp32) and stores h + attention; pass 1 re-loads the updated rows
+    // (L2 hits) and stores LayerNorm(h) as bf16.  Buffer j % NB; NB - 1 loads in flight ahead of the epilogue.
+    regs_shrink_ctrl();
+    if (lane == 0) {
+      const int my_tiles = first < p.num_tiles ? (p.num_tiles - 1 - first) / step + 1 : 0;
+      const int jobs_per_tile = 2 * p.num_hc;
+      const int J = my_tiles * jobs_per_tile;
+      auto job_coords = [&](int j, int& seq, int& row, int& pass, int& hc) {
+        const int ti = j / jobs_per_tile, r = j - ti * jobs_per_tile;
+        const int tile = first + ti * step;
+        seq = tile / p.m_tiles;
+        row = (tile - seq * p.m_tiles) * XF_BM;
+        pass = r / p.num_hc;
+        hc = r - pass * p.num_hc;
+      };
+      auto issue_load = [&](int j) {
+        int seq, row, pass, hc;
+        job_coords(j, seq, row, pass, hc);
+        const int b = j % XF_NB;
+        uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+        mbar_expect_tx(&hin_full[b], XF_HBUF_BYTES);
+        tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
+        tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
+      };
+      for (int j = 0; j < XF_NB - 1 && j < J; ++j) issue_load(j);
+      for (int j = 0; j < J; ++j) {
+        const int b = j % XF_NB;
+        mbar_wait(&hout_full[b], (j / XF_NB) & 1u);
+        int seq, row, pass, hc;
+        job_coords(j, seq, row, pass, hc);
+        const uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+        if (pass == 0) {
+          tma_store_4d(&tmap_h, buf, hc * XF_HC, row, 0, seq);
+          tma_store_4d(&tmap_h, buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
+        } else {
+          tma_store_4d(&tmap_uo, buf, hc * XF_HC, row, 0, seq);
+        }
+        bulk_commit();
+        const int jn = j + XF_NB - 1;  // goes into the buffer of job j - 1
+        if (jn < J) {
+          bulk_wait_read<1>();  // every store but the one just issued has read its source: buffer (j-1) % NB is free
+          // a pass-1 job re-loads what pass-0 job jn - num_hc stored, num_hc - NB + 1 groups before the newest one:
+          // that store must have COMPLETED (be visible), not just have read its source
+          if ((jn % jobs_per_tile) >= p.num_hc) {
+            if (p.num_hc - XF_NB + 1 > 8) bulk_wait<8>();
+            else bulk_wait<1>();
+          }
+          issue_load(jn);
+        }
+      }
+      bulk_wait<0>();
+    }
+  } else if (warp >= XF_EPI_WARP0) {
+    // =========================== softmax + epilogue ===========================
+    regs_grow_epi();
+    const int ew = warp - XF_EPI_WARP0;
+    const int quarter = warp & 3;   // TMEM lanes [32 quarter, +32)
+    const int hsel = ew >> 2;       // softmax: 16-row half of the quarter; output: 32-column slab of the half-chunk
+    const int g = lane >> 2, q = lane & 3, q2 = q * 2;
+    const bool writer = q == 0;
+    uint32_t it = 0, oc = 0, job = 0;
+    for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+      const int seq = tile / p.m_tiles;
+      const uint32_t sb = it & 1u;
+      // ---------------- softmax of the 128 x 64 score tile -> bf16 probabilities in shared memory ----------------
+      {
+        const int trow = quarter * 32 + hsel * 16;
+        const float* bias = p.sbias + seq * p.sb_seq;
+        float2 bb[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const int c = kb * 8 + q2;
+          bb[kb].x = c < p.S ? __ldg(bias + c) * 1.4426950408889634f : 0.f;
+          bb[kb].y = c + 1 < p.S ? __ldg(bias + c + 1) * 1.4426950408889634f : 0.f;
+        }
+        mbar_wait(&s_full[sb], (it >> 1) & 1u);
+        tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld_16x64(tmem_base + (static_cast<uint32_t>(trow) << 16) + XF_S_COL0 + sb * XF_NS, r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);  // the scores are in registers: the buffer may take tile it + 2
+        float sA[16], sB[16];
+        float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const int c = kb * 8 + q2;
+          sA[2 * kb] = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) : -INFINITY;
+          sA[2 * kb + 1] = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) : -INFINITY;
+          sB[2 * kb] = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) : -INFINITY;
+          sB[2 * kb + 1] = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) : -INFINITY;
+          mA = fmaxf(mA, fmaxf(sA[2 * kb], sA[2 * kb + 1]));
+          mB = fmaxf(mB, fmaxf(sB[2 * kb], sB[2 * kb + 1]));
+        }
+        mA = quad_max(mA);
+        mB = quad_max(mB);
+        float sumA = 0.f, sumB = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          sA[j] = ex2_approx(sA[j] - mA);   // exp2(-inf) = 0 for the padded columns
+          sB[j] = ex2_approx(sB[j] - mB);
+          sumA += sA[j];
+          sumB += sB[j];
+        }
+        const float iA = 1.0f / quad_sum(sumA), iB = 1.0f / quad_sum(sumB);
+        // K-major A operand, 128-B swizzle: row r at r * 128 B, its 16-B chunk kb stored at chunk position kb ^ (r & 7)
+        const int rA = trow + g, rB = rA + 8;
+        uint8_t* pa = p_smem + rA * 128 + q2 * 2;
+        uint8_t* pb = p_smem + rB * 128 + q2 * 2;
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          *reinterpret_cast<uint32_t*>(pa + ((kb ^ (rA & 7)) << 4)) = pack_bf16x2(sA[2 * kb] * iA, sA[2 * kb + 1] * iA);
+          *reinterpret_cast<uint32_t*>(pb + ((kb ^ (rB & 7)) << 4)) = pack_bf16x2(sB[2 * kb] * iB, sB[2 * kb + 1] * iB);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---------------- pass 0: h <- h + O + bo, half-chunk by half-chunk in the staging buffers; row statistics -------
+      // This warp: tile rows lrow0 + hh * 16 + g (+ 8), columns hsel * 32 + kbl * 8 + q2 (+ 1) of the half-chunk.
+      // fp32 slab in shared memory (TMA 128-B swizzle): row r at r * 128 B, 16-B chunk j at position j ^ (r & 7).
+      const int lrow0 = quarter * 32;
+      float st[8];                                            // [hh][A|B] (sum, sumsq)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st[j] = 0.f;
+      uint32_t ob = 0;
+#pragma unroll 1
+      for (int hc = 0; hc < p.num_hc; ++hc, ++job) {
+        const uint32_t b = job % XF_NB;
+        uint8_t* slab = hbuf + b * XF_HBUF_BYTES + hsel * XF_SLAB_BYTES;
+        const int col0 = hc * XF_HC + hsel * 32 + q2;
+        float2 b2[4];
+#pragma unroll
+        for (int kbl = 0; kbl < 4; ++kbl) b2[kbl] = __ldg(reinterpret_cast<const float2*>(p.out_bias + col0 + kbl * 8));
+        if ((hc & 1) == 0) {
+          ob = oc % XF_O_BUFS;
+          mbar_wait(&o_full[ob], (oc / XF_O_BUFS) & 1u);
+          tcgen05_fence_after();
+        }
+        mbar_wait(&hin_full[b], (job / XF_NB) & 1u);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
+          uint8_t* sa = slab + rA * 128 + (q & 1) * 8;
+          uint8_t* sbp = slab + rB * 128 + (q & 1) * 8;
+          uint32_t r[16];
+          tmem_ld_16x32(tmem_base + (static_cast<uint32_t>(lrow0 + hh * 16) << 16) + ob * XF_CH + (hc & 1) * XF_HC + hsel * 32, r);
+          float2 rsA[4], rsB[4];
+#pragma unroll
+          for (int kbl = 0; kbl < 4; ++kbl) {
+            const int j = kbl * 2 + (q >> 1);
+            rsA[kbl] = *reinterpret_cast<const float2*>(sa + ((j ^ (rA & 7)) << 4));
+            rsB[kbl] = *reinterpret_cast<const float2*>(sbp + ((j ^ (rB & 7)) << 4));
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int kbl = 0; kbl < 4; ++kbl) {
+            const int j = kbl * 2 + (q >> 1);
+            float2 vA, vB;
+            vA.x = __uint_as_float(r[4 * kbl]) + b2[kbl].x + rsA[kbl].x;
+            vA.y = __uint_as_float(r[4 * kbl + 1]) + b2[kbl].y + rsA[kbl].y;
+            vB.x = __uint_as_float(r[4 * kbl + 2]) + b2[kbl].x + rsB[kbl].x;
+            vB.y = __uint_as_float(r[4 * kbl + 3]) + b2[kbl].y + rsB[kbl].y;
+            st[4 * hh] += vA.x + vA.y;
+            st[4 * hh + 1] = fmaf(vA.x, vA.x, fmaf(vA.y, vA.y, st[4 * hh + 1]));
+            st[4 * hh + 2] += vB.x + vB.y;
+            st[4 * hh + 3] = fmaf(vB.x, vB.x, fmaf(vB.y, vB.y, st[4 * hh + 3]));
+            *reinterpret_cast<float2*>(sa + ((j ^ (rA & 7)) << 4)) = vA;   // in place: every element is owned by one thread
+            *reinterpret_cast<float2*>(sbp + ((j ^ (rB & 7)) << 4)) = vB;
+          }
+        }
+        fence_proxy_async_smem();  // the TMA store reads these generic-proxy writes
+        if (hc & 1) tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&hout_full[b]);
+          if (hc & 1) mbar_arrive(&o_empty[ob]);
+        }
+        if (hc & 1) ++oc;
+      }
+      // ---------------- row statistics: the two column slabs of a row live in two warps ----------------
+      float2* sp = stat + (it & 1u) * (XF_BM * 2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st[j] = quad_sum(st[j]);
+      if (writer) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int lr = lrow0 + hh * 16 + g;
+          sp[lr * 2 + hsel] = make_float2(st[4 * hh], st[4 * hh + 1]);
+          sp[(lr + 8) * 2 + hsel] = make_float2(st[4 * hh + 2], st[4 * hh + 3]);
+        }
+      }
+      epi_bar_sync();
+      float mean[4], rstd[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lr = lrow0 + (j >> 1) * 16 + g + (j & 1) * 8;
+        const float2 a = sp[lr * 2], bq = sp[lr * 2 + 1];
+        const float m = (a.x + bq.x) * p.inv_h;
+        const float var = fmaxf(fmaf(-m, m, (a.y + bq.y) * p.inv_h), 0.f);
+        mean[j] = m;
+        rstd[j] = rsqrtf(var + 1e-5f);
+      }
+      // ---------------- pass 1: LayerNorm of the updated rows -> bf16, written over the staging buffer ----------------
+      // bf16 box in shared memory: row r at r * 128 B (64 columns), 16-B chunk j (8 columns) at position j ^ (r & 7)
+#pragma unroll 1
+      for (int hc = 0; hc < p.num_hc; ++hc, ++job) {
+        const uint32_t b = job % XF_NB;
+        uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+        const uint8_t* slab = buf + hsel * XF_SLAB_BYTES;
+        const int col0 = hc * XF_HC + hsel * 32 + q2;
+        float2 gm[4], bt[4];
+#pragma unroll
+        for (int kbl = 0; kbl < 4; ++kbl) {
+          gm[kbl] = __ldg(reinterpret_cast<const float2*>(p.gamma + col0 + kbl * 8));
+          bt[kbl] = __ldg(reinterpret_cast<const float2*>(p.beta + col0 + kbl * 8));
+        }
+        mbar_wait(&hin_full[b], (job / XF_NB) & 1u);
+        float2 v[2][8];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
+#pragma unroll
+          for (int kbl = 0; kbl < 4; ++kbl) {
+            const int j = kbl * 2 + (q >> 1);
+            v[hh][2 * kbl] = *reinterpret_cast<const float2*>(slab + rA * 128 + (q & 1) * 8 + ((j ^ (rA & 7)) << 4));
+            v[hh][2 * kbl + 1] = *reinterpret_cast<const float2*>(slab + rB * 128 + (q & 1) * 8 + ((j ^ (rB & 7)) << 4));
+          }
+        }
+        epi_bar_sync();  // every warp has its fp32 values in registers: the buffer may be overwritten with the bf16 result
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
+          const float mA = mean[2 * hh], iA = rstd[2 * hh], mB = mean[2 * hh + 1], iB = rstd[2 * hh + 1];
+#pragma unroll
+          for (int kbl = 0; kbl < 4; ++kbl) {
+            const int j = hsel * 4 + kbl;
+            const float2 a = v[hh][2 * kbl], c = v[hh][2 * kbl + 1];
+            *reinterpret_cast<uint32_t*>(buf + rA * 128 + ((j ^ (rA & 7)) << 4) + q * 4) =
+                pack_bf16x2(fmaf((a.x - mA) * iA, gm[kbl].x, bt[kbl].x), fmaf((a.y - mA) * iA, gm[kbl].y, bt[kbl].y));
+            *reinterpret_cast<uint32_t*>(buf + rB * 128 + ((j ^ (rB & 7)) << 4) + q * 4) =
+                pack_bf16x2(fmaf((c.x - mB) * iB, gm[kbl].x, bt[kbl].x), fmaf((c.y - mB) * iB, gm[kbl].y, bt[kbl].y));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hout_full[b]);
+      }
+    }
+  } else {
+    regs_shrink_ctrl();  // warp 2 idles after the TMEM allocation; the whole warpgroup has to execute the setmaxnreg
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<XF_TMEM_COLS>(tmem_base);
+  }
+}
+
+typedef CUresult (*XfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+XfEncodeFn g_xf_encode = nullptr;
+
+// fp32 residual stream as a 4-D map (cols, rows of one utterance, 1, utterance): box 32 x 128, 128-B swizzle
+int make_map_h(CUtensorMap* m, float* h, int64_t n_seq, int64_t T, int H) {
+  if (g_xf_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DITTO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DITTO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, DITTO_E_CUDA, "cuTensorMapEncodeTiled not available");
+    g_xf_encode = reinterpret_cast<XfEncodeFn>(fn);
+  }
+  DITTO_REQUIRE((reinterpret_cast<uintptr_t>(h) & 15) == 0, DITTO_E_BADARG, "cross_fused: h must be 16-B aligned");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(T), 1, static_cast<cuuint64_t>(n_seq)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(H) * 4, static_cast<cuuint64_t>(T) * H * 4, static_cast<cuuint64_t>(T) * H * 4};
+  cuuint32_t box[4] = {32, XF_BM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_xf_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cross_fused: cuTensorMapEncodeTiled (fp32) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return DITTO_E_CUDA;
+  }
+  return 0;
+}
+
+bool g_xf_attr_done = false;
+
+}  // namespace
+
+bool cross_fused_supported(int64_t T, int64_t S, int H, int heads) {
+  // H >= 4 half-chunks: the mover re-loads a row block only after the store that produced it has completed (NB <= H / 64)
+  return heads == 1 && S >= 1 && S <= XF_NS && H % XF_CH == 0 && H >= XF_NB * XF_HC && H <= XF_MAX_H && T >= 1;
+}
+
+int launch_cross_fused(const CrossFusedParams& q, cudaStream_t st) {
+  DITTO_TRY(tc_gemm_init());
+  DITTO_REQUIRE(cross_fused_supported(q.T, q.S, q.H, 1), DITTO_E_UNSUPPORTED, "cross_fused: unsupported shape");
+  DITTO_REQUIRE(q.u && q.kfold && q.vfold && q.sbias && q.out_bias && q.h && q.gamma && q.beta && q.u_out, DITTO_E_BADARG,
+                "cross_fused: null argument");
+  DITTO_REQUIRE(q.n_seq >= 1 && q.Sp >= q.S && q.Sp % 8 == 0, DITTO_E_BADARG, "cross_fused: bad sizes");
+  if (!g_xf_attr_done) {
+    DITTO_CUDA(cudaFuncSetAttribute(cross_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XF_SMEM_BYTES));
+    g_xf_attr_done = true;
+  }
+  TcOperand U, Kf, Vf, Uo;
+  U.ptr = q.u; U.rows = q.T; U.cols = q.H; U.ld = q.H; U.s_outer = q.T * q.H;
+  Kf.ptr = q.kfold; Kf.rows = q.S; Kf.cols = q.H; Kf.ld = q.H; Kf.s_outer = q.kf_seq;
+  Vf.ptr = q.vfold; Vf.rows = q.Sp; Vf.cols = q.H; Vf.ld = q.H; Vf.s_outer = q.vf_seq;
+  Uo.ptr = q.u_out; Uo.rows = q.T; Uo.cols = q.H; Uo.ld = q.H; Uo.s_outer = q.T * q.H;
+  CUtensorMap mu, mk, mv, mh, mo;
+  DITTO_TRY(tc_make_map(&mu, U, 1, q.n_seq, XF_BK, XF_BM));
+  DITTO_TRY(tc_make_map(&mk, Kf, 1, q.n_seq, XF_BK, XF_NS));
+  DITTO_TRY(tc_make_map(&mv, Vf, 1, q.n_seq, 64, XF_NS));
+  DITTO_TRY(tc_make_map(&mo, Uo, 1, q.n_seq, XF_HC, XF_BM));
+  DITTO_TRY(make_map_h(&mh, q.h, q.n_seq, q.T, q.H));
+  XfDev p;
+  p.n_seq = static_cast<int>(q.n_seq); p.T = static_cast<int>(q.T); p.S = static_cast<int>(q.S); p.H = q.H;
+  p.m_tiles = static_cast<int>(ceil_div(q.T, XF_BM));
+  const int64_t tiles = static_cast<int64_t>(p.m_tiles) * q.n_seq;
+  DITTO_REQUIRE(tiles < (1ll << 31), DITTO_E_UNSUPPORTED, "cross_fused: too many tiles");
+  p.num_tiles = static_cast<int>(tiles);
+  p.num_kb = q.H / XF_BK;
+  p.num_ch = q.H / XF_CH;
+  p.num_hc = q.H / XF_HC;
+  p.alpha2 = q.alpha * 1.4426950408889634f;
+  p.sbias = q.sbias; p.sb_seq = q.sb_seq;
+  p.out_bias = q.out_bias;
+  p.gamma = q.gamma; p.beta = q.beta;
+  p.inv_h = 1.0f / static_cast<float>(q.H);
+  // flops: both contractions; bytes: u read, h read + write, u3 write (the HBM stream that bounds the kernel)
+  const double rows = static_cast<double>(q.n_seq) * q.T;
+  ProfScope prof(q.tag, st, 4.0 * rows * q.S * q.H, rows * q.H * 12.0);
+  const int grid = static_cast<int>(std::min<int64_t>(tc_num_sms(), tiles));
+  cross_fused_kernel<<<grid, XF_THREADS, XF_SMEM_BYTES, st>>>(mu, mk, mv, mh, mo, p);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ditto

@@ -37,7 +37,7 @@ ProfAcc g_prof_acc[PC_COUNT];
 const char* kProfNames[PC_COUNT] = {"tc_gemm.proj_in", "tc_gemm.qkv_rope", "tc_gemm.self_scores", "tc_gemm.self_pv", "tc_gemm.cross_q",
                                     "tc_gemm.cross_scores", "tc_gemm.cross_pv", "tc_gemm.cross_out", "tc_gemm.glu", "tc_gemm.fc2",
                                     "tc_gemm.proj_out", "tc_gemm.text_kv", "tc_gemm.other", "sgemm_f32", "layernorm", "adaln_ln",
-                                    "rope", "softmax", "cfg_ddpm_update", "elementwise"};
+                                    "rope", "softmax", "cfg_ddpm_update", "elementwise", "tc_gemm.cross_fused_ln"};
 }  // namespace
 ProfScope::ProfScope(int cls, cudaStream_t stream, double flops, double bytes) : st(stream) {
   if (!g_prof_enabled) return;
@@ -84,6 +84,7 @@ struct ditto_engine {
   int H = 0, L = 0, heads = 0, d = 0, half = 0, Td = 0, Xd = 0, steps = 0, maxT = 0;
   bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
   int rope_pd = 0;
+  bool fused_cross = true;  // folded cross-attention + residual + norm3 in one kernel (cross_fused.cu); DITTO_NO_FUSED_CROSS=1 disables
   bool fused_attn = false;  // scores + softmax fused (cluster kernel); falls back per call when a row needs > 16 tiles
   bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
   bool defer_ln = false;    // block LayerNorms folded into the neighbouring GEMM epilogues (no LayerNorm launches)
@@ -465,6 +466,10 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
                          1.f, static_cast<int>(gs[gi].n_x * gs[gi].T), H, H, st));
   }
 
+  // the fused cross-attention kernel also produces norm3's output, so it is used only when EVERY group qualifies
+  bool fuse_cross = b16 && e->fused_cross && !dln;
+  for (int gi = 0; gi < ng && fuse_cross; ++gi)
+    fuse_cross = fold_active(e, gs[gi].S) && cross_fused_supported(gs[gi].T, gs[gi].S, H, e->heads);
   for (int i = 0; i < e->L; ++i) {
     const LayerPack& lp = e->layers[i];
     const bool last = (i == e->L - 1);
@@ -512,6 +517,16 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
           const int heads = e->heads;
           const int64_t Sp = round_up(S, 8);
+          if (fuse_cross) {
+            // scores + softmax + P.V + out bias + residual + norm3 in one kernel (cross_fused.cu); u is overwritten with LN3(h)
+            CrossFusedParams f;
+            f.u = ug; f.kfold = c.kfold0 + c.kfold_stride * i; f.kf_seq = S * H; f.vfold = c.vfold0 + c.vfold_stride * i; f.vf_seq = Sp * H;
+            f.sbias = c.sbias0 + c.sbias_stride * i; f.sb_seq = Sp; f.out_bias = e->LW(i, "cross_attn.out_proj.bias");
+            f.h = hg; f.gamma = e->LW(i, "norm3.weight"); f.beta = e->LW(i, "norm3.bias"); f.u_out = ug;
+            f.n_seq = n; f.T = T; f.S = S; f.Sp = Sp; f.H = H; f.alpha = sqrt_inv_d; f.tag = PC_TC_CROSS_FUSED;
+            DITTO_TRY(launch_cross_fused(f, st));
+            continue;
+          }
           if (e->fused_attn && tc_scores_softmax_csize(static_cast<int>(S)) == 1) {
             TcScoresSoftmaxParams f;
             f.Q.ptr = ug; f.Q.rows = T; f.Q.cols = H; f.Q.ld = H; f.Q.s_inner = 0; f.Q.s_outer = T * H;
@@ -560,7 +575,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
       }
       DITTO_TRY(fork.end());
       // ---- gated MLP                                                                                  DiT.py:150-155
-      if (!dln) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
+      if (!dln && !fuse_cross) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
       {
         TcGemmParams g;
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
@@ -730,6 +745,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     e->defer_ln = (cfg->flags & DITTO_F_DEFER_LN) != 0 && e->fused_rope && e->fused_attn;
     if (const char* ed = getenv("DITTO_NO_DEFER_LN")) if (ed[0] == '1') e->defer_ln = false;
     if (const char* ef = getenv("DITTO_NO_FUSED_ATTN")) if (ef[0] == '1') e->fused_attn = false;
+    e->fused_cross = e->fused_attn;
+    if (const char* ef = getenv("DITTO_NO_FUSED_CROSS")) if (ef[0] == '1') e->fused_cross = false;
     const char* env = getenv("DITTO_PV_TRANSPOSE");
     e->pv_transpose = env && env[0] == '1';
     const char* env2 = getenv("DITTO_ROPE_TABLE");

@@ -87,24 +87,6 @@ struct DevParams {
 // ---------------------------------------------------------------------------------------------------
 // epilogue math
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float quad_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-}
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v + __shfl_xor_sync(0xffffffffu, v, 2);
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 // per-row LayerNorm coefficients from the producer's partial statistics: LN(h)_k = a h_k + nm  (before gamma / beta);
 // eps 1e-5, biased variance (nn.LayerNorm).  stat == nullptr: identity (a = 1, nm = 0).
 __device__ __forceinline__ void ln_row_coef(const float2* stat, int parts, long long row, bool ok, float inv_h, float& a, float& nm) {
@@ -154,19 +136,6 @@ __device__ __forceinline__ float geglu_fast(float a, float g) {
 // writes whole 32-B sectors; no shared-memory staging (the UMMA operand reads own the smem bandwidth), the bias of a
 // column pair is loaded once for all rows, and RoPE / GLU partners (a multiple of 8 columns apart) sit in the same thread.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_ld_16x64(uint32_t taddr, uint32_t (&r)[32]) {  // 16 lanes x 64 fp32 columns
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
 // Residual fragment of one 16 x 64 block in the accumulator-fragment layout: v[2*kb + rr] = columns
 // (col0 + kb*8 + q2, +1) of row rowA + 8*rr.  Loaded BEFORE the matching TMEM load is waited for (and one block ahead of
 // the stores), so that the global-load latency overlaps the MMA / the previous block's stores.  The residual may alias
@@ -738,11 +707,6 @@ __device__ __forceinline__ ClusterPos cluster_pos(int cm, int cn) {
 // MMA issuer, TMEM allocator, idle) shrink to 56 registers, the two epilogue warpgroups grow from the launch-bound limit
 // of 168 to 224 -- the fused epilogues (RoPE, GLU, residual + statistics) keep two accumulator blocks, their constants and
 // the prefetched residual live at once and spilled at 168.
-constexpr int REGS_CTRL = 56, REGS_EPI = 224;
-static_assert(128 * REGS_CTRL + 256 * REGS_EPI <= 65536, "register re-distribution exceeds the register file");
-__device__ __forceinline__ void regs_shrink_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL)); }
-__device__ __forceinline__ void regs_grow_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI)); }
-
 template <int EPI, bool B_KN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
@@ -1576,6 +1540,10 @@ int launch_clustered(const void* func, int csize, int smem_bytes, int64_t num_wo
 }  // namespace
 
 void tc_gemm_set_debug_counters(unsigned long long* dev_ptr) { g_dbg = dev_ptr; }
+int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
+  return make_map(m, op, n_inner, n_outer, box_cols, box_rows);
+}
+int tc_num_sms() { return g_num_sms; }
 
 int tc_gemm_init() {
   if (g_init_done) return 0;

@@ -118,7 +118,27 @@ struct TcScoresSoftmaxParams {
 };
 int tc_scores_softmax_csize(int N);             // cluster size the kernel will use for N key columns (0: unsupported)
 int launch_tc_scores_softmax(const TcScoresSoftmaxParams& p, cudaStream_t st);
+// ---- cross_fused.cu: folded single-head cross-attention + residual + the LayerNorm that follows, one kernel -------------
+struct CrossFusedParams {
+  const bf16* u = nullptr;                     // [n_seq * T, H] LayerNorm-2 output (query operand)
+  const bf16* kfold = nullptr; int64_t kf_seq = 0;   // [n_seq, S, H]  K Wq,  element stride between sequences
+  const bf16* vfold = nullptr; int64_t vf_seq = 0;   // [n_seq, Sp, H] V Wo^T (rows >= S zero)
+  const float* sbias = nullptr; int64_t sb_seq = 0;  // [n_seq, Sp] additive score bias
+  const float* out_bias = nullptr;             // [H] cross_attn.out_proj.bias
+  float* h = nullptr;                          // [n_seq * T, H] residual stream, updated in place
+  const float* gamma = nullptr; const float* beta = nullptr;  // the next LayerNorm (norm3)
+  bf16* u_out = nullptr;                       // [n_seq * T, H] its bf16 output (may alias u)
+  int64_t n_seq = 0, T = 0, S = 0, Sp = 0; int H = 0;
+  float alpha = 1.f;
+  int tag = PC_TC_OTHER;
+};
+bool cross_fused_supported(int64_t T, int64_t S, int H, int heads);
+int launch_cross_fused(const CrossFusedParams& p, cudaStream_t st);
+
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
+// 4-D bf16 tensor map (cols, rows, inner batch, outer batch) with a (box_cols, box_rows, 1, 1) box, 128-B swizzle, zero OOB fill
+int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows);
+int tc_num_sms();
 void tc_gemm_set_debug_counters(unsigned long long* dev_ptr);  // ditto_debug_set_counters
 
 }  // namespace ditto

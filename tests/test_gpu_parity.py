@@ -284,3 +284,29 @@ def test_full_size_batch_properties_bf16(dev):
     w1 = s.p_sample(xd, t, td, noise=zd, guidance_scale=1.0)
     assert rel(w1, unguided) <= 1e-5
     assert _lib.launch_count() > 0
+
+
+# ------------------------------------------------------------------------------------------ fused cross-attention block
+@pytest.mark.parametrize("B,T,S", [(2, 750, 64), (3, 130, 5), (1, 1, 1), (2, 257, 33), (1, 128, 64)])
+def test_fused_cross_attention_block(dev, B, T, S):
+    """cross_fused.cu (scores + softmax + P.V + residual + norm3 in one kernel) against the oracle and against the
+    separate-kernel composition (DITTO_NO_FUSED_CROSS=1), default single-head model, bf16 path."""
+    cfg = O.OracleConfig(768, 2, 1, 256, 768, 50)
+    sd = O.make_state_dict(cfg, 21)
+    x, text, _ = O.make_inputs(B, T, S, cfg, 22)
+    t = torch.arange(B) * 7 + 3
+    want = O.ditto_forward(sd, cfg, x, text, t)
+    outs = {}
+    for fused in (True, False):
+        os.environ["DITTO_NO_FUSED_CROSS"] = "0" if fused else "1"
+        try:
+            m = build_model(cfg, sd, "bf16", dev)
+            _lib.profile_start()
+            outs[fused] = m(x.to(dev), text.to(dev), t.to(dev))
+            prof = _lib.profile_stop()
+        finally:
+            os.environ.pop("DITTO_NO_FUSED_CROSS", None)
+        assert ("tc_gemm.cross_fused_ln" in prof) == fused, sorted(prof)
+        assert ("tc_gemm.cross_pv" in prof) == (not fused)
+        assert rel(outs[fused], want) <= BAR["bf16"]
+    assert rel(outs[True], outs[False]) <= 6e-3     # same operands, different rounding points of P / LN statistics
