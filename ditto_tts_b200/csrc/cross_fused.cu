@@ -24,6 +24,7 @@
 //            over the rows just written (TMA re-load, L2 hits): normalise, gamma/beta, bf16 in place (-> TMA store to u3)
 // TMEM: columns [0, 384) O ring, [384, 512) two score buffers.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -31,9 +32,14 @@
 namespace ditto {
 namespace {
 
-constexpr int XF_THREADS = 384;
+constexpr int XF_THREADS = 640;            // 4 control warps + 16 softmax / epilogue warps
 constexpr int XF_EPI_WARP0 = 4;
-constexpr int XF_EPI_WARPS = 8;
+constexpr int XF_EPI_WARPS = 16;          // 4 per TMEM lane quarter: 4 warps per scheduler hide the TMEM / shared-memory latencies
+constexpr int XF_SM_WARPS = 8;            // of which the first 8 also do the softmax (16 rows x 64 score columns each)
+// setmaxnreg moves registers inside the CTA's own pool only: what the control warps release is all the epilogue warps can
+// take, on top of the launch allocation of 96 per thread (640 threads)
+constexpr int XF_REGS_LAUNCH = 96, XF_REGS_CTRL = 56, XF_REGS_EPI = 104;
+static_assert(128 * XF_REGS_CTRL + 32 * XF_EPI_WARPS * XF_REGS_EPI <= XF_THREADS * XF_REGS_LAUNCH, "register re-distribution exceeds the CTA pool");
 constexpr int XF_BM = 128;          // rows per tile
 constexpr int XF_BK = 64;           // k-block (one 128-B swizzle span of bf16)
 constexpr int XF_NS = 64;           // score columns (text tokens, padded)
@@ -45,7 +51,9 @@ constexpr int XF_B_BYTES = XF_NS * XF_BK * 2;   //  8 KiB
 constexpr int XF_STAGE_BYTES = XF_A_BYTES + XF_B_BYTES;
 constexpr int XF_MAX_H = 768;
 constexpr int XF_P_BYTES = XF_BM * XF_NS * 2;   // 16 KiB
-constexpr int XF_VF_BYTES = XF_NS * XF_CH * 2;  // 16 KiB: V-fold rows of one output chunk
+constexpr int XF_VF_BOX = XF_NS * 64 * 2;      //  8 KiB: V-fold [64 k-rows x 64 n] box of one output half-chunk
+constexpr int XF_VF_RING = 3;
+constexpr int XF_VF_BYTES = XF_VF_RING * XF_VF_BOX;
 constexpr int XF_NB = 4;                        // staging buffers for the residual stream
 constexpr int XF_SLAB_BYTES = XF_BM * 32 * 4;   // 16 KiB: 128 rows x 32 fp32 columns (one TMA box)
 constexpr int XF_HBUF_BYTES = 2 * XF_SLAB_BYTES;
@@ -55,7 +63,7 @@ constexpr int XF_OFF_HB = XF_OFF_VF + XF_VF_BYTES;
 constexpr int XF_OFF_BAR = XF_OFF_HB + XF_NB * XF_HBUF_BYTES;
 constexpr int XF_BAR_BYTES = 256;
 constexpr int XF_OFF_STAT = XF_OFF_BAR + XF_BAR_BYTES;
-constexpr int XF_STAT_BYTES = 2 * XF_BM * 2 * 8;  // [tile parity][row][column half] (sum, sum of squares)
+constexpr int XF_STAT_BYTES = 2 * XF_BM * 4 * 8;  // [tile parity][row][column quarter] (sum, sum of squares)
 constexpr int XF_SMEM_BYTES = XF_OFF_STAT + XF_STAT_BYTES + 1024 /*align slack*/;
 static_assert(XF_SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
 static_assert(XF_OFF_P % 1024 == 0 && XF_OFF_VF % 1024 == 0 && XF_OFF_HB % 1024 == 0 && XF_STAGE_BYTES % 1024 == 0,
@@ -66,6 +74,7 @@ constexpr int XF_S_COL0 = XF_O_BUFS * XF_CH;  // 384
 
 struct XfDev {
   int n_seq, T, S, H;
+  int rt;                                     // rows per tile (<= 128, multiple of 8): the TMA boxes carry rt rows, the MMA computes 128
   int m_tiles, num_tiles, num_kb, num_ch, num_hc;
   float alpha2;                               // alpha * log2(e)
   const float* sbias; long long sb_seq;       // [n_seq, sb_seq] additive score bias
@@ -74,14 +83,14 @@ struct XfDev {
   float inv_h;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_16x32(uint32_t taddr, uint32_t (&r)[16]) {  // 16 lanes x 32 fp32 columns, fragment layout
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * XF_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ void xf_regs_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XF_REGS_CTRL)); }
+__device__ __forceinline__ void xf_regs_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(XF_REGS_EPI)); }
+__device__ __forceinline__ void tmem_ld_16x16(uint32_t taddr, uint32_t (&r)[8]) {  // 16 lanes x 16 fp32 columns, fragment layout
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 // shared -> global tiled store (bulk async-group completion); out-of-range rows are clipped by the TMA unit
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
@@ -110,15 +119,15 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
   uint64_t* s_full = empty_bar + XF_STAGES;   // [2] scores accumulator complete        (MMA -> epilogue)
   uint64_t* s_empty = s_full + 2;             // [2] scores accumulator read            (epilogue -> MMA)
   uint64_t* p_full = s_empty + 2;             //     probabilities in shared memory     (epilogue -> MMA)
-  uint64_t* vf_full = p_full + 1;             //     V-fold chunk landed                (TMA -> MMA)
-  uint64_t* vf_empty = vf_full + 1;           //     P.V chunk retired                  (MMA -> TMA)
-  uint64_t* o_full = vf_empty + 1;            // [3] output chunk complete              (MMA -> epilogue)
+  uint64_t* vf_full = p_full + 1;             // [3] V-fold box landed                  (TMA -> MMA)
+  uint64_t* vf_empty = vf_full + XF_VF_RING;  // [3] its MMAs retired                   (MMA -> TMA)
+  uint64_t* o_full = vf_empty + XF_VF_RING;   // [3] output chunk complete              (MMA -> epilogue)
   uint64_t* o_empty = o_full + XF_O_BUFS;     // [3] output chunk read                  (epilogue -> MMA)
   uint64_t* hin_full = o_empty + XF_O_BUFS;   // [NB] residual half-chunk landed        (mover TMA -> epilogue)
   uint64_t* hout_full = hin_full + XF_NB;     // [NB] result half-chunk in place        (epilogue -> mover)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hout_full + XF_NB);
   float2* stat = reinterpret_cast<float2*>(smem + XF_OFF_STAT);
-  static_assert((2 * XF_STAGES + 2 + 2 + 3 + 2 * XF_O_BUFS + 2 * XF_NB) * 8 + 4 <= XF_BAR_BYTES, "barrier block too small");
+  static_assert((2 * XF_STAGES + 2 + 2 + 1 + 2 * XF_VF_RING + 2 * XF_O_BUFS + 2 * XF_NB) * 8 + 4 <= XF_BAR_BYTES, "barrier block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,11 +146,13 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], XF_EPI_WARPS);
+      mbar_init(&s_empty[s], XF_SM_WARPS);
     }
-    mbar_init(p_full, XF_EPI_WARPS);
-    mbar_init(vf_full, 1);
-    mbar_init(vf_empty, 1);
+    mbar_init(p_full, XF_SM_WARPS);
+    for (int s = 0; s < XF_VF_RING; ++s) {
+      mbar_init(&vf_full[s], 1);
+      mbar_init(&vf_empty[s], 1);
+    }
     for (int s = 0; s < XF_O_BUFS; ++s) {
       mbar_init(&o_full[s], 1);
       mbar_init(&o_empty[s], XF_EPI_WARPS);
@@ -161,41 +172,43 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
 
   if (warp == 0) {
     // =========================== TMA producer: MMA operands ===========================
-    regs_shrink_ctrl();
+    xf_regs_ctrl();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t vc = 0;  // V-fold chunks loaded so far
+      uint32_t vc = 0;  // V-fold boxes loaded so far
+      const uint32_t stage_tx = static_cast<uint32_t>(p.rt) * (XF_BK * 2) + XF_B_BYTES;
       auto load_scores_operands = [&](int tile) {
         const int seq = tile / p.m_tiles, mb = tile - seq * p.m_tiles;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * XF_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], XF_STAGE_BYTES);
-          tma_load_4d(&tmap_u, &full_bar[stage], sa, kb * XF_BK, mb * XF_BM, 0, seq);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_4d(&tmap_u, &full_bar[stage], sa, kb * XF_BK, mb * p.rt, 0, seq);
           tma_load_4d(&tmap_kf, &full_bar[stage], sa + XF_A_BYTES, kb * XF_BK, 0, 0, seq);  // rows >= S: zero-filled
           if (++stage == XF_STAGES) { stage = 0; phase ^= 1u; }
         }
       };
-      // same order as the MMA issuer consumes: scores(0), then per tile scores(next) before the tile's P.V chunks
+      // same order as the MMA issuer consumes: scores(0), then per tile its P.V boxes followed by scores(next tile)
       if (first < p.num_tiles) load_scores_operands(first);
       for (int tile = first; tile < p.num_tiles; tile += step) {
-        if (tile + step < p.num_tiles) load_scores_operands(tile + step);
         const int seq = tile / p.m_tiles;
-        for (int c = 0; c < p.num_ch; ++c, ++vc) {
-          mbar_wait(vf_empty, (vc & 1u) ^ 1u);  // the previous chunk's MMAs have retired
-          mbar_expect_tx(vf_full, XF_VF_BYTES);
-          for (int j = 0; j < XF_CH / 64; ++j)  // [64 k-rows x 64 n] boxes, n contiguous (MN-major operand); rows >= Sp zero-filled
-            tma_load_4d(&tmap_vf, vf_full, vf_smem + j * (XF_NS * 128), c * XF_CH + j * 64, 0, 0, seq);
+        for (int hc = 0; hc < p.num_hc; ++hc, ++vc) {
+          const uint32_t vs = vc % XF_VF_RING;
+          mbar_wait(&vf_empty[vs], ((vc / XF_VF_RING) & 1u) ^ 1u);  // the MMAs that read this box have retired
+          mbar_expect_tx(&vf_full[vs], XF_VF_BOX);
+          // [64 k-rows x 64 n] box, n contiguous (MN-major operand); rows >= Sp zero-filled
+          tma_load_4d(&tmap_vf, &vf_full[vs], vf_smem + vs * XF_VF_BOX, hc * XF_HC, 0, 0, seq);
         }
+        if (tile + step < p.num_tiles) load_scores_operands(tile + step);
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (single thread) ===========================
-    regs_shrink_ctrl();
+    xf_regs_ctrl();
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(XF_BM, XF_NS, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(XF_BM, XF_CH, false, true);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(XF_BM, XF_HC, false, true);
       int stage = 0;
       uint32_t phase = 0;
       auto issue_scores = [&](uint32_t j) {  // scores of this CTA's j-th tile into score buffer j & 1
@@ -216,32 +229,38 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         }
         umma_commit(&s_full[sb]);
       };
-      uint32_t it = 0, oc = 0;
+      uint32_t it = 0, oc = 0, vc = 0;
       if (first < p.num_tiles) issue_scores(0);
-      const uint32_t pa = smem_u32(p_smem), vb = smem_u32(vf_smem);
+      const uint32_t pa = smem_u32(p_smem);
       for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
-        if (tile + step < p.num_tiles) issue_scores(it + 1);
         mbar_wait(p_full, it & 1u);
-        for (int c = 0; c < p.num_ch; ++c, ++oc) {
-          const uint32_t ob = oc % XF_O_BUFS;
-          mbar_wait(vf_full, oc & 1u);
-          mbar_wait(&o_empty[ob], ((oc / XF_O_BUFS) & 1u) ^ 1u);
+        for (int hc = 0; hc < p.num_hc; ++hc, ++vc) {
+          const uint32_t ob = oc % XF_O_BUFS, vs = vc % XF_VF_RING;
+          mbar_wait(&vf_full[vs], (vc / XF_VF_RING) & 1u);
+          if ((hc & 1) == 0) mbar_wait(&o_empty[ob], ((oc / XF_O_BUFS) & 1u) ^ 1u);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + ob * XF_CH;
+          const uint32_t d_tmem = tmem_base + ob * XF_CH + (hc & 1) * XF_HC;
+          const uint32_t vb = smem_u32(vf_smem) + vs * XF_VF_BOX;
 #pragma unroll
           for (int k = 0; k < XF_NS / 16; ++k)
-            umma_bf16(d_tmem, umma_smem_desc(pa + k * 32, 16, 1024), umma_smem_desc(vb + k * (16 * 128), XF_NS * 128, 1024), idesc_o,
+            umma_bf16(d_tmem, umma_smem_desc(pa + k * 32, 16, 1024), umma_smem_desc(vb + k * (16 * 128), XF_VF_BOX, 1024), idesc_o,
                       k != 0 ? 1u : 0u);
-          umma_commit(&o_full[ob]);
-          umma_commit(vf_empty);  // the V-fold buffer (and, after the last chunk, P) may be overwritten once these MMAs retire
+          umma_commit(&vf_empty[vs]);  // the box (and, after the last one, P) may be overwritten once these MMAs retire
+          if (hc & 1) {
+            umma_commit(&o_full[ob]);
+            ++oc;
+          }
         }
+        // the next tile's scores AFTER this tile's P.V (the issuer is sequential: ahead of the P.V they would put their
+        // operand stream on the critical path); they still overlap the rest of this tile's epilogue
+        if (tile + step < p.num_tiles) issue_scores(it + 1);
       }
     }
   } else if (warp == 3) {
     // =========================== mover: residual stream global <-> shared by TMA ===========================
     // job j = (tile, pass, half-chunk): pass 0 loads h (fp32) and stores h + attention; pass 1 re-loads the updated rows
     // (L2 hits) and stores LayerNorm(h) as bf16.  Buffer j % NB; NB - 1 loads in flight ahead of the epilogue.
-    regs_shrink_ctrl();
+    xf_regs_ctrl();
     if (lane == 0) {
       const int my_tiles = first < p.num_tiles ? (p.num_tiles - 1 - first) / step + 1 : 0;
       const int jobs_per_tile = 2 * p.num_hc;
@@ -250,7 +269,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         const int ti = j / jobs_per_tile, r = j - ti * jobs_per_tile;
         const int tile = first + ti * step;
         seq = tile / p.m_tiles;
-        row = (tile - seq * p.m_tiles) * XF_BM;
+        row = (tile - seq * p.m_tiles) * p.rt;
         pass = r / p.num_hc;
         hc = r - pass * p.num_hc;
       };
@@ -259,7 +278,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         job_coords(j, seq, row, pass, hc);
         const int b = j % XF_NB;
         uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
-        mbar_expect_tx(&hin_full[b], XF_HBUF_BYTES);
+        mbar_expect_tx(&hin_full[b], static_cast<uint32_t>(p.rt) * 256);  // two slabs of rt rows x 128 B
         tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
         tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
       };
@@ -293,10 +312,10 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
     }
   } else if (warp >= XF_EPI_WARP0) {
     // =========================== softmax + epilogue ===========================
-    regs_grow_epi();
+    xf_regs_epi();
     const int ew = warp - XF_EPI_WARP0;
     const int quarter = warp & 3;   // TMEM lanes [32 quarter, +32)
-    const int hsel = ew >> 2;       // softmax: 16-row half of the quarter; output: 32-column slab of the half-chunk
+    const int sub = ew >> 2;        // softmax (sub < 2): 16-row half of the quarter; output: 16-column quarter of the half-chunk
     const int g = lane >> 2, q = lane & 3, q2 = q * 2;
     const bool writer = q == 0;
     uint32_t it = 0, oc = 0, job = 0;
@@ -304,8 +323,8 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
       const int seq = tile / p.m_tiles;
       const uint32_t sb = it & 1u;
       // ---------------- softmax of the 128 x 64 score tile -> bf16 probabilities in shared memory ----------------
-      {
-        const int trow = quarter * 32 + hsel * 16;
+      if (sub < 2) {
+        const int trow = quarter * 32 + sub * 16;
         const float* bias = p.sbias + seq * p.sb_seq;
         float2 bb[8];
 #pragma unroll
@@ -322,27 +341,30 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[sb]);  // the scores are in registers: the buffer may take tile it + 2
-        float sA[16], sB[16];
         float mA = -INFINITY, mB = -INFINITY;
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
+        for (int kb = 0; kb < 8; ++kb) {  // s' = (alpha acc + bias) log2 e, in place in r; padded columns -> -inf
           const int c = kb * 8 + q2;
-          sA[2 * kb] = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) : -INFINITY;
-          sA[2 * kb + 1] = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) : -INFINITY;
-          sB[2 * kb] = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) : -INFINITY;
-          sB[2 * kb + 1] = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) : -INFINITY;
-          mA = fmaxf(mA, fmaxf(sA[2 * kb], sA[2 * kb + 1]));
-          mB = fmaxf(mB, fmaxf(sB[2 * kb], sB[2 * kb + 1]));
+          const float a0 = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) : -INFINITY;
+          const float a1 = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) : -INFINITY;
+          const float b0 = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) : -INFINITY;
+          const float b1 = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) : -INFINITY;
+          r[4 * kb] = __float_as_uint(a0); r[4 * kb + 1] = __float_as_uint(a1);
+          r[4 * kb + 2] = __float_as_uint(b0); r[4 * kb + 3] = __float_as_uint(b1);
+          mA = fmaxf(mA, fmaxf(a0, a1));
+          mB = fmaxf(mB, fmaxf(b0, b1));
         }
         mA = quad_max(mA);
         mB = quad_max(mB);
         float sumA = 0.f, sumB = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          sA[j] = ex2_approx(sA[j] - mA);   // exp2(-inf) = 0 for the padded columns
-          sB[j] = ex2_approx(sB[j] - mB);
-          sumA += sA[j];
-          sumB += sB[j];
+        for (int kb = 0; kb < 8; ++kb) {
+          const float a0 = ex2_approx(__uint_as_float(r[4 * kb]) - mA), a1 = ex2_approx(__uint_as_float(r[4 * kb + 1]) - mA);
+          const float b0 = ex2_approx(__uint_as_float(r[4 * kb + 2]) - mB), b1 = ex2_approx(__uint_as_float(r[4 * kb + 3]) - mB);
+          r[4 * kb] = __float_as_uint(a0); r[4 * kb + 1] = __float_as_uint(a1);   // exp2(-inf) = 0 for the padded columns
+          r[4 * kb + 2] = __float_as_uint(b0); r[4 * kb + 3] = __float_as_uint(b1);
+          sumA += a0 + a1;
+          sumB += b0 + b1;
         }
         const float iA = 1.0f / quad_sum(sumA), iB = 1.0f / quad_sum(sumB);
         // K-major A operand, 128-B swizzle: row r at r * 128 B, its 16-B chunk kb stored at chunk position kb ^ (r & 7)
@@ -351,64 +373,68 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         uint8_t* pb = p_smem + rB * 128 + q2 * 2;
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
-          *reinterpret_cast<uint32_t*>(pa + ((kb ^ (rA & 7)) << 4)) = pack_bf16x2(sA[2 * kb] * iA, sA[2 * kb + 1] * iA);
-          *reinterpret_cast<uint32_t*>(pb + ((kb ^ (rB & 7)) << 4)) = pack_bf16x2(sB[2 * kb] * iB, sB[2 * kb + 1] * iB);
+          *reinterpret_cast<uint32_t*>(pa + ((kb ^ (rA & 7)) << 4)) =
+              pack_bf16x2(__uint_as_float(r[4 * kb]) * iA, __uint_as_float(r[4 * kb + 1]) * iA);
+          *reinterpret_cast<uint32_t*>(pb + ((kb ^ (rB & 7)) << 4)) =
+              pack_bf16x2(__uint_as_float(r[4 * kb + 2]) * iB, __uint_as_float(r[4 * kb + 3]) * iB);
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
       // ---------------- pass 0: h <- h + O + bo, half-chunk by half-chunk in the staging buffers; row statistics -------
-      // This warp: tile rows lrow0 + hh * 16 + g (+ 8), columns hsel * 32 + kbl * 8 + q2 (+ 1) of the half-chunk.
-      // fp32 slab in shared memory (TMA 128-B swizzle): row r at r * 128 B, 16-B chunk j at position j ^ (r & 7).
+      // This warp: tile rows lrow0 + hh * 16 + g (+ 8), columns sub * 16 + kbl * 8 + q2 (+ 1) of the 64-column half-chunk.
+      // fp32 slab (32 columns) in shared memory, TMA 128-B swizzle: row r at r * 128 B, 16-B chunk j at position j ^ (r & 7).
       const int lrow0 = quarter * 32;
-      float st[8];                                            // [hh][A|B] (sum, sumsq)
+      const int slab_sel = sub >> 1, jbase = (sub & 1) * 4 + (q >> 1);   // 32-column slab, first 16-B chunk of this thread
+      float2 sm2[4], sq2[4];                                  // [hh][A|B] packed (sum, sum) / (sumsq, sumsq) accumulators
 #pragma unroll
-      for (int j = 0; j < 8; ++j) st[j] = 0.f;
+      for (int j = 0; j < 4; ++j) sm2[j] = sq2[j] = make_float2(0.f, 0.f);
       uint32_t ob = 0;
 #pragma unroll 1
       for (int hc = 0; hc < p.num_hc; ++hc, ++job) {
         const uint32_t b = job % XF_NB;
-        uint8_t* slab = hbuf + b * XF_HBUF_BYTES + hsel * XF_SLAB_BYTES;
-        const int col0 = hc * XF_HC + hsel * 32 + q2;
-        float2 b2[4];
+        uint8_t* slab = hbuf + b * XF_HBUF_BYTES + slab_sel * XF_SLAB_BYTES + (q & 1) * 8;
+        const int col0 = hc * XF_HC + sub * 16 + q2;
+        float2 b2[2];
 #pragma unroll
-        for (int kbl = 0; kbl < 4; ++kbl) b2[kbl] = __ldg(reinterpret_cast<const float2*>(p.out_bias + col0 + kbl * 8));
+        for (int kbl = 0; kbl < 2; ++kbl) b2[kbl] = __ldg(reinterpret_cast<const float2*>(p.out_bias + col0 + kbl * 8));
         if ((hc & 1) == 0) {
           ob = oc % XF_O_BUFS;
           mbar_wait(&o_full[ob], (oc / XF_O_BUFS) & 1u);
           tcgen05_fence_after();
         }
         mbar_wait(&hin_full[b], (job / XF_NB) & 1u);
+        uint32_t r[2][8];
+        float2 rsA[2][2], rsB[2][2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // every load of the job first (TMEM and shared memory), then the arithmetic
+          const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
+          tmem_ld_16x16(tmem_base + (static_cast<uint32_t>(lrow0 + hh * 16) << 16) + ob * XF_CH + (hc & 1) * XF_HC + sub * 16, r[hh]);
+#pragma unroll
+          for (int kbl = 0; kbl < 2; ++kbl) {
+            const int j = jbase + kbl * 2;
+            rsA[hh][kbl] = *reinterpret_cast<const float2*>(slab + rA * 128 + ((j ^ (rA & 7)) << 4));
+            rsB[hh][kbl] = *reinterpret_cast<const float2*>(slab + rB * 128 + ((j ^ (rB & 7)) << 4));
+          }
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
-          uint8_t* sa = slab + rA * 128 + (q & 1) * 8;
-          uint8_t* sbp = slab + rB * 128 + (q & 1) * 8;
-          uint32_t r[16];
-          tmem_ld_16x32(tmem_base + (static_cast<uint32_t>(lrow0 + hh * 16) << 16) + ob * XF_CH + (hc & 1) * XF_HC + hsel * 32, r);
-          float2 rsA[4], rsB[4];
 #pragma unroll
-          for (int kbl = 0; kbl < 4; ++kbl) {
-            const int j = kbl * 2 + (q >> 1);
-            rsA[kbl] = *reinterpret_cast<const float2*>(sa + ((j ^ (rA & 7)) << 4));
-            rsB[kbl] = *reinterpret_cast<const float2*>(sbp + ((j ^ (rB & 7)) << 4));
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int kbl = 0; kbl < 4; ++kbl) {
-            const int j = kbl * 2 + (q >> 1);
-            float2 vA, vB;
-            vA.x = __uint_as_float(r[4 * kbl]) + b2[kbl].x + rsA[kbl].x;
-            vA.y = __uint_as_float(r[4 * kbl + 1]) + b2[kbl].y + rsA[kbl].y;
-            vB.x = __uint_as_float(r[4 * kbl + 2]) + b2[kbl].x + rsB[kbl].x;
-            vB.y = __uint_as_float(r[4 * kbl + 3]) + b2[kbl].y + rsB[kbl].y;
-            st[4 * hh] += vA.x + vA.y;
-            st[4 * hh + 1] = fmaf(vA.x, vA.x, fmaf(vA.y, vA.y, st[4 * hh + 1]));
-            st[4 * hh + 2] += vB.x + vB.y;
-            st[4 * hh + 3] = fmaf(vB.x, vB.x, fmaf(vB.y, vB.y, st[4 * hh + 3]));
-            *reinterpret_cast<float2*>(sa + ((j ^ (rA & 7)) << 4)) = vA;   // in place: every element is owned by one thread
-            *reinterpret_cast<float2*>(sbp + ((j ^ (rB & 7)) << 4)) = vB;
+          for (int kbl = 0; kbl < 2; ++kbl) {
+            const int j = jbase + kbl * 2;
+            const float2 vA = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[hh][4 * kbl]), __uint_as_float(r[hh][4 * kbl + 1])), b2[kbl]),
+                                         rsA[hh][kbl]);
+            const float2 vB = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[hh][4 * kbl + 2]), __uint_as_float(r[hh][4 * kbl + 3])), b2[kbl]),
+                                         rsB[hh][kbl]);
+            sm2[2 * hh] = __fadd2_rn(sm2[2 * hh], vA);
+            sq2[2 * hh] = __ffma2_rn(vA, vA, sq2[2 * hh]);
+            sm2[2 * hh + 1] = __fadd2_rn(sm2[2 * hh + 1], vB);
+            sq2[2 * hh + 1] = __ffma2_rn(vB, vB, sq2[2 * hh + 1]);
+            *reinterpret_cast<float2*>(slab + rA * 128 + ((j ^ (rA & 7)) << 4)) = vA;   // in place: one owner per element
+            *reinterpret_cast<float2*>(slab + rB * 128 + ((j ^ (rB & 7)) << 4)) = vB;
           }
         }
         fence_proxy_async_smem();  // the TMA store reads these generic-proxy writes
@@ -420,26 +446,21 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         }
         if (hc & 1) ++oc;
       }
-      // ---------------- row statistics: the two column slabs of a row live in two warps ----------------
-      float2* sp = stat + (it & 1u) * (XF_BM * 2);
+      // ---------------- row statistics: the four column quarters of a row live in four warps ----------------
+      float2* sp = stat + (it & 1u) * (XF_BM * 4);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) st[j] = quad_sum(st[j]);
-      if (writer) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int lr = lrow0 + hh * 16 + g;
-          sp[lr * 2 + hsel] = make_float2(st[4 * hh], st[4 * hh + 1]);
-          sp[(lr + 8) * 2 + hsel] = make_float2(st[4 * hh + 2], st[4 * hh + 3]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float s1 = quad_sum(sm2[j].x + sm2[j].y), s2 = quad_sum(sq2[j].x + sq2[j].y);
+        if (writer) sp[(lrow0 + (j >> 1) * 16 + g + (j & 1) * 8) * 4 + sub] = make_float2(s1, s2);
       }
       epi_bar_sync();
       float mean[4], rstd[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int lr = lrow0 + (j >> 1) * 16 + g + (j & 1) * 8;
-        const float2 a = sp[lr * 2], bq = sp[lr * 2 + 1];
-        const float m = (a.x + bq.x) * p.inv_h;
-        const float var = fmaxf(fmaf(-m, m, (a.y + bq.y) * p.inv_h), 0.f);
+        const float4 a = *reinterpret_cast<const float4*>(sp + lr * 4), c = *reinterpret_cast<const float4*>(sp + lr * 4 + 2);
+        const float m = (a.x + a.z + c.x + c.z) * p.inv_h;
+        const float var = fmaxf(fmaf(-m, m, (a.y + a.w + c.y + c.w) * p.inv_h), 0.f);
         mean[j] = m;
         rstd[j] = rsqrtf(var + 1e-5f);
       }
@@ -449,24 +470,24 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
       for (int hc = 0; hc < p.num_hc; ++hc, ++job) {
         const uint32_t b = job % XF_NB;
         uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
-        const uint8_t* slab = buf + hsel * XF_SLAB_BYTES;
-        const int col0 = hc * XF_HC + hsel * 32 + q2;
-        float2 gm[4], bt[4];
+        const uint8_t* slab = buf + slab_sel * XF_SLAB_BYTES + (q & 1) * 8;
+        const int col0 = hc * XF_HC + sub * 16 + q2;
+        float2 gm[2], bt[2];
 #pragma unroll
-        for (int kbl = 0; kbl < 4; ++kbl) {
+        for (int kbl = 0; kbl < 2; ++kbl) {
           gm[kbl] = __ldg(reinterpret_cast<const float2*>(p.gamma + col0 + kbl * 8));
           bt[kbl] = __ldg(reinterpret_cast<const float2*>(p.beta + col0 + kbl * 8));
         }
         mbar_wait(&hin_full[b], (job / XF_NB) & 1u);
-        float2 v[2][8];
+        float2 v[2][4];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
 #pragma unroll
-          for (int kbl = 0; kbl < 4; ++kbl) {
-            const int j = kbl * 2 + (q >> 1);
-            v[hh][2 * kbl] = *reinterpret_cast<const float2*>(slab + rA * 128 + (q & 1) * 8 + ((j ^ (rA & 7)) << 4));
-            v[hh][2 * kbl + 1] = *reinterpret_cast<const float2*>(slab + rB * 128 + (q & 1) * 8 + ((j ^ (rB & 7)) << 4));
+          for (int kbl = 0; kbl < 2; ++kbl) {
+            const int j = jbase + kbl * 2;
+            v[hh][2 * kbl] = *reinterpret_cast<const float2*>(slab + rA * 128 + ((j ^ (rA & 7)) << 4));
+            v[hh][2 * kbl + 1] = *reinterpret_cast<const float2*>(slab + rB * 128 + ((j ^ (rB & 7)) << 4));
           }
         }
         epi_bar_sync();  // every warp has its fp32 values in registers: the buffer may be overwritten with the bf16 result
@@ -475,8 +496,8 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
           const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
           const float mA = mean[2 * hh], iA = rstd[2 * hh], mB = mean[2 * hh + 1], iB = rstd[2 * hh + 1];
 #pragma unroll
-          for (int kbl = 0; kbl < 4; ++kbl) {
-            const int j = hsel * 4 + kbl;
+          for (int kbl = 0; kbl < 2; ++kbl) {
+            const int j = sub * 2 + kbl;
             const float2 a = v[hh][2 * kbl], c = v[hh][2 * kbl + 1];
             *reinterpret_cast<uint32_t*>(buf + rA * 128 + ((j ^ (rA & 7)) << 4) + q * 4) =
                 pack_bf16x2(fmaf((a.x - mA) * iA, gm[kbl].x, bt[kbl].x), fmaf((a.y - mA) * iA, gm[kbl].y, bt[kbl].y));
@@ -490,7 +511,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
       }
     }
   } else {
-    regs_shrink_ctrl();  // warp 2 idles after the TMEM allocation; the whole warpgroup has to execute the setmaxnreg
+    xf_regs_ctrl();  // warp 2 idles after the TMEM allocation; the whole warpgroup has to execute the setmaxnreg
   }
 
   __syncwarp();
@@ -508,7 +529,7 @@ typedef CUresult (*XfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
 XfEncodeFn g_xf_encode = nullptr;
 
 // fp32 residual stream as a 4-D map (cols, rows of one utterance, 1, utterance): box 32 x 128, 128-B swizzle
-int make_map_h(CUtensorMap* m, float* h, int64_t n_seq, int64_t T, int H) {
+int make_map_h(CUtensorMap* m, float* h, int64_t n_seq, int64_t T, int H, int box_rows) {
   if (g_xf_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -519,7 +540,7 @@ int make_map_h(CUtensorMap* m, float* h, int64_t n_seq, int64_t T, int H) {
   DITTO_REQUIRE((reinterpret_cast<uintptr_t>(h) & 15) == 0, DITTO_E_BADARG, "cross_fused: h must be 16-B aligned");
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(T), 1, static_cast<cuuint64_t>(n_seq)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(H) * 4, static_cast<cuuint64_t>(T) * H * 4, static_cast<cuuint64_t>(T) * H * 4};
-  cuuint32_t box[4] = {32, XF_BM, 1, 1};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(box_rows), 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_xf_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -554,15 +575,22 @@ int launch_cross_fused(const CrossFusedParams& q, cudaStream_t st) {
   Kf.ptr = q.kfold; Kf.rows = q.S; Kf.cols = q.H; Kf.ld = q.H; Kf.s_outer = q.kf_seq;
   Vf.ptr = q.vfold; Vf.rows = q.Sp; Vf.cols = q.H; Vf.ld = q.H; Vf.s_outer = q.vf_seq;
   Uo.ptr = q.u_out; Uo.rows = q.T; Uo.cols = q.H; Uo.ld = q.H; Uo.s_outer = q.T * q.H;
+  // Rows per tile: the MMAs always compute 128 rows, the TMA boxes (and so the HBM traffic) carry `rt` of them.  Measured at
+  // C2 (profiles/README.md): 128 / 96 / 88 rows all take ~70 us and 64 rows 90 us -- the tile loop is bound by the latency of
+  // its 24 staging jobs per tile, not by their bytes, so fewer, larger tiles win; DITTO_XF_ROWS overrides for experiments.
+  const int sms = tc_num_sms();
+  int rt = XF_BM;
+  if (const char* er = getenv("DITTO_XF_ROWS")) { const int v = atoi(er); if (v >= 8 && v <= XF_BM && v % 8 == 0) rt = v; }
   CUtensorMap mu, mk, mv, mh, mo;
-  DITTO_TRY(tc_make_map(&mu, U, 1, q.n_seq, XF_BK, XF_BM));
+  DITTO_TRY(tc_make_map(&mu, U, 1, q.n_seq, XF_BK, rt));
   DITTO_TRY(tc_make_map(&mk, Kf, 1, q.n_seq, XF_BK, XF_NS));
   DITTO_TRY(tc_make_map(&mv, Vf, 1, q.n_seq, 64, XF_NS));
-  DITTO_TRY(tc_make_map(&mo, Uo, 1, q.n_seq, XF_HC, XF_BM));
-  DITTO_TRY(make_map_h(&mh, q.h, q.n_seq, q.T, q.H));
+  DITTO_TRY(tc_make_map(&mo, Uo, 1, q.n_seq, XF_HC, rt));
+  DITTO_TRY(make_map_h(&mh, q.h, q.n_seq, q.T, q.H, rt));
   XfDev p;
   p.n_seq = static_cast<int>(q.n_seq); p.T = static_cast<int>(q.T); p.S = static_cast<int>(q.S); p.H = q.H;
-  p.m_tiles = static_cast<int>(ceil_div(q.T, XF_BM));
+  p.rt = rt;
+  p.m_tiles = static_cast<int>(ceil_div(q.T, rt));
   const int64_t tiles = static_cast<int64_t>(p.m_tiles) * q.n_seq;
   DITTO_REQUIRE(tiles < (1ll << 31), DITTO_E_UNSUPPORTED, "cross_fused: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
@@ -577,7 +605,7 @@ int launch_cross_fused(const CrossFusedParams& q, cudaStream_t st) {
   // flops: both contractions; bytes: u read, h read + write, u3 write (the HBM stream that bounds the kernel)
   const double rows = static_cast<double>(q.n_seq) * q.T;
   ProfScope prof(q.tag, st, 4.0 * rows * q.S * q.H, rows * q.H * 12.0);
-  const int grid = static_cast<int>(std::min<int64_t>(tc_num_sms(), tiles));
+  const int grid = static_cast<int>(std::min<int64_t>(sms, tiles));
   cross_fused_kernel<<<grid, XF_THREADS, XF_SMEM_BYTES, st>>>(mu, mk, mv, mh, mo, p);
   DITTO_LAUNCH_CHECK();
   return 0;
