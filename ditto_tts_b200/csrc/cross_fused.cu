@@ -61,7 +61,7 @@ constexpr int XF_OFF_P = XF_STAGES * XF_STAGE_BYTES;
 constexpr int XF_OFF_VF = XF_OFF_P + XF_P_BYTES;
 constexpr int XF_OFF_HB = XF_OFF_VF + XF_VF_BYTES;
 constexpr int XF_OFF_BAR = XF_OFF_HB + XF_NB * XF_HBUF_BYTES;
-constexpr int XF_BAR_BYTES = 256;
+constexpr int XF_BAR_BYTES = 512;
 constexpr int XF_OFF_STAT = XF_OFF_BAR + XF_BAR_BYTES;
 constexpr int XF_STAT_BYTES = 2 * XF_BM * 4 * 8;  // [tile parity][row][column quarter] (sum, sum of squares)
 constexpr int XF_SMEM_BYTES = XF_OFF_STAT + XF_STAT_BYTES + 1024 /*align slack*/;
@@ -96,6 +96,12 @@ __device__ __forceinline__ void tmem_ld_16x16(uint32_t taddr, uint32_t (&r)[8]) 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// L2 prefetch of one box (no shared memory, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -282,9 +288,19 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
         tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
       };
+      // The staging ring keeps only 3 x 32 KiB of loads in flight per SM -- too little to cover the HBM latency -- so the
+      // fp32 rows of a tile are pulled into L2 a whole tile ahead (24 boxes of 16 KiB); the ring then streams L2 hits.
+      auto prefetch_tile = [&](int ti) {
+        if (ti >= my_tiles) return;
+        const int tile = first + ti * step;
+        const int seq = tile / p.m_tiles, row = (tile - seq * p.m_tiles) * p.rt;
+        for (int c = 0; c < p.H; c += 32) tma_prefetch_4d(&tmap_h, c, row, 0, seq);
+      };
+      prefetch_tile(0);
       for (int j = 0; j < XF_NB - 1 && j < J; ++j) issue_load(j);
       for (int j = 0; j < J; ++j) {
         const int b = j % XF_NB;
+        if (j % jobs_per_tile == 0) prefetch_tile(j / jobs_per_tile + 1);
         mbar_wait(&hout_full[b], (j / XF_NB) & 1u);
         int seq, row, pass, hc;
         job_coords(j, seq, row, pass, hc);

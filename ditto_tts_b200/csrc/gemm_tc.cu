@@ -68,6 +68,7 @@ struct DevParams {
   const float* rope_cos; const float* rope_sin; const float* rope_freq;
   int rope_half, rope_pd, seq_T, hidden;
   const int* rope_pos;  // optional [M] row -> position table (ragged batches); nullptr: position = row % seq_T
+  int rope_fast;        // lean pd = 128 epilogue allowed (DITTO_ROPE_GENERIC=1 forces the generic one)
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
@@ -425,6 +426,99 @@ __device__ __forceinline__ void store_blk_bf16_ln(const uint32_t (&r)[32], const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lean QKV + RoPE epilogue for the common case (pair distance 128 = head_dim 768, cos/sin computed on the fly, no deferred
+// LayerNorm, row % T positions, tile completely inside the matrix).  The generic path below spends ~21 instructions per
+// output element, 40 % of them address / predicate / branch work, and with two epilogue warps per scheduler that latency
+// chain -- not the tensor pipe -- set the pace of the GEMM (ncu: 46 % tensor-active).  Here: no predicates, packed f32x2
+// arithmetic (bias add, Cody-Waite reduction, rotation), ~6 instructions per element.  Arithmetic identical to the generic
+// path (same reduction constants, same MUFU approximations).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_reduced2(float2 a, float2& s, float2& c) {
+  const float2 t = __fmul2_rn(a, make_float2(0.15915494309189535f, 0.15915494309189535f));
+  const float2 k = make_float2(rintf(t.x), rintf(t.y));
+  float2 r = __ffma2_rn(k, make_float2(-6.28125f, -6.28125f), a);
+  r = __ffma2_rn(k, make_float2(-1.9353071795864769e-3f, -1.9353071795864769e-3f), r);
+  s = make_float2(__sinf(r.x), __sinf(r.y));
+  c = make_float2(__cosf(r.x), __cosf(r.y));
+}
+
+__device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
+                                                      long long out_off, const float* bias, uint64_t* full_bar, uint32_t full_parity) {
+  const int g = lane >> 2, q2 = (lane & 3) * 2;
+  const int b1 = half_sel * 64;                      // tile column of this warp's x1 block; partners 128 columns further
+  const int pc1 = n_blk * BLOCK_N + b1;              // permuted GEMM column
+  const bool is_v = pc1 >= 2 * p.hidden;             // warp-uniform: v third = identity layout, plain bias store
+  int jbase = 0, dbase = pc1, off2 = 128;
+  if (!is_v) {
+    const int region = pc1 / p.hidden;               // 0 = q, 1 = k
+    const int lp = pc1 - region * p.hidden;
+    const int grp = lp >> 8, w = lp & 255;           // groups of 2 * 128 permuted columns; w < 128 by construction
+    const int e0 = grp * 128;
+    const int head = e0 / p.rope_half;
+    jbase = e0 - head * p.rope_half + w;
+    dbase = region * p.hidden + head * 2 * p.rope_half + jbase;
+    off2 = p.rope_half;
+  }
+  float2 fr[8], bx1[8], bx2[8];
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    bx1[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
+    bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + 128 + q2 + kb * 8));
+    fr[kb] = is_v ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(p.rope_freq + jbase + q2 + kb * 8));
+  }
+  float fpos[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    fpos[i] = static_cast<float>(static_cast<unsigned>(row0 + g + 8 * i) % static_cast<unsigned>(p.seq_T));
+  mbar_wait(full_bar, full_parity);
+  tcgen05_fence_after();
+  bf16* o1 = static_cast<bf16*>(p.out) + out_off + (row0 + g) * p.ldo + dbase + q2;
+#pragma unroll 1
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r1[32], r2[32];
+    const uint32_t tbase = t_row + (static_cast<uint32_t>(hh * 16) << 16) + b1;
+    tmem_ld_16x64(tbase, r1);
+    tmem_ld_16x64(tbase + 128, r2);
+    bf16* oA = o1 + static_cast<long long>(hh * 16) * p.ldo;
+    bf16* oB = oA + 8 * p.ldo;
+    const float2 pA = make_float2(fpos[2 * hh], fpos[2 * hh]), pB = make_float2(fpos[2 * hh + 1], fpos[2 * hh + 1]);
+    tmem_ld_wait();
+    if (is_v) {
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {
+        const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * kb]), __uint_as_float(r1[4 * kb + 1])), bx1[kb]);
+        const float2 c1 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * kb + 2]), __uint_as_float(r1[4 * kb + 3])), bx1[kb]);
+        const float2 a2 = __fadd2_rn(make_float2(__uint_as_float(r2[4 * kb]), __uint_as_float(r2[4 * kb + 1])), bx2[kb]);
+        const float2 c2 = __fadd2_rn(make_float2(__uint_as_float(r2[4 * kb + 2]), __uint_as_float(r2[4 * kb + 3])), bx2[kb]);
+        *reinterpret_cast<uint32_t*>(oA + kb * 8) = pack_bf16x2(a1.x, a1.y);
+        *reinterpret_cast<uint32_t*>(oB + kb * 8) = pack_bf16x2(c1.x, c1.y);
+        *reinterpret_cast<uint32_t*>(oA + 128 + kb * 8) = pack_bf16x2(a2.x, a2.y);
+        *reinterpret_cast<uint32_t*>(oB + 128 + kb * 8) = pack_bf16x2(c2.x, c2.y);
+      }
+    } else {
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {
+        float2 sA, cA, sB, cB;   // angle = float(pos) * inv_freq[j] exactly as the reference forms it (DiT.py:56-59)
+        sincos_reduced2(__fmul2_rn(pA, fr[kb]), sA, cA);
+        sincos_reduced2(__fmul2_rn(pB, fr[kb]), sB, cB);
+        const float2 x1A = __fadd2_rn(make_float2(__uint_as_float(r1[4 * kb]), __uint_as_float(r1[4 * kb + 1])), bx1[kb]);
+        const float2 x1B = __fadd2_rn(make_float2(__uint_as_float(r1[4 * kb + 2]), __uint_as_float(r1[4 * kb + 3])), bx1[kb]);
+        const float2 x2A = __fadd2_rn(make_float2(__uint_as_float(r2[4 * kb]), __uint_as_float(r2[4 * kb + 1])), bx2[kb]);
+        const float2 x2B = __fadd2_rn(make_float2(__uint_as_float(r2[4 * kb + 2]), __uint_as_float(r2[4 * kb + 3])), bx2[kb]);
+        // x1' = x1 cos - x2 sin ; x2' = x2 cos + x1 sin   (DiT.py:52-54,72)
+        const float2 nA = make_float2(-sA.x, -sA.y), nB = make_float2(-sB.x, -sB.y);
+        const float2 y1A = __ffma2_rn(x2A, nA, __fmul2_rn(x1A, cA)), y2A = __ffma2_rn(x1A, sA, __fmul2_rn(x2A, cA));
+        const float2 y1B = __ffma2_rn(x2B, nB, __fmul2_rn(x1B, cB)), y2B = __ffma2_rn(x1B, sB, __fmul2_rn(x2B, cB));
+        *reinterpret_cast<uint32_t*>(oA + kb * 8) = pack_bf16x2(y1A.x, y1A.y);
+        *reinterpret_cast<uint32_t*>(oA + off2 + kb * 8) = pack_bf16x2(y2A.x, y2A.y);
+        *reinterpret_cast<uint32_t*>(oB + kb * 8) = pack_bf16x2(y1B.x, y1B.y);
+        *reinterpret_cast<uint32_t*>(oB + off2 + kb * 8) = pack_bf16x2(y2B.x, y2B.y);
+      }
+    }
+  }
+}
+
 // One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.  Waits for the
 // accumulator itself (after the first residual block has been requested).
 template <int EPI>
@@ -533,6 +627,11 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       }
     }
   } else {  // K_QKV_ROPE
+    if (p.rope_pd == 128 && p.ln_stat == nullptr && p.rope_freq != nullptr && p.rope_pos == nullptr && p.rope_fast &&
+        row0 + 32 <= p.M && (n_blk + 1) * BLOCK_N <= p.N && p.hidden % BLOCK_N == 0) {  // warp-uniform
+      rope_epilogue_fast128(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      return;
+    }
     // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load.  Everything that
     // is read from global memory (rotary frequencies, biases) is requested BEFORE the accumulator wait: with the L2 busy
     // feeding the operand ring, a dependent load after the wait costs ~1 us and made this epilogue the bottleneck (ncu).
@@ -647,8 +746,11 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
                 fmaf(ar, __uint_as_float(pd == 32 ? r1[4 * k2 + 2 * rr + 1] : r2[4 * kb + 2 * rr + 1]), fmaf(nr, cx2[kb].y, bx2[kb].y));
             if (rr == 0 ? okA : okB) {
               bf16* dst = outp + rr * 8 * p.ldo + kb * 8;
-              *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(x1a * c2.x - x2a * s2.x, x1b * c2.y - x2b * s2.y);
-              *reinterpret_cast<uint32_t*>(dst + p.rope_half) = pack_bf16x2(x2a * c2.x + x1a * s2.x, x2b * c2.y + x1b * s2.y);
+              // explicit rounding order (product with cos first), the same as the packed arithmetic of the lean path: a row
+              // gives bit-identical results whichever of the two epilogues its tile takes
+              *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(__fmaf_rn(x2a, -s2.x, __fmul_rn(x1a, c2.x)), __fmaf_rn(x2b, -s2.y, __fmul_rn(x1b, c2.y)));
+              *reinterpret_cast<uint32_t*>(dst + p.rope_half) =
+                  pack_bf16x2(__fmaf_rn(x1a, s2.x, __fmul_rn(x2a, c2.x)), __fmaf_rn(x1b, s2.y, __fmul_rn(x2b, c2.y)));
             }
           }
         }
@@ -1453,6 +1555,7 @@ int g_num_sms = 0;
 bool g_init_done = false;
 bool g_use_pair = true;
 int g_cluster_m = 0, g_cluster_n = 0;  // DITTO_CLUSTER="cm,cn": default cluster shape of the 1-CTA GEMM kernel (0 = heuristic)
+bool g_rope_fast = true;
 bool g_force_generic = false;  // DITTO_GENERIC_EPI=1: route every STORE epilogue through the generic path (tests)
 int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
 unsigned long long* g_dbg = nullptr;
@@ -1587,6 +1690,7 @@ int tc_gemm_init() {
     }
     const char* eg = getenv("DITTO_GENERIC_EPI");
     g_force_generic = eg && eg[0] == '1';
+    if (const char* er = getenv("DITTO_ROPE_GENERIC")) g_rope_fast = !(er[0] == '1');
     if (const char* e1 = getenv("DITTO_STAGES_1CTA")) g_stages_1cta = std::max(2, std::min(STAGES, atoi(e1)));
     if (const char* e2 = getenv("DITTO_STAGES_PAIR")) g_stages_pair = std::max(2, std::min(P_STAGES, atoi(e2)));
   }
@@ -1640,7 +1744,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.resid = q.resid; p.ldr = q.ldr; p.sr_inner = q.sr_inner; p.sr_outer = q.sr_outer; p.resid_row_mod = q.resid_row_mod;
   p.out2 = q.out2; p.ldo2 = q.ldo2;
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
-  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos;
+  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos; p.rope_fast = g_rope_fast ? 1 : 0;
   p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.stat_out = q.stat_out; p.stat_parts = q.stat_parts; p.stat_rows_outer = q.stat_rows_outer;
   p.stat_parts_item = static_cast<int>(ceil_div(q.N, 128));

@@ -18,9 +18,14 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 3 --warmup 3 > $O/${TAG}_ncu_bench.log 2>&1
 tail -2 $O/${TAG}_ncu_bench.log
 echo "##### ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_gemm|softmax|adaln|layernorm|cfg_ddpm' -s 120 -c 40 \
-    -o $O/${TAG}_prof -f python bench.py --steps 3 --warmup 3 > $O/${TAG}_ncu_full.log 2>&1
+# one forward's kernels of the eager warm-up step (one DiT block and a half); the report stays in /tmp unless it is small:
+# gpurun copies back at most 64 MiB
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_gemm|tc_scores|cross_fused|softmax|adaln|layernorm|cfg_ddpm' -s 20 -c 12 \
+    -o /tmp/${TAG}_prof -f python tools/step_profile.py --steps 3 > $O/${TAG}_ncu_full.log 2>&1
 tail -2 $O/${TAG}_ncu_full.log
+ncu -i /tmp/${TAG}_prof.ncu-rep --page raw --csv > $O/${TAG}_full_raw.csv 2>/dev/null
+SZ=$(stat -c %s /tmp/${TAG}_prof.ncu-rep); echo "report size $SZ"
+if [ "$SZ" -lt 30000000 ]; then cp /tmp/${TAG}_prof.ncu-rep $O/; fi
 fi
 echo "##### reference arm"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 | tee $O/${TAG}_bench_ref.json
