@@ -84,6 +84,8 @@ struct ditto_engine {
   int H = 0, L = 0, heads = 0, d = 0, half = 0, Td = 0, Xd = 0, steps = 0, maxT = 0;
   bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
   int rope_pd = 0;
+  bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
+  bool qkv_perm16 = false;  // QKV weight rows also permuted inside 64-row blocks for the lean RoPE epilogue (TcGemmParams::rope_perm16)
   bool fused_cross = true;  // folded cross-attention + residual + norm3 in one kernel (cross_fused.cu); DITTO_NO_FUSED_CROSS=1 disables
   bool fused_attn = false;  // scores + softmax fused (cluster kernel); falls back per call when a row needs > 16 tiles
   bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
@@ -488,6 +490,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           g.rope_freq = e->rope_table_in_epilogue ? nullptr : e->rope_freq;
           g.rope_pd = e->rope_pd; g.seq_T = static_cast<int>(g0.T); g.hidden = H;
           g.rope_pos = ragged ? w.row_pos : nullptr;
+          g.rope_perm16 = e->qkv_perm16;
         }
         if (dln) { g.ln_stat = w.lnstat; g.ln_parts = ln1_parts; g.ln_width = H; g.ln_c = lp.c_qkv; }
         DITTO_TRY(launch_tc_gemm(g, st));
@@ -581,7 +584,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
         g.B.ptr = lp.w_glu; g.B.rows = 8 * H; g.B.cols = H; g.B.ld = H;
         g.M = static_cast<int>(M); g.N = 8 * H; g.K = H; g.bias = lp.b_glu; g.out = w.hid; g.out_bf16 = true; g.ldo = 4 * H;
-        g.epilogue = TC_EPI_GEGLU;
+        g.epilogue = TC_EPI_GEGLU; g.glu_perm16 = e->glu_perm16;
         if (dln) { g.ln_stat = w.lnstat; g.ln_parts = w.ln_parts_h; g.ln_width = H; g.ln_c = lp.c_glu; }
         g.tag = PC_TC_GLU;
         DITTO_TRY(launch_tc_gemm(g, st));
@@ -751,6 +754,13 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     e->pv_transpose = env && env[0] == '1';
     const char* env2 = getenv("DITTO_ROPE_TABLE");
     e->rope_table_in_epilogue = env2 && env2[0] == '1';
+    {
+      const char* eg = getenv("DITTO_ROPE_GENERIC");
+      const char* egl = getenv("DITTO_GLU_GENERIC");
+      e->glu_perm16 = !e->defer_ln && e->H % 32 == 0 && !(egl && egl[0] == '1');
+      e->qkv_perm16 = e->fused_rope && e->rope_pd == 128 && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 &&
+                      !(eg && eg[0] == '1');
+    }
   }
   build_expected(e);
   e->layers.resize(e->L);
@@ -886,6 +896,23 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
           const int x1 = head * 2 * half + j0 + (w % pd);
           qkv_perm[region * H + lp] = region * H + (w < pd ? x1 : x1 + half);
         }
+    }
+    if (e->glu_perm16) {  // 64-row block B: row kb*8 + 2q + e <- fc1 (kb%4 < 2) or gate row of output 32B + q*8 + ((kb/4)*2 + kb%2)*2 + e
+      for (int r = 0; r < 8 * H; ++r) {
+        const int blk = r / 64, c = r % 64;
+        const int kb = c / 8, q = (c % 8) / 2, ee = c % 2;
+        const int gi = kb / 4, kk = kb % 4;
+        const int o = 32 * blk + q * 8 + (gi * 2 + (kk & 1)) * 2 + ee;
+        glu_perm[r] = kk < 2 ? o : 4 * H + o;
+      }
+    }
+    if (e->qkv_perm16) {  // GEMM column kb*8 + 2q + e of every 64-column block <- what stood at q*16 + kb*2 + e
+      std::vector<int> base(qkv_perm);
+      for (int r = 0; r < 3 * H; ++r) {
+        const int blk = r / 64, c = r % 64;
+        const int kb = c / 8, q = (c % 8) / 2, ee = c % 2;
+        qkv_perm[r] = base[blk * 64 + q * 16 + kb * 2 + ee];
+      }
     }
     int *d_glu = nullptr, *d_qkv = nullptr;
     float* cat = nullptr;

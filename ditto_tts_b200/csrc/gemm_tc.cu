@@ -68,7 +68,8 @@ struct DevParams {
   const float* rope_cos; const float* rope_sin; const float* rope_freq;
   int rope_half, rope_pd, seq_T, hidden;
   const int* rope_pos;  // optional [M] row -> position table (ragged batches); nullptr: position = row % seq_T
-  int rope_fast;        // lean pd = 128 epilogue allowed (DITTO_ROPE_GENERIC=1 forces the generic one)
+  int rope_fast;        // weights packed for the lean pd = 128 epilogue (TcGemmParams::rope_perm16)
+  int glu_fast;         // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
@@ -443,9 +444,16 @@ __device__ __forceinline__ void sincos_reduced2(float2 a, float2& s, float2& c) 
   c = make_float2(__cosf(r.x), __cosf(r.y));
 }
 
+// Store-friendly column order (TcGemmParams::rope_perm16): inside every 64-column block of the packed weight the engine
+// additionally permutes the rows so that accumulator column kb * 8 + 2 q + e (the fragment a thread holds) is OUTPUT column
+// q * 16 + kb * 2 + e of the block: a thread's 16 values of a row are then 16 consecutive bf16 = two 16-byte stores, and a
+// quad writes whole 128-byte lines (was: 4-byte stores, 16 bytes per line and instruction -- the top stall of this
+// epilogue in ncu).  Biases follow the GEMM column (they are packed with the weight); rotary frequencies and output
+// addresses follow the output column.
+template <bool FULL>
 __device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
                                                       long long out_off, const float* bias, uint64_t* full_bar, uint32_t full_parity) {
-  const int g = lane >> 2, q2 = (lane & 3) * 2;
+  const int g = lane >> 2, q = lane & 3, q2 = q * 2;
   const int b1 = half_sel * 64;                      // tile column of this warp's x1 block; partners 128 columns further
   const int pc1 = n_blk * BLOCK_N + b1;              // permuted GEMM column
   const bool is_v = pc1 >= 2 * p.hidden;             // warp-uniform: v third = identity layout, plain bias store
@@ -465,24 +473,31 @@ __device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int la
   for (int kb = 0; kb < 8; ++kb) {
     bx1[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
     bx2[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + 128 + q2 + kb * 8));
-    fr[kb] = is_v ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(p.rope_freq + jbase + q2 + kb * 8));
+    fr[kb] = is_v ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(p.rope_freq + jbase + q * 16 + kb * 2));
   }
   float fpos[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    fpos[i] = static_cast<float>(static_cast<unsigned>(row0 + g + 8 * i) % static_cast<unsigned>(p.seq_T));
+  for (int i = 0; i < 4; ++i) {
+    const long long rr = row0 + g + 8 * i;
+    fpos[i] = p.rope_pos != nullptr ? static_cast<float>((FULL || rr < p.M) ? __ldg(p.rope_pos + rr) : 0)
+                                    : static_cast<float>(static_cast<unsigned>(rr) % static_cast<unsigned>(p.seq_T));
+  }
   mbar_wait(full_bar, full_parity);
   tcgen05_fence_after();
-  bf16* o1 = static_cast<bf16*>(p.out) + out_off + (row0 + g) * p.ldo + dbase + q2;
+  if (!FULL && row0 >= p.M) return;                  // warp-uniform
+  bf16* o1 = static_cast<bf16*>(p.out) + out_off + (row0 + g) * p.ldo + dbase + q * 16;
 #pragma unroll 1
   for (int hh = 0; hh < 2; ++hh) {
+    if (!FULL && row0 + hh * 16 >= p.M) break;       // warp-uniform
     uint32_t r1[32], r2[32];
     const uint32_t tbase = t_row + (static_cast<uint32_t>(hh * 16) << 16) + b1;
     tmem_ld_16x64(tbase, r1);
     tmem_ld_16x64(tbase + 128, r2);
     bf16* oA = o1 + static_cast<long long>(hh * 16) * p.ldo;
     bf16* oB = oA + 8 * p.ldo;
+    const bool okA = FULL || row0 + hh * 16 + g < p.M, okB = FULL || row0 + hh * 16 + g + 8 < p.M;
     const float2 pA = make_float2(fpos[2 * hh], fpos[2 * hh]), pB = make_float2(fpos[2 * hh + 1], fpos[2 * hh + 1]);
+    uint32_t w1A[8], w1B[8], w2A[8], w2B[8];         // packed bf16 pairs: output columns q * 16 + 2 kb (+1) of both blocks
     tmem_ld_wait();
     if (is_v) {
 #pragma unroll
@@ -491,10 +506,10 @@ __device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int la
         const float2 c1 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * kb + 2]), __uint_as_float(r1[4 * kb + 3])), bx1[kb]);
         const float2 a2 = __fadd2_rn(make_float2(__uint_as_float(r2[4 * kb]), __uint_as_float(r2[4 * kb + 1])), bx2[kb]);
         const float2 c2 = __fadd2_rn(make_float2(__uint_as_float(r2[4 * kb + 2]), __uint_as_float(r2[4 * kb + 3])), bx2[kb]);
-        *reinterpret_cast<uint32_t*>(oA + kb * 8) = pack_bf16x2(a1.x, a1.y);
-        *reinterpret_cast<uint32_t*>(oB + kb * 8) = pack_bf16x2(c1.x, c1.y);
-        *reinterpret_cast<uint32_t*>(oA + 128 + kb * 8) = pack_bf16x2(a2.x, a2.y);
-        *reinterpret_cast<uint32_t*>(oB + 128 + kb * 8) = pack_bf16x2(c2.x, c2.y);
+        w1A[kb] = pack_bf16x2(a1.x, a1.y);
+        w1B[kb] = pack_bf16x2(c1.x, c1.y);
+        w2A[kb] = pack_bf16x2(a2.x, a2.y);
+        w2B[kb] = pack_bf16x2(c2.x, c2.y);
       }
     } else {
 #pragma unroll
@@ -510,11 +525,83 @@ __device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int la
         const float2 nA = make_float2(-sA.x, -sA.y), nB = make_float2(-sB.x, -sB.y);
         const float2 y1A = __ffma2_rn(x2A, nA, __fmul2_rn(x1A, cA)), y2A = __ffma2_rn(x1A, sA, __fmul2_rn(x2A, cA));
         const float2 y1B = __ffma2_rn(x2B, nB, __fmul2_rn(x1B, cB)), y2B = __ffma2_rn(x1B, sB, __fmul2_rn(x2B, cB));
-        *reinterpret_cast<uint32_t*>(oA + kb * 8) = pack_bf16x2(y1A.x, y1A.y);
-        *reinterpret_cast<uint32_t*>(oA + off2 + kb * 8) = pack_bf16x2(y2A.x, y2A.y);
-        *reinterpret_cast<uint32_t*>(oB + kb * 8) = pack_bf16x2(y1B.x, y1B.y);
-        *reinterpret_cast<uint32_t*>(oB + off2 + kb * 8) = pack_bf16x2(y2B.x, y2B.y);
+        w1A[kb] = pack_bf16x2(y1A.x, y1A.y);
+        w2A[kb] = pack_bf16x2(y2A.x, y2A.y);
+        w1B[kb] = pack_bf16x2(y1B.x, y1B.y);
+        w2B[kb] = pack_bf16x2(y2B.x, y2B.y);
       }
+    }
+    if (okA) {
+      reinterpret_cast<uint4*>(oA)[0] = make_uint4(w1A[0], w1A[1], w1A[2], w1A[3]);
+      reinterpret_cast<uint4*>(oA)[1] = make_uint4(w1A[4], w1A[5], w1A[6], w1A[7]);
+      reinterpret_cast<uint4*>(oA + off2)[0] = make_uint4(w2A[0], w2A[1], w2A[2], w2A[3]);
+      reinterpret_cast<uint4*>(oA + off2)[1] = make_uint4(w2A[4], w2A[5], w2A[6], w2A[7]);
+    }
+    if (okB) {
+      reinterpret_cast<uint4*>(oB)[0] = make_uint4(w1B[0], w1B[1], w1B[2], w1B[3]);
+      reinterpret_cast<uint4*>(oB)[1] = make_uint4(w1B[4], w1B[5], w1B[6], w1B[7]);
+      reinterpret_cast<uint4*>(oB + off2)[0] = make_uint4(w2B[0], w2B[1], w2B[2], w2B[3]);
+      reinterpret_cast<uint4*>(oB + off2)[1] = make_uint4(w2B[4], w2B[5], w2B[6], w2B[7]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lean GEGLU epilogue (TcGemmParams::glu_perm16): no deferred LayerNorm, N % 256 == 0, packed f32x2 arithmetic, and the
+// [fc1; gate] rows of the packed weight ordered so that a thread's 8 outputs of a row and 64-column block are consecutive:
+// accumulator 8-column block kb = gi * 4 + kk holds, for kk < 2, the fc1 rows (kk >= 2: the gate rows, block kb - 2) of
+// outputs  q * 8 + (gi * 2 + kk) * 2 + e  (column kb * 8 + 2 q + e) -> one 16-byte store per row instead of four 4-byte ones.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 geglu_fast2(float2 a, float2 g) {   // geglu_fast on a pair, same operations
+  const float2 ac = make_float2(fminf(fmaxf(a.x, -6.0f), 6.0f), fminf(fmaxf(a.y, -6.0f), 6.0f));
+  const float2 a2 = __fmul2_rn(ac, ac);
+  float2 sp = __ffma2_rn(a2, make_float2(2.377971153e-05f, 2.377971153e-05f), make_float2(7.501817227e-04f, 7.501817227e-04f));
+  sp = __ffma2_rn(a2, sp, make_float2(-1.060307563e-01f, -1.060307563e-01f));
+  sp = __ffma2_rn(a2, sp, make_float2(-2.301608248e+00f, -2.301608248e+00f));
+  const float2 t1 = __fmul2_rn(ac, sp), t2 = __fmul2_rn(g, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e1 = make_float2(ex2_approx(t1.x), ex2_approx(t1.y)), e2 = make_float2(ex2_approx(t2.x), ex2_approx(t2.y));
+  const float2 one = make_float2(1.0f, 1.0f);
+  const float2 den = __fmul2_rn(__fadd2_rn(one, e1), __fadd2_rn(one, e2));
+  return __fmul2_rn(a, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+}
+
+template <bool FULL>
+__device__ __forceinline__ void geglu_epilogue_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
+                                                    long long out_off, const float* bias, uint64_t* full_bar, uint32_t full_parity) {
+  const int g = lane >> 2, q = lane & 3, q2 = q * 2;
+  const int colw = n_blk * BLOCK_N + half_sel * 128;   // first GEMM column of this warp's 128
+  float2 bb[2][8];
+#pragma unroll
+  for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) bb[cb][kb] = __ldg(reinterpret_cast<const float2*>(bias + colw + cb * 64 + kb * 8 + q2));
+  mbar_wait(full_bar, full_parity);
+  tcgen05_fence_after();
+  if (!FULL && row0 >= p.M) return;                    // warp-uniform
+  bf16* outp = static_cast<bf16*>(p.out) + out_off + (row0 + g) * p.ldo + (colw >> 1) + q * 8;
+#pragma unroll
+  for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      if (!FULL && row0 + hh * 16 >= p.M) break;       // warp-uniform
+      uint32_t r[32];
+      tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + half_sel * 128 + cb * 64, r);
+      tmem_ld_wait();
+      uint32_t wA[4], wB[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                    // j = gi * 2 + kk
+        const int ka = (j >> 1) * 4 + (j & 1), kg = ka + 2;
+        const float2 aA = __fadd2_rn(make_float2(__uint_as_float(r[4 * ka]), __uint_as_float(r[4 * ka + 1])), bb[cb][ka]);
+        const float2 gA = __fadd2_rn(make_float2(__uint_as_float(r[4 * kg]), __uint_as_float(r[4 * kg + 1])), bb[cb][kg]);
+        const float2 aB = __fadd2_rn(make_float2(__uint_as_float(r[4 * ka + 2]), __uint_as_float(r[4 * ka + 3])), bb[cb][ka]);
+        const float2 gB = __fadd2_rn(make_float2(__uint_as_float(r[4 * kg + 2]), __uint_as_float(r[4 * kg + 3])), bb[cb][kg]);
+        const float2 oA = geglu_fast2(aA, gA), oB = geglu_fast2(aB, gB);
+        wA[j] = pack_bf16x2(oA.x, oA.y);
+        wB[j] = pack_bf16x2(oB.x, oB.y);
+      }
+      bf16* o = outp + static_cast<long long>(hh * 16) * p.ldo + cb * 32;
+      if (FULL || row0 + hh * 16 + g < p.M) *reinterpret_cast<uint4*>(o) = make_uint4(wA[0], wA[1], wA[2], wA[3]);
+      if (FULL || row0 + hh * 16 + g + 8 < p.M) *reinterpret_cast<uint4*>(o + 8 * p.ldo) = make_uint4(wB[0], wB[1], wB[2], wB[3]);
     }
   }
 }
@@ -562,6 +649,11 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       }
     }
   } else if (EPI == K_GEGLU) {
+    if (p.glu_fast) {  // weights packed in the store-friendly order: every tile takes the lean epilogue
+      if (row0 + 32 <= p.M) geglu_epilogue_fast<true>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      else geglu_epilogue_fast<false>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      return;
+    }
     // 64 accumulator columns = two interleave groups [a16 | g16]; a_j and g_j (16 columns apart) live in the same thread.
     // Biases of this thread's column pairs for both 64-column halves are requested before the accumulator wait.
     // Deferred LayerNorm (ln_stat != nullptr): a = rstd acc + (nm c + b') per row -- one extra FMA per element; without
@@ -627,9 +719,9 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
       }
     }
   } else {  // K_QKV_ROPE
-    if (p.rope_pd == 128 && p.ln_stat == nullptr && p.rope_freq != nullptr && p.rope_pos == nullptr && p.rope_fast &&
-        row0 + 32 <= p.M && (n_blk + 1) * BLOCK_N <= p.N && p.hidden % BLOCK_N == 0) {  // warp-uniform
-      rope_epilogue_fast128(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+    if (p.rope_fast) {  // weights packed in the store-friendly column order: every tile takes the lean epilogue
+      if (row0 + 32 <= p.M) rope_epilogue_fast128<true>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      else rope_epilogue_fast128<false>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
       return;
     }
     // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load.  Everything that
@@ -1555,7 +1647,6 @@ int g_num_sms = 0;
 bool g_init_done = false;
 bool g_use_pair = true;
 int g_cluster_m = 0, g_cluster_n = 0;  // DITTO_CLUSTER="cm,cn": default cluster shape of the 1-CTA GEMM kernel (0 = heuristic)
-bool g_rope_fast = true;
 bool g_force_generic = false;  // DITTO_GENERIC_EPI=1: route every STORE epilogue through the generic path (tests)
 int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
 unsigned long long* g_dbg = nullptr;
@@ -1690,7 +1781,6 @@ int tc_gemm_init() {
     }
     const char* eg = getenv("DITTO_GENERIC_EPI");
     g_force_generic = eg && eg[0] == '1';
-    if (const char* er = getenv("DITTO_ROPE_GENERIC")) g_rope_fast = !(er[0] == '1');
     if (const char* e1 = getenv("DITTO_STAGES_1CTA")) g_stages_1cta = std::max(2, std::min(STAGES, atoi(e1)));
     if (const char* e2 = getenv("DITTO_STAGES_PAIR")) g_stages_pair = std::max(2, std::min(P_STAGES, atoi(e2)));
   }
@@ -1744,7 +1834,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.resid = q.resid; p.ldr = q.ldr; p.sr_inner = q.sr_inner; p.sr_outer = q.sr_outer; p.resid_row_mod = q.resid_row_mod;
   p.out2 = q.out2; p.ldo2 = q.ldo2;
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
-  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos; p.rope_fast = g_rope_fast ? 1 : 0;
+  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos; p.rope_fast = q.rope_perm16 ? 1 : 0; p.glu_fast = q.glu_perm16 ? 1 : 0;
   p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.stat_out = q.stat_out; p.stat_parts = q.stat_parts; p.stat_rows_outer = q.stat_rows_outer;
   p.stat_parts_item = static_cast<int>(ceil_div(q.N, 128));
@@ -1764,6 +1854,13 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
   p.stages = pair ? g_stages_pair : g_stages_1cta;
   p.cm = 1; p.cn = 1;
+  if (q.glu_perm16)
+    DITTO_REQUIRE(q.epilogue == TC_EPI_GEGLU && q.ln_stat == nullptr && q.N % BLOCK_N == 0 && q.out_bf16 && q.ldo % 8 == 0 && q.bias != nullptr,
+                  DITTO_E_BADARG, "tc_gemm: glu_perm16 needs the GEGLU epilogue, no deferred LayerNorm, a bias and N % 256 == 0");
+  if (q.rope_perm16)
+    DITTO_REQUIRE(q.epilogue == TC_EPI_QKV_ROPE && q.rope_pd == 128 && q.rope_freq != nullptr && q.ln_stat == nullptr &&
+                      q.N % BLOCK_N == 0 && q.hidden % BLOCK_N == 0 && q.out_bf16 && q.ldo % 8 == 0,
+                  DITTO_E_BADARG, "tc_gemm: rope_perm16 needs pd = 128, on-the-fly frequencies, no deferred LayerNorm, N and hidden % 256 == 0");
   // kernel variant: the lean compile-time epilogues cover the hot cases, anything else takes the generic one
   int ke;
   if (q.epilogue == TC_EPI_GEGLU) ke = K_GEGLU;

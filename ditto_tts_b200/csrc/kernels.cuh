@@ -81,6 +81,11 @@ struct TcGemmParams {
   const float* rope_freq = nullptr;            // [d/2] inv_freq: when set, cos/sin are computed in the epilogue (no table reads)
   int rope_half = 0, rope_pd = 0, seq_T = 0, hidden = 0;
   const int* rope_pos = nullptr;               // optional [M] row -> position table (ragged batches) instead of row % seq_T
+  // weight rows additionally permuted inside every 64-row block (GEMM column kb*8 + 2q + e = output column q*16 + kb*2 + e):
+  // lean epilogue with 16-byte stores; needs rope_pd == 128, rope_freq, no deferred LayerNorm, N % 256 == 0, hidden % 256 == 0
+  bool rope_perm16 = false;
+  // TC_EPI_GEGLU: [fc1; gate] rows packed in the store-friendly order of geglu_epilogue_fast (gemm_tc.cu) instead of [a16 | g16]
+  bool glu_perm16 = false;
   // optional per-row scale 1 / sum_c row_lsum[row*row_lparts + c] applied to the accumulator (softmax normalisation of an
   // unnormalised P operand, see launch_tc_scores_softmax); batch strides in elements
   const float* row_lsum = nullptr; int row_lparts = 0; int64_t sl_inner = 0, sl_outer = 0;
