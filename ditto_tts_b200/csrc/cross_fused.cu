@@ -98,12 +98,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-// L2 prefetch of one box (no shared memory, no completion tracking)
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
-               "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -131,9 +125,10 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
   uint64_t* o_empty = o_full + XF_O_BUFS;     // [3] output chunk read                  (epilogue -> MMA)
   uint64_t* hin_full = o_empty + XF_O_BUFS;   // [NB] residual half-chunk landed        (mover TMA -> epilogue)
   uint64_t* hout_full = hin_full + XF_NB;     // [NB] result half-chunk in place        (epilogue -> mover)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hout_full + XF_NB);
+  uint64_t* hfree = hout_full + XF_NB;        // [NB] staging buffer reusable           (storer -> loader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hfree + XF_NB);
   float2* stat = reinterpret_cast<float2*>(smem + XF_OFF_STAT);
-  static_assert((2 * XF_STAGES + 2 + 2 + 1 + 2 * XF_VF_RING + 2 * XF_O_BUFS + 2 * XF_NB) * 8 + 4 <= XF_BAR_BYTES, "barrier block too small");
+  static_assert((2 * XF_STAGES + 2 + 2 + 1 + 2 * XF_VF_RING + 2 * XF_O_BUFS + 3 * XF_NB) * 8 + 4 <= XF_BAR_BYTES, "barrier block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,6 +161,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
     for (int s = 0; s < XF_NB; ++s) {
       mbar_init(&hin_full[s], 1);
       mbar_init(&hout_full[s], XF_EPI_WARPS);
+      mbar_init(&hfree[s], 1);
     }
     fence_barrier_init();
   }
@@ -262,10 +258,12 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         if (tile + step < p.num_tiles) issue_scores(it + 1);
       }
     }
-  } else if (warp == 3) {
-    // =========================== mover: residual stream global <-> shared by TMA ===========================
+  } else if (warp == 2 || warp == 3) {
+    // =========================== movers: residual stream global <-> shared by TMA ===========================
     // job j = (tile, pass, half-chunk): pass 0 loads h (fp32) and stores h + attention; pass 1 re-loads the updated rows
-    // (L2 hits) and stores LayerNorm(h) as bf16.  Buffer j % NB; NB - 1 loads in flight ahead of the epilogue.
+    // (L2 hits) and stores LayerNorm(h) as bf16.  Buffer j % NB.  Two threads so that the TMA issue latency of the loads
+    // and of the stores is not paid in one serial chain: warp 2 loads (as soon as a buffer is free), warp 3 stores and
+    // frees the buffers.
     xf_regs_ctrl();
     if (lane == 0) {
       const int my_tiles = first < p.num_tiles ? (p.num_tiles - 1 - first) / step + 1 : 0;
@@ -279,52 +277,45 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         pass = r / p.num_hc;
         hc = r - pass * p.num_hc;
       };
-      auto issue_load = [&](int j) {
-        int seq, row, pass, hc;
-        job_coords(j, seq, row, pass, hc);
-        const int b = j % XF_NB;
-        uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
-        mbar_expect_tx(&hin_full[b], static_cast<uint32_t>(p.rt) * 256);  // two slabs of rt rows x 128 B
-        tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
-        tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
-      };
-      // The staging ring keeps only 3 x 32 KiB of loads in flight per SM -- too little to cover the HBM latency -- so the
-      // fp32 rows of a tile are pulled into L2 a whole tile ahead (24 boxes of 16 KiB); the ring then streams L2 hits.
-      auto prefetch_tile = [&](int ti) {
-        if (ti >= my_tiles) return;
-        const int tile = first + ti * step;
-        const int seq = tile / p.m_tiles, row = (tile - seq * p.m_tiles) * p.rt;
-        for (int c = 0; c < p.H; c += 32) tma_prefetch_4d(&tmap_h, c, row, 0, seq);
-      };
-      prefetch_tile(0);
-      for (int j = 0; j < XF_NB - 1 && j < J; ++j) issue_load(j);
-      for (int j = 0; j < J; ++j) {
-        const int b = j % XF_NB;
-        if (j % jobs_per_tile == 0) prefetch_tile(j / jobs_per_tile + 1);
-        mbar_wait(&hout_full[b], (j / XF_NB) & 1u);
-        int seq, row, pass, hc;
-        job_coords(j, seq, row, pass, hc);
-        const uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
-        if (pass == 0) {
-          tma_store_4d(&tmap_h, buf, hc * XF_HC, row, 0, seq);
-          tma_store_4d(&tmap_h, buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
-        } else {
-          tma_store_4d(&tmap_uo, buf, hc * XF_HC, row, 0, seq);
+      if (warp == 2) {
+        for (int j = 0; j < J; ++j) {
+          int seq, row, pass, hc;
+          job_coords(j, seq, row, pass, hc);
+          const int b = j % XF_NB;
+          uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+          mbar_wait(&hfree[b], ((j / XF_NB) & 1u) ^ 1u);   // the store that last used this buffer has read it
+          mbar_expect_tx(&hin_full[b], static_cast<uint32_t>(p.rt) * 256);  // two slabs of rt rows x 128 B
+          tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
+          tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
         }
-        bulk_commit();
-        const int jn = j + XF_NB - 1;  // goes into the buffer of job j - 1
-        if (jn < J) {
-          bulk_wait_read<1>();  // every store but the one just issued has read its source: buffer (j-1) % NB is free
-          // a pass-1 job re-loads what pass-0 job jn - num_hc stored, num_hc - NB + 1 groups before the newest one:
-          // that store must have COMPLETED (be visible), not just have read its source
-          if ((jn % jobs_per_tile) >= p.num_hc) {
-            if (p.num_hc - XF_NB + 1 > 8) bulk_wait<8>();
-            else bulk_wait<1>();
+      } else {
+        for (int j = 0; j < J; ++j) {
+          const int b = j % XF_NB;
+          mbar_wait(&hout_full[b], (j / XF_NB) & 1u);
+          int seq, row, pass, hc;
+          job_coords(j, seq, row, pass, hc);
+          const uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+          if (pass == 0) {
+            tma_store_4d(&tmap_h, buf, hc * XF_HC, row, 0, seq);
+            tma_store_4d(&tmap_h, buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
+          } else {
+            tma_store_4d(&tmap_uo, buf, hc * XF_HC, row, 0, seq);
           }
-          issue_load(jn);
+          bulk_commit();
+          const int jn = j - 1 + XF_NB;  // the job that takes over the buffer of job j - 1
+          if (j >= 1 && jn < J) {
+            bulk_wait_read<1>();  // every store but the one just issued has read its source
+            // a pass-1 job re-loads what pass-0 job jn - num_hc stored, num_hc - NB + 1 groups before the newest one:
+            // that store must have COMPLETED (be visible), not just have read its source
+            if ((jn % jobs_per_tile) >= p.num_hc) {
+              if (p.num_hc - XF_NB + 1 > 8) bulk_wait<8>();
+              else bulk_wait<1>();
+            }
+            mbar_arrive(&hfree[(j - 1) % XF_NB]);
+          }
         }
+        bulk_wait<0>();
       }
-      bulk_wait<0>();
     }
   } else if (warp >= XF_EPI_WARP0) {
     // =========================== softmax + epilogue ===========================
