@@ -81,6 +81,7 @@ struct XfDev {
   const float* out_bias;                      // [H]
   const float* gamma; const float* beta;      // LayerNorm after the block
   float inv_h;
+  const float2* ln_stat; int ln_parts; const float* ln_c;   // deferred LayerNorm of the query operand (nullptr: off)
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * XF_EPI_WARPS) : "memory"); }
@@ -340,6 +341,38 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
           bb[kb].x = c < p.S ? __ldg(bias + c) * 1.4426950408889634f : 0.f;
           bb[kb].y = c + 1 < p.S ? __ldg(bias + c + 1) * 1.4426950408889634f : 0.f;
         }
+        // deferred LayerNorm of the query rows: s' = aX acc + (nX c + bias log2e); (alpha2, 0) without it
+        float aA = p.alpha2, nA = 0.f, aB = p.alpha2, nB = 0.f;
+        float2 cc[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) cc[kb] = make_float2(0.f, 0.f);
+        if (p.ln_stat != nullptr) {
+          const float* lnc = p.ln_c + seq * p.sb_seq;
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const int c = kb * 8 + q2;
+            cc[kb].x = c < p.S ? __ldg(lnc + c) : 0.f;
+            cc[kb].y = c + 1 < p.S ? __ldg(lnc + c + 1) : 0.f;
+          }
+          const int mbt = tile - seq * p.m_tiles;
+          const int lrA = mbt * p.rt + trow + g;            // row inside the utterance
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int lr = lrA + half * 8;
+            float sm = 0.f, sq = 0.f;
+            if (lr < p.T) {
+              const float2* sp2 = p.ln_stat + (static_cast<long long>(seq) * p.T + lr) * p.ln_parts;
+              for (int c = 0; c < p.ln_parts; ++c) {
+                const float2 v = __ldg(sp2 + c);
+                sm += v.x; sq += v.y;
+              }
+            }
+            const float mean = sm * p.inv_h;
+            const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * p.inv_h), 0.f) + 1e-5f);
+            if (half == 0) { aA = rstd * p.alpha2; nA = -mean * aA; }
+            else { aB = rstd * p.alpha2; nB = -mean * aB; }
+          }
+        }
         mbar_wait(&s_full[sb], (it >> 1) & 1u);
         tcgen05_fence_after();
         uint32_t r[32];
@@ -352,10 +385,10 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {  // s' = (alpha acc + bias) log2 e, in place in r; padded columns -> -inf
           const int c = kb * 8 + q2;
-          const float a0 = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb]), bb[kb].x) : -INFINITY;
-          const float a1 = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 1]), bb[kb].y) : -INFINITY;
-          const float b0 = c < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 2]), bb[kb].x) : -INFINITY;
-          const float b1 = c + 1 < p.S ? fmaf(p.alpha2, __uint_as_float(r[4 * kb + 3]), bb[kb].y) : -INFINITY;
+          const float a0 = c < p.S ? fmaf(aA, __uint_as_float(r[4 * kb]), fmaf(nA, cc[kb].x, bb[kb].x)) : -INFINITY;
+          const float a1 = c + 1 < p.S ? fmaf(aA, __uint_as_float(r[4 * kb + 1]), fmaf(nA, cc[kb].y, bb[kb].y)) : -INFINITY;
+          const float b0 = c < p.S ? fmaf(aB, __uint_as_float(r[4 * kb + 2]), fmaf(nB, cc[kb].x, bb[kb].x)) : -INFINITY;
+          const float b1 = c + 1 < p.S ? fmaf(aB, __uint_as_float(r[4 * kb + 3]), fmaf(nB, cc[kb].y, bb[kb].y)) : -INFINITY;
           r[4 * kb] = __float_as_uint(a0); r[4 * kb + 1] = __float_as_uint(a1);
           r[4 * kb + 2] = __float_as_uint(b0); r[4 * kb + 3] = __float_as_uint(b1);
           mA = fmaxf(mA, fmaxf(a0, a1));
@@ -609,6 +642,8 @@ int launch_cross_fused(const CrossFusedParams& q, cudaStream_t st) {
   p.out_bias = q.out_bias;
   p.gamma = q.gamma; p.beta = q.beta;
   p.inv_h = 1.0f / static_cast<float>(q.H);
+  p.ln_stat = q.ln_stat; p.ln_parts = q.ln_parts; p.ln_c = q.ln_c;
+  if (q.ln_stat != nullptr) DITTO_REQUIRE(q.ln_parts > 0 && q.ln_c != nullptr, DITTO_E_BADARG, "cross_fused: deferred LayerNorm arguments");
   // flops: both contractions; bytes: u read, h read + write, u3 write (the HBM stream that bounds the kernel)
   const double rows = static_cast<double>(q.n_seq) * q.T;
   ProfScope prof(q.tag, st, 4.0 * rows * q.S * q.H, rows * q.H * 12.0);

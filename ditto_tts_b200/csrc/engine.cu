@@ -86,6 +86,7 @@ struct ditto_engine {
   int rope_pd = 0;
   bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   bool qkv_perm16 = false;  // QKV weight rows also permuted inside 64-row blocks for the lean RoPE epilogue (TcGemmParams::rope_perm16)
+  bool defer_ln2 = false;   // norm2 only: row statistics from the self-attention P.V epilogue, LayerNorm folded into cross_fused's scores
   bool fused_cross = true;  // folded cross-attention + residual + norm3 in one kernel (cross_fused.cu); DITTO_NO_FUSED_CROSS=1 disables
   bool fused_attn = false;  // scores + softmax fused (cluster kernel); falls back per call when a row needs > 16 tiles
   bool fold_cross = false;  // cross-attn q/out projections folded into the per-utterance text K/V (heads == 1 only)
@@ -197,7 +198,8 @@ static bool fold_active(const ditto_engine* e, int64_t S) {
 }
 // LN2 is folded into the cross-attention scores only on the folded path with a single key tile (fused scores kernel)
 static bool fold_ln_active(const ditto_engine* e, int64_t S) {
-  return e->defer_ln && fold_active(e, S) && tc_scores_softmax_csize(static_cast<int>(S)) == 1;
+  const bool want = e->defer_ln || (e->defer_ln2 && cross_fused_supported(1, S, e->H, e->heads));
+  return want && fold_active(e, S) && tc_scores_softmax_csize(static_cast<int>(S)) == 1;
 }
 static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_t S) {
   Arena a(base);
@@ -216,7 +218,7 @@ static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_
     c.kfold0 = a.take<bf16>(static_cast<int64_t>(c.kfold_stride) * e->L);
     c.vfold0 = a.take<bf16>(static_cast<int64_t>(c.vfold_stride) * e->L);
     c.sbias0 = a.take<float>(static_cast<int64_t>(c.sbias_stride) * e->L);
-    if (e->defer_ln) c.cvec0 = a.take<float>(static_cast<int64_t>(c.sbias_stride) * e->L);
+    if (e->defer_ln || e->defer_ln2) c.cvec0 = a.take<float>(static_cast<int64_t>(c.sbias_stride) * e->L);
   }
   c.total = a.off + 256;
   return c;
@@ -287,7 +289,7 @@ static Workspace ws_layout(const ditto_engine* e, void* base, SeqGroup* gs, int 
   if (e->bf16_mode) w.lpart = a.take<float>(l_el);
   w.ln_parts_h = static_cast<int>(ceil_div(H, 128));
   w.ln_parts_attn = static_cast<int>(e->heads * ceil_div(e->d, 128));
-  if (e->defer_ln) w.lnstat = a.take<float2>(M * std::max(w.ln_parts_h, w.ln_parts_attn));
+  if (e->defer_ln || e->defer_ln2) w.lnstat = a.take<float2>(M * std::max(w.ln_parts_h, w.ln_parts_attn));
   w.tmp_small = a.take<float>(n_tot * e->Xd);
   w.text16 = a.take<bf16>(text_el * e->Xd);
   if (ng > 1) w.row_pos = a.take<int>(M);
@@ -441,7 +443,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
 
   // deferred LayerNorm: `u` holds bf16(h) and w.lnstat the row statistics; ln1_parts = parts written by the last producer
   const bool dln = e->defer_ln;
-  const bool dln2 = dln && fold_ln_active(e, g0.S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
+  const bool dln2_all = dln && fold_ln_active(e, g0.S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
   int ln1_parts = 1;
   // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
   DITTO_TRY(fork.begin(ng));
@@ -510,9 +512,12 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         bf16* q = qkv + grp.row0 * 3 * H;
         bf16* ug = u + grp.row0 * H;
         float* hg = w.h + grp.row0 * H;
+        // norm2 deferred for this group (context built with the gamma2-folded K): whole-model DITTO_F_DEFER_LN, or norm2 only
+        const bool dln2 = dln ? dln2_all : fold_ln_active(e, S);
+        float2* lnstat_g = w.lnstat ? w.lnstat + grp.row0 * std::max(w.ln_parts_h, w.ln_parts_attn) : nullptr;
         DITTO_TRY(attention_bf16(e, wg, q, 3 * H, T * 3 * H, q + H, 3 * H, T * 3 * H, q + 2 * H, 3 * H, T * 3 * H, n, static_cast<int>(T),
-                                 static_cast<int>(T), inv_sqrt_d, hg, false, H, T * H, hg, st, false, dln2 ? u : nullptr,
-                                 dln2 ? w.lnstat : nullptr));
+                                 static_cast<int>(T), inv_sqrt_d, hg, false, H, T * H, hg, st, false, dln2 ? ug : nullptr,
+                                 dln2 ? lnstat_g : nullptr));
         // ---- cross-attention (torch MHA math path)                                                   DiT.py:141-148
         if (!dln2) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), ug, true, Mg, H, st));
         void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
@@ -527,6 +532,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
             f.sbias = c.sbias0 + c.sbias_stride * i; f.sb_seq = Sp; f.out_bias = e->LW(i, "cross_attn.out_proj.bias");
             f.h = hg; f.gamma = e->LW(i, "norm3.weight"); f.beta = e->LW(i, "norm3.bias"); f.u_out = ug;
             f.n_seq = n; f.T = T; f.S = S; f.Sp = Sp; f.H = H; f.alpha = sqrt_inv_d; f.tag = PC_TC_CROSS_FUSED;
+            if (dln2) { f.ln_stat = lnstat_g; f.ln_parts = w.ln_parts_attn; f.ln_c = c.cvec0 + c.sbias_stride * i; }
             DITTO_TRY(launch_cross_fused(f, st));
             continue;
           }
@@ -539,7 +545,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
             f.alpha = sqrt_inv_d; f.bias = c.sbias0 + c.sbias_stride * i; f.sb_inner = Sp; f.sb_outer = heads * Sp;
             f.P = static_cast<bf16*>(wg.P); f.ldp = heads * Sp; f.sp_inner = Sp; f.sp_outer = T * heads * Sp; f.npad = static_cast<int>(Sp);
             f.tag = PC_TC_CROSS_SCORES;
-            if (dln2) { f.ln_stat = w.lnstat; f.ln_parts = w.ln_parts_attn; f.ln_width = H; f.ln_c = c.cvec0 + c.sbias_stride * i; }
+            if (dln2) { f.ln_stat = lnstat_g; f.ln_parts = w.ln_parts_attn; f.ln_width = H; f.ln_c = c.cvec0 + c.sbias_stride * i; }
             DITTO_TRY(launch_tc_scores_softmax(f, st));
           } else {
             DITTO_REQUIRE(!dln2, DITTO_E_UNSUPPORTED, "forward: deferred LayerNorm needs the fused scores kernel on the folded cross path");
@@ -750,6 +756,10 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     if (const char* ef = getenv("DITTO_NO_FUSED_ATTN")) if (ef[0] == '1') e->fused_attn = false;
     e->fused_cross = e->fused_attn;
     if (const char* ef = getenv("DITTO_NO_FUSED_CROSS")) if (ef[0] == '1') e->fused_cross = false;
+    {
+      const char* e2 = getenv("DITTO_DEFER_LN2");
+      e->defer_ln2 = !e->defer_ln && e->fused_cross && e->bf16_mode && e->heads == 1 && e2 && e2[0] == '1';
+    }
     const char* env = getenv("DITTO_PV_TRANSPOSE");
     e->pv_transpose = env && env[0] == '1';
     const char* env2 = getenv("DITTO_ROPE_TABLE");
@@ -939,7 +949,7 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
       const bool dl = e->defer_ln;
       rc = launch_pack_rows(e->LW(i, "attn.in_proj_weight"), lp.w_qkv, lp.b_qkv, e->LW(i, "attn.in_proj_bias"), d_qkv, 3 * H, H, st,
                             dl ? e->LW(i, "norm1.weight") : nullptr, dl ? e->LW(i, "norm1.bias") : nullptr, lp.c_qkv);
-      if (!rc && dl)
+      if (!rc && (dl || e->defer_ln2))
         rc = launch_pack_rows(e->LW(i, "cross_attn.in_proj_weight"), lp.wq_g, lp.bq_g, e->LW(i, "cross_attn.in_proj_bias"), nullptr, H, H, st,
                               e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), nullptr);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.in_proj_weight"), 3ll * H * H, &lp.wc_in);

@@ -133,6 +133,9 @@ struct CrossFusedParams {
   float* h = nullptr;                          // [n_seq * T, H] residual stream, updated in place
   const float* gamma = nullptr; const float* beta = nullptr;  // the next LayerNorm (norm3)
   bf16* u_out = nullptr;                       // [n_seq * T, H] its bf16 output (may alias u)
+  // deferred norm2: u is the raw bf16 residual stream, kfold carries gamma2, sbias carries the beta2 term; the scores are
+  // rstd (u kfold^T) - rstd mean c + sbias with (sum, sum of squares) partials ln_stat[row * ln_parts + part] over H columns
+  const float2* ln_stat = nullptr; int ln_parts = 0; const float* ln_c = nullptr;  // ln_c [n_seq, Sp] like sbias
   int64_t n_seq = 0, T = 0, S = 0, Sp = 0; int H = 0;
   float alpha = 1.f;
   int tag = PC_TC_OTHER;
