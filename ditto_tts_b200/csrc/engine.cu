@@ -85,6 +85,7 @@ struct ditto_engine {
   bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
   int rope_pd = 0;
   bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
+  bool pv_perm4 = false;    // v columns stored in the order the float4 P.V epilogue wants (TcGemmParams::out_perm4)
   bool qkv_perm16 = false;  // QKV weight rows also permuted inside 64-row blocks for the lean RoPE epilogue (TcGemmParams::rope_perm16)
   bool defer_ln2 = false;   // norm2 only: row statistics from the self-attention P.V epilogue, LayerNorm folded into cross_fused's scores
   bool fused_cross = true;  // folded cross-attention + residual + norm3 in one kernel (cross_fused.cu); DITTO_NO_FUSED_CROSS=1 disables
@@ -360,6 +361,7 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
     o.sl_outer = static_cast<int64_t>(heads) * Tq * csize;
   }
   o.tag = cross ? PC_TC_CROSS_PV : PC_TC_SELF_PV;
+  o.out_perm4 = e->pv_perm4 && !cross && !out_bf16 && resid != nullptr && out2 == nullptr && stat_out == nullptr && e->fused_rope;
   if (out2 != nullptr) { o.out2 = out2; o.ldo2 = ldo; }
   if (stat_out != nullptr) { o.stat_out = stat_out; o.stat_parts = w.ln_parts_attn; o.stat_rows_outer = Tq; }
   DITTO_TRY(launch_tc_gemm(o, st));
@@ -770,6 +772,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
       e->glu_perm16 = !e->defer_ln && e->H % 32 == 0 && !(egl && egl[0] == '1');
       e->qkv_perm16 = e->fused_rope && e->rope_pd == 128 && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 &&
                       !(eg && eg[0] == '1');
+      const char* ep = getenv("DITTO_NO_PV_PERM4");
+      e->pv_perm4 = e->qkv_perm16 && !e->pv_transpose && !e->defer_ln2 && e->d % 128 == 0 && !(ep && ep[0] == '1');
     }
   }
   build_expected(e);
@@ -921,7 +925,14 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
       for (int r = 0; r < 3 * H; ++r) {
         const int blk = r / 64, c = r % 64;
         const int kb = c / 8, q = (c % 8) / 2, ee = c % 2;
-        qkv_perm[r] = base[blk * 64 + q * 16 + kb * 2 + ee];
+        int l = q * 16 + kb * 2 + ee;   // storage position (inside the block) the lean QKV epilogue writes this accumulator to
+        // v third with the float4 P.V epilogue: storage position l must hold logical column 16 (K / 2) + 4 Q + 2 (K % 2) + E,
+        // where K, Q, E are the fragment coordinates of P.V accumulator column l
+        if (e->pv_perm4 && r >= 2 * H) {
+          const int K = l / 8, Q = (l % 8) / 2, E = l % 2;
+          l = 16 * (K / 2) + 4 * Q + 2 * (K % 2) + E;
+        }
+        qkv_perm[r] = base[blk * 64 + l];
       }
     }
     int *d_glu = nullptr, *d_qkv = nullptr;

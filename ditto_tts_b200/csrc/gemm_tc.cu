@@ -70,6 +70,7 @@ struct DevParams {
   const int* rope_pos;  // optional [M] row -> position table (ragged batches); nullptr: position = row % seq_T
   int rope_fast;        // weights packed for the lean pd = 128 epilogue (TcGemmParams::rope_perm16)
   int glu_fast;         // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
+  int out_perm4;        // fp32 + residual result in the 16-byte column order (TcGemmParams::out_perm4)
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
@@ -387,12 +388,102 @@ __device__ __forceinline__ void epilogue_store_fast_impl(const DevParams& p, int
   }
 }
 
+// fp32 result + fp32 residual with 16-byte accesses (TcGemmParams::out_perm4): the producer of the B operand stored its
+// columns so that accumulator column 8 kb + 2 q + e of every 64-column block is output column 16 (kb / 2) + 4 q + 2 (kb % 2) + e.
+// A thread then owns four consecutive floats per 16-column group and a quad 64 contiguous bytes of a row: half the LSU
+// wavefronts of the float2 path for the same bytes (the P.V epilogue is bound by exactly those: +37 MB of 4-byte stores
+// cost it 18 us).  No bias, no bf16 copy, no statistics; per-row 1 / sum scale supported.
+template <bool FULL>
+__device__ __forceinline__ void perm4_load(const float* ra, const float* rb, bool okA, bool okB, float4 (&f)[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[j] = (FULL || okA) ? *reinterpret_cast<const float4*>(ra + j * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+    f[4 + j] = (FULL || okB) ? *reinterpret_cast<const float4*>(rb + j * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void perm4_store(const uint32_t (&r)[32], const float4 (&f)[8], float* oa, float* ob, bool okA, bool okB, float aA,
+                                            float aB) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0 = 2 * j, k1 = 2 * j + 1;
+    float4 vA, vB;
+    vA.x = fmaf(aA, __uint_as_float(r[4 * k0]), f[j].x);
+    vA.y = fmaf(aA, __uint_as_float(r[4 * k0 + 1]), f[j].y);
+    vA.z = fmaf(aA, __uint_as_float(r[4 * k1]), f[j].z);
+    vA.w = fmaf(aA, __uint_as_float(r[4 * k1 + 1]), f[j].w);
+    vB.x = fmaf(aB, __uint_as_float(r[4 * k0 + 2]), f[4 + j].x);
+    vB.y = fmaf(aB, __uint_as_float(r[4 * k0 + 3]), f[4 + j].y);
+    vB.z = fmaf(aB, __uint_as_float(r[4 * k1 + 2]), f[4 + j].z);
+    vB.w = fmaf(aB, __uint_as_float(r[4 * k1 + 3]), f[4 + j].w);
+    if (FULL || okA) *reinterpret_cast<float4*>(oa + j * 16) = vA;
+    if (FULL || okB) *reinterpret_cast<float4*>(ob + j * 16) = vB;
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void epilogue_store_perm4(const DevParams& p, int lane, int half_sel, uint32_t t_row, int row0, int n_blk,
+                                                     long long out_off, long long res_off, long long ls_off, uint64_t* full_bar,
+                                                     uint32_t full_parity) {
+  const int g = lane >> 2, q = lane & 3;
+  const int colt = n_blk * BLOCK_N + half_sel * 128 + q * 4;  // first output column of this thread
+  const int M = p.M;
+  const int r00 = row0 + g;
+  const bool ok00 = FULL || r00 < M, ok01 = FULL || r00 + 8 < M, ok10 = FULL || r00 + 16 < M, ok11 = FULL || r00 + 24 < M;
+  const bool half1 = FULL || row0 + 16 < M;  // warp-uniform
+  float a00 = p.alpha, a01 = p.alpha, a10 = p.alpha, a11 = p.alpha;
+  if (p.row_lsum != nullptr) {
+    const float* lp = p.row_lsum + ls_off + static_cast<long long>(r00) * p.row_lparts;
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+    for (int c = 0; c < p.row_lparts; ++c) {
+      if (ok00) s00 += __ldg(lp + c);
+      if (ok01) s01 += __ldg(lp + 8 * p.row_lparts + c);
+      if (ok10) s10 += __ldg(lp + 16 * p.row_lparts + c);
+      if (ok11) s11 += __ldg(lp + 24 * p.row_lparts + c);
+    }
+    a00 = ok00 ? p.alpha / s00 : 0.f; a01 = ok01 ? p.alpha / s01 : 0.f;
+    a10 = ok10 ? p.alpha / s10 : 0.f; a11 = ok11 ? p.alpha / s11 : 0.f;
+  }
+  const float* rp00 = p.resid + res_off + static_cast<long long>(r00) * p.ldr + colt;
+  const long long r8 = 8 * p.ldr;
+  float* o00 = static_cast<float*>(p.out) + out_off + static_cast<long long>(r00) * p.ldo + colt;
+  const long long o8 = 8 * p.ldo;
+  float4 f0[8], f1[8];
+  perm4_load<FULL>(rp00, rp00 + r8, ok00, ok01, f0);
+  mbar_wait(full_bar, full_parity);
+  tcgen05_fence_after();
+  if (row0 >= M) return;  // warp-uniform
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    uint32_t r[32];
+    tmem_ld_16x64(t_row + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
+    if (half1) perm4_load<FULL>(rp00 + 2 * r8 + cb * 64, rp00 + 3 * r8 + cb * 64, ok10, ok11, f1);
+    tmem_ld_wait();
+    perm4_store<FULL>(r, f0, o00 + cb * 64, o00 + o8 + cb * 64, ok00, ok01, a00, a01);
+    if (half1) tmem_ld_16x64(t_row + (16u << 16) + static_cast<uint32_t>(half_sel * 128 + cb * 64), r);
+    if (cb == 0) perm4_load<FULL>(rp00 + 64, rp00 + r8 + 64, ok00, ok01, f0);
+    if (half1) {
+      tmem_ld_wait();
+      perm4_store<FULL>(r, f1, o00 + 2 * o8 + cb * 64, o00 + 3 * o8 + cb * 64, ok10, ok11, a10, a11);
+    }
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_fast(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0,
                                                     int n_blk, long long out_off, long long res_off, long long bias_off,
                                                     long long ls_off, long long st_off, uint64_t* full_bar, uint32_t full_parity) {
   const int r0 = static_cast<int>(row0);  // rows of one GEMM fit in 31 bits (checked at launch)
   const bool full = r0 + 32 <= p.M && n_blk * BLOCK_N + half_sel * 128 + 128 <= p.N;  // warp-uniform
+  if (EPI == K_STORE_F32_RESID && p.out_perm4) {  // warp-uniform; N % 128 == 0 checked at launch
+    if (n_blk * BLOCK_N + half_sel * 128 >= p.N) {  // this warp's 128 columns lie past the matrix: only the accumulator hand-shake
+      mbar_wait(full_bar, full_parity);
+      tcgen05_fence_after();
+      return;
+    }
+    if (full) epilogue_store_perm4<true>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, ls_off, full_bar, full_parity);
+    else epilogue_store_perm4<false>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, ls_off, full_bar, full_parity);
+    return;
+  }
   if (EPI == K_STORE_F32_RESID && p.stat_out != nullptr) {  // warp-uniform
     if (full)
       epilogue_store_fast_impl<EPI, true, EPI == K_STORE_F32_RESID>(p, lane, half_sel, t_row, r0, n_blk, out_off, res_off, bias_off, ls_off,
@@ -1870,7 +1961,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.resid = q.resid; p.ldr = q.ldr; p.sr_inner = q.sr_inner; p.sr_outer = q.sr_outer; p.resid_row_mod = q.resid_row_mod;
   p.out2 = q.out2; p.ldo2 = q.ldo2;
   p.rope_cos = q.rope_cos; p.rope_sin = q.rope_sin; p.rope_freq = q.rope_freq;
-  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos; p.rope_fast = q.rope_perm16 ? 1 : 0; p.glu_fast = q.glu_perm16 ? 1 : 0;
+  p.rope_half = q.rope_half; p.rope_pd = q.rope_pd; p.seq_T = q.seq_T; p.hidden = q.hidden; p.rope_pos = q.rope_pos; p.rope_fast = q.rope_perm16 ? 1 : 0; p.glu_fast = q.glu_perm16 ? 1 : 0; p.out_perm4 = q.out_perm4 ? 1 : 0;
   p.row_lsum = q.row_lsum; p.row_lparts = q.row_lparts; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
   p.stat_out = q.stat_out; p.stat_parts = q.stat_parts; p.stat_rows_outer = q.stat_rows_outer;
   p.stat_parts_item = static_cast<int>(ceil_div(q.N, 128));
@@ -1890,6 +1981,11 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
   p.stages = pair ? g_stages_pair : g_stages_1cta;
   p.cm = 1; p.cn = 1;
+  if (q.out_perm4)
+    DITTO_REQUIRE(q.epilogue == TC_EPI_STORE && !q.out_bf16 && q.resid != nullptr && q.bias == nullptr && q.out2 == nullptr &&
+                      q.stat_out == nullptr && q.resid_row_mod == 0 && q.N % 128 == 0 && q.ldo % 4 == 0 && q.ldr % 4 == 0 &&
+                      q.so_inner % 4 == 0 && q.so_outer % 4 == 0 && q.sr_inner % 4 == 0 && q.sr_outer % 4 == 0,
+                  DITTO_E_BADARG, "tc_gemm: out_perm4 needs an fp32 result with residual, no bias / copy / statistics, N % 128 == 0");
   if (q.glu_perm16)
     DITTO_REQUIRE(q.epilogue == TC_EPI_GEGLU && q.ln_stat == nullptr && q.N % BLOCK_N == 0 && q.out_bf16 && q.ldo % 8 == 0 && q.bias != nullptr,
                   DITTO_E_BADARG, "tc_gemm: glu_perm16 needs the GEGLU epilogue, no deferred LayerNorm, a bias and N % 256 == 0");

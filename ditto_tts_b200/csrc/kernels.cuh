@@ -86,6 +86,9 @@ struct TcGemmParams {
   bool rope_perm16 = false;
   // TC_EPI_GEGLU: [fc1; gate] rows packed in the store-friendly order of geglu_epilogue_fast (gemm_tc.cu) instead of [a16 | g16]
   bool glu_perm16 = false;
+  // TC_EPI_STORE, fp32 + residual: the B operand's columns are stored so that accumulator column 8 kb + 2 q + e of a 64-column
+  // block is output column 16 (kb / 2) + 4 q + 2 (kb % 2) + e -> 16-byte residual loads / result stores (self-attention P.V)
+  bool out_perm4 = false;
   // optional per-row scale 1 / sum_c row_lsum[row*row_lparts + c] applied to the accumulator (softmax normalisation of an
   // unnormalised P operand, see launch_tc_scores_softmax); batch strides in elements
   const float* row_lsum = nullptr; int row_lparts = 0; int64_t sl_inner = 0, sl_outer = 0;
