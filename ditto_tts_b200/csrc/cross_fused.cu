@@ -9,20 +9,25 @@
 // being re-read by a separate LayerNorm launch.  The kernel is an HBM stream over u (bf16), h (fp32, in place) and u3
 // (bf16): 12 B per element of h -> 221 MB per launch at C2 (24 000 x 768).
 //
-// Per CTA (persistent over 128-row tiles; a tile never crosses an utterance):
+// Per CTA (640 threads, persistent over 128-row tiles; a tile never crosses an utterance):
 //   warp 0   TMA producer of the MMA operands: u tile [128 x H] and K-fold [64 x H] through a 2-stage ring (64-column
-//            k-blocks, 128-B swizzle), then per output chunk the V-fold rows [64 x 128] as an MN-major operand
-//   warp 1   MMA issuer:  scores S[128 x 64] = U Kf^T (tcgen05.mma, fp32 in TMEM, one tile AHEAD of the rest so the
-//            operand loads of tile i+1 overlap the epilogue of tile i);  O chunk c [128 x 128] = P[128 x 64] Vf[64 x 128c..]
-//            into a ring of three 128-column TMEM buffers
-//   warp 3   mover: the residual stream goes global <-> shared memory by TMA only (4 staging buffers of 128 rows x 64
-//            fp32 columns, 3 loads in flight): no LSU wavefronts are spent on HBM traffic -- the first version of this
-//            kernel moved h with 8-byte register accesses (8 wavefronts per warp instruction) and was LSU-bound at 117 us
-//   warps 4-11  softmax on the accumulator fragments (tcgen05.ld.16x256b), probabilities written as the bf16 K-major
-//            A operand into shared memory (128-B swizzle by hand);  pass 0: O + bias + residual in place in the staging
-//            buffer (-> TMA store to h) with running row sums;  row statistics exchanged through shared memory;  pass 1
-//            over the rows just written (TMA re-load, L2 hits): normalise, gamma/beta, bf16 in place (-> TMA store to u3)
-// TMEM: columns [0, 384) O ring, [384, 512) two score buffers.
+//            k-blocks, 128-B swizzle); per output half-chunk one V-fold box [64 k x 64 n] (MN-major operand, ring of 3)
+//   warp 1   MMA issuer:  scores S[128 x 64] = U Kf^T (tcgen05.mma, fp32 in TMEM, two buffers; the NEXT tile's scores are
+//            issued right after the current tile's P.V, so their operand stream overlaps the rest of the epilogue without
+//            sitting in front of the P.V);  O chunk c [128 x 128] = P[128 x 64] Vf[64 x 128c..] as two N = 64 MMAs into a
+//            ring of three 128-column TMEM buffers
+//   warps 2, 3  movers: the residual stream goes global <-> shared memory by TMA only (4 staging buffers of 128 rows x 64
+//            fp32 columns; warp 2 loads as soon as a buffer is free, warp 3 stores and frees): no LSU wavefronts are spent
+//            on HBM traffic -- the first version of this kernel moved h with 8-byte register accesses (8 wavefronts per warp
+//            instruction) and was LSU-bound at 117 us
+//   warps 4-19  (4 per TMEM lane quarter) the first 8: softmax on the accumulator fragments (tcgen05.ld.16x256b), probabilities
+//            written as the bf16 K-major A operand into shared memory (128-B swizzle by hand);  all 16: pass 0, O + bias +
+//            residual in place in the staging buffer (-> TMA store to h) with packed f32x2 running row sums;  row statistics
+//            exchanged through shared memory;  pass 1 over the rows just written (TMA re-load, L2 hits): normalise,
+//            gamma/beta, bf16 in place (-> TMA store to u3)
+// TMEM: columns [0, 384) O ring, [384, 512) two score buffers.  Optional deferred norm2 of the query operand (ln_stat).
+// Measured (profiles/README.md): 63-70 us per launch at C2 against 104 us for the three kernels it replaces; the tile loop is
+// bound by the latency of its 24 staging jobs per tile (96 KiB of loads in flight per SM), not by bytes or instructions.
 #include <algorithm>
 #include <cstdlib>
 
