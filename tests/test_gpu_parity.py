@@ -310,3 +310,25 @@ def test_fused_cross_attention_block(dev, B, T, S):
         assert ("tc_gemm.cross_pv" in prof) == (not fused)
         assert rel(outs[fused], want) <= BAR["bf16"]
     assert rel(outs[True], outs[False]) <= 6e-3     # same operands, different rounding points of P / LN statistics
+
+
+@pytest.mark.parametrize("env", [{"DITTO_XF_ROWS": "88"}, {"DITTO_DEFER_LN2": "1"}, {"DITTO_ROPE_GENERIC": "1", "DITTO_GLU_GENERIC": "1"},
+                                 {"DITTO_NO_PV_PERM4": "1"}], ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
+def test_kernel_variants_behind_switches(dev, env):
+    """Every developer switch of DESIGN.md section 9 selects a different kernel / weight packing for the same arithmetic: each
+    must stay within the bf16 bar of the oracle and within rounding of the default build (C2 width, ragged T, S = 40)."""
+    cfg = O.OracleConfig(768, 2, 1, 256, 768, 50)
+    sd = O.make_state_dict(cfg, 41)
+    x, text, _ = O.make_inputs(2, 300, 40, cfg, 42)
+    t = torch.tensor([49, 0])
+    want = O.ditto_forward(sd, cfg, x, text, t)
+    base = build_model(cfg, sd, "bf16", dev)(x.to(dev), text.to(dev), t.to(dev))
+    os.environ.update(env)
+    try:
+        got = build_model(cfg, sd, "bf16", dev)(x.to(dev), text.to(dev), t.to(dev))
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    assert rel(got, want) <= BAR["bf16"]
+    assert rel(base, want) <= BAR["bf16"]
+    assert rel(got, base) <= 8e-3

@@ -81,3 +81,23 @@ def test_variant_ragged_batch(dev, setup):
     for i in range(3):
         want = O.sample_latents_variant(sd, cfg, texts[i][None], xs[i][None], zs[i][:, None], 5.0, method="ddim", num_steps=6)
         assert O.rel_l2(got[i].cpu()[None], want) <= 1e-4
+
+
+def test_update_table_argument_checks(dev, setup):
+    """ditto_engine_load_update_table: wrong shape is refused on the host; the C entry point reports bad sizes / a missing
+    schedule through its status code (no exception crosses the ABI)."""
+    import ctypes as C
+    from ditto_tts_b200 import _lib
+    cfg, sd, *_ = setup
+    m = model(cfg, sd, "fp32", dev)
+    with pytest.raises(D.DittoError):
+        m.load_update_table(torch.zeros(cfg.diffusion_steps - 1, 3))
+    lib = _lib.load()
+    tab = torch.zeros(cfg.diffusion_steps, 3, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    eng = m.engine()
+    assert lib.ditto_engine_load_update_table(eng, None, cfg.diffusion_steps, st) == -1          # DITTO_E_BADARG
+    assert lib.ditto_engine_load_update_table(eng, C.c_void_p(tab.data_ptr()), 3, st) == -1
+    assert b"steps" in lib.ditto_last_error()
+    m2 = model(cfg, sd, "fp32", dev)                                                             # no schedule loaded yet
+    assert lib.ditto_engine_load_update_table(m2.engine(), C.c_void_p(tab.data_ptr()), cfg.diffusion_steps, st) == -4  # DITTO_E_STATE
