@@ -90,6 +90,8 @@ struct XfDev {
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * XF_EPI_WARPS) : "memory"); }
+// the four warps that share a TMEM lane quarter (= the same 32 tile rows): named barriers 2..5
+__device__ __forceinline__ void quarter_bar_sync(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory"); }
 __device__ __forceinline__ void xf_regs_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XF_REGS_CTRL)); }
 __device__ __forceinline__ void xf_regs_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(XF_REGS_EPI)); }
 __device__ __forceinline__ void tmem_ld_16x16(uint32_t taddr, uint32_t (&r)[8]) {  // 16 lanes x 16 fp32 columns, fragment layout
@@ -436,6 +438,9 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 4; ++j) sm2[j] = sq2[j] = make_float2(0.f, 0.f);
       uint32_t ob = 0;
+      float2 b2N[2];
+#pragma unroll
+      for (int kbl = 0; kbl < 2; ++kbl) b2N[kbl] = __ldg(reinterpret_cast<const float2*>(p.out_bias + sub * 16 + q2 + kbl * 8));
 #pragma unroll 1
       for (int hc = 0; hc < p.num_hc; ++hc, ++job) {
         const uint32_t b = job % XF_NB;
@@ -443,7 +448,11 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         const int col0 = hc * XF_HC + sub * 16 + q2;
         float2 b2[2];
 #pragma unroll
-        for (int kbl = 0; kbl < 2; ++kbl) b2[kbl] = __ldg(reinterpret_cast<const float2*>(p.out_bias + col0 + kbl * 8));
+        for (int kbl = 0; kbl < 2; ++kbl) b2[kbl] = b2N[kbl];
+        if (hc + 1 < p.num_hc) {
+#pragma unroll
+          for (int kbl = 0; kbl < 2; ++kbl) b2N[kbl] = __ldg(reinterpret_cast<const float2*>(p.out_bias + col0 + XF_HC + kbl * 8));
+        }
         if ((hc & 1) == 0) {
           ob = oc % XF_O_BUFS;
           mbar_wait(&o_full[ob], (oc / XF_O_BUFS) & 1u);
@@ -511,6 +520,12 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
       }
       // ---------------- pass 1: LayerNorm of the updated rows -> bf16, written over the staging buffer ----------------
       // bf16 box in shared memory: row r at r * 128 B (64 columns), 16-B chunk j (8 columns) at position j ^ (r & 7)
+      float2 gmN[2], btN[2];
+#pragma unroll
+      for (int kbl = 0; kbl < 2; ++kbl) {
+        gmN[kbl] = __ldg(reinterpret_cast<const float2*>(p.gamma + sub * 16 + q2 + kbl * 8));
+        btN[kbl] = __ldg(reinterpret_cast<const float2*>(p.beta + sub * 16 + q2 + kbl * 8));
+      }
 #pragma unroll 1
       for (int hc = 0; hc < p.num_hc; ++hc, ++job) {
         const uint32_t b = job % XF_NB;
@@ -519,9 +534,13 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         const int col0 = hc * XF_HC + sub * 16 + q2;
         float2 gm[2], bt[2];
 #pragma unroll
-        for (int kbl = 0; kbl < 2; ++kbl) {
-          gm[kbl] = __ldg(reinterpret_cast<const float2*>(p.gamma + col0 + kbl * 8));
-          bt[kbl] = __ldg(reinterpret_cast<const float2*>(p.beta + col0 + kbl * 8));
+        for (int kbl = 0; kbl < 2; ++kbl) { gm[kbl] = gmN[kbl]; bt[kbl] = btN[kbl]; }
+        if (hc + 1 < p.num_hc) {  // gamma / beta of the next half-chunk: their L2 latency (the L1 is almost all shared memory) hides behind this job
+#pragma unroll
+          for (int kbl = 0; kbl < 2; ++kbl) {
+            gmN[kbl] = __ldg(reinterpret_cast<const float2*>(p.gamma + col0 + XF_HC + kbl * 8));
+            btN[kbl] = __ldg(reinterpret_cast<const float2*>(p.beta + col0 + XF_HC + kbl * 8));
+          }
         }
         mbar_wait(&hin_full[b], (job / XF_NB) & 1u);
         float2 v[2][4];
@@ -535,7 +554,9 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
             v[hh][2 * kbl + 1] = *reinterpret_cast<const float2*>(slab + rB * 128 + ((j ^ (rB & 7)) << 4));
           }
         }
-        epi_bar_sync();  // every warp has its fp32 values in registers: the buffer may be overwritten with the bf16 result
+        // the bf16 result of rows r overwrites bytes of the fp32 slab-0 data of the SAME rows only, which the four warps of this
+        // lane quarter read: once those have their values in registers the buffer may be overwritten
+        quarter_bar_sync(quarter);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int rA = lrow0 + hh * 16 + g, rB = rA + 8;
