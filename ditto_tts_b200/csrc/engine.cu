@@ -37,7 +37,7 @@ ProfAcc g_prof_acc[PC_COUNT];
 const char* kProfNames[PC_COUNT] = {"tc_gemm.proj_in", "tc_gemm.qkv_rope", "tc_gemm.self_scores", "tc_gemm.self_pv", "tc_gemm.cross_q",
                                     "tc_gemm.cross_scores", "tc_gemm.cross_pv", "tc_gemm.cross_out", "tc_gemm.glu", "tc_gemm.fc2",
                                     "tc_gemm.proj_out", "tc_gemm.text_kv", "tc_gemm.other", "sgemm_f32", "layernorm", "adaln_ln",
-                                    "rope", "softmax", "cfg_ddpm_update", "elementwise", "tc_gemm.cross_fused_ln"};
+                                    "rope", "softmax", "cfg_ddpm_update", "elementwise", "tc_gemm.cross_fused_ln", "tc_gemm.flash_attn"};
 }  // namespace
 ProfScope::ProfScope(int cls, cudaStream_t stream, double flops, double bytes) : st(stream) {
   if (!g_prof_enabled) return;
@@ -87,6 +87,7 @@ struct ditto_engine {
   bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   bool pv_perm4 = false;    // v columns stored in the order the float4 P.V epilogue wants (TcGemmParams::out_perm4)
   bool qkv_perm16 = false;  // QKV weight rows also permuted inside 64-row blocks for the lean RoPE epilogue (TcGemmParams::rope_perm16)
+  bool flash_attn = true;   // head_dim 64: self-attention without materialised scores (flash_attn.cu); DITTO_NO_FLASH=1 disables
   bool defer_ln2 = false;   // norm2 only: row statistics from the self-attention P.V epilogue, LayerNorm folded into cross_fused's scores
   bool fused_cross = true;  // folded cross-attention + residual + norm3 in one kernel (cross_fused.cu); DITTO_NO_FUSED_CROSS=1 disables
   bool fused_attn = false;  // scores + softmax fused (cluster kernel); falls back per call when a row needs > 16 tiles
@@ -316,6 +317,16 @@ static int attention_bf16(ditto_engine* e, const Workspace& w, const bf16* q, in
                           int Tk, float alpha, void* out, bool out_bf16, int64_t ldo, int64_t o_seq_stride, const float* resid,
                           cudaStream_t st, bool cross, bf16* out2 = nullptr, float2* stat_out = nullptr) {
   const int d = e->d, heads = e->heads;
+  if (e->flash_attn && !cross && !out_bf16 && resid != nullptr && out2 == nullptr && stat_out == nullptr && flash_attn_supported(d, Tq, Tk)) {
+    FlashAttnParams f;
+    f.Q.ptr = q; f.Q.rows = Tq; f.Q.cols = d; f.Q.ld = ldq; f.Q.s_inner = d; f.Q.s_outer = q_seq_stride;
+    f.Km.ptr = k; f.Km.rows = Tk; f.Km.cols = d; f.Km.ld = ldk; f.Km.s_inner = d; f.Km.s_outer = k_seq_stride;
+    f.V.ptr = v; f.V.rows = Tk; f.V.cols = d; f.V.ld = ldv; f.V.s_inner = d; f.V.s_outer = v_seq_stride;
+    f.n_seq = n; f.heads = heads; f.d = d; f.Tq = Tq; f.Tk = Tk; f.alpha = alpha;
+    f.out = static_cast<float*>(out); f.resid = resid; f.ldo = ldo; f.o_seq = o_seq_stride; f.ldr = ldo; f.r_seq = o_seq_stride;
+    f.tag = PC_FLASH_ATTN;
+    return launch_flash_attn(f, st);
+  }
   const int64_t ldp = round_up(Tk, 8);
   const int csize = e->fused_attn ? tc_scores_softmax_csize(Tk) : 0;
   if (csize > 0) {
@@ -757,6 +768,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     if (const char* ed = getenv("DITTO_NO_DEFER_LN")) if (ed[0] == '1') e->defer_ln = false;
     if (const char* ef = getenv("DITTO_NO_FUSED_ATTN")) if (ef[0] == '1') e->fused_attn = false;
     e->fused_cross = e->fused_attn;
+    e->flash_attn = e->fused_attn;
+    if (const char* ef = getenv("DITTO_NO_FLASH")) if (ef[0] == '1') e->flash_attn = false;
     if (const char* ef = getenv("DITTO_NO_FUSED_CROSS")) if (ef[0] == '1') e->fused_cross = false;
     {
       const char* e2 = getenv("DITTO_DEFER_LN2");

@@ -146,6 +146,18 @@ struct CrossFusedParams {
 bool cross_fused_supported(int64_t T, int64_t S, int H, int heads);
 int launch_cross_fused(const CrossFusedParams& p, cudaStream_t st);
 
+// ---- flash_attn.cu: self-attention for head_dim 64 without materialised scores (two passes over the keys) ---------------
+struct FlashAttnParams {
+  TcOperand Q, Km, V;                          // [Tq, d], [Tk, d], [Tk, d] per (head, utterance): s_inner = head stride, s_outer = utterance stride
+  int64_t n_seq = 0; int heads = 0, d = 0, Tq = 0, Tk = 0;
+  float alpha = 1.f;
+  float* out = nullptr; const float* resid = nullptr;   // fp32 [n_seq, Tq, ld]; head h = columns [d h, d h + d); may alias
+  int64_t ldo = 0, o_seq = 0, ldr = 0, r_seq = 0;
+  int tag = PC_TC_OTHER;
+};
+bool flash_attn_supported(int d, int Tq, int Tk);
+int launch_flash_attn(const FlashAttnParams& p, cudaStream_t st);
+
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 // 4-D bf16 tensor map (cols, rows, inner batch, outer batch) with a (box_cols, box_rows, 1, 1) box, 128-B swizzle, zero OOB fill
 int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows);

@@ -332,3 +332,30 @@ def test_kernel_variants_behind_switches(dev, env):
     assert rel(got, want) <= BAR["bf16"]
     assert rel(base, want) <= BAR["bf16"]
     assert rel(got, base) <= 8e-3
+
+
+@pytest.mark.parametrize("B,T,S,hidden,heads", [(2, 750, 20, 256, 4), (3, 130, 7, 128, 2), (1, 1, 3, 64, 1), (2, 257, 9, 768, 12),
+                                                (1, 128, 5, 192, 3)])
+def test_flash_attention_d64(dev, B, T, S, hidden, heads):
+    """flash_attn.cu (head_dim 64: two-pass attention, scores and probabilities never in HBM) against the oracle and
+    against the GEMM formulation (DITTO_NO_FLASH=1): multi-head models, ragged T, partial key tiles."""
+    cfg = O.OracleConfig(hidden, 2, heads, 64, hidden, 20)
+    sd = O.make_state_dict(cfg, 51)
+    x, text, _ = O.make_inputs(B, T, S, cfg, 52)
+    t = (torch.arange(B) * 5 + 1) % 20
+    want = O.ditto_forward(sd, cfg, x, text, t)
+    outs = {}
+    for flash in (True, False):
+        os.environ["DITTO_NO_FLASH"] = "0" if flash else "1"
+        try:
+            m = build_model(cfg, sd, "bf16", dev)
+            _lib.profile_start()
+            outs[flash] = m(x.to(dev), text.to(dev), t.to(dev))
+            prof = _lib.profile_stop()
+        finally:
+            os.environ.pop("DITTO_NO_FLASH", None)
+        assert ("tc_gemm.flash_attn" in prof) == flash, sorted(prof)
+        assert ("tc_gemm.self_pv" in prof) == (not flash)
+        assert bool(torch.isfinite(outs[flash]).all())
+        assert rel(outs[flash], want) <= BAR["bf16"]
+    assert rel(outs[True], outs[False]) <= 8e-3
