@@ -22,7 +22,9 @@
 // Measured at C2 with the constructor-default model (L = 12, h = 12): 176 us per layer against 381 us for scores+softmax and
 // P.V of the GEMM formulation.  Tried, no gain: 16 softmax warps (196 us), all key tiles of a head resident in shared memory
 // and shared by two query tiles (175 us) -- the kernel is paced by the softmax warps (MUFU ex2 at 16 / clk / SM is ~45 % of
-// their time), not by operand traffic or warp count.
+// their time), not by operand traffic or warp count.  ncu: XU pipe 90 % busy (ex2 + the bf16 packs), FMA 10 %; moving half of
+// the exponentials to a degree-3 polynomial on the FMA pipe (FA4-style) made it slower (201 us): with two softmax warps per
+// scheduler the 9 extra dependent instructions per element cost more issue latency than the MUFU slots they free.
 #include <algorithm>
 
 #include "common.cuh"
