@@ -783,7 +783,7 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
       const char* eg = getenv("DITTO_ROPE_GENERIC");
       const char* egl = getenv("DITTO_GLU_GENERIC");
       e->glu_perm16 = !e->defer_ln && e->H % 32 == 0 && !(egl && egl[0] == '1');
-      e->qkv_perm16 = e->fused_rope && e->rope_pd == 128 && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 &&
+      e->qkv_perm16 = e->fused_rope && (e->rope_pd == 128 || e->rope_pd == 32) && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 &&
                       !(eg && eg[0] == '1');
       const char* ep = getenv("DITTO_NO_PV_PERM4");
       e->pv_perm4 = e->qkv_perm16 && !e->pv_transpose && !e->defer_ln2 && e->d % 128 == 0 && !(ep && ep[0] == '1');
@@ -939,6 +939,8 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
         const int blk = r / 64, c = r % 64;
         const int kb = c / 8, q = (c % 8) / 2, ee = c % 2;
         int l = q * 16 + kb * 2 + ee;   // storage position (inside the block) the lean QKV epilogue writes this accumulator to
+        // pair distance 32 (q and k thirds): 8-column blocks kb < 4 are x1 elements q * 8 + kb * 2 + e, kb >= 4 their partners
+        if (e->rope_pd == 32 && r < 2 * H) l = (kb < 4 ? 0 : 32) + q * 8 + (kb & 3) * 2 + ee;
         // v third with the float4 P.V epilogue: storage position l must hold logical column 16 (K / 2) + 4 Q + 2 (K % 2) + E,
         // where K, Q, E are the fragment coordinates of P.V accumulator column l
         if (e->pv_perm4 && r >= 2 * H) {

@@ -697,6 +697,114 @@ __device__ __forceinline__ void geglu_epilogue_fast(const DevParams& p, int lane
   }
 }
 
+// The same for pair distance 32 (head_dim 64 and other d / 2 = 32 (2k + 1)): a 64-column block holds 32 x1 columns (8-column
+// blocks kb 0..3) and their 32 partners (kb 4..7).  Store-friendly order inside the block: accumulator column 8 kb + 2 q + e is
+// x1 element q * 8 + kb * 2 + e (kb < 4) resp. its partner (kb >= 4), so a thread's 8 x1' and 8 x2' outputs of a row are two
+// 16-byte stores; v blocks use the q * 16 + kb * 2 + e order of the pd = 128 path.
+template <bool FULL>
+__device__ __forceinline__ void rope_epilogue_fast32(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
+                                                     long long out_off, const float* bias, uint64_t* full_bar, uint32_t full_parity) {
+  const int g = lane >> 2, q = lane & 3, q2 = q * 2;
+  float fpos[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long rr = row0 + g + 8 * i;
+    fpos[i] = p.rope_pos != nullptr ? static_cast<float>((FULL || rr < p.M) ? __ldg(p.rope_pos + rr) : 0)
+                                    : static_cast<float>(static_cast<unsigned>(rr) % static_cast<unsigned>(p.seq_T));
+  }
+  bool waited = false;
+#pragma unroll 1
+  for (int u = 0; u < 2; ++u) {
+    const int b1 = half_sel * 128 + u * 64;            // tile column of this 64-column block
+    const int pc1 = n_blk * BLOCK_N + b1;              // permuted GEMM column
+    const bool is_v = pc1 >= 2 * p.hidden;             // warp-uniform
+    int jbase = 0, dbase = pc1;
+    if (!is_v) {
+      const int region = pc1 / p.hidden;
+      const int lp = pc1 - region * p.hidden;
+      const int grp = lp >> 6;                         // groups of 2 * 32 permuted columns
+      const int e0 = grp * 32;
+      const int head = e0 / p.rope_half;
+      jbase = e0 - head * p.rope_half;
+      dbase = region * p.hidden + head * 2 * p.rope_half + jbase;
+    }
+    float2 fr[4], bx[8];
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) bx[kb] = __ldg(reinterpret_cast<const float2*>(bias + pc1 + q2 + kb * 8));
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+      fr[kb] = is_v ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(p.rope_freq + jbase + q * 8 + kb * 2));
+    if (!waited) {
+      mbar_wait(full_bar, full_parity);
+      tcgen05_fence_after();
+      waited = true;
+    }
+    if (!FULL && row0 >= p.M) continue;                // warp-uniform
+    bf16* o1 = static_cast<bf16*>(p.out) + out_off + (row0 + g) * p.ldo + dbase;
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      if (!FULL && row0 + hh * 16 >= p.M) break;       // warp-uniform
+      uint32_t r[32];
+      tmem_ld_16x64(t_row + (static_cast<uint32_t>(hh * 16) << 16) + b1, r);
+      bf16* oA = o1 + static_cast<long long>(hh * 16) * p.ldo;
+      bf16* oB = oA + 8 * p.ldo;
+      const bool okA = FULL || row0 + hh * 16 + g < p.M, okB = FULL || row0 + hh * 16 + g + 8 < p.M;
+      tmem_ld_wait();
+      if (is_v) {
+        uint32_t wA[8], wB[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const float2 a = __fadd2_rn(make_float2(__uint_as_float(r[4 * kb]), __uint_as_float(r[4 * kb + 1])), bx[kb]);
+          const float2 c = __fadd2_rn(make_float2(__uint_as_float(r[4 * kb + 2]), __uint_as_float(r[4 * kb + 3])), bx[kb]);
+          wA[kb] = pack_bf16x2(a.x, a.y);
+          wB[kb] = pack_bf16x2(c.x, c.y);
+        }
+        if (okA) {
+          reinterpret_cast<uint4*>(oA + q * 16)[0] = make_uint4(wA[0], wA[1], wA[2], wA[3]);
+          reinterpret_cast<uint4*>(oA + q * 16)[1] = make_uint4(wA[4], wA[5], wA[6], wA[7]);
+        }
+        if (okB) {
+          reinterpret_cast<uint4*>(oB + q * 16)[0] = make_uint4(wB[0], wB[1], wB[2], wB[3]);
+          reinterpret_cast<uint4*>(oB + q * 16)[1] = make_uint4(wB[4], wB[5], wB[6], wB[7]);
+        }
+        continue;
+      }
+      const float2 pA = make_float2(fpos[2 * hh], fpos[2 * hh]), pB = make_float2(fpos[2 * hh + 1], fpos[2 * hh + 1]);
+      uint32_t w1A[4], w2A[4], w1B[4], w2B[4];
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        float2 sA, cA, sB, cB;
+        sincos_reduced2(__fmul2_rn(pA, fr[kb]), sA, cA);
+        sincos_reduced2(__fmul2_rn(pB, fr[kb]), sB, cB);
+        const int k2 = kb + 4;
+        const float2 x1A = __fadd2_rn(make_float2(__uint_as_float(r[4 * kb]), __uint_as_float(r[4 * kb + 1])), bx[kb]);
+        const float2 x1B = __fadd2_rn(make_float2(__uint_as_float(r[4 * kb + 2]), __uint_as_float(r[4 * kb + 3])), bx[kb]);
+        const float2 x2A = __fadd2_rn(make_float2(__uint_as_float(r[4 * k2]), __uint_as_float(r[4 * k2 + 1])), bx[k2]);
+        const float2 x2B = __fadd2_rn(make_float2(__uint_as_float(r[4 * k2 + 2]), __uint_as_float(r[4 * k2 + 3])), bx[k2]);
+        const float2 nA = make_float2(-sA.x, -sA.y), nB = make_float2(-sB.x, -sB.y);
+        const float2 y1A = __ffma2_rn(x2A, nA, __fmul2_rn(x1A, cA)), y2A = __ffma2_rn(x1A, sA, __fmul2_rn(x2A, cA));
+        const float2 y1B = __ffma2_rn(x2B, nB, __fmul2_rn(x1B, cB)), y2B = __ffma2_rn(x1B, sB, __fmul2_rn(x2B, cB));
+        w1A[kb] = pack_bf16x2(y1A.x, y1A.y);
+        w2A[kb] = pack_bf16x2(y2A.x, y2A.y);
+        w1B[kb] = pack_bf16x2(y1B.x, y1B.y);
+        w2B[kb] = pack_bf16x2(y2B.x, y2B.y);
+      }
+      if (okA) {
+        *reinterpret_cast<uint4*>(oA + q * 8) = make_uint4(w1A[0], w1A[1], w1A[2], w1A[3]);
+        *reinterpret_cast<uint4*>(oA + p.rope_half + q * 8) = make_uint4(w2A[0], w2A[1], w2A[2], w2A[3]);
+      }
+      if (okB) {
+        *reinterpret_cast<uint4*>(oB + q * 8) = make_uint4(w1B[0], w1B[1], w1B[2], w1B[3]);
+        *reinterpret_cast<uint4*>(oB + p.rope_half + q * 8) = make_uint4(w2B[0], w2B[1], w2B[2], w2B[3]);
+      }
+    }
+  }
+  if (!waited) {
+    mbar_wait(full_bar, full_parity);
+    tcgen05_fence_after();
+  }
+}
+
 // One accumulator tile: this warp's 32 rows (two 16-lane halves) x its 128 of the 256 tile columns.  Waits for the
 // accumulator itself (after the first residual block has been requested).
 template <int EPI>
@@ -811,8 +919,14 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, int lane, int 
     }
   } else {  // K_QKV_ROPE
     if (p.rope_fast) {  // weights packed in the store-friendly column order: every tile takes the lean epilogue
-      if (row0 + 32 <= p.M) rope_epilogue_fast128<true>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
-      else rope_epilogue_fast128<false>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      const bool full = row0 + 32 <= p.M;
+      if (p.rope_pd == 128) {
+        if (full) rope_epilogue_fast128<true>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+        else rope_epilogue_fast128<false>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      } else {
+        if (full) rope_epilogue_fast32<true>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+        else rope_epilogue_fast32<false>(p, lane, half_sel, t_row, row0, n_blk, out_off, bias, full_bar, full_parity);
+      }
       return;
     }
     // units of (x1 block, partner block PD columns further); PD = 32: both inside one 64-column load.  Everything that
@@ -1990,7 +2104,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
     DITTO_REQUIRE(q.epilogue == TC_EPI_GEGLU && q.ln_stat == nullptr && q.N % BLOCK_N == 0 && q.out_bf16 && q.ldo % 8 == 0 && q.bias != nullptr,
                   DITTO_E_BADARG, "tc_gemm: glu_perm16 needs the GEGLU epilogue, no deferred LayerNorm, a bias and N % 256 == 0");
   if (q.rope_perm16)
-    DITTO_REQUIRE(q.epilogue == TC_EPI_QKV_ROPE && q.rope_pd == 128 && q.rope_freq != nullptr && q.ln_stat == nullptr &&
+    DITTO_REQUIRE(q.epilogue == TC_EPI_QKV_ROPE && (q.rope_pd == 128 || q.rope_pd == 32) && q.rope_freq != nullptr && q.ln_stat == nullptr &&
                       q.N % BLOCK_N == 0 && q.hidden % BLOCK_N == 0 && q.out_bf16 && q.ldo % 8 == 0,
                   DITTO_E_BADARG, "tc_gemm: rope_perm16 needs pd = 128, on-the-fly frequencies, no deferred LayerNorm, N and hidden % 256 == 0");
   // kernel variant: the lean compile-time epilogues cover the hot cases, anything else takes the generic one
