@@ -783,8 +783,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
       const char* eg = getenv("DITTO_ROPE_GENERIC");
       const char* egl = getenv("DITTO_GLU_GENERIC");
       e->glu_perm16 = !e->defer_ln && e->H % 32 == 0 && !(egl && egl[0] == '1');
-      const char* e32 = getenv("DITTO_ROPE_FAST32");   // pair distance 32: opt-in until its GPU parity run is on record
-      const bool pd_ok = e->rope_pd == 128 || (e->rope_pd == 32 && e32 && e32[0] == '1');
+      const char* e32 = getenv("DITTO_ROPE_FAST32");   // =0: pair distance 32 (head_dim 64) through the generic epilogue
+      const bool pd_ok = e->rope_pd == 128 || (e->rope_pd == 32 && !(e32 && e32[0] == '0'));
       e->qkv_perm16 = e->fused_rope && pd_ok && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 &&
                       !(eg && eg[0] == '1');
       const char* ep = getenv("DITTO_NO_PV_PERM4");
