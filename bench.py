@@ -25,6 +25,7 @@ Parity bars (tests/, BASELINE.json): rel-L2 <= 2e-2 (bf16 path) and <= 1e-4 (fp3
 from __future__ import annotations
 
 import argparse
+import atexit
 import json
 import os
 import statistics
@@ -57,39 +58,50 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started well before the timed region (nvidia-smi needs up
+    to a second to come up on an 8-GPU box, the timed region of 50 steps lasts ~150 ms); summary() keeps the samples whose
+    arrival time falls inside the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            atexit.register(self.stop)   # never leave the sampler behind, whatever path the bench exits through
         except OSError:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
-        if self.proc is not None:
+    def stop(self):
+        if self.proc is not None and self.proc.poll() is None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0, t1):
+        """Samples that arrived in [t0, t1 + one period]; when the region was shorter than the sampling period, the sample
+        nearest to it (taken under the same load: warm-up steps precede and the eager profile follows the timed region)."""
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.06]
+        window = "timed region"
+        if not inside and self.rows:
+            mid = 0.5 * (t0 + t1)
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - mid))[1]]
+            window = "nearest sample to the timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -100,7 +112,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # =====================================================================================================
@@ -191,6 +204,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     B, T, S, K, W = args.batch, FRAMES_10S, TEXT_LEN, args.steps, args.warmup
+    clocks = ClockSampler(local).start()
     torch.manual_seed(0)  # random-init weights of the named architecture (default torch initialisers)
     model = D.DiTTO(hidden_dim=HIDDEN, num_layers=LAYERS, num_heads=HEADS, time_dim=TIME_DIM, text_dim=HIDDEN,
                     diffusion_steps=K, precision=args.precision).to(dev)
@@ -214,12 +228,13 @@ def run_ours(args):
     graph.reset(x0, K - 1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        e0.record()
-        for i in range(K):
-            graph.replay()
-        e1.record()
-        barrier()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        graph.replay()
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     launches = graph.launches_per_step * K      # kernels of libditto_b200 inside the K replayed graphs
     xa = graph.x
@@ -256,6 +271,7 @@ def run_ours(args):
     for i in range(prof_steps):
         one_step(i)
     prof = _lib.profile_stop()
+    clocks.stop()
 
     times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,7 +333,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": (text_host.numel() + x_host.numel()) * 4 / K,
                     "d2h_bytes_per_step": out_host.numel() * 4 / K, "ms_total": ms_e2e,
                     "api": "DiTTOSampler.sample_latents(text_emb, x_init) from pinned host tensors, final latents to host"},
-            "gpu_launches": int(launches), "launches_per_step": int(graph.launches_per_step), "stepping": "cuda-graph replay per step", "clocks": clocks.summary(), "outputs_finite": finite,
+            "gpu_launches": int(launches), "launches_per_step": int(graph.launches_per_step), "stepping": "cuda-graph replay per step", "clocks": clocks.summary(t_wall0, t_wall1), "outputs_finite": finite,
             "output_gather_ms": gather_ms,
         }
         print(json.dumps(line), flush=True)
