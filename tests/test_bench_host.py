@@ -1,0 +1,38 @@
+"""Host-side pieces of bench.py that run without a GPU: the work model and the clock-sample window."""
+import importlib.util
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
+
+
+def test_flop_model_matches_survey_numbers():
+    """86.35 GFLOP per sequence per forward at T = 750, S = 64 (repo-default model)."""
+    assert abs(bench.forward_flops(750, 64) / 1e9 - 86.35) < 0.01
+    assert abs(bench.forward_flops(2250, 192) / 1e9 - 315.3) < 0.1
+
+
+def test_clock_sampler_keeps_samples_of_the_timed_region():
+    s = bench.ClockSampler(0)
+    row = lambda mhz, cap: [str(mhz), "1965", "700.0", "Not Active", "Not Active", "Not Active", "Active" if cap else "Not Active"]
+    s.rows = [(9.90, row(1965, False)), (10.02, row(1850, True)), (10.07, row(1800, True)), (10.12, row(1840, False)),
+              (10.40, row(1965, False))]
+    out = s.summary(10.0, 10.15)
+    assert out["samples"] == 3 and out["sm_mhz"] == 1840.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    # a region shorter than the sampling period falls back to the nearest sample and says so
+    out = s.summary(10.20, 10.22)
+    assert out["samples"] == 1 and out["window"].startswith("nearest")
+    s.rows = []
+    assert s.summary(0.0, 1.0)["samples"] == 0
+
+
+def test_traffic_file_names_known_profile_classes():
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        t = json.load(f)
+    keys = [k for k in t if not k.startswith("_")]
+    assert "tc_gemm.glu" in keys                       # the dominant kernel of the bench line
+    assert all(isinstance(t[k], float) and t[k] > 0 for k in keys)
