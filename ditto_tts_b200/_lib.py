@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libditto_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
-F_FUSED_ROPE, F_FOLD_CROSS, F_FUSED_ATTN, F_DEFER_LN = 1, 2, 4, 8
+F_FUSED_ROPE, F_FOLD_CROSS, F_FUSED_ATTN, F_DEFER_LN, F_BLOCKS_ONLY = 1, 2, 4, 8, 16
 
 
 class DittoError(RuntimeError):
@@ -42,6 +42,7 @@ SIGNATURES = {
     "ditto_profile_get": (_I32, [_I32, C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double)]),
     "ditto_debug_set_counters": (_I32, [_P]),
+    "ditto_debug_option": (_I32, [C.c_char_p, _I32]),
     "ditto_engine_create": (_I32, [C.POINTER(Config), C.POINTER(_P)]),
     "ditto_engine_destroy": (_I32, [_P]),
     "ditto_engine_load_weight": (_I32, [_P, C.c_char_p, _P, _I64, _P]),
@@ -54,10 +55,18 @@ SIGNATURES = {
     "ditto_forward": (_I32, [_P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
     "ditto_cfg_ddpm_update": (_I32, [_P, _P, _P, _P, _P, _P, _F, _P, _I64, _I64, _P]),
     "ditto_p_sample": (_I32, [_P, _P, _P, _P, _P, _I32, _F, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
+    "ditto_p_sample_rng": (_I32, [_P, _P, _P, _P, _P, _I32, _F, _I64, _I64, _I64, _P, _P, _P, _I64, _I32, _P]),
+    "ditto_cfg_ddpm_update_rng": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _F, _P, _I64, _I64, _I32, _P]),
+    "ditto_randn": (_I32, [_P, _I64, _P, _I64, _P]),
     "ditto_q_sample": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _P]),
     "ditto_workspace_bytes_ragged": (_I64, [_P, C.POINTER(SeqGroup), _I64]),
     "ditto_forward_ragged": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _P, _I64, _P]),
     "ditto_p_sample_ragged": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _I32, _F, _P, _P, _P, _I64, _P]),
+    "ditto_p_sample_ragged_rng": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _I32, _F, _P, _P, _P, _I64, _I32, _P]),
+    "ditto_dit_block": (_I32, [_P, _I32, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "ditto_adaln_workspace_bytes": (_I64, [_I64, _I64, _I64, _I64]),
+    "ditto_adaln": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
+    "ditto_rope": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "ditto_layernorm": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _P]),
     "ditto_gemm_f32": (_I32, [_P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64, _I64, _P, _P, _F, _I64, _I64, _I64,
                               _I64, _P]),
@@ -96,6 +105,12 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().ditto_last_error().decode("utf-8", "replace")
         raise DittoError(f"{what or 'libditto_b200'} failed (code {rc}): {msg}")
+
+
+def debug_option(name: str, value: int):
+    """Developer A/B switch of the kernels; ``debug_option("reset", 0)`` restores the product path.
+    Engine-level options are sampled when an engine is created."""
+    check(load().ditto_debug_option(name.encode(), int(value)), f"ditto_debug_option({name})")
 
 
 def launch_count() -> int:

@@ -617,8 +617,6 @@ int make_map_h(CUtensorMap* m, float* h, int64_t n_seq, int64_t T, int H, int bo
   return 0;
 }
 
-bool g_xf_attr_done = false;
-
 }  // namespace
 
 bool cross_fused_supported(int64_t T, int64_t S, int H, int heads) {
@@ -632,9 +630,11 @@ int launch_cross_fused(const CrossFusedParams& q, cudaStream_t st) {
   DITTO_REQUIRE(q.u && q.kfold && q.vfold && q.sbias && q.out_bias && q.h && q.gamma && q.beta && q.u_out, DITTO_E_BADARG,
                 "cross_fused: null argument");
   DITTO_REQUIRE(q.n_seq >= 1 && q.Sp >= q.S && q.Sp % 8 == 0, DITTO_E_BADARG, "cross_fused: bad sizes");
-  if (!g_xf_attr_done) {
+  DeviceState* ds = device_state();
+  if (ds == nullptr) return DITTO_E_CUDA;
+  if (!ds->xf_attr) {  // per device
     DITTO_CUDA(cudaFuncSetAttribute(cross_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XF_SMEM_BYTES));
-    g_xf_attr_done = true;
+    ds->xf_attr = true;
   }
   TcOperand U, Kf, Vf, Uo;
   U.ptr = q.u; U.rows = q.T; U.cols = q.H; U.ld = q.H; U.s_outer = q.T * q.H;
@@ -643,10 +643,10 @@ int launch_cross_fused(const CrossFusedParams& q, cudaStream_t st) {
   Uo.ptr = q.u_out; Uo.rows = q.T; Uo.cols = q.H; Uo.ld = q.H; Uo.s_outer = q.T * q.H;
   // Rows per tile: the MMAs always compute 128 rows, the TMA boxes (and so the HBM traffic) carry `rt` of them.  Measured at
   // C2 (profiles/README.md): 128 / 96 / 88 rows all take ~70 us and 64 rows 90 us -- the tile loop is bound by the latency of
-  // its 24 staging jobs per tile, not by their bytes, so fewer, larger tiles win; DITTO_XF_ROWS overrides for experiments.
+  // its 24 staging jobs per tile, not by their bytes, so fewer, larger tiles win; the xf_rows debug option overrides for experiments.
   const int sms = tc_num_sms();
   int rt = XF_BM;
-  if (const char* er = getenv("DITTO_XF_ROWS")) { const int v = atoi(er); if (v >= 8 && v <= XF_BM && v % 8 == 0) rt = v; }
+  if (g_opt.xf_rows >= 8 && g_opt.xf_rows <= XF_BM && g_opt.xf_rows % 8 == 0) rt = g_opt.xf_rows;
   CUtensorMap mu, mk, mv, mh, mo;
   DITTO_TRY(tc_make_map(&mu, U, 1, q.n_seq, XF_BK, rt));
   DITTO_TRY(tc_make_map(&mk, Kf, 1, q.n_seq, XF_BK, XF_NS));

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256)
   const int64_t seq = row / T;
   const int64_t pos = row - seq * T;
   const int64_t xrow = (seq % n_x) * T + pos;
-  int64_t tt = t[seq];
+  int64_t tt = t != nullptr ? t[seq] : seq;   // t == nullptr: the table already holds one row per sequence (ditto_adaln)
   tt = tt < 0 ? 0 : (tt >= steps ? steps - 1 : tt);
   const float* tm = time_table + tt * 2 * H;
   const float* xm = text_mod + seq * 2 * H;
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(256)
       v[i].w = (v[i].w - mean) * rstd * ((1.f + ts.w) + xs.w) + (tb.w + xb.w);
       *reinterpret_cast<float4*>(h + row * H + c) = v[i];
     }
+  if (u == nullptr) return;  // GlobalAdaLN alone (ditto_adaln)
   if (stat != nullptr) {
     // deferred LayerNorm: u = bf16(h) and the row's (sum, sum of squares); the consuming GEMM epilogue normalises
     float sm = 0.f, sq = 0.f;
@@ -523,6 +524,13 @@ int launch_transpose_v(const bf16* v, int64_t ld, bf16* vt, int64_t n_seq, int T
 //   coef[t] = { 1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-acp_t), [t>0]*sqrt(beta_t) }
 // 20 B/element with guidance + noise (4 reads, 1 write), 128-bit accesses, grid = multiple of 148.
 // =====================================================================================================
+// one element: eps = eps_u + w (eps_c - eps_u);  x_out = c1 (x - c2 eps) + c3 z   -- explicit roundings so that the variant
+// with caller-supplied noise and the one that draws it in the kernel agree bit for bit
+__device__ __forceinline__ float cfg_combine(float ec, float eu, float w) { return __fmaf_rn(w, __fsub_rn(ec, eu), eu); }
+__device__ __forceinline__ float ddpm_update(float x, float e, float z, float c1, float c2, float c3) {
+  return __fmaf_rn(c3, z, __fmul_rn(c1, __fmaf_rn(-c2, e, x)));
+}
+
 __global__ void __launch_bounds__(256)
     cfg_ddpm_update_kernel(const float4* __restrict__ eps_c, const float4* __restrict__ eps_u, const float4* __restrict__ x,
                            const float4* __restrict__ z, const int64_t* __restrict__ t, const float* __restrict__ coef,
@@ -536,25 +544,12 @@ __global__ void __launch_bounds__(256)
     float4 e = eps_c[i];
     if (eps_u != nullptr) {
       const float4 u = eps_u[i];
-      e.x = u.x + w * (e.x - u.x);
-      e.y = u.y + w * (e.y - u.y);
-      e.z = u.z + w * (e.z - u.z);
-      e.w = u.w + w * (e.w - u.w);
+      e = make_float4(cfg_combine(e.x, u.x, w), cfg_combine(e.y, u.y, w), cfg_combine(e.z, u.z, w), cfg_combine(e.w, u.w, w));
     }
     const float4 xv = x[i];
-    float4 o;
-    o.x = c1 * (xv.x - c2 * e.x);
-    o.y = c1 * (xv.y - c2 * e.y);
-    o.z = c1 * (xv.z - c2 * e.z);
-    o.w = c1 * (xv.w - c2 * e.w);
-    if (z != nullptr) {
-      const float4 zv = z[i];
-      o.x += c3 * zv.x;
-      o.y += c3 * zv.y;
-      o.z += c3 * zv.z;
-      o.w += c3 * zv.w;
-    }
-    out[i] = o;
+    const float4 zv = z != nullptr ? z[i] : make_float4(0.f, 0.f, 0.f, 0.f);   // + c3 * 0 == the reference's masked noise term
+    out[i] = make_float4(ddpm_update(xv.x, e.x, zv.x, c1, c2, c3), ddpm_update(xv.y, e.y, zv.y, c1, c2, c3),
+                         ddpm_update(xv.z, e.z, zv.z, c1, c2, c3), ddpm_update(xv.w, e.w, zv.w, c1, c2, c3));
   }
 }
 
@@ -570,6 +565,159 @@ int launch_cfg_ddpm_update(const float* eps_c, const float* eps_u, const float* 
   cfg_ddpm_update_kernel<<<blocks, 256, 0, st>>>(
       reinterpret_cast<const float4*>(eps_c), reinterpret_cast<const float4*>(eps_u), reinterpret_cast<const float4*>(x),
       reinterpret_cast<const float4*>(z), t, coef, steps, w, reinterpret_cast<float4*>(out), elems_per_seq / 4, total_vec);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// The same with the step's noise drawn in the kernel: z = randn_like(x) of SpeechGenerator.py:145 without the separate
+// generator launch and its 8 B / element of HBM round trip.  Philox4x32-10 (Salmon et al., SC'11: the counter-based generator
+// behind curand and torch's CUDA randn) keyed by the 64-bit seed, counter = (vector index, draw counter); four uniforms ->
+// two Box-Muller pairs -> the four normals of one float4.  The draw counter lives in device memory so that a captured CUDA
+// graph draws fresh noise on every replay; with `advance` the LAST block to finish (ticket counter) adds 1 to it and
+// subtracts 1 from every t[i] -- the bookkeeping of `for t_val in reversed(range(steps))` (SpeechGenerator.py:161-162).
+// rng: device uint64[4] = {seed, draw counter, ticket (kept 0 between launches), reserved}.
+// =====================================================================================================
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// four N(0, 1) samples for vector index v of draw `draw`
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long draw, unsigned long long v) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(v), static_cast<uint32_t>(v >> 32), static_cast<uint32_t>(draw),
+                                           static_cast<uint32_t>(draw >> 32)),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  // u in (0, 1): 24 random bits + half an ulp, so that log(u) is finite and cos / sin see [0, 2 pi)
+  const float u0 = fmaf(static_cast<float>(r.x >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+  const float u1 = fmaf(static_cast<float>(r.z >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+  const float a0 = static_cast<float>(r.y >> 8) * (6.283185307179586f * 5.9604644775390625e-08f);
+  const float a1 = static_cast<float>(r.w >> 8) * (6.283185307179586f * 5.9604644775390625e-08f);
+  const float m0 = sqrtf(-1.3862943611198906f * __log2f(u0)), m1 = sqrtf(-1.3862943611198906f * __log2f(u1));  // sqrt(-2 ln u)
+  float s0, c0, s1, c1;
+  __sincosf(a0, &s0, &c0);
+  __sincosf(a1, &s1, &c1);
+  return make_float4(m0 * c0, m0 * s0, m1 * c1, m1 * s1);
+}
+
+__global__ void __launch_bounds__(256)
+    cfg_ddpm_update_rng_kernel(const float4* __restrict__ eps_c, const float4* __restrict__ eps_u, const float4* __restrict__ x,
+                               unsigned long long* rng, int64_t* t, int64_t n_t, const float* __restrict__ coef, int steps, float w,
+                               float4* __restrict__ out, int64_t vec_per_seq, int64_t total_vec, int64_t vec_offset, int advance) {
+  const unsigned long long seed = rng[0], draw = rng[1];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t seq = i / vec_per_seq;
+    int64_t tt = t[seq];
+    tt = tt < 0 ? 0 : (tt >= steps ? steps - 1 : tt);
+    const float c1 = coef[tt * 3 + 0], c2 = coef[tt * 3 + 1], c3 = coef[tt * 3 + 2];
+    float4 e = eps_c[i];
+    if (eps_u != nullptr) {
+      const float4 u = eps_u[i];
+      e = make_float4(cfg_combine(e.x, u.x, w), cfg_combine(e.y, u.y, w), cfg_combine(e.z, u.z, w), cfg_combine(e.w, u.w, w));
+    }
+    const float4 xv = x[i];
+    const float4 zv = philox_normal4(seed, draw, static_cast<unsigned long long>(vec_offset + i));
+    out[i] = make_float4(ddpm_update(xv.x, e.x, zv.x, c1, c2, c3), ddpm_update(xv.y, e.y, zv.y, c1, c2, c3),
+                         ddpm_update(xv.z, e.z, zv.z, c1, c2, c3), ddpm_update(xv.w, e.w, zv.w, c1, c2, c3));
+  }
+  if (!advance) return;
+  // every thread of every block has read rng / t before its block takes a ticket; the block holding the last ticket owns them
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long tk = atomicAdd(rng + 2, 1ull);
+    s_last = tk == static_cast<unsigned long long>(gridDim.x) - 1ull;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int64_t i = threadIdx.x; i < n_t; i += blockDim.x) t[i] -= 1;
+  if (threadIdx.x == 0) {
+    rng[1] = draw + 1ull;
+    rng[2] = 0ull;
+  }
+}
+
+int launch_cfg_ddpm_update_rng(const float* eps_c, const float* eps_u, const float* x, unsigned long long* rng, int64_t* t, int64_t n_t,
+                               const float* coef, int steps, float w, float* out, int64_t B, int64_t elems_per_seq,
+                               int64_t elem_offset, bool advance, cudaStream_t st) {
+  DITTO_REQUIRE(elems_per_seq % 4 == 0 && elem_offset % 4 == 0, DITTO_E_UNSUPPORTED, "cfg_ddpm_update_rng: elems_per_seq % 4");
+  const int64_t total_vec = B * elems_per_seq / 4;
+  if (total_vec == 0) return advance ? launch_step_advance(rng, t, n_t, st) : 0;
+  const int64_t want = ceil_div(total_vec, 256 * 4);
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(round_up(want, 148), 148 * 32));
+  ProfScope prof(PC_CFG_UPDATE, st, 0.0, static_cast<double>(total_vec) * 16 * (3 + (eps_u ? 1 : 0)));
+  cfg_ddpm_update_rng_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(eps_c), reinterpret_cast<const float4*>(eps_u),
+                                                     reinterpret_cast<const float4*>(x), rng, t, n_t, coef, steps, w,
+                                                     reinterpret_cast<float4*>(out), elems_per_seq / 4, total_vec, elem_offset / 4,
+                                                     advance ? 1 : 0);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// the bookkeeping alone (ragged batches: their per-group update kernels run concurrently, so none of them can own it)
+__global__ void step_advance_kernel(unsigned long long* rng, int64_t* t, int64_t n_t) {
+  for (int64_t i = threadIdx.x; i < n_t; i += blockDim.x) t[i] -= 1;
+  if (threadIdx.x == 0 && rng != nullptr) rng[1] += 1ull;
+}
+int launch_step_advance(unsigned long long* rng, int64_t* t, int64_t n_t, cudaStream_t st) {
+  step_advance_kernel<<<1, 256, 0, st>>>(rng, t, n_t);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[i] = the normal the update kernel draws for element elem_offset + i at the current draw counter (tests, and a
+// stand-alone randn for callers that want the library's stream)
+__global__ void randn_kernel(const unsigned long long* __restrict__ rng, int64_t vec_offset, float* __restrict__ out, int64_t n) {
+  const unsigned long long seed = rng[0], draw = rng[1];
+  const int64_t nv = (n + 3) / 4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 z = philox_normal4(seed, draw, static_cast<unsigned long long>(vec_offset + i));
+    if (4 * i + 3 < n) {
+      *reinterpret_cast<float4*>(out + 4 * i) = z;
+    } else {
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+      for (int j = 0; 4 * i + j < n; ++j) out[4 * i + j] = zz[j];
+    }
+  }
+}
+int launch_randn(const unsigned long long* rng, int64_t elem_offset, float* out, int64_t n, cudaStream_t st) {
+  DITTO_REQUIRE(elem_offset % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, DITTO_E_BADARG, "randn: offset % 4 and 16-B aligned output");
+  if (n <= 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(round_up(ceil_div(n, 1024), 148), 148 * 32));
+  randn_kernel<<<blocks, 256, 0, st>>>(rng, elem_offset / 4, out, n);
+  DITTO_LAUNCH_CHECK();
+  return 0;
+}
+
+// RotaryEmbedding.apply_rope (DiT.py:61-72) on its own: out = t cos(pos) + rotate_half(t) sin(pos); t [batch, T, heads, d],
+// pos [T, d] fp32 ANGLES (what RotaryEmbedding.forward returns; both halves are read, as the reference does)
+__global__ void rope_angles_kernel(const float* __restrict__ t, const float* __restrict__ pos, float* __restrict__ out, int64_t total,
+                                   int T, int heads, int d) {
+  const int half = d >> 1;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % d);
+    const int64_t r = i / d;                               // (batch, T, head)
+    const int p = static_cast<int>((r / heads) % T);
+    const float a = pos[static_cast<int64_t>(p) * d + j];
+    const float rot = j < half ? -t[i + half] : t[i - half];  // cat(-x2, x1)
+    out[i] = t[i] * cosf(a) + rot * sinf(a);
+  }
+}
+int launch_rope_angles(const float* t, const float* pos, float* out, int64_t batch, int T, int heads, int d, cudaStream_t st) {
+  const int64_t total = batch * T * heads * d;
+  if (total <= 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(total, 256), 148 * 32));
+  ProfScope prof(PC_ROPE, st, 0.0, static_cast<double>(total) * 12);
+  rope_angles_kernel<<<blocks, 256, 0, st>>>(t, pos, out, total, T, heads, d);
   DITTO_LAUNCH_CHECK();
   return 0;
 }

@@ -18,6 +18,7 @@ namespace ditto {
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string t_last_error;
 std::atomic<long long> g_launches{0};
+DebugOptions g_opt;
 void set_error(const std::string& msg) { t_last_error = msg; }
 int cuda_fail(cudaError_t err, const char* what, const char* file, int line) {
   t_last_error = std::string("CUDA error ") + std::to_string(static_cast<int>(err)) + " (" + cudaGetErrorString(err) + ") at " +
@@ -83,6 +84,8 @@ struct ditto_engine {
   ditto_config_t cfg;
   int H = 0, L = 0, heads = 0, d = 0, half = 0, Td = 0, Xd = 0, steps = 0, maxT = 0;
   bool bf16_mode = false, fused_rope = false, finalized = false, have_schedule = false;
+  bool blocks_only = false;  // DITTO_F_BLOCKS_ONLY: a stack of DiT blocks without the DiTTO wrapper (stand-alone DiT modules)
+  int device = -1;           // CUDA device the engine was created on (kernel attributes / SM count are per device)
   int rope_pd = 0;
   bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   bool pv_perm4 = false;    // v columns stored in the order the float4 P.V epilogue wants (TcGemmParams::out_perm4)
@@ -128,11 +131,15 @@ static int dev_alloc(ditto_engine* e, void** p, size_t bytes) {
 static void build_expected(ditto_engine* e) {
   const int64_t H = e->H, Td = e->Td, Xd = e->Xd, St = e->steps;
   auto& m = e->expected;
-  m["t_embedding.weight"] = St * Td;
-  m["time_embed.0.weight"] = Td * Td; m["time_embed.0.bias"] = Td;
-  m["time_embed.2.weight"] = Td * Td; m["time_embed.2.bias"] = Td;
-  m["ada_ln.time_mlp.1.weight"] = 2 * H * Td; m["ada_ln.time_mlp.1.bias"] = 2 * H;
-  m["ada_ln.text_mlp.1.weight"] = 2 * H * Xd; m["ada_ln.text_mlp.1.bias"] = 2 * H;
+  if (!e->blocks_only) {
+    m["t_embedding.weight"] = St * Td;
+    m["time_embed.0.weight"] = Td * Td; m["time_embed.0.bias"] = Td;
+    m["time_embed.2.weight"] = Td * Td; m["time_embed.2.bias"] = Td;
+    m["ada_ln.time_mlp.1.weight"] = 2 * H * Td; m["ada_ln.time_mlp.1.bias"] = 2 * H;
+    m["ada_ln.text_mlp.1.weight"] = 2 * H * Xd; m["ada_ln.text_mlp.1.bias"] = 2 * H;
+    m["proj_in.weight"] = H * H; m["proj_in.bias"] = H;
+    m["proj_out.weight"] = H * H; m["proj_out.bias"] = H;
+  }
   for (int i = 0; i < e->L; ++i) {
     const std::string p = "blocks." + std::to_string(i) + ".";
     for (const char* n : {"norm1", "norm2", "norm3"}) { m[p + n + ".weight"] = H; m[p + n + ".bias"] = H; }
@@ -143,8 +150,6 @@ static void build_expected(ditto_engine* e) {
     m[p + "gate.weight"] = 4 * H * H; m[p + "gate.bias"] = 4 * H;
     m[p + "mlp_fc2.weight"] = 4 * H * H; m[p + "mlp_fc2.bias"] = H;
   }
-  m["proj_in.weight"] = H * H; m["proj_in.bias"] = H;
-  m["proj_out.weight"] = H * H; m["proj_out.bias"] = H;
   m["rotary.inv_freq"] = e->half;  // optional
 }
 
@@ -437,9 +442,13 @@ struct Fork {
 // contiguous).  Everything that works on single rows (LayerNorm, the QKV / GLU / fc2 / projection GEMMs) runs ONCE over
 // all packed rows; only what depends on sequence boundaries (AdaLN modulation, attention, RoPE positions) runs per group.
 // ng == 1 is the uniform batch of ditto_forward (x shared between CFG branches through n_x).
+// block_layer >= 0: ONE DiT block on its own (DiT.forward, DiT.py:100-157 -> ditto_dit_block): x [n, T, H] is the block's input
+// residual stream, out its output; no AdaLN / proj_in / proj_out, t unused.
 static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGroup* gs, int ng, float* out, void* workspace,
-                        int64_t workspace_bytes, cudaStream_t st) {
+                        int64_t workspace_bytes, cudaStream_t st, int block_layer = -1) {
   const int H = e->H, d = e->d;
+  const bool block_only = block_layer >= 0;
+  const int l_begin = block_only ? block_layer : 0, l_end = block_only ? block_layer + 1 : e->L;
   Workspace w = ws_layout(e, workspace, gs, ng);
   const int64_t M = w.M;
   DITTO_REQUIRE(M < (1ll << 31) / 8, DITTO_E_UNSUPPORTED, "forward: batch too large for one call (split it)");
@@ -458,9 +467,14 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
   const bool dln = e->defer_ln;
   const bool dln2_all = dln && fold_ln_active(e, g0.S);  // LN2 feeds the folded scores kernel; the unfolded q projection needs a real LN
   int ln1_parts = 1;
+  if (block_only) {
+    DITTO_REQUIRE(!ragged && !dln, DITTO_E_UNSUPPORTED, "dit_block: uniform batches without DITTO_F_DEFER_LN only");
+    DITTO_CUDA(cudaMemcpyAsync(w.h, x, static_cast<size_t>(M) * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DITTO_TRY(launch_layernorm(w.h, e->LW(l_begin, "norm1.weight"), e->LW(l_begin, "norm1.bias"), w.u, b16, M, H, st));  // DiT.py:105
+  }
   // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
-  DITTO_TRY(fork.begin(ng));
-  for (int gi = 0; gi < ng; ++gi) {
+  DITTO_TRY(fork.begin(block_only ? 0 : ng));
+  for (int gi = 0; gi < ng && !block_only; ++gi) {
     const SeqGroup& g = gs[gi];
     CtxLayout c = ctx_layout(e, const_cast<void*>(g.ctx), g.n, g.S);
     const int es = b16 ? 2 : 4;
@@ -473,7 +487,8 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
   }
   DITTO_TRY(fork.end());
   // x_skip = proj_in(x): once per distinct x (uniform batch) / per packed row (ragged)      DiTTO.py:83
-  if (b16) {
+  if (block_only) {
+  } else if (b16) {
     const int Mp = static_cast<int>(ragged ? M : g0.n_x * g0.T);
     DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_in16, H, w.xskip, false, H, e->W("proj_in.bias"), nullptr, 0, 0, nullptr, 0, Mp, H,
                     H, st, PC_TC_PROJ_IN));
@@ -487,9 +502,9 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
   bool fuse_cross = b16 && e->fused_cross && !dln;
   for (int gi = 0; gi < ng && fuse_cross; ++gi)
     fuse_cross = fold_active(e, gs[gi].S) && cross_fused_supported(gs[gi].T, gs[gi].S, H, e->heads);
-  for (int i = 0; i < e->L; ++i) {
+  for (int i = l_begin; i < l_end; ++i) {
     const LayerPack& lp = e->layers[i];
-    const bool last = (i == e->L - 1);
+    const bool last = (i == l_end - 1);
     if (b16) {
       bf16* u = static_cast<bf16*>(w.u);
       bf16* qkv = static_cast<bf16*>(w.qkv);
@@ -657,6 +672,10 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         DITTO_TRY(launch_layernorm(w.h, e->LW(i + 1, "norm1.weight"), e->LW(i + 1, "norm1.bias"), u, false, M, H, st));
     }
   }
+  if (block_only) {
+    DITTO_CUDA(cudaMemcpyAsync(out, w.h, static_cast<size_t>(M) * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   // eps = x_skip + proj_out(h)                                              DiTTO.py:93-94
   if (b16) {
     DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_out16, H, out, false, H, e->W("proj_out.bias"), w.xskip, H,
@@ -750,6 +769,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
   e->Td = cfg->time_dim; e->Xd = cfg->text_dim; e->steps = cfg->diffusion_steps;
   e->maxT = cfg->max_seq_len > 0 ? cfg->max_seq_len : 4096;
   e->bf16_mode = cfg->precision == DITTO_PREC_BF16;
+  e->blocks_only = (cfg->flags & DITTO_F_BLOCKS_ONLY) != 0;
+  if (cudaGetDevice(&e->device) != cudaSuccess) e->device = -1;
   if (e->bf16_mode) {
     if (e->bf16_mode && e->d % 8 != 0) {
       delete e;
@@ -765,36 +786,25 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     e->fold_cross = (cfg->flags & DITTO_F_FOLD_CROSS) != 0;
     e->fused_attn = (cfg->flags & DITTO_F_FUSED_ATTN) != 0;
     e->defer_ln = (cfg->flags & DITTO_F_DEFER_LN) != 0 && e->fused_rope && e->fused_attn;
-    if (const char* ed = getenv("DITTO_NO_DEFER_LN")) if (ed[0] == '1') e->defer_ln = false;
-    if (const char* ef = getenv("DITTO_NO_FUSED_ATTN")) if (ef[0] == '1') e->fused_attn = false;
+    if (g_opt.no_defer_ln) e->defer_ln = false;
+    if (g_opt.no_fused_attn) e->fused_attn = false;
     e->fused_cross = e->fused_attn;
     e->flash_attn = e->fused_attn;
-    if (const char* ef = getenv("DITTO_NO_FLASH")) if (ef[0] == '1') e->flash_attn = false;
-    if (const char* ef = getenv("DITTO_NO_FUSED_CROSS")) if (ef[0] == '1') e->fused_cross = false;
-    {
-      const char* e2 = getenv("DITTO_DEFER_LN2");
-      e->defer_ln2 = !e->defer_ln && e->fused_cross && e->bf16_mode && e->heads == 1 && e2 && e2[0] == '1';
-    }
-    const char* env = getenv("DITTO_PV_TRANSPOSE");
-    e->pv_transpose = env && env[0] == '1';
-    const char* env2 = getenv("DITTO_ROPE_TABLE");
-    e->rope_table_in_epilogue = env2 && env2[0] == '1';
-    {
-      const char* eg = getenv("DITTO_ROPE_GENERIC");
-      const char* egl = getenv("DITTO_GLU_GENERIC");
-      e->glu_perm16 = !e->defer_ln && e->H % 32 == 0 && !(egl && egl[0] == '1');
-      const char* e32 = getenv("DITTO_ROPE_FAST32");   // =0: pair distance 32 (head_dim 64) through the generic epilogue
-      const bool pd_ok = e->rope_pd == 128 || (e->rope_pd == 32 && !(e32 && e32[0] == '0'));
-      e->qkv_perm16 = e->fused_rope && pd_ok && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 &&
-                      !(eg && eg[0] == '1');
-      const char* ep = getenv("DITTO_NO_PV_PERM4");
-      e->pv_perm4 = e->qkv_perm16 && !e->pv_transpose && !e->defer_ln2 && e->d % 128 == 0 && !(ep && ep[0] == '1');
-    }
+    if (g_opt.no_flash) e->flash_attn = false;
+    if (g_opt.no_fused_cross) e->fused_cross = false;
+    e->defer_ln2 = !e->defer_ln && e->fused_cross && e->bf16_mode && e->heads == 1 && g_opt.defer_ln2 != 0;
+    e->pv_transpose = g_opt.pv_transpose != 0;
+    e->rope_table_in_epilogue = g_opt.rope_table != 0;
+    e->glu_perm16 = !e->defer_ln && e->H % 32 == 0 && !g_opt.glu_generic;
+    // no_rope_fast32: pair distance 32 (head_dim 64) through the generic epilogue
+    const bool pd_ok = e->rope_pd == 128 || (e->rope_pd == 32 && !g_opt.no_rope_fast32);
+    e->qkv_perm16 = e->fused_rope && pd_ok && !e->defer_ln && !e->rope_table_in_epilogue && e->H % 256 == 0 && !g_opt.rope_generic;
+    e->pv_perm4 = e->qkv_perm16 && !e->pv_transpose && !e->defer_ln2 && e->d % 128 == 0 && !g_opt.no_pv_perm4;
   }
   build_expected(e);
   e->layers.resize(e->L);
   int want_side = ditto_engine::kSide;
-  if (const char* es = getenv("DITTO_SIDE_STREAMS")) want_side = std::max(0, std::min(ditto_engine::kSide, atoi(es)));
+  if (g_opt.side_streams >= 0) want_side = std::min(ditto_engine::kSide, g_opt.side_streams);
   if (want_side > 0 && cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess) {
     for (int k = 0; k < want_side; ++k) {
       if (cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking) != cudaSuccess ||
@@ -876,23 +886,27 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
     }
   }
   const int H = e->H, Td = e->Td, St = e->steps;
+  int rc = 0;
+  cudaError_t se = cudaSuccess;
+  if (!e->blocks_only) {
   // ---- per-step modulation table: time_mlp(SiLU(time_embed(t_embedding[t])))  (DiTTO.py:75-76, DiT.py:30)
   if (!e->time_table) DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->time_table), sizeof(float) * St * 2 * H));
   float *t1 = nullptr, *t2 = nullptr;
   DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t1), sizeof(float) * St * Td));
   DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&t2), sizeof(float) * St * Td));
-  int rc = sgemm_nt(e->W("t_embedding.weight"), Td, e->W("time_embed.0.weight"), Td, t1, Td, e->W("time_embed.0.bias"), nullptr, 0,
-                    1.f, St, Td, Td, st);
+  rc = sgemm_nt(e->W("t_embedding.weight"), Td, e->W("time_embed.0.weight"), Td, t1, Td, e->W("time_embed.0.bias"), nullptr, 0,
+                1.f, St, Td, Td, st);
   if (!rc) rc = launch_silu(t1, static_cast<int64_t>(St) * Td, st);
   if (!rc) rc = sgemm_nt(t1, Td, e->W("time_embed.2.weight"), Td, t2, Td, e->W("time_embed.2.bias"), nullptr, 0, 1.f, St, Td, Td, st);
   if (!rc) rc = launch_silu(t2, static_cast<int64_t>(St) * Td, st);
   if (!rc) rc = sgemm_nt(t2, Td, e->W("ada_ln.time_mlp.1.weight"), Td, e->time_table, 2 * H, e->W("ada_ln.time_mlp.1.bias"), nullptr,
                          0, 1.f, St, 2 * H, Td, st);
-  cudaError_t se = cudaStreamSynchronize(st);
+  se = cudaStreamSynchronize(st);
   cudaFree(t1);
   cudaFree(t2);
   if (rc) return rc;
   DITTO_CUDA(se);
+  }
   // ---- RoPE tables (DiT.py:46-59)
   if (!e->rope_cos) {
     DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(&e->rope_cos), sizeof(float) * e->maxT * e->half));
@@ -907,8 +921,10 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
       if (!*dst) DITTO_TRY(dev_alloc(e, reinterpret_cast<void**>(dst), sizeof(bf16) * n));
       return launch_cast_bf16(src, *dst, n, st);
     };
-    DITTO_TRY(cast_new(e->W("proj_in.weight"), static_cast<int64_t>(H) * H, &e->w_in16));
-    DITTO_TRY(cast_new(e->W("proj_out.weight"), static_cast<int64_t>(H) * H, &e->w_out16));
+    if (!e->blocks_only) {
+      DITTO_TRY(cast_new(e->W("proj_in.weight"), static_cast<int64_t>(H) * H, &e->w_in16));
+      DITTO_TRY(cast_new(e->W("proj_out.weight"), static_cast<int64_t>(H) * H, &e->w_out16));
+    }
     // row permutations (host-built, tiny)
     std::vector<int> glu_perm(8 * H), qkv_perm(3 * H);
     for (int r = 0; r < 8 * H; ++r) {
@@ -1024,9 +1040,11 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
   DITTO_REQUIRE(static_cast<int64_t>(w.total) <= workspace_bytes, DITTO_E_WORKSPACE, "text_context: workspace too small");
   CtxLayout c = ctx_layout(e, ctx, n, S);
   // text modulation: text_mlp(SiLU(mean_S(text)))  (DiT.py:27,31)
-  DITTO_TRY(launch_mean_silu(text_emb, w.tmp_small, n, static_cast<int>(S), Xd, st));
-  DITTO_TRY(sgemm_nt(w.tmp_small, Xd, e->W("ada_ln.text_mlp.1.weight"), Xd, c.text_mod, 2 * H, e->W("ada_ln.text_mlp.1.bias"), nullptr,
-                     0, 1.f, static_cast<int>(n), 2 * H, Xd, st));
+  if (!e->blocks_only) {
+    DITTO_TRY(launch_mean_silu(text_emb, w.tmp_small, n, static_cast<int>(S), Xd, st));
+    DITTO_TRY(sgemm_nt(w.tmp_small, Xd, e->W("ada_ln.text_mlp.1.weight"), Xd, c.text_mod, 2 * H, e->W("ada_ln.text_mlp.1.bias"), nullptr,
+                       0, 1.f, static_cast<int>(n), 2 * H, Xd, st));
+  }
   // per-layer K|V = text @ in_proj[H:3H]^T + b  (torch MHA packed in_proj, rows H..3H)
   if (e->bf16_mode) DITTO_TRY(launch_cast_bf16(text_emb, w.text16, n * S * Xd, st));
   for (int i = 0; i < e->L; ++i) {
@@ -1079,7 +1097,7 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
 int32_t ditto_forward(ditto_engine_t* e, const float* x, int64_t n_x, const void* ctx, const int64_t* t, int64_t n_seq, int64_t T,
                       int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   DITTO_REQUIRE(e && x && ctx && t && out && workspace, DITTO_E_BADARG, "forward: null argument");
-  DITTO_REQUIRE(e->finalized, DITTO_E_STATE, "forward: engine not finalized");
+  DITTO_REQUIRE(e->finalized && !e->blocks_only, DITTO_E_STATE, "forward: engine not finalized (or a blocks-only engine)");
   DITTO_REQUIRE(n_seq > 0 && T > 0 && S > 0 && n_x > 0 && n_seq % n_x == 0, DITTO_E_BADARG, "forward: bad batch sizes");
   DITTO_REQUIRE(T <= e->maxT, DITTO_E_UNSUPPORTED, "forward: T exceeds max_seq_len of the engine");
   return forward_impl(e, x, n_x, ctx, t, n_seq, T, S, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
@@ -1098,7 +1116,7 @@ int32_t ditto_p_sample(ditto_engine_t* e, const float* x, const void* ctx, const
                        float guidance_scale, int64_t B, int64_t T, int64_t S, float* eps_scratch, float* x_out, void* workspace,
                        int64_t workspace_bytes, void* stream) {
   DITTO_REQUIRE(e && x && ctx && t && eps_scratch && x_out && workspace, DITTO_E_BADARG, "p_sample: null argument");
-  DITTO_REQUIRE(e->finalized && e->have_schedule, DITTO_E_STATE, "p_sample: engine not finalized / schedule not loaded");
+  DITTO_REQUIRE(e->finalized && e->have_schedule && !e->blocks_only, DITTO_E_STATE, "p_sample: engine not finalized / schedule not loaded");
   DITTO_REQUIRE(B > 0 && T > 0 && S > 0 && T <= e->maxT, DITTO_E_BADARG, "p_sample: bad sizes");
   const int64_t n = guided ? 2 * B : B;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1106,6 +1124,35 @@ int32_t ditto_p_sample(ditto_engine_t* e, const float* x, const void* ctx, const
   const int64_t per = T * e->H;
   return launch_cfg_ddpm_update(eps_scratch, guided ? eps_scratch + B * per : nullptr, x, z, t, e->coef, e->steps, guidance_scale, x_out,
                                 B, per, st);
+}
+
+int32_t ditto_p_sample_rng(ditto_engine_t* e, const float* x, const void* ctx, int64_t* t, uint64_t* rng, int32_t guided,
+                           float guidance_scale, int64_t B, int64_t T, int64_t S, float* eps_scratch, float* x_out, void* workspace,
+                           int64_t workspace_bytes, int32_t advance, void* stream) {
+  DITTO_REQUIRE(e && x && ctx && t && rng && eps_scratch && x_out && workspace, DITTO_E_BADARG, "p_sample_rng: null argument");
+  DITTO_REQUIRE(e->finalized && e->have_schedule && !e->blocks_only, DITTO_E_STATE, "p_sample_rng: engine not finalized / schedule not loaded");
+  DITTO_REQUIRE(B > 0 && T > 0 && S > 0 && T <= e->maxT, DITTO_E_BADARG, "p_sample_rng: bad sizes");
+  const int64_t n = guided ? 2 * B : B;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DITTO_TRY(forward_impl(e, x, B, ctx, t, n, T, S, eps_scratch, workspace, workspace_bytes, st));
+  const int64_t per = T * e->H;
+  return launch_cfg_ddpm_update_rng(eps_scratch, guided ? eps_scratch + B * per : nullptr, x, reinterpret_cast<unsigned long long*>(rng), t, n,
+                                    e->coef, e->steps, guidance_scale, x_out, B, per, 0, advance != 0, st);
+}
+
+int32_t ditto_cfg_ddpm_update_rng(ditto_engine_t* e, const float* eps_c, const float* eps_u, const float* x, uint64_t* rng, int64_t* t,
+                                  int64_t n_t, float guidance_scale, float* x_out, int64_t B, int64_t elems_per_seq, int32_t advance,
+                                  void* stream) {
+  DITTO_REQUIRE(e && eps_c && x && t && rng && x_out, DITTO_E_BADARG, "cfg_ddpm_update_rng: null argument");
+  DITTO_REQUIRE(e->have_schedule, DITTO_E_STATE, "cfg_ddpm_update_rng: schedule not loaded");
+  DITTO_REQUIRE(B >= 0 && elems_per_seq >= 0 && n_t >= B, DITTO_E_BADARG, "cfg_ddpm_update_rng: bad sizes");
+  return launch_cfg_ddpm_update_rng(eps_c, eps_u, x, reinterpret_cast<unsigned long long*>(rng), t, n_t, e->coef, e->steps, guidance_scale,
+                                    x_out, B, elems_per_seq, 0, advance != 0, static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_randn(const uint64_t* rng, int64_t elem_offset, float* out, int64_t n, void* stream) {
+  DITTO_REQUIRE(rng && out && n >= 0 && elem_offset >= 0, DITTO_E_BADARG, "randn: bad argument");
+  return launch_randn(reinterpret_cast<const unsigned long long*>(rng), elem_offset, out, n, static_cast<cudaStream_t>(stream));
 }
 
 int32_t ditto_q_sample(ditto_engine_t* e, const float* x_start, const float* noise, const int64_t* t, float* out, int64_t B,
@@ -1171,6 +1218,110 @@ int32_t ditto_p_sample_ragged(ditto_engine_t* e, const float* x, const ditto_seq
   }
   DITTO_TRY(fork.end());
   return 0;
+}
+
+int32_t ditto_p_sample_ragged_rng(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups, int64_t* t,
+                                  uint64_t* rng, int32_t guided, float guidance_scale, float* eps_scratch, float* x_out, void* workspace,
+                                  int64_t workspace_bytes, int32_t advance, void* stream) {
+  DITTO_REQUIRE(e && x && t && rng && eps_scratch && x_out && workspace, DITTO_E_BADARG, "p_sample_ragged_rng: null argument");
+  DITTO_REQUIRE(e->finalized && e->have_schedule && !e->blocks_only, DITTO_E_STATE, "p_sample_ragged_rng: engine not finalized / schedule not loaded");
+  std::vector<SeqGroup> gs;
+  DITTO_TRY(parse_groups(e, groups, n_groups, true, gs));
+  int64_t n_t = 0;
+  for (const SeqGroup& g : gs) {
+    DITTO_REQUIRE(g.n == (guided ? 2 : 1) * g.n_x, DITTO_E_BADARG, "p_sample_ragged_rng: n_seq must be n_x (unguided) or 2 n_x (guided)");
+    n_t += g.n;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DITTO_TRY(forward_impl(e, x, t, gs.data(), static_cast<int>(gs.size()), eps_scratch, workspace, workspace_bytes, st));
+  const int64_t H = e->H;
+  std::unique_lock<std::recursive_mutex> fork_lock(e->fork_mutex, std::defer_lock);
+  if (gs.size() > 1 && e->n_side > 0) fork_lock.lock();
+  Fork fork(e, st);
+  DITTO_TRY(fork.begin(static_cast<int>(gs.size())));
+  for (size_t gi = 0; gi < gs.size(); ++gi) {
+    const SeqGroup& g = gs[gi];
+    const int64_t per = g.T * H;
+    const float* ec = eps_scratch + g.row0 * H;
+    // element offset = position in the packed latent buffer: every element of the batch draws its own normal
+    DITTO_TRY(launch_cfg_ddpm_update_rng(ec, guided ? ec + g.n_x * per : nullptr, x + g.xrow0 * H, reinterpret_cast<unsigned long long*>(rng),
+                                         t + g.seq0, g.n, e->coef, e->steps, guidance_scale, x_out + g.xrow0 * H, g.n_x, per, g.xrow0 * H,
+                                         false, fork.stream(static_cast<int>(gi))));
+  }
+  DITTO_TRY(fork.end());
+  if (advance) DITTO_TRY(launch_step_advance(reinterpret_cast<unsigned long long*>(rng), t, n_t, st));
+  return 0;
+}
+
+// ---- block-level operators (the reference's component signatures, src/components/DiT.py) -----------------------------
+int32_t ditto_dit_block(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T, int64_t S, float* out,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && x && ctx && out && workspace, DITTO_E_BADARG, "dit_block: null argument");
+  DITTO_REQUIRE(e->finalized, DITTO_E_STATE, "dit_block: engine not finalized");
+  DITTO_REQUIRE(layer >= 0 && layer < e->L, DITTO_E_BADARG, "dit_block: layer out of range");
+  DITTO_REQUIRE(n_seq > 0 && T > 0 && S > 0 && T <= e->maxT, DITTO_E_BADARG, "dit_block: bad sizes");
+  SeqGroup g;
+  g.n = n_seq; g.n_x = n_seq; g.T = T; g.S = S; g.ctx = ctx;
+  return forward_impl(e, x, nullptr, &g, 1, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), layer);
+}
+
+int64_t ditto_adaln_workspace_bytes(int64_t n_seq, int64_t H, int64_t time_dim, int64_t text_dim) {
+  if (n_seq <= 0 || H <= 0 || time_dim <= 0 || text_dim <= 0) return -1;
+  Arena a(nullptr);
+  a.take<float>(n_seq * time_dim); a.take<float>(n_seq * 2 * H); a.take<float>(n_seq * text_dim); a.take<float>(n_seq * 2 * H);
+  return static_cast<int64_t>(a.off + 256);
+}
+
+int32_t ditto_adaln(const float* x, const float* time_emb, const float* text_emb, const float* w_time, const float* b_time,
+                    const float* w_text, const float* b_text, float* out, int64_t n_seq, int64_t T, int64_t S, int64_t H, int64_t time_dim,
+                    int64_t text_dim, void* workspace, int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(x && time_emb && text_emb && w_time && b_time && w_text && b_text && out && workspace, DITTO_E_BADARG, "adaln: null argument");
+  DITTO_REQUIRE(n_seq > 0 && T > 0 && S > 0 && H > 0 && H % 4 == 0 && H <= 1024 && time_dim % 4 == 0 && text_dim > 0, DITTO_E_UNSUPPORTED,
+                "adaln: need H % 4 == 0, H <= 1024, time_dim % 4 == 0");
+  DITTO_REQUIRE(ditto_adaln_workspace_bytes(n_seq, H, time_dim, text_dim) <= workspace_bytes, DITTO_E_WORKSPACE, "adaln: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(workspace);
+  float* ts = a.take<float>(n_seq * time_dim);
+  float* tm = a.take<float>(n_seq * 2 * H);
+  float* pooled = a.take<float>(n_seq * text_dim);
+  float* xm = a.take<float>(n_seq * 2 * H);
+  // [time_scale | time_shift] = Linear(SiLU(time_emb))  (DiT.py:14-17,30);  [text_scale | text_shift] = Linear(SiLU(mean_S text))  (:27,31)
+  DITTO_CUDA(cudaMemcpyAsync(ts, time_emb, sizeof(float) * n_seq * time_dim, cudaMemcpyDeviceToDevice, st));
+  DITTO_TRY(launch_silu(ts, n_seq * time_dim, st));
+  DITTO_TRY(sgemm_nt(ts, time_dim, w_time, time_dim, tm, 2 * H, b_time, nullptr, 0, 1.f, static_cast<int>(n_seq), static_cast<int>(2 * H),
+                     static_cast<int>(time_dim), st));
+  DITTO_TRY(launch_mean_silu(text_emb, pooled, n_seq, static_cast<int>(S), static_cast<int>(text_dim), st));
+  DITTO_TRY(sgemm_nt(pooled, text_dim, w_text, text_dim, xm, 2 * H, b_text, nullptr, 0, 1.f, static_cast<int>(n_seq), static_cast<int>(2 * H),
+                     static_cast<int>(text_dim), st));
+  // LN_noaffine(x) (1 + ts + xs) + (tb + xb)  (DiT.py:34-39): the fused kernel with one table row per sequence and no LN1 stage
+  return launch_adaln_ln(x, n_seq, tm, xm, nullptr, static_cast<int>(n_seq), nullptr, nullptr, out, nullptr, false, nullptr, n_seq,
+                         static_cast<int>(T), static_cast<int>(H), st);
+}
+
+int32_t ditto_rope(const float* t, const float* pos, float* out, int64_t batch, int64_t T, int64_t heads, int64_t head_dim, void* stream) {
+  DITTO_REQUIRE(t && pos && out, DITTO_E_BADARG, "rope: null argument");
+  DITTO_REQUIRE(batch >= 0 && T > 0 && heads > 0 && head_dim > 0 && head_dim % 2 == 0, DITTO_E_BADARG, "rope: bad sizes (head_dim must be even)");
+  return launch_rope_angles(t, pos, out, batch, static_cast<int>(T), static_cast<int>(heads), static_cast<int>(head_dim),
+                            static_cast<cudaStream_t>(stream));
+}
+
+// ---- developer options: A/B switches of the kernels (tools/, tests/); the library never reads the environment ------
+int32_t ditto_debug_option(const char* name, int32_t value) {
+  DITTO_REQUIRE(name != nullptr, DITTO_E_BADARG, "debug_option: null name");
+  struct Opt { const char* n; int* p; };
+  const Opt opts[] = {
+      {"no_pair", &g_opt.no_pair}, {"cluster_m", &g_opt.cluster_m}, {"cluster_n", &g_opt.cluster_n}, {"generic_epi", &g_opt.generic_epi},
+      {"stages_1cta", &g_opt.stages_1cta}, {"stages_pair", &g_opt.stages_pair}, {"no_mcast", &g_opt.no_mcast}, {"xf_rows", &g_opt.xf_rows},
+      {"no_defer_ln", &g_opt.no_defer_ln}, {"no_fused_attn", &g_opt.no_fused_attn}, {"no_flash", &g_opt.no_flash},
+      {"no_flash768", &g_opt.no_flash768}, {"no_fused_cross", &g_opt.no_fused_cross}, {"defer_ln2", &g_opt.defer_ln2},
+      {"pv_transpose", &g_opt.pv_transpose}, {"rope_table", &g_opt.rope_table}, {"rope_generic", &g_opt.rope_generic},
+      {"glu_generic", &g_opt.glu_generic}, {"no_rope_fast32", &g_opt.no_rope_fast32}, {"no_pv_perm4", &g_opt.no_pv_perm4},
+      {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}};
+  if (strcmp(name, "reset") == 0) { g_opt = DebugOptions(); return 0; }
+  for (const Opt& o : opts)
+    if (strcmp(name, o.n) == 0) { *o.p = value; return 0; }
+  set_error(std::string("debug_option: unknown option '") + name + "'");
+  return DITTO_E_BADARG;
 }
 
 // ---- single operators ---------------------------------------------------------------------------------

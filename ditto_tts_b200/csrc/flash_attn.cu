@@ -322,8 +322,6 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   }
 }
 
-bool g_fa_attr_done = false;
-
 }  // namespace
 
 bool flash_attn_supported(int d, int Tq, int Tk) { return d == FA_D && Tq >= 1 && Tk >= 1; }
@@ -334,9 +332,11 @@ int launch_flash_attn(const FlashAttnParams& q, cudaStream_t st) {
   DITTO_REQUIRE(q.Q.ptr && q.Km.ptr && q.V.ptr && q.out && q.resid, DITTO_E_BADARG, "flash_attn: null argument");
   DITTO_REQUIRE(q.n_seq >= 1 && q.heads >= 1 && q.ldo % 2 == 0 && q.ldr % 2 == 0 && q.o_seq % 2 == 0 && q.r_seq % 2 == 0, DITTO_E_BADARG,
                 "flash_attn: bad sizes / strides");
-  if (!g_fa_attr_done) {
+  DeviceState* ds = device_state();
+  if (ds == nullptr) return DITTO_E_CUDA;
+  if (!ds->fa_attr) {  // per device
     DITTO_CUDA(cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    g_fa_attr_done = true;
+    ds->fa_attr = true;
   }
   CUtensorMap mq, mk, mv;
   DITTO_TRY(tc_make_map(&mq, q.Q, q.heads, q.n_seq, FA_D, FA_BM));

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <mutex>
+#include <tuple>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -1884,13 +1886,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
-bool g_init_done = false;
-bool g_use_pair = true;
-int g_cluster_m = 0, g_cluster_n = 0;  // DITTO_CLUSTER="cm,cn": default cluster shape of the 1-CTA GEMM kernel (0 = heuristic)
-bool g_force_generic = false;  // DITTO_GENERIC_EPI=1: route every STORE epilogue through the generic path (tests)
-int g_stages_1cta = STAGES, g_stages_pair = P_STAGES;
 unsigned long long* g_dbg = nullptr;
+constexpr int kMaxDevices = 64;
+DeviceState g_dev_state[kMaxDevices];
+std::mutex g_dev_mutex;
 
 // 4-D bf16 map: dims (cols, rows, inner, outer), box (box_cols, box_rows, 1, 1), 128B swizzle, zero OOB fill.
 int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
@@ -1933,7 +1932,7 @@ int set_attr() {
 
 // Launch a persistent 1-CTA kernel as clusters of `csize` CTAs (csize == 1: plain launch): grid = csize x min(work items,
 // co-resident clusters).  The co-residency query is cached per (kernel, cluster size).
-std::map<std::pair<const void*, int>, int> g_max_clusters;
+std::map<std::tuple<int, const void*, int>, int> g_max_clusters;  // (device, kernel, cluster size)
 template <typename Params>
 int launch_clustered(const void* func, int csize, int smem_bytes, int64_t num_work, const CUtensorMap& ma, const CUtensorMap& mb,
                      const Params& p, cudaStream_t st) {
@@ -1944,18 +1943,24 @@ int launch_clustered(const void* func, int csize, int smem_bytes, int64_t num_wo
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 0;
-  int clusters = g_num_sms;
+  DeviceState* ds = device_state();
+  if (ds == nullptr) return DITTO_E_CUDA;
+  const int num_sms = ds->num_sms;
+  int dev_id = 0;
+  DITTO_CUDA(cudaGetDevice(&dev_id));
+  int clusters = num_sms;
   if (csize > 1) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.numAttrs = 1;
-    auto key = std::make_pair(func, csize);
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    auto key = std::make_tuple(dev_id, func, csize);
     auto it = g_max_clusters.find(key);
     if (it == g_max_clusters.end()) {
       if (csize > 8) (void)cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      cfg.gridDim = dim3(static_cast<unsigned>(csize * g_num_sms), 1, 1);
+      cfg.gridDim = dim3(static_cast<unsigned>(csize * num_sms), 1, 1);
       int n = 0;
       cudaError_t e = cudaOccupancyMaxActiveClusters(&n, func, &cfg);
       if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
@@ -1978,21 +1983,42 @@ void tc_gemm_set_debug_counters(unsigned long long* dev_ptr) { g_dbg = dev_ptr; 
 int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
   return make_map(m, op, n_inner, n_outer, box_cols, box_rows);
 }
-int tc_num_sms() { return g_num_sms; }
+int tc_num_sms() {
+  DeviceState* ds = device_state();
+  return ds ? ds->num_sms : 0;
+}
 
+DeviceState* device_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    set_error("libditto_b200: cudaGetDevice failed (or device ordinal >= 64)");
+    return nullptr;
+  }
+  return &g_dev_state[dev];
+}
+
+// Per device: kernel attributes (dynamic shared memory opt-in, non-portable cluster sizes) and the SM count belong to the
+// device that is current when they are set / read, so a process that holds engines on several GPUs initialises each one.
 int tc_gemm_init() {
-  if (g_init_done) return 0;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  DITTO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  DITTO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, DITTO_E_CUDA, "cuTensorMapEncodeTiled not available");
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  DeviceState* ds = device_state();
+  if (ds == nullptr) return DITTO_E_CUDA;
+  if (ds->tc_init) return 0;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (ds->tc_init) return 0;
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DITTO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DITTO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, DITTO_E_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
   int dev = 0;
   DITTO_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  DITTO_CUDA(cudaGetDeviceProperties(&prop, dev));
-  DITTO_REQUIRE(prop.major == 10, DITTO_E_UNSUPPORTED, "libditto_b200 needs an sm_100a device (B200)");
-  g_num_sms = prop.multiProcessorCount;
+  int major = 0, sms = 0;
+  DITTO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DITTO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DITTO_REQUIRE(major == 10, DITTO_E_UNSUPPORTED, "libditto_b200 needs an sm_100a device (B200)");
+  ds->num_sms = sms;
   DITTO_TRY((set_attr<K_STORE_F32, false>()));
   DITTO_TRY((set_attr<K_STORE_F32, true>()));
   DITTO_TRY((set_attr<K_STORE_F32_RESID, false>()));
@@ -2013,19 +2039,7 @@ int tc_gemm_init() {
   DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
   DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   DITTO_CUDA(cudaFuncSetAttribute(tc_scores_softmax_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  {
-    const char* env = getenv("DITTO_NO_PAIR");
-    g_use_pair = !(env && env[0] == '1');
-    if (const char* ec = getenv("DITTO_CLUSTER")) {
-      int a = 0, b = 0;
-      if (sscanf(ec, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 16) { g_cluster_m = a; g_cluster_n = b; }
-    }
-    const char* eg = getenv("DITTO_GENERIC_EPI");
-    g_force_generic = eg && eg[0] == '1';
-    if (const char* e1 = getenv("DITTO_STAGES_1CTA")) g_stages_1cta = std::max(2, std::min(STAGES, atoi(e1)));
-    if (const char* e2 = getenv("DITTO_STAGES_PAIR")) g_stages_pair = std::max(2, std::min(P_STAGES, atoi(e2)));
-  }
-  g_init_done = true;
+  ds->tc_init = true;
   return 0;
 }
 
@@ -2049,7 +2063,9 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   CUtensorMap ma, mb;
   TcOperand A = q.A, B = q.B;
   // paired (cta_group::2) kernel for the large un-batched weight GEMMs
-  const bool pair = g_use_pair && !q.b_kn && q.batch_inner == 1 && q.batch_outer == 1 && q.M >= 2 * BLOCK_M && (g_num_sms % 2 == 0);
+  const int g_num_sms = tc_num_sms();
+  const bool g_force_generic = g_opt.generic_epi != 0;
+  const bool pair = !g_opt.no_pair && !q.b_kn && q.batch_inner == 1 && q.batch_outer == 1 && q.M >= 2 * BLOCK_M && (g_num_sms % 2 == 0);
   DITTO_TRY(make_map(&ma, A, q.batch_inner, q.batch_outer, BLOCK_K, BLOCK_M));
   if (pair)
     DITTO_TRY(make_map(&mb, B, 1, 1, BLOCK_K, BLOCK_N / 2));
@@ -2093,7 +2109,8 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
 
   unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, g_num_sms));
   ProfScope prof(q.tag, st, 2.0 * q.M * q.N * q.K * q.batch_inner * q.batch_outer, 0.0);
-  p.stages = pair ? g_stages_pair : g_stages_1cta;
+  p.stages = pair ? (g_opt.stages_pair >= 2 ? std::min(P_STAGES, g_opt.stages_pair) : P_STAGES)
+                  : (g_opt.stages_1cta >= 2 ? std::min(STAGES, g_opt.stages_1cta) : STAGES);
   p.cm = 1; p.cn = 1;
   if (q.out_perm4)
     DITTO_REQUIRE(q.epilogue == TC_EPI_STORE && !q.out_bf16 && q.resid != nullptr && q.bias == nullptr && q.out2 == nullptr &&
@@ -2159,7 +2176,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
     // cluster shape: explicit > DITTO_CLUSTER > 1 x 1.  Measured on B200 (profiles/README.md): for the epilogue-heavy
     // batched attention GEMMs the lock-step coupling of a multicast cluster costs more than the saved L2 traffic, so
     // multicast stays opt-in here; the fused scores kernel always shares the Q block across its key-tile cluster.
-    int cm = q.cluster_m > 0 ? q.cluster_m : g_cluster_m, cn = q.cluster_n > 0 ? q.cluster_n : g_cluster_n;
+    int cm = q.cluster_m > 0 ? q.cluster_m : g_opt.cluster_m, cn = q.cluster_n > 0 ? q.cluster_n : g_opt.cluster_n;
     if (cm <= 0 || cn <= 0) cm = cn = 1;
     cm = std::min(cm, p.m_tiles);
     cn = std::min(cn, p.n_tiles);
@@ -2210,12 +2227,12 @@ int launch_tc_scores_softmax(const TcScoresSoftmaxParams& q, cudaStream_t st) {
   p.P = q.P; p.ldp = q.ldp; p.sp_inner = q.sp_inner; p.sp_outer = q.sp_outer;
   p.npad = q.npad;
   p.lpart = q.lpart; p.sl_inner = q.sl_inner; p.sl_outer = q.sl_outer;
-  p.csize = csize; p.stages = g_stages_1cta;
+  p.csize = csize; p.stages = g_opt.stages_1cta >= 2 ? std::min(STAGES, g_opt.stages_1cta) : STAGES;
   p.ln_stat = q.ln_stat; p.ln_parts = q.ln_parts; p.ln_inv_h = q.ln_width > 0 ? 1.0f / static_cast<float>(q.ln_width) : 0.f;
   p.ln_c = q.ln_c;
   if (q.ln_stat != nullptr)
     DITTO_REQUIRE(q.bias && q.ln_c && q.ln_parts > 0 && q.ln_width > 0, DITTO_E_BADARG, "tc_scores_softmax: deferred LayerNorm arguments");
-  int cm = q.cluster_m > 0 ? q.cluster_m : (g_cluster_m > 0 ? g_cluster_m : 1);
+  int cm = q.cluster_m > 0 ? q.cluster_m : (g_opt.cluster_m > 0 ? g_opt.cluster_m : 1);
   cm = std::max(1, std::min(cm, std::min(p.m_tiles, SM_MAX_CLUSTER / csize)));
   p.cm = cm;
   // flops: the contraction; bytes: nothing (the fused softmax saves 12 B per score of HBM round trips)

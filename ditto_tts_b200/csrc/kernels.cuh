@@ -6,6 +6,26 @@
 
 namespace ditto {
 
+// ---- developer options (ditto_debug_option): A/B switches of the kernels, all 0 = the product path.  The library never
+// reads the environment; tools / tests set these through the C-ABI before creating an engine.
+struct DebugOptions {
+  // gemm_tc.cu (read at launch time)
+  int no_pair = 0, cluster_m = 0, cluster_n = 0, generic_epi = 0, stages_1cta = 0, stages_pair = 0, no_mcast = 0;
+  // cross_fused.cu
+  int xf_rows = 0;
+  // engine.cu (read by ditto_engine_create)
+  int no_defer_ln = 0, no_fused_attn = 0, no_flash = 0, no_flash768 = 0, no_fused_cross = 0, defer_ln2 = 0, pv_transpose = 0,
+      rope_table = 0, rope_generic = 0, glu_generic = 0, no_rope_fast32 = 0, no_pv_perm4 = 0, side_streams = -1, no_fused_ln = 0;
+};
+extern DebugOptions g_opt;
+
+// ---- per-device one-time state (kernel attributes are per device: an engine on cuda:1 must not reuse cuda:0's set-up)
+struct DeviceState {
+  bool tc_init = false, xf_attr = false, fa_attr = false, f768_attr = false;
+  int num_sms = 0;
+};
+DeviceState* device_state();  // state of the CURRENT device (nullptr + error set when cudaGetDevice fails)
+
 // ---- elementwise.cu ----------------------------------------------------------------------------------
 int launch_cast_bf16(const float* x, bf16* y, int64_t n, cudaStream_t st);
 int launch_pack_rows(const float* x, bf16* y, float* bias_out, const float* bias_in, const int* perm, int rows, int K,
@@ -31,6 +51,14 @@ int launch_transpose_v(const bf16* v, int64_t ld, bf16* vt, int64_t n_seq, int T
 int launch_cfg_ddpm_update(const float* eps_c, const float* eps_u, const float* x, const float* z, const int64_t* t,
                            const float* coef, int steps, float w, float* out, int64_t B, int64_t elems_per_seq,
                            cudaStream_t st);
+// noise drawn in the kernel (Philox4x32-10 + Box-Muller from rng = {seed, draw counter, ticket, -}); advance: the last block
+// to finish adds 1 to the counter and subtracts 1 from t[0 .. n_t)
+int launch_cfg_ddpm_update_rng(const float* eps_c, const float* eps_u, const float* x, unsigned long long* rng, int64_t* t, int64_t n_t,
+                               const float* coef, int steps, float w, float* out, int64_t B, int64_t elems_per_seq,
+                               int64_t elem_offset, bool advance, cudaStream_t st);
+int launch_step_advance(unsigned long long* rng, int64_t* t, int64_t n_t, cudaStream_t st);
+int launch_randn(const unsigned long long* rng, int64_t elem_offset, float* out, int64_t n, cudaStream_t st);
+int launch_rope_angles(const float* t, const float* pos, float* out, int64_t batch, int T, int heads, int d, cudaStream_t st);
 int launch_schedule_coef(const float* betas, const float* alphas, const float* acp, float* coef, int steps, cudaStream_t st);
 int launch_q_sample(const float* x0, const float* noise, const int64_t* t, const float* buf, int steps, float* out, int64_t B,
                     int64_t elems_per_seq, cudaStream_t st);

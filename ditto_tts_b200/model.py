@@ -8,6 +8,7 @@ C-ABI of include/ditto_b200.h).  Inference only; no autograd; no CPU fallback (C
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -27,6 +28,16 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _check_t_range(t: torch.Tensor, steps: int, what: str):
+    """The reference's ``t_embedding(t)`` / ``betas[t]`` raise on an out-of-range index; the kernels clamp (the captured step
+    graph leaves t = -1 after its last step), so the eager API checks on the host (one small device->host read)."""
+    if t.numel() == 0:
+        return
+    lo, hi = int(t.min()), int(t.max())
+    if lo < 0 or hi >= steps:
+        raise DittoError(f"{what}: timestep index out of range [0, {steps}): min {lo}, max {hi}")
+
+
 def _need_cuda_f32(name: str, t: torch.Tensor) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise DittoError(f"{name} must be a CUDA tensor: ditto_tts_b200 has no CPU fallback")
@@ -36,8 +47,9 @@ def _need_cuda_f32(name: str, t: torch.Tensor) -> torch.Tensor:
 
 
 class GlobalAdaLN(nn.Module):
-    """Parameters of the global AdaLN (reference: components/DiT.py:8-23).  The modulation
-    LN(x)*(1+ts+xs)+(tb+xb) (DiT.py:25-40) is fused with block 0's LayerNorm inside the engine."""
+    """Global AdaLN (reference: components/DiT.py:8-40).  Inside ``DiTTO.forward`` the modulation
+    LN(x)*(1+ts+xs)+(tb+xb) is fused with block 0's LayerNorm; called on its own (same signature as the reference)
+    it runs through ``ditto_adaln``."""
 
     def __init__(self, hidden_dim, time_dim, text_dim):
         super().__init__()
@@ -45,8 +57,29 @@ class GlobalAdaLN(nn.Module):
         self.text_mlp = nn.Sequential(nn.SiLU(), nn.Linear(text_dim, 2 * hidden_dim))
         self.norm = nn.LayerNorm(hidden_dim, elementwise_affine=False)
 
+    @torch.no_grad()
     def forward(self, x, time_emb, text_emb):
-        raise DittoError("GlobalAdaLN runs fused inside DiTTO.forward (libditto_b200); call the DiTTO module")
+        """x [n,T,H], time_emb [n,time_dim] (output of ``time_embed``), text_emb [n,S,text_dim] -> [n,T,H]  (DiT.py:25-40)."""
+        lib = _lib.load()
+        x = _need_cuda_f32("x", x)
+        time_emb = _need_cuda_f32("time_emb", time_emb)
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        wt, bt = self.time_mlp[1].weight, self.time_mlp[1].bias
+        wx, bx = self.text_mlp[1].weight, self.text_mlp[1].bias
+        if not wt.is_cuda:
+            raise DittoError("GlobalAdaLN parameters are on the CPU: there is no CPU fallback")
+        n, T, H = x.shape
+        S, Xd, Td = text_emb.shape[1], text_emb.shape[2], time_emb.shape[1]
+        if time_emb.shape[0] != n or text_emb.shape[0] != n or wt.shape != (2 * H, Td) or wx.shape != (2 * H, Xd):
+            raise DittoError("GlobalAdaLN: shapes of x / time_emb / text_emb do not match the module")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            nbytes = lib.ditto_adaln_workspace_bytes(n, H, Td, Xd)
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+            w = [v.detach().float().contiguous() for v in (wt, bt, wx, bx)]
+            _lib.check(lib.ditto_adaln(_ptr(x), _ptr(time_emb), _ptr(text_emb), _ptr(w[0]), _ptr(w[1]), _ptr(w[2]), _ptr(w[3]),
+                                       _ptr(out), n, T, S, H, Td, Xd, _ptr(ws), ws.numel(), _stream()), "ditto_adaln")
+        return out
 
 
 class RotaryEmbedding(nn.Module):
@@ -63,6 +96,20 @@ class RotaryEmbedding(nn.Module):
         t = torch.arange(seq_len, device=device).type_as(self.inv_freq)
         freqs = torch.einsum("i,j->ij", t, self.inv_freq)
         return torch.cat((freqs, freqs), dim=-1)
+
+    @torch.no_grad()
+    def apply_rope(self, pos, t):
+        """``t * cos(pos) + rotate_half(t) * sin(pos)`` (DiT.py:52-54,61-72): pos [T, head_dim] angles, t
+        [batch, T, heads, head_dim] -> same shape.  (Inside DiTTO.forward the rotation is fused into the QKV GEMM epilogue.)"""
+        t = _need_cuda_f32("t", t)
+        pos = _need_cuda_f32("pos", pos)
+        if t.dim() != 4 or pos.dim() != 2 or pos.shape[0] != t.shape[1] or pos.shape[1] != t.shape[3]:
+            raise DittoError("apply_rope expects pos [T, head_dim] and t [batch, T, heads, head_dim]")
+        out = torch.empty_like(t)
+        b, T, h, d = t.shape
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.load().ditto_rope(_ptr(t), _ptr(pos), _ptr(out), b, T, h, d, _stream()), "ditto_rope")
+        return out
 
 
 class DiT(nn.Module):
@@ -83,8 +130,42 @@ class DiT(nn.Module):
         self.gate = nn.Linear(hidden_dim, 4 * hidden_dim)
         self.mlp_fc2 = nn.Linear(4 * hidden_dim, hidden_dim)
 
-    def forward(self, x, text_emb, time_emb, rotary_pos):
-        raise DittoError("DiT blocks run fused inside DiTTO.forward (libditto_b200); call the DiTTO module")
+        self.hidden_dim, self.time_dim, self.text_dim = hidden_dim, time_dim, text_dim
+        self._owner = None          # (weakref to the DiTTO that holds this block, layer index); None: stand-alone block
+        self._own = None            # stand-alone block: a private one-block DiTTO-less engine holder
+
+    @torch.no_grad()
+    def forward(self, x, text_emb, time_emb=None, rotary_pos=None):
+        """One DiT block, reference signature (DiT.py:100-157): x [n,T,H], text_emb [n,S,text_dim] -> [n,T,H].
+        ``time_emb`` is accepted and ignored exactly as the reference block ignores it; ``rotary_pos`` must be the
+        standard table ``RotaryEmbedding.forward(T)`` (None = that table): the kernels rotate with positions 0..T-1."""
+        x = _need_cuda_f32("x", x)
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        if x.dim() != 3 or text_emb.dim() != 3 or x.shape[0] != text_emb.shape[0]:
+            raise DittoError("expected x [n,T,H] and text_emb [n,S,text_dim] with the same n")
+        n, T, H = x.shape
+        if rotary_pos is not None:
+            std = self.rotary(T, x.device)
+            if tuple(rotary_pos.shape) != tuple(std.shape) or not torch.equal(rotary_pos.to(std), std):
+                raise DittoError("DiT.forward: rotary_pos must equal RotaryEmbedding.forward(seq_len) (positions 0..T-1)")
+        host, layer = self._engine_host()
+        lib = _lib.load()
+        ctx = host.text_context(text_emb, name="block_ctx", T_hint=T)
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            ws = host.workspace(n, T, text_emb.shape[1])
+            _lib.check(lib.ditto_dit_block(host.engine(), layer, _ptr(x), _ptr(ctx), n, T, text_emb.shape[1], _ptr(out), _ptr(ws),
+                                           ws.numel(), _stream()), "ditto_dit_block")
+        return out
+
+    def _engine_host(self):
+        if self._owner is not None:
+            owner = self._owner[0]()
+            if owner is not None:
+                return owner, self._owner[1]
+        if self._own is None:
+            self._own = _BlockEngine(self)
+        return self._own, 0
 
 
 class _Buffers:
@@ -101,7 +182,111 @@ class _Buffers:
         return b
 
 
-class DiTTO(nn.Module):
+class _EngineHost:
+    """What DiTTO and a stand-alone DiT block share: a native engine built from a state_dict-like set of tensors, refreshed
+    when they change, plus the caller-owned scratch the C-ABI wants."""
+
+    def _host_init(self):
+        self._engine = None
+        self._engine_key = None
+        self._tensors = None       # cached [(key, tensor)] of the engine's weights (invalidated by _apply / load_state_dict)
+        self._bufs = _Buffers()
+
+    # -- to be provided: _engine_config() -> _lib.Config, _engine_tensors() -> [(key, tensor)], _device()
+    def _weights_key(self):
+        """(data_ptr, version) of every weight: cheap enough for every call (no state_dict rebuild).  In-place edits through
+        ``.data`` do not bump ``_version`` -- call ``refresh_weights()`` after those."""
+        if self._tensors is None:
+            self._tensors = self._engine_tensors()
+        return tuple((v.data_ptr(), v._version) for _, v in self._tensors)
+
+    def refresh_weights(self):
+        """Force the engine to re-read (and re-pack) every weight on its next use.  Needed after edits the version counter
+        does not see: ``p.data.copy_(...)``, ``p.data.mul_(...)`` (EMA swaps), external writes through raw pointers.
+        CUDA graphs captured earlier keep working: the engine's packed buffers are refreshed in place."""
+        self._engine_key = None
+        self._tensors = None
+
+    def engine(self):
+        """Create / refresh the native engine from the current parameters (must live on a CUDA device)."""
+        lib = _lib.load()
+        dev = self._device()
+        if dev.type != "cuda":
+            raise DittoError("parameters are on the CPU: move the module to a B200 (module.cuda()); there is no CPU fallback")
+        key = self._weights_key()
+        if self._engine is not None and key == self._engine_key:
+            return self._engine
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                cfg = self._engine_config()
+                h = C.c_void_p()
+                _lib.check(lib.ditto_engine_create(C.byref(cfg), C.byref(h)), "ditto_engine_create")
+                self._engine = h
+            for k, v in self._tensors:
+                w = v.detach().to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(lib.ditto_engine_load_weight(self._engine, k.encode(), _ptr(w), w.numel(), _stream()),
+                           f"ditto_engine_load_weight({k})")
+            _lib.check(lib.ditto_engine_finalize(self._engine, _stream()), "ditto_engine_finalize")
+        self._engine_key = key
+        return self._engine
+
+    def workspace(self, n_seq: int, T: int, S: int) -> torch.Tensor:
+        eng = self.engine()
+        nbytes = _lib.load().ditto_workspace_bytes(eng, n_seq, T, S)
+        if nbytes < 0:
+            raise DittoError("ditto_workspace_bytes: bad sizes")
+        return self._bufs.get("ws", nbytes, self._device())
+
+    def text_context(self, text_emb: torch.Tensor, name: str = "ctx", T_hint: int = 1) -> torch.Tensor:
+        """Step-invariant text work (cross-attention K/V of every layer + text modulation) for a batch."""
+        eng = self.engine()
+        lib = _lib.load()
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        n, S, Xd = text_emb.shape
+        if Xd != self.text_dim:
+            raise DittoError(f"text_emb last dim {Xd} != text_dim {self.text_dim}")
+        with torch.cuda.device(text_emb.device):
+            ctx = self._bufs.get(name, lib.ditto_text_context_bytes(eng, n, S), text_emb.device)
+            ws = self.workspace(n, T_hint, S)
+            _lib.check(lib.ditto_text_context(eng, _ptr(text_emb), n, S, _ptr(ctx), _ptr(ws), ws.numel(), _stream()),
+                       "ditto_text_context")
+        return ctx
+
+    def _destroy_engine(self):
+        try:
+            if getattr(self, "_engine", None) is not None:
+                _lib.load().ditto_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+
+class _BlockEngine(_EngineHost):
+    """Engine holder of a stand-alone ``DiT`` block (DITTO_F_BLOCKS_ONLY, one layer, keys ``blocks.0.*``)."""
+
+    def __init__(self, block: "DiT"):
+        self._block = weakref.ref(block)
+        self.text_dim = block.text_dim
+        self._host_init()
+
+    def _device(self):
+        return self._block().norm1.weight.device
+
+    def _engine_config(self):
+        b = self._block()
+        return _lib.Config(hidden_dim=b.hidden_dim, num_layers=1, num_heads=b.num_heads, time_dim=b.time_dim, text_dim=b.text_dim,
+                           diffusion_steps=1, precision=_lib.PREC_BF16 if getattr(b, "precision", "bf16") == "bf16" else _lib.PREC_FP32,
+                           max_seq_len=getattr(b, "max_seq_len", 4096),
+                           flags=_lib.F_FUSED_ROPE | _lib.F_FOLD_CROSS | _lib.F_FUSED_ATTN | _lib.F_BLOCKS_ONLY)
+
+    def _engine_tensors(self):
+        return [("blocks.0." + k, v) for k, v in self._block().state_dict(keep_vars=True).items()]
+
+    def __del__(self):
+        self._destroy_engine()
+
+
+class DiTTO(nn.Module, _EngineHost):
     """Drop-in for ``model.DiTTO.DiTTO`` (reference: src/model/DiTTO.py:7-126) on the inference path.
 
     Same constructor keywords; ``forward(x, text_emb, t)`` -> eps_hat with x [n,T,H] fp32, text_emb
@@ -141,10 +326,10 @@ class DiTTO(nn.Module):
         self.proj_out = nn.Linear(hidden_dim, hidden_dim)
         self.rotary = RotaryEmbedding(hidden_dim // num_heads)
         self.register_buffer("alphas_cumprod", self.cosine_beta_schedule(diffusion_steps))
-        self._engine = None
-        self._engine_key = None
+        for i, blk in enumerate(self.blocks):      # block.forward(x, text_emb, t, rotary_pos) runs block i of THIS engine
+            blk._owner = (weakref.ref(self), i)
+        self._host_init()
         self._schedule_loaded = False
-        self._bufs = _Buffers()
         self.eval()
 
     # ------------------------------------------------------------------ reference API (host side)
@@ -162,47 +347,28 @@ class DiTTO(nn.Module):
         if not hasattr(self, "nac"):
             state_dict = {k: v for k, v in state_dict.items() if not k.startswith("nac.")}
         out = super().load_state_dict(state_dict, strict=strict, assign=assign)
-        self._engine_key = None
+        self.refresh_weights()
         return out
 
-    # ------------------------------------------------------------------ engine plumbing
-    def _weights_key(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items()
-                     if not k.startswith("nac."))
+    # ------------------------------------------------------------------ engine plumbing (_EngineHost)
+    def _device(self):
+        return self.proj_in.weight.device
 
-    def engine(self):
-        """Create / refresh the native engine from the current parameters (must live on a CUDA device)."""
-        lib = _lib.load()
-        dev = self.proj_in.weight.device
-        if dev.type != "cuda":
-            raise DittoError("DiTTO parameters are on the CPU: move the module to a B200 (model.cuda()); "
-                             "there is no CPU fallback")
-        key = self._weights_key()
-        if self._engine is not None and key == self._engine_key:
-            return self._engine
-        with torch.cuda.device(dev):
-            if self._engine is None:
-                cfg = _lib.Config(hidden_dim=self.hidden_dim, num_layers=self.num_layers, num_heads=self.num_heads,
-                                  time_dim=self.time_dim, text_dim=self.text_dim,
-                                  diffusion_steps=self.diffusion_steps,
-                                  precision=_lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32,
-                                  max_seq_len=self.max_seq_len,
-                                  flags=(_lib.F_FUSED_ROPE if self.fused_rope else 0) |
-                                  (_lib.F_FOLD_CROSS if self.fold_cross else 0) |
-                                  (_lib.F_FUSED_ATTN if self.fused_attn else 0) |
-                                  (_lib.F_DEFER_LN if self.defer_ln else 0))
-                h = C.c_void_p()
-                _lib.check(lib.ditto_engine_create(C.byref(cfg), C.byref(h)), "ditto_engine_create")
-                self._engine = h
-            for k, v in self.state_dict().items():
-                if k.startswith("nac."):
-                    continue
-                w = v.detach().to(device=dev, dtype=torch.float32).contiguous()
-                _lib.check(lib.ditto_engine_load_weight(self._engine, k.encode(), _ptr(w), w.numel(), _stream()),
-                           f"ditto_engine_load_weight({k})")
-            _lib.check(lib.ditto_engine_finalize(self._engine, _stream()), "ditto_engine_finalize")
-        self._engine_key = key
-        return self._engine
+    def _engine_config(self):
+        return _lib.Config(hidden_dim=self.hidden_dim, num_layers=self.num_layers, num_heads=self.num_heads,
+                           time_dim=self.time_dim, text_dim=self.text_dim, diffusion_steps=self.diffusion_steps,
+                           precision=_lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32,
+                           max_seq_len=self.max_seq_len,
+                           flags=(_lib.F_FUSED_ROPE if self.fused_rope else 0) | (_lib.F_FOLD_CROSS if self.fold_cross else 0) |
+                           (_lib.F_FUSED_ATTN if self.fused_attn else 0) | (_lib.F_DEFER_LN if self.defer_ln else 0))
+
+    def _engine_tensors(self):
+        return [(k, v) for k, v in self.state_dict(keep_vars=True).items() if not k.startswith("nac.")]
+
+    def _apply(self, fn, *a, **k):   # .to() / .cuda() re-create buffers: drop the cached tensor list
+        out = super()._apply(fn, *a, **k)
+        self._tensors = None
+        return out
 
     def load_schedule(self, betas: torch.Tensor, alphas: torch.Tensor, alphas_cumprod: torch.Tensor, owner=None):
         """Hand the sampler tables (SpeechGenerator.py:70-72) to the engine.  ``owner`` tags whose tables the engine
@@ -236,28 +402,6 @@ class DiTTO(nn.Module):
             alphas = 1.0 - betas
             self.load_schedule(betas, alphas, torch.cumprod(alphas, dim=0))
 
-    def workspace(self, n_seq: int, T: int, S: int) -> torch.Tensor:
-        eng = self.engine()
-        nbytes = _lib.load().ditto_workspace_bytes(eng, n_seq, T, S)
-        if nbytes < 0:
-            raise DittoError("ditto_workspace_bytes: bad sizes")
-        return self._bufs.get("ws", nbytes, self.proj_in.weight.device)
-
-    def text_context(self, text_emb: torch.Tensor, name: str = "ctx", T_hint: int = 1) -> torch.Tensor:
-        """Step-invariant text work (cross-attention K/V of every layer + text modulation) for a batch."""
-        eng = self.engine()
-        lib = _lib.load()
-        text_emb = _need_cuda_f32("text_emb", text_emb)
-        n, S, Xd = text_emb.shape
-        if Xd != self.text_dim:
-            raise DittoError(f"text_emb last dim {Xd} != text_dim {self.text_dim}")
-        with torch.cuda.device(text_emb.device):
-            ctx = self._bufs.get(name, lib.ditto_text_context_bytes(eng, n, S), text_emb.device)
-            ws = self.workspace(n, T_hint, S)
-            _lib.check(lib.ditto_text_context(eng, _ptr(text_emb), n, S, _ptr(ctx), _ptr(ws), ws.numel(), _stream()),
-                       "ditto_text_context")
-        return ctx
-
     def forward_with_context(self, x: torch.Tensor, ctx: torch.Tensor, t: torch.Tensor, n_seq: int, S: int,
                              out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """eps_hat for n_seq sequences whose text context is already built; x [n_x,T,H] with n_seq % n_x == 0."""
@@ -286,6 +430,7 @@ class DiTTO(nn.Module):
         if x.dim() != 3 or text_emb.dim() != 3 or x.shape[0] != text_emb.shape[0]:
             raise DittoError("expected x [n,T,H] and text_emb [n,S,text_dim] with the same n")
         t = t.to(device=x.device, dtype=torch.int64)
+        _check_t_range(t, self.diffusion_steps, "DiTTO.forward")
         ctx = self.text_context(text_emb, T_hint=x.shape[1])
         return self.forward_with_context(x, ctx, t, x.shape[0], text_emb.shape[1])
 
@@ -308,6 +453,7 @@ class DiTTO(nn.Module):
         noise = _need_cuda_f32("noise", noise)
         self._ensure_schedule()
         t = t.to(device=x_start.device, dtype=torch.int64).contiguous()
+        _check_t_range(t, self.diffusion_steps, "DiTTO.q_sample")
         out = torch.empty_like(x_start)
         B = x_start.shape[0]
         with torch.cuda.device(x_start.device):
@@ -316,8 +462,4 @@ class DiTTO(nn.Module):
         return out
 
     def __del__(self):
-        try:
-            if getattr(self, "_engine", None) is not None:
-                _lib.load().ditto_engine_destroy(self._engine)
-        except Exception:
-            pass
+        self._destroy_engine()

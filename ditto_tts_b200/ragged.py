@@ -29,8 +29,15 @@ class RaggedBatch:
     group holds its conditional sequences followed by the unconditional ones (zero text embedding unless
     ``null_texts`` supplies them), sharing the group's latents."""
 
+    @staticmethod
+    def signature(texts, lengths, guided: bool):
+        """What a captured step graph depends on: the sorted (frames, tokens) pairs, guidance, device."""
+        keys = sorted((int(t), int(x.shape[0])) for t, x in zip(lengths, texts))
+        return (tuple(keys), bool(guided), str(texts[0].device) if len(texts) else "")
+
     def __init__(self, model: DiTTO, texts: Sequence[torch.Tensor], lengths: Sequence[int], guided: bool = False,
-                 null_texts: Optional[Sequence[torch.Tensor]] = None, name: str = "ragged"):
+                 null_texts: Optional[Sequence[torch.Tensor]] = None, name: str = "ragged",
+                 ctx_storage: Optional[List[torch.Tensor]] = None):
         if len(texts) == 0 or len(texts) != len(lengths):
             raise DittoError("RaggedBatch needs one text embedding and one length per utterance")
         self.model, self.guided = model, guided
@@ -69,7 +76,14 @@ class RaggedBatch:
                 if null.shape != tg.shape:
                     raise DittoError("null_texts must match texts in shape")
                 tg = torch.cat([tg, null], dim=0)
-            ctx = model.text_context(tg, name="ragged_ctx", T_hint=1).clone()   # owned by this batch (offset-based layout)
+            ctx = model.text_context(tg, name="ragged_ctx", T_hint=1)
+            if ctx_storage is not None:       # buffers a cached step graph reads (same batch signature): refill in place
+                store = ctx_storage[gi]
+                k = min(store.numel(), ctx.numel())   # both hold at least ditto_text_context_bytes of this group
+                store[:k].copy_(ctx[:k])
+                ctx = store
+            else:
+                ctx = ctx.clone()             # owned by this batch (offset-based layout)
             self._ctx.append(ctx)
             arr[gi] = _lib.SeqGroup(n_seq=mult * len(idx), n_x=len(idx), T=T, S=S, ctx=ctx.data_ptr())
             for i in idx:
@@ -149,7 +163,9 @@ class RaggedStepGraph:
         self.batch, self.w, self.draw_noise = batch, w, draw_noise
         dev = batch.device
         self.x = torch.zeros((batch.x_rows, batch.H), dtype=torch.float32, device=dev)
-        self.z = torch.zeros_like(self.x)
+        self.z = None if draw_noise else torch.zeros_like(self.x)
+        self.rng = torch.zeros((4,), dtype=torch.int64, device=dev)
+        self._ctx_ptrs = [c.data_ptr() for c in batch._ctx]
         self.eps = torch.empty((batch.seq_rows, batch.H), dtype=torch.float32, device=dev)
         self.t = torch.zeros((batch.n_seq,), dtype=torch.int64, device=dev)
         self.ws = batch.workspace()
@@ -166,14 +182,32 @@ class RaggedStepGraph:
         self.launches_per_step = _lib.launch_count() - n0
 
     def _step(self):
-        if self.draw_noise:
-            self.z.normal_()
-        self.batch.p_sample(self.x, self.t, self.z, self.w, self.eps, self.x, ws=self.ws)
+        b = self.batch
+        if self.draw_noise:   # noise drawn inside the per-group update kernels, bookkeeping in a one-block kernel after them
+            with torch.cuda.device(b.device):
+                _lib.check(_lib.load().ditto_p_sample_ragged_rng(b.model.engine(), _ptr(self.x), b.c_groups, len(b.groups), _ptr(self.t),
+                                                                 _ptr(self.rng), 1 if b.guided else 0, float(self.w), _ptr(self.eps),
+                                                                 _ptr(self.x), _ptr(self.ws), self.ws.numel(), 1, _stream()),
+                           "ditto_p_sample_ragged_rng")
+            return
+        b.p_sample(self.x, self.t, self.z, self.w, self.eps, self.x, ws=self.ws)
         self.t.sub_(1)
 
-    def reset(self, x_packed: torch.Tensor, t_start: int):
+    def valid_for(self, batch: "RaggedBatch") -> bool:
+        """The captured kernels read the context buffers and the workspace by address."""
+        return (self._ctx_ptrs == [c.data_ptr() for c in batch._ctx] and self.ws.data_ptr() == batch.workspace().data_ptr()
+                and batch.x_rows == self.x.shape[0])
+
+    def rebind(self, batch: "RaggedBatch"):
+        self.batch = batch
+
+    def reset(self, x_packed: torch.Tensor, t_start: int, seed: Optional[int] = None):
         self.x.copy_(x_packed)
         self.t.fill_(t_start)
+        if self.draw_noise:
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self.rng.copy_(torch.tensor([seed, 0, 0, 0], dtype=torch.int64))
 
     def replay(self):
         self.graph.replay()

@@ -10,13 +10,14 @@ CFG-combine + update kernel; the text K/V and modulation vectors are built once 
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from typing import List, Optional
 
 import torch
 
 from . import _lib, schedules
 from ._lib import DittoError
-from .model import DiTTO, _need_cuda_f32, _ptr, _stream
+from .model import DiTTO, _check_t_range, _need_cuda_f32, _ptr, _stream
 
 __all__ = ["DiTTOSampler", "StepGraph"]
 
@@ -24,10 +25,11 @@ __all__ = ["DiTTOSampler", "StepGraph"]
 class StepGraph:
     """One sampler iteration captured as a CUDA graph and replayed once per step.
 
-    The graph holds: (optional) the step's noise draw, the 2B-sequence forward, the fused CFG + DDPM update
-    (in place on ``x``) and the decrement of the device-resident step index ``t`` -- so the host issues ONE
-    launch per denoising step instead of ~70.  All buffers the graph touches are owned here (or pinned by
-    reference) so that the captured pointers stay valid."""
+    The graph holds the 2B-sequence forward and the fused CFG + DDPM update (in place on ``x``); when the noise is not
+    supplied by the caller that same kernel draws it (Philox, ``ditto_p_sample_rng``) and, as its last act, decrements
+    the device-resident step index ``t`` and bumps the draw counter -- so the host issues ONE launch per denoising step
+    instead of ~70 and the graph contains kernels of libditto_b200 only.  All buffers the graph touches are owned here
+    (or pinned by reference) so that the captured pointers stay valid."""
 
     def __init__(self, sampler: "DiTTOSampler", B: int, T: int, S: int, guided: bool, w: float, ctx: torch.Tensor,
                  draw_noise: bool, device):
@@ -35,15 +37,16 @@ class StepGraph:
         H = m.hidden_dim
         n = 2 * B if guided else B
         self.B, self.T, self.S, self.guided, self.w, self.draw_noise = B, T, S, guided, w, draw_noise
-        self.x = torch.empty((B, T, H), dtype=torch.float32, device=device)
-        self.z = torch.empty((B, T, H), dtype=torch.float32, device=device)
+        self.x = torch.zeros((B, T, H), dtype=torch.float32, device=device)
+        # caller-supplied noise lands here; drawn noise never touches HBM
+        self.z = None if draw_noise else torch.zeros((B, T, H), dtype=torch.float32, device=device)
+        self.rng = torch.zeros((4,), dtype=torch.int64, device=device)   # {seed, draw counter, ticket, -} of ditto_p_sample_rng
         self.eps = torch.empty((n, T, H), dtype=torch.float32, device=device)
         self.t = torch.zeros((n,), dtype=torch.int64, device=device)
         self.ctx = ctx
         self.ws = m.workspace(n, T, S)
         self.launches_per_step = 0
-        self.x.zero_()
-        self.z.zero_()
+        self._sampler_model = m
         # eager warm-up (engine set-up, lazy initialisation) on a side stream, then capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
@@ -59,17 +62,27 @@ class StepGraph:
         self._keys = (self.ctx.data_ptr(), self.ws.data_ptr())
 
     def _step(self, sampler):
-        if self.draw_noise:
-            self.z.normal_()                      # drawn every step incl. t = 0, like the reference's randn_like
+        if self.draw_noise:   # drawn every step incl. t = 0, like the reference's randn_like (SpeechGenerator.py:145)
+            m = self._sampler_model
+            with torch.cuda.device(self.x.device):
+                _lib.check(_lib.load().ditto_p_sample_rng(m.engine(), _ptr(self.x), _ptr(self.ctx), _ptr(self.t), _ptr(self.rng),
+                                                          1 if self.guided else 0, float(self.w), self.B, self.T, self.S,
+                                                          _ptr(self.eps), _ptr(self.x), _ptr(self.ws), self.ws.numel(), 1, _stream()),
+                           "ditto_p_sample_rng")
+            return
         sampler._p_sample_raw(self.x, self.ctx, self.t, self.z, self.guided, self.w, self.S, self.eps, self.x, ws=self.ws)
         self.t.sub_(1)
 
     def valid_for(self, ctx: torch.Tensor, ws: torch.Tensor) -> bool:
         return self._keys == (ctx.data_ptr(), ws.data_ptr())
 
-    def reset(self, x_init: torch.Tensor, t_start: int):
+    def reset(self, x_init: torch.Tensor, t_start: int, seed: Optional[int] = None):
         self.x.copy_(x_init)
         self.t.fill_(t_start)
+        if self.draw_noise:   # fresh seed per sampling job (from torch's CPU generator: torch.manual_seed makes runs repeatable)
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self.rng.copy_(torch.tensor([seed, 0, 0, 0], dtype=torch.int64), non_blocking=False)
 
     def replay(self):
         self.graph.replay()
@@ -103,7 +116,11 @@ class DiTTOSampler:
             self.update_table = schedules.coef_table(steps, taus, coef)
         self._variant = self.update_table is not None or schedule_scale is not None
         self._tau_dev = None
-        self._graphs = {}
+        # captured step graphs pin x / eps / a private memory pool (hundreds of MB at B = 16, T = 750) and TTS serving sees a
+        # new predicted length on almost every request: keep the few most recently used shapes only
+        self.max_cached_graphs = 4
+        self._graphs = OrderedDict()
+        self._ragged_graphs = OrderedDict()
         self._activate()
 
     def _activate(self):
@@ -170,6 +187,7 @@ class DiTTOSampler:
         self._activate()
         ctx = self._context(text_emb, guided, null_text_emb, T)
         t = t.to(device=x.device, dtype=torch.int64)
+        _check_t_range(t, self.model.diffusion_steps, "p_sample")
         t_n = (torch.cat([t, t]) if guided else t).contiguous()
         z = torch.randn_like(x) if noise is None else _need_cuda_f32("noise", noise)
         eps = torch.empty((t_n.numel(), T, H), dtype=torch.float32, device=x.device)
@@ -183,8 +201,13 @@ class DiTTOSampler:
         g = self._graphs.get(key)
         n = 2 * B if guided else B
         if g is None or not g.valid_for(ctx, self.model.workspace(n, T, S)):
+            self._graphs.pop(key, None)
+            while len(self._graphs) >= self.max_cached_graphs:
+                self._graphs.popitem(last=False)          # least recently used; its buffers and graph pool are released
             g = StepGraph(self, B, T, S, guided, float(w), ctx, draw_noise, device)
             self._graphs[key] = g
+        else:
+            self._graphs.move_to_end(key)
         return g
 
     @torch.no_grad()
@@ -258,7 +281,12 @@ class DiTTOSampler:
         m = self.model
         w = self.guidance_scale if guidance_scale is None else guidance_scale
         guided = w is not None
-        rb = RaggedBatch(m, texts, lengths, guided=guided, null_texts=null_texts)
+        # graphs (and the text-context buffers their kernels read) are cached per batch signature: a new batch with the same
+        # (frames, tokens, count) groups re-fills the cached context buffers instead of capturing again
+        sig = RaggedBatch.signature(texts, lengths, guided)
+        cached = self._ragged_graphs.get(sig) if (use_graph and record is None) else None
+        rb = RaggedBatch(m, texts, lengths, guided=guided, null_texts=null_texts,
+                         ctx_storage=cached[0] if cached is not None else None)
         dev, H, steps = rb.device, m.hidden_dim, m.diffusion_steps
         self._activate()
         taus = self.timesteps.tolist()
@@ -274,7 +302,19 @@ class DiTTOSampler:
                 z = _need_cuda_f32(f"noise[{i}]", z)
                 zs[:, rb.x_offset[i]:rb.x_offset[i] + rb.lengths[i]] = z
         if use_graph and record is None:
-            g = RaggedStepGraph(rb, w if guided else 0.0, zs is None)
+            wv, draw = (w if guided else 0.0), zs is None
+            g = cached[1].get((float(wv), draw)) if cached is not None else None
+            if g is None or not g.valid_for(rb):
+                g = RaggedStepGraph(rb, wv, draw)
+                if cached is None:
+                    while len(self._ragged_graphs) >= self.max_cached_graphs:
+                        self._ragged_graphs.popitem(last=False)
+                    cached = (rb._ctx, {})
+                    self._ragged_graphs[sig] = cached
+                cached[1][(float(wv), draw)] = g
+            else:
+                g.rebind(rb)
+            self._ragged_graphs.move_to_end(sig)
             g.reset(x, taus[0])
             for t_val in taus:
                 if zs is not None:

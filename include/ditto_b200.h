@@ -49,6 +49,8 @@ enum {
   DITTO_F_FUSED_ROPE = 1 << 0, /* RoPE fused into the QKV GEMM epilogue (column-permuted weights) */
   DITTO_F_FOLD_CROSS = 1 << 1, /* fold cross-attn q/out projections into the per-utterance text K/V */
   DITTO_F_FUSED_ATTN = 1 << 2, /* scores + softmax in one cluster kernel (fp32 scores never leave TMEM)   */
+  DITTO_F_BLOCKS_ONLY = 1 << 4, /* the engine holds DiT blocks only (keys "blocks.i.*"): a stand-alone components/DiT.py module;
+                                   ditto_dit_block / ditto_text_context work, ditto_forward / ditto_p_sample do not        */
   DITTO_F_DEFER_LN = 1 << 3    /* block LayerNorms (DiT.py:105,143,151) folded into the neighbouring GEMMs: the producer
                                   epilogue emits bf16(h) + per-row partial (sum, sum of squares), gamma/beta live in the
                                   consumer's weights/bias and its epilogue applies rstd / mean (needs DITTO_F_FUSED_ROPE)  */
@@ -89,6 +91,9 @@ int32_t ditto_profile_get(int32_t i, int64_t* launches, double* total_ms, double
  * receive SM clock cycles summed over CTA pairs: [0] MMA issuer waiting for operands, [1] waiting for a drained
  * accumulator, [2] MMA issuer total; [3] TMA producer waiting for a free ring slot, [4] TMA producer total. */
 int32_t ditto_debug_set_counters(uint64_t* counters);
+/* Developer A/B switches of the kernels (tools/, tests/; all 0 = the product path, "reset" restores that).  The library
+ * never reads the environment.  Engine-level options are sampled by ditto_engine_create.  Names: DESIGN.md section 9. */
+int32_t ditto_debug_option(const char* name, int32_t value);
 
 /* ---- engine life cycle == DiTTO.__init__ + load_state_dict (src/model/DiTTO.py:10-64) -------------- */
 int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out);
@@ -145,6 +150,23 @@ int32_t ditto_p_sample(ditto_engine_t* e, const float* x, const void* ctx, const
                        float* eps_scratch, float* x_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
+/* The same with the step's noise z = randn_like(x) (SpeechGenerator.py:145) drawn INSIDE the fused update kernel: Philox4x32-10
+ * + Box-Muller, element i of draw k of seed s always gets the same normal.  rng: device uint64[4] = {seed, draw counter,
+ * 0 (ticket, owned by the kernel), reserved}; t is read-write here.  advance != 0: when the update is done the kernel adds 1 to
+ * the draw counter and subtracts 1 from every t[i] (i < n_seq) -- the bookkeeping of `for t_val in reversed(range(steps))`
+ * (SpeechGenerator.py:161-162) -- so that ONE captured CUDA graph of this call can be replayed step after step and contains
+ * kernels of this library only. */
+int32_t ditto_p_sample_rng(ditto_engine_t* e, const float* x, const void* ctx, int64_t* t, uint64_t* rng, int32_t guided,
+                           float guidance_scale, int64_t B, int64_t T, int64_t S, float* eps_scratch, float* x_out,
+                           void* workspace, int64_t workspace_bytes, int32_t advance, void* stream);
+/* ditto_cfg_ddpm_update with in-kernel noise; t [n_t] (n_t >= B; all n_t entries are decremented when advance != 0). */
+int32_t ditto_cfg_ddpm_update_rng(ditto_engine_t* e, const float* eps_c, const float* eps_u, const float* x, uint64_t* rng,
+                                  int64_t* t, int64_t n_t, float guidance_scale, float* x_out, int64_t B,
+                                  int64_t elems_per_seq, int32_t advance, void* stream);
+/* out[i] = the N(0,1) sample the update kernels draw for element elem_offset + i at the current {seed, draw counter}
+ * (elem_offset % 4 == 0, out 16-B aligned): stand-alone randn on the library's stream of numbers; parity tests. */
+int32_t ditto_randn(const uint64_t* rng, int64_t elem_offset, float* out, int64_t n, void* stream);
+
 /* DiTTO.q_sample (DiTTO.py:106-126) with the reference's betas-as-alphas_cumprod buffer. */
 int32_t ditto_q_sample(ditto_engine_t* e, const float* x_start, const float* noise, const int64_t* t,
                        float* out, int64_t B, int64_t elems_per_seq, void* stream);
@@ -171,6 +193,30 @@ int32_t ditto_forward_ragged(ditto_engine_t* e, const float* x, const ditto_seq_
 int32_t ditto_p_sample_ragged(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups,
                               const int64_t* t, const float* z, int32_t guided, float guidance_scale,
                               float* eps_scratch, float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ditto_p_sample_ragged with in-kernel noise (element offset = position in the packed latent buffer) and, with advance != 0,
+ * the t / draw-counter bookkeeping in a one-block kernel after the per-group updates.  t [sum n_seq] is read-write. */
+int32_t ditto_p_sample_ragged_rng(ditto_engine_t* e, const float* x, const ditto_seq_group_t* groups, int64_t n_groups,
+                                  int64_t* t, uint64_t* rng, int32_t guided, float guidance_scale, float* eps_scratch,
+                                  float* x_out, void* workspace, int64_t workspace_bytes, int32_t advance, void* stream);
+
+/* ---- block-level operators: the component signatures of src/components/DiT.py ------------------------------- */
+/* DiT.forward(x, text_emb, time_emb, rotary_pos) (DiT.py:100-157) for block `layer` of the engine: x [n_seq, T, H] -> out
+ * [n_seq, T, H] (may alias x).  time_emb is ignored by the reference block (DiT.py:100: never read); rotary_pos is the
+ * engine's own table = RotaryEmbedding.forward(T) (DiT.py:56-59).  ctx: ditto_text_context of the block's text_emb. */
+int32_t ditto_dit_block(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T,
+                        int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* GlobalAdaLN.forward(x, time_emb, text_emb) (DiT.py:25-40), no engine needed: x [n_seq, T, H], time_emb [n_seq, time_dim],
+ * text_emb [n_seq, S, text_dim]; w_time [2H, time_dim], b_time [2H] = time_mlp.1.*; w_text [2H, text_dim], b_text [2H] =
+ * text_mlp.1.*; out [n_seq, T, H] (may alias x). */
+int64_t ditto_adaln_workspace_bytes(int64_t n_seq, int64_t H, int64_t time_dim, int64_t text_dim);
+int32_t ditto_adaln(const float* x, const float* time_emb, const float* text_emb, const float* w_time, const float* b_time,
+                    const float* w_text, const float* b_text, float* out, int64_t n_seq, int64_t T, int64_t S, int64_t H,
+                    int64_t time_dim, int64_t text_dim, void* workspace, int64_t workspace_bytes, void* stream);
+/* RotaryEmbedding.apply_rope(pos, t) (DiT.py:52-54,61-72): out = t cos(pos) + rotate_half(t) sin(pos); t, out
+ * [batch, T, heads, head_dim], pos [T, head_dim] fp32 angles (RotaryEmbedding.forward's return value). */
+int32_t ditto_rope(const float* t, const float* pos, float* out, int64_t batch, int64_t T, int64_t heads, int64_t head_dim,
+                   void* stream);
 
 /* ---- single operators (unit-tested against the oracle; also usable on their own) --------------------- */
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5, biased variance; DiT.py:84,89,94).

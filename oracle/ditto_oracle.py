@@ -461,3 +461,42 @@ def forward_flops(T: int, S: int, cfg: OracleConfig) -> float:
     L(34 T H^2 + 4 T^2 H + 4 T S H) + 4 T H^2 (dead self-attn out_proj excluded)."""
     H, L = cfg.hidden_dim, cfg.num_layers
     return L * (34.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * S * H) + 4.0 * T * H * H
+
+
+# ------------------------------------------------------------------------------------------------
+# Noise stream of the fused update kernel (extension: the reference calls torch.randn_like, SpeechGenerator.py:145,
+# whose CPU and CUDA streams differ anyway).  Philox4x32-10 as published (Salmon, Moraes, Dror, Shaw: "Parallel random
+# numbers: as easy as 1, 2, 3", SC'11; Random123 known-answer vectors in tests/test_oracle_golden.py) + Box-Muller,
+# restated in numpy exactly as csrc/elementwise.cu:philox_normal4 forms it: counter = (vector index lo, hi, draw lo, hi),
+# key = (seed lo, hi); u = (r >> 8) 2^-24 + 2^-25; z = sqrt(-2 ln u0) (cos, sin)(2 pi (r1 >> 8) 2^-24), two pairs per vector.
+# ------------------------------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """counter [..., 4] uint32, key [..., 2] uint32 -> [..., 4] uint32."""
+    import numpy as np
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k = [np.asarray(key[..., i], dtype=np.uint64) for i in range(2)]
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k[0], lo1, hi0 ^ c[3] ^ k[1], lo0]
+        k = [(k[0] + W0) & MASK, (k[1] + W1) & MASK]
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_normal(seed: int, draw: int, n: int, elem_offset: int = 0):
+    """The n normals the CUDA update kernel draws for elements elem_offset .. elem_offset + n (float64 arithmetic)."""
+    import numpy as np
+    assert elem_offset % 4 == 0
+    nv = (n + 3) // 4
+    v = np.arange(nv, dtype=np.uint64) + np.uint64(elem_offset // 4)
+    ctr = np.stack([v & np.uint64(0xFFFFFFFF), v >> np.uint64(32), np.full(nv, draw & 0xFFFFFFFF, np.uint64),
+                    np.full(nv, (draw >> 32) & 0xFFFFFFFF, np.uint64)], axis=-1).astype(np.uint32)
+    key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32), (nv, 2))
+    r = philox4x32_10(ctr, key).astype(np.float64)
+    r = np.floor(r / 256.0)
+    u0, u1 = r[:, 0] * 2.0 ** -24 + 2.0 ** -25, r[:, 2] * 2.0 ** -24 + 2.0 ** -25
+    a0, a1 = r[:, 1] * (2.0 * np.pi * 2.0 ** -24), r[:, 3] * (2.0 * np.pi * 2.0 ** -24)
+    m0, m1 = np.sqrt(-2.0 * np.log(u0)), np.sqrt(-2.0 * np.log(u1))
+    z = np.stack([m0 * np.cos(a0), m0 * np.sin(a0), m1 * np.cos(a1), m1 * np.sin(a1)], axis=-1).reshape(-1)
+    return torch.from_numpy(z[:n].astype(np.float32))

@@ -30,6 +30,40 @@ def test_clock_sampler_keeps_samples_of_the_timed_region():
     assert s.summary(0.0, 1.0)["samples"] == 0
 
 
+def test_peak_choice_follows_the_sampled_clock():
+    peaks = dict(burst=1674.1, sustained=1428.7, hbm=6554.6, source="t")
+    assert bench.choose_peak(peaks, {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0}) == ("burst", 1674.1)
+    assert bench.choose_peak(peaks, {"sm_mhz": 1400.0, "sm_max_mhz": 1965.0}) == ("sustained", 1428.7)
+    assert bench.choose_peak(peaks, {"sm_mhz": None, "sm_max_mhz": None})[0] == "burst"   # no sample: the stricter denominator
+
+
+def test_workloads_follow_baseline_configs():
+    """BASELINE.json configs[3]: 256 utterances sharded 256 / N (strong scaling); configs[1]: 16 per GPU; configs[2]: 4 x 30 s."""
+    for n in (1, 2, 4, 8):
+        w = bench.workload_spec("c4", n)
+        assert w["B"] * n == 256 and w["scaling"] == "strong" and (w["T"], w["S"]) == (750, 64)
+    assert bench.workload_spec("c2", 8)["B"] == 16 and bench.workload_spec("c2", 8)["scaling"] == "weak"
+    w = bench.workload_spec("c3", 1)
+    assert (w["B"], w["T"], w["S"]) == (4, 2250, 192)
+    assert bench.workload_spec("c5", 8)["kind"] == "ragged"
+    # the default (what the driver runs) is C4
+    import argparse
+    assert "c4" in open(os.path.join(ROOT, "bench.py")).read().split('"--workload"')[1].split(")")[0]
+
+
+def test_traffic_is_reported_only_for_the_source_it_was_captured_from(tmp_path, monkeypatch):
+    sha = bench.csrc_sha()
+    assert len(sha) == 16
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "csrc_sha", lambda: sha)
+    (prof / "traffic.json").write_text(json.dumps({"_csrc_sha": "stale", "tc_gemm.glu": 1.5e8}))
+    assert bench.traffic_for("tc_gemm.glu")[0] is None
+    (prof / "traffic.json").write_text(json.dumps({"_csrc_sha": sha, "tc_gemm.glu": 1.5e8}))
+    assert bench.traffic_for("tc_gemm.glu")[0] == 1.5e8
+
+
 def test_traffic_file_names_known_profile_classes():
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
         t = json.load(f)

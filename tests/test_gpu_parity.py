@@ -290,7 +290,7 @@ def test_full_size_batch_properties_bf16(dev):
 @pytest.mark.parametrize("B,T,S", [(2, 750, 64), (3, 130, 5), (1, 1, 1), (2, 257, 33), (1, 128, 64)])
 def test_fused_cross_attention_block(dev, B, T, S):
     """cross_fused.cu (scores + softmax + P.V + residual + norm3 in one kernel) against the oracle and against the
-    separate-kernel composition (DITTO_NO_FUSED_CROSS=1), default single-head model, bf16 path."""
+    separate-kernel composition (debug option no_fused_cross), default single-head model, bf16 path."""
     cfg = O.OracleConfig(768, 2, 1, 256, 768, 50)
     sd = O.make_state_dict(cfg, 21)
     x, text, _ = O.make_inputs(B, T, S, cfg, 22)
@@ -298,22 +298,23 @@ def test_fused_cross_attention_block(dev, B, T, S):
     want = O.ditto_forward(sd, cfg, x, text, t)
     outs = {}
     for fused in (True, False):
-        os.environ["DITTO_NO_FUSED_CROSS"] = "0" if fused else "1"
+        _lib.debug_option("no_fused_cross", 0 if fused else 1)
         try:
             m = build_model(cfg, sd, "bf16", dev)
             _lib.profile_start()
             outs[fused] = m(x.to(dev), text.to(dev), t.to(dev))
             prof = _lib.profile_stop()
         finally:
-            os.environ.pop("DITTO_NO_FUSED_CROSS", None)
+            _lib.debug_option("reset", 0)
         assert ("tc_gemm.cross_fused_ln" in prof) == fused, sorted(prof)
         assert ("tc_gemm.cross_pv" in prof) == (not fused)
         assert rel(outs[fused], want) <= BAR["bf16"]
     assert rel(outs[True], outs[False]) <= 6e-3     # same operands, different rounding points of P / LN statistics
 
 
-@pytest.mark.parametrize("env", [{"DITTO_XF_ROWS": "88"}, {"DITTO_DEFER_LN2": "1"}, {"DITTO_ROPE_GENERIC": "1", "DITTO_GLU_GENERIC": "1"},
-                                 {"DITTO_NO_PV_PERM4": "1"}], ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
+@pytest.mark.parametrize("env", [{"xf_rows": 88}, {"defer_ln2": 1}, {"rope_generic": 1, "glu_generic": 1}, {"no_pv_perm4": 1},
+                                 {"no_flash768": 1}, {"no_fused_ln": 1}],
+                         ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
 def test_kernel_variants_behind_switches(dev, env):
     """Every developer switch of DESIGN.md section 9 selects a different kernel / weight packing for the same arithmetic: each
     must stay within the bf16 bar of the oracle and within rounding of the default build (C2 width, ragged T, S = 40)."""
@@ -323,12 +324,12 @@ def test_kernel_variants_behind_switches(dev, env):
     t = torch.tensor([49, 0])
     want = O.ditto_forward(sd, cfg, x, text, t)
     base = build_model(cfg, sd, "bf16", dev)(x.to(dev), text.to(dev), t.to(dev))
-    os.environ.update(env)
+    for k, v in env.items():
+        _lib.debug_option(k, v)
     try:
         got = build_model(cfg, sd, "bf16", dev)(x.to(dev), text.to(dev), t.to(dev))
     finally:
-        for k in env:
-            os.environ.pop(k, None)
+        _lib.debug_option("reset", 0)
     assert rel(got, want) <= BAR["bf16"]
     assert rel(base, want) <= BAR["bf16"]
     assert rel(got, base) <= 8e-3
@@ -338,7 +339,7 @@ def test_kernel_variants_behind_switches(dev, env):
                                                 (1, 128, 5, 192, 3)])
 def test_flash_attention_d64(dev, B, T, S, hidden, heads):
     """flash_attn.cu (head_dim 64: two-pass attention, scores and probabilities never in HBM) against the oracle and
-    against the GEMM formulation (DITTO_NO_FLASH=1): multi-head models, ragged T, partial key tiles."""
+    against the GEMM formulation (debug option no_flash): multi-head models, ragged T, partial key tiles."""
     cfg = O.OracleConfig(hidden, 2, heads, 64, hidden, 20)
     sd = O.make_state_dict(cfg, 51)
     x, text, _ = O.make_inputs(B, T, S, cfg, 52)
@@ -346,14 +347,14 @@ def test_flash_attention_d64(dev, B, T, S, hidden, heads):
     want = O.ditto_forward(sd, cfg, x, text, t)
     outs = {}
     for flash in (True, False):
-        os.environ["DITTO_NO_FLASH"] = "0" if flash else "1"
+        _lib.debug_option("no_flash", 0 if flash else 1)
         try:
             m = build_model(cfg, sd, "bf16", dev)
             _lib.profile_start()
             outs[flash] = m(x.to(dev), text.to(dev), t.to(dev))
             prof = _lib.profile_stop()
         finally:
-            os.environ.pop("DITTO_NO_FLASH", None)
+            _lib.debug_option("reset", 0)
         assert ("tc_gemm.flash_attn" in prof) == flash, sorted(prof)
         assert ("tc_gemm.self_pv" in prof) == (not flash)
         assert bool(torch.isfinite(outs[flash]).all())

@@ -7,6 +7,9 @@ import torch
 
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from ditto_tts_b200 import _lib  # noqa: E402
+from _opts import apply_opts  # noqa: E402
+
+apply_opts()   # --opt name=value -> ditto_debug_option
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 M, N, K = (int(a) for a in args[:3]) if len(args) >= 3 else (24000, 2304, 768)

@@ -1,8 +1,8 @@
 #!/bin/bash
 # mainloop experiments: big square GEMM and the hot shapes, 1-CTA vs pair, ring depth sweep
 for shape in "8192 8192 8192" "24000 2304 768" "24000 768 3072"; do
-  for st in 2 3 4 5 6; do echo -n "pair stages=$st  "; DITTO_STAGES_PAIR=$st python tools/gemm_bench.py $shape --iters 20 | tail -1; done
-  for st in 2 3 4; do echo -n "1cta stages=$st  "; DITTO_NO_PAIR=1 DITTO_STAGES_1CTA=$st python tools/gemm_bench.py $shape --iters 20 | tail -1; done
+  for st in 2 3 4 5 6; do echo -n "pair stages=$st  "; python tools/gemm_bench.py $shape --iters 20 --opt stages_pair=$st | tail -1; done
+  for st in 2 3 4; do echo -n "1cta stages=$st  "; python tools/gemm_bench.py $shape --iters 20 --opt no_pair=1 --opt stages_1cta=$st | tail -1; done
 done
 python - <<'PY'
 import torch

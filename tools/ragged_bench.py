@@ -17,6 +17,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ditto_tts_b200 as D  # noqa: E402
 from ditto_tts_b200 import parallel  # noqa: E402
 from ditto_tts_b200.ragged import RaggedBatch, RaggedStepGraph  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _opts import apply_opts  # noqa: E402
+
+apply_opts()   # --opt name=value -> ditto_debug_option
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--utts", type=int, default=256)

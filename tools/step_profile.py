@@ -10,6 +10,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ditto_tts_b200 as D  # noqa: E402
 from ditto_tts_b200 import _lib  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _opts import apply_opts  # noqa: E402
+
+OPTS = apply_opts()   # --opt name=value -> ditto_debug_option (before the engine is created)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
@@ -48,14 +52,13 @@ ms = e0.elapsed_time(e1) / K
 flops = n * (a.layers * (34.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * S * H) + 4.0 * T * H * H)
 print(f"graph step: {ms:.3f} ms  -> {B * T / ms * 1e3:.0f} frames/s/step, {flops / ms / 1e9:.0f} algorithmic TFLOP/s "
       f"({graph.launches_per_step} launches/step)")
-t_all = torch.arange(K - 1, -1, -1, device=dev, dtype=torch.int64).unsqueeze(1).repeat(1, n).contiguous()
-eps = torch.empty((n, T, H), dtype=torch.float32, device=dev)
-xe, z = x0.clone(), torch.empty_like(x0)
+from ditto_tts_b200.model import _ptr, _stream  # noqa: E402
+graph.reset(x0, K - 1)
 _lib.profile_start()
 P = min(K, 3)
-for i in range(P):
-    z.normal_()
-    s._p_sample_raw(xe, ctx, t_all[i], z, True, 3.0, S, eps, xe)
+for i in range(P):   # the graph's own step, un-graphed: forward + fused CFG / DDPM update with in-kernel noise
+    _lib.check(_lib.load().ditto_p_sample_rng(m.engine(), _ptr(graph.x), _ptr(graph.ctx), _ptr(graph.t), _ptr(graph.rng), 1, 3.0, B, T, S,
+                                              _ptr(graph.eps), _ptr(graph.x), _ptr(graph.ws), graph.ws.numel(), 1, _stream()))
 prof = _lib.profile_stop()
 tot = sum(v["ms"] for v in prof.values())
 print(f"{'class':<24s}{'launches/step':>14s}{'ms/step':>10s}{'us/launch':>11s}{'TFLOP/s':>9s}{'GB/s':>8s}{'share':>7s}")
