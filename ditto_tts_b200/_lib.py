@@ -67,6 +67,7 @@ SIGNATURES = {
     "ditto_adaln_workspace_bytes": (_I64, [_I64, _I64, _I64, _I64]),
     "ditto_adaln": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
     "ditto_rope": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "ditto_attn_self768": (_I32, [_P, _I64, _I64, _I64, _F, _P, _P, _P, _P, _I32, _P]),
     "ditto_layernorm": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _P]),
     "ditto_gemm_f32": (_I32, [_P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64, _I64, _P, _P, _F, _I64, _I64, _I64,
                               _I64, _P]),

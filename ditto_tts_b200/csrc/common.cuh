@@ -55,7 +55,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 enum ProfClass {
   PC_TC_PROJ_IN = 0, PC_TC_QKV, PC_TC_SELF_SCORES, PC_TC_SELF_PV, PC_TC_CROSS_Q, PC_TC_CROSS_SCORES, PC_TC_CROSS_PV,
   PC_TC_CROSS_OUT, PC_TC_GLU, PC_TC_FC2, PC_TC_PROJ_OUT, PC_TC_TEXT_KV, PC_TC_OTHER,
-  PC_SGEMM, PC_LAYERNORM, PC_ADALN, PC_ROPE, PC_SOFTMAX, PC_CFG_UPDATE, PC_ELEMENTWISE, PC_TC_CROSS_FUSED, PC_FLASH_ATTN, PC_COUNT
+  PC_SGEMM, PC_LAYERNORM, PC_ADALN, PC_ROPE, PC_SOFTMAX, PC_CFG_UPDATE, PC_ELEMENTWISE, PC_TC_CROSS_FUSED, PC_FLASH_ATTN, PC_FLASH768, PC_COUNT
 };
 extern bool g_prof_enabled;
 struct ProfScope {  // records start/stop events around the launches issued in its lifetime (no-op unless enabled)
@@ -97,6 +97,20 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f +
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ---- warp-uniform control (single-thread-issue roles) ----------------------------------------------
+// tcgen05.mma / cp.async.bulk.tensor / tcgen05.commit take their operands from UNIFORM registers.  When the issuing code sits
+// inside `if (lane == 0)`, every operand lives in a vector register of a divergent region and the compiler wraps each
+// instruction in a "waterfall" (ELECT + five R2UR.BROADCAST + loop): ~21 SASS instructions per MMA, more than a 64- or
+// 128-cycle MMA lasts -- the issuer, not the tensor pipe, paced the kernels (ncu: 33 % tensor-active in flash_attn768 with the
+// issuing warp never waiting on a barrier).  Instead the WHOLE warp runs the role's loops on provably warp-uniform values
+// (warp index through a shuffle, constants, kernel parameters) and one elected lane executes the instruction.
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {   // one lane of the (fully converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -12,7 +12,7 @@
 // Per CTA (640 threads, persistent over 128-row tiles; a tile never crosses an utterance):
 //   warp 0   TMA producer of the MMA operands: u tile [128 x H] and K-fold [64 x H] through a 2-stage ring (64-column
 //            k-blocks, 128-B swizzle); per output half-chunk one V-fold box [64 k x 64 n] (MN-major operand, ring of 3)
-//   warp 1   MMA issuer:  scores S[128 x 64] = U Kf^T (tcgen05.mma, fp32 in TMEM, two buffers; the NEXT tile's scores are
+//   warp 1   MMA issuer (whole warp on warp-uniform values, one elected lane issues):  scores S[128 x 64] = U Kf^T (tcgen05.mma, fp32 in TMEM, two buffers; the NEXT tile's scores are
 //            issued right after the current tile's P.V, so their operand stream overlaps the rest of the epilogue without
 //            sitting in front of the P.V);  O chunk c [128 x 128] = P[128 x 64] Vf[64 x 128c..] as two N = 64 MMAs into a
 //            ring of three 128-column TMEM buffers
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
   float2* stat = reinterpret_cast<float2*>(smem + XF_OFF_STAT);
   static_assert((2 * XF_STAGES + 2 + 2 + 1 + 2 * XF_VF_RING + 2 * XF_O_BUFS + 3 * XF_NB) * 8 + 4 <= XF_BAR_BYTES, "barrier block too small");
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();   // control warps run on warp-uniform values, one elected lane issues (common.cuh: elect_one)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
   if (warp == 0) {
     // =========================== TMA producer: MMA operands ===========================
     xf_regs_ctrl();
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t vc = 0;  // V-fold boxes loaded so far
@@ -192,10 +193,13 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         const int seq = tile / p.m_tiles, mb = tile - seq * p.m_tiles;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * XF_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], stage_tx);
-          tma_load_4d(&tmap_u, &full_bar[stage], sa, kb * XF_BK, mb * p.rt, 0, seq);
-          tma_load_4d(&tmap_kf, &full_bar[stage], sa + XF_A_BYTES, kb * XF_BK, 0, 0, seq);  // rows >= S: zero-filled
+          if (leader) {
+            uint8_t* sa = smem + stage * XF_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_4d(&tmap_u, &full_bar[stage], sa, kb * XF_BK, mb * p.rt, 0, seq);
+            tma_load_4d(&tmap_kf, &full_bar[stage], sa + XF_A_BYTES, kb * XF_BK, 0, 0, seq);  // rows >= S: zero-filled
+          }
+          __syncwarp();
           if (++stage == XF_STAGES) { stage = 0; phase ^= 1u; }
         }
       };
@@ -206,9 +210,12 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         for (int hc = 0; hc < p.num_hc; ++hc, ++vc) {
           const uint32_t vs = vc % XF_VF_RING;
           mbar_wait(&vf_empty[vs], ((vc / XF_VF_RING) & 1u) ^ 1u);  // the MMAs that read this box have retired
-          mbar_expect_tx(&vf_full[vs], XF_VF_BOX);
-          // [64 k-rows x 64 n] box, n contiguous (MN-major operand); rows >= Sp zero-filled
-          tma_load_4d(&tmap_vf, &vf_full[vs], vf_smem + vs * XF_VF_BOX, hc * XF_HC, 0, 0, seq);
+          if (leader) {
+            mbar_expect_tx(&vf_full[vs], XF_VF_BOX);
+            // [64 k-rows x 64 n] box, n contiguous (MN-major operand); rows >= Sp zero-filled
+            tma_load_4d(&tmap_vf, &vf_full[vs], vf_smem + vs * XF_VF_BOX, hc * XF_HC, 0, 0, seq);
+          }
+          __syncwarp();
         }
         if (tile + step < p.num_tiles) load_scores_operands(tile + step);
       }
@@ -216,9 +223,13 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
   } else if (warp == 1) {
     // =========================== MMA issuer (single thread) ===========================
     xf_regs_ctrl();
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_bf16(XF_BM, XF_NS, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(XF_BM, XF_HC, false, true);
+      const uint64_t ds0 = umma_smem_desc(smem_u32(smem), 16, 1024);               // ring slot 0, K-major
+      const uint64_t dp0 = umma_smem_desc(smem_u32(p_smem), 16, 1024);
+      const uint64_t dv0 = umma_smem_desc(smem_u32(vf_smem), XF_VF_BOX, 1024);     // MN-major V-fold box 0
       int stage = 0;
       uint32_t phase = 0;
       auto issue_scores = [&](uint32_t j) {  // scores of this CTA's j-th tile into score buffer j & 1
@@ -229,19 +240,21 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * XF_STAGE_BYTES);
-          const uint32_t sbm = sa + XF_A_BYTES;
+          if (leader) {
+            const uint64_t da = ds0 + static_cast<uint64_t>((stage * XF_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < XF_BK / 16; ++k)
-            umma_bf16(d_tmem, umma_smem_desc(sa + k * 32, 16, 1024), umma_smem_desc(sbm + k * 32, 16, 1024), idesc_s, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < XF_BK / 16; ++k)
+              umma_bf16(d_tmem, da + ((k * 32) >> 4), da + ((XF_A_BYTES + k * 32) >> 4), idesc_s, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == XF_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&s_full[sb]);
+        if (leader) umma_commit(&s_full[sb]);
+        __syncwarp();
       };
       uint32_t it = 0, oc = 0, vc = 0;
       if (first < p.num_tiles) issue_scores(0);
-      const uint32_t pa = smem_u32(p_smem);
       for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
         mbar_wait(p_full, it & 1u);
         for (int hc = 0; hc < p.num_hc; ++hc, ++vc) {
@@ -249,17 +262,17 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
           mbar_wait(&vf_full[vs], (vc / XF_VF_RING) & 1u);
           if ((hc & 1) == 0) mbar_wait(&o_empty[ob], ((oc / XF_O_BUFS) & 1u) ^ 1u);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + ob * XF_CH + (hc & 1) * XF_HC;
-          const uint32_t vb = smem_u32(vf_smem) + vs * XF_VF_BOX;
+          if (leader) {
+            const uint32_t d_tmem = tmem_base + ob * XF_CH + (hc & 1) * XF_HC;
+            const uint64_t dv = dv0 + static_cast<uint64_t>((vs * XF_VF_BOX) >> 4);
 #pragma unroll
-          for (int k = 0; k < XF_NS / 16; ++k)
-            umma_bf16(d_tmem, umma_smem_desc(pa + k * 32, 16, 1024), umma_smem_desc(vb + k * (16 * 128), XF_VF_BOX, 1024), idesc_o,
-                      k != 0 ? 1u : 0u);
-          umma_commit(&vf_empty[vs]);  // the box (and, after the last one, P) may be overwritten once these MMAs retire
-          if (hc & 1) {
-            umma_commit(&o_full[ob]);
-            ++oc;
+            for (int k = 0; k < XF_NS / 16; ++k)
+              umma_bf16(d_tmem, dp0 + ((k * 32) >> 4), dv + ((k * (16 * 128)) >> 4), idesc_o, k != 0 ? 1u : 0u);
+            umma_commit(&vf_empty[vs]);  // the box (and, after the last one, P) may be overwritten once these MMAs retire
+            if (hc & 1) umma_commit(&o_full[ob]);
           }
+          __syncwarp();
+          if (hc & 1) ++oc;
         }
         // the next tile's scores AFTER this tile's P.V (the issuer is sequential: ahead of the P.V they would put their
         // operand stream on the critical path); they still overlap the rest of this tile's epilogue
@@ -273,7 +286,8 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
     // and of the stores is not paid in one serial chain: warp 2 loads (as soon as a buffer is free), warp 3 stores and
     // frees the buffers.
     xf_regs_ctrl();
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       const int my_tiles = first < p.num_tiles ? (p.num_tiles - 1 - first) / step + 1 : 0;
       const int jobs_per_tile = 2 * p.num_hc;
       const int J = my_tiles * jobs_per_tile;
@@ -290,11 +304,14 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
           int seq, row, pass, hc;
           job_coords(j, seq, row, pass, hc);
           const int b = j % XF_NB;
-          uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
           mbar_wait(&hfree[b], ((j / XF_NB) & 1u) ^ 1u);   // the store that last used this buffer has read it
-          mbar_expect_tx(&hin_full[b], static_cast<uint32_t>(p.rt) * 256);  // two slabs of rt rows x 128 B
-          tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
-          tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
+          if (leader) {
+            uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+            mbar_expect_tx(&hin_full[b], static_cast<uint32_t>(p.rt) * 256);  // two slabs of rt rows x 128 B
+            tma_load_4d(&tmap_h, &hin_full[b], buf, hc * XF_HC, row, 0, seq);
+            tma_load_4d(&tmap_h, &hin_full[b], buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
+          }
+          __syncwarp();
         }
       } else {
         for (int j = 0; j < J; ++j) {
@@ -302,27 +319,31 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
           mbar_wait(&hout_full[b], (j / XF_NB) & 1u);
           int seq, row, pass, hc;
           job_coords(j, seq, row, pass, hc);
-          const uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
-          if (pass == 0) {
-            tma_store_4d(&tmap_h, buf, hc * XF_HC, row, 0, seq);
-            tma_store_4d(&tmap_h, buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
-          } else {
-            tma_store_4d(&tmap_uo, buf, hc * XF_HC, row, 0, seq);
-          }
-          bulk_commit();
-          const int jn = j - 1 + XF_NB;  // the job that takes over the buffer of job j - 1
-          if (j >= 1 && jn < J) {
-            bulk_wait_read<1>();  // every store but the one just issued has read its source
-            // a pass-1 job re-loads what pass-0 job jn - num_hc stored, num_hc - NB + 1 groups before the newest one:
-            // that store must have COMPLETED (be visible), not just have read its source
-            if ((jn % jobs_per_tile) >= p.num_hc) {
-              if (p.num_hc - XF_NB + 1 > 8) bulk_wait<8>();
-              else bulk_wait<1>();
+          if (leader) {   // bulk async-groups belong to the issuing thread: commit / wait on the same lane
+            const uint8_t* buf = hbuf + b * XF_HBUF_BYTES;
+            if (pass == 0) {
+              tma_store_4d(&tmap_h, buf, hc * XF_HC, row, 0, seq);
+              tma_store_4d(&tmap_h, buf + XF_SLAB_BYTES, hc * XF_HC + 32, row, 0, seq);
+            } else {
+              tma_store_4d(&tmap_uo, buf, hc * XF_HC, row, 0, seq);
             }
-            mbar_arrive(&hfree[(j - 1) % XF_NB]);
+            bulk_commit();
+            const int jn = j - 1 + XF_NB;  // the job that takes over the buffer of job j - 1
+            if (j >= 1 && jn < J) {
+              bulk_wait_read<1>();  // every store but the one just issued has read its source
+              // a pass-1 job re-loads what pass-0 job jn - num_hc stored, num_hc - NB + 1 groups before the newest one:
+              // that store must have COMPLETED (be visible), not just have read its source
+              if ((jn % jobs_per_tile) >= p.num_hc) {
+                if (p.num_hc - XF_NB + 1 > 8) bulk_wait<8>();
+                else bulk_wait<1>();
+              }
+              mbar_arrive(&hfree[(j - 1) % XF_NB]);
+            }
           }
+          __syncwarp();
         }
-        bulk_wait<0>();
+        if (leader) bulk_wait<0>();
+        __syncwarp();
       }
     }
   } else if (warp >= XF_EPI_WARP0) {

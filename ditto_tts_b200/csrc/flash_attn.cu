@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_empty + 1);
   static_assert((2 + 2 * FA_K_STAGES + 2 * FA_V_STAGES + 4 + 2 * FA_P_BUFS + 2) * 8 + 4 <= 256, "barrier block too small");
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();   // control warps run on warp-uniform values, one elected lane issues (common.cuh: elect_one)
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -115,54 +115,70 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   if (warp == 0) {
     // =========================== TMA producer ===========================
     regs_shrink_ctrl();
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       uint32_t it = 0, kc = 0, vc = 0;
       for (int item = first; item < p.num_items; item += step, ++it) {
         const int qt = item % p.m_tiles;
         const int sh = item / p.m_tiles;
         const int head = sh % p.heads, seq = sh / p.heads;
         mbar_wait(q_empty, (it & 1u) ^ 1u);
-        mbar_expect_tx(q_full, FA_Q_BYTES);
-        tma_load_4d(&tmap_q, q_full, q_smem, 0, qt * FA_BM, head, seq);
+        if (leader) {
+          mbar_expect_tx(q_full, FA_Q_BYTES);
+          tma_load_4d(&tmap_q, q_full, q_smem, 0, qt * FA_BM, head, seq);
+        }
+        __syncwarp();
         for (int pass = 0; pass < 2; ++pass)
           for (int kt = 0; kt < KT; ++kt) {
             const uint32_t ks = kc % FA_K_STAGES;
             mbar_wait(&k_empty[ks], ((kc / FA_K_STAGES) & 1u) ^ 1u);
-            mbar_expect_tx(&k_full[ks], FA_K_BYTES);
-            tma_load_4d(&tmap_k, &k_full[ks], k_smem + ks * FA_K_BYTES, 0, kt * FA_BN, head, seq);   // keys >= Tk: zero-filled
+            if (leader) {
+              mbar_expect_tx(&k_full[ks], FA_K_BYTES);
+              tma_load_4d(&tmap_k, &k_full[ks], k_smem + ks * FA_K_BYTES, 0, kt * FA_BN, head, seq);   // keys >= Tk: zero-filled
+            }
+            __syncwarp();
             ++kc;
             if (pass == 1) {
               const uint32_t vs = vc % FA_V_STAGES;
               mbar_wait(&v_empty[vs], ((vc / FA_V_STAGES) & 1u) ^ 1u);
-              mbar_expect_tx(&v_full[vs], FA_V_BYTES);
-              // two [64 key-rows x 64 n] boxes, n contiguous (MN-major operand)
-              tma_load_4d(&tmap_v, &v_full[vs], v_smem + vs * FA_V_BYTES, 0, kt * FA_BN, head, seq);
-              tma_load_4d(&tmap_v, &v_full[vs], v_smem + vs * FA_V_BYTES + 64 * 128, 0, kt * FA_BN + 64, head, seq);
+              if (leader) {
+                mbar_expect_tx(&v_full[vs], FA_V_BYTES);
+                // two [64 key-rows x 64 n] boxes, n contiguous (MN-major operand)
+                tma_load_4d(&tmap_v, &v_full[vs], v_smem + vs * FA_V_BYTES, 0, kt * FA_BN, head, seq);
+                tma_load_4d(&tmap_v, &v_full[vs], v_smem + vs * FA_V_BYTES + 64 * 128, 0, kt * FA_BN + 64, head, seq);
+              }
+              __syncwarp();
               ++vc;
             }
           }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread) ===========================
+    // =========================== MMA issuer (whole warp on warp-uniform values, one elected lane issues) ===========================
     regs_shrink_ctrl();
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(FA_BM, FA_D, false, true);
-      const uint32_t qa = smem_u32(q_smem);
+      const uint64_t dq = umma_smem_desc(smem_u32(q_smem), 16, 1024);
+      const uint64_t dk0 = umma_smem_desc(smem_u32(k_smem), 16, 1024);
+      const uint64_t dp0 = umma_smem_desc(smem_u32(p_smem), 16, 1024);
+      const uint64_t dv0 = umma_smem_desc(smem_u32(v_smem), 64 * 128, 1024);
       uint32_t it = 0, kc = 0, vc = 0, sc = 0, pc = 0;
       auto issue_s = [&]() {   // next score tile of the K stream: S[sc & 1] = Q K^T
         const uint32_t ks = kc % FA_K_STAGES, sb = sc & 1u;
         mbar_wait(&k_full[ks], (kc / FA_K_STAGES) & 1u);
         mbar_wait(&s_empty[sb], ((sc >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t kb = smem_u32(k_smem + ks * FA_K_BYTES);
+        if (leader) {
+          const uint64_t dk = dk0 + static_cast<uint64_t>((ks * FA_K_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)
-          umma_bf16(tmem_base + sb * FA_BN, umma_smem_desc(qa + k * 32, 16, 1024), umma_smem_desc(kb + k * 32, 16, 1024), idesc_s,
-                    k != 0 ? 1u : 0u);
-        umma_commit(&k_empty[ks]);
-        umma_commit(&s_full[sb]);
+          for (int k = 0; k < FA_D / 16; ++k)
+            umma_bf16(tmem_base + sb * FA_BN, dq + ((k * 32) >> 4), dk + ((k * 32) >> 4), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&k_empty[ks]);
+          umma_commit(&s_full[sb]);
+        }
+        __syncwarp();
         ++kc; ++sc;
       };
       for (int item = first; item < p.num_items; item += step, ++it) {
@@ -171,25 +187,33 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         for (int kt = 0; kt < KT; ++kt) issue_s();          // pass 1: row maxima only
         issue_s();                                          // pass 2, tile 0
         for (int kt = 0; kt < KT; ++kt) {
-          if (kt + 1 < KT) issue_s();                       // the next tile's scores go ahead of this tile's P.V
-          else umma_commit(q_empty);                        // every Q K^T of the item has been issued: Q may be reloaded once they retire
+          if (kt + 1 < KT) {
+            issue_s();                                      // the next tile's scores go ahead of this tile's P.V
+          } else {
+            if (leader) umma_commit(q_empty);               // every Q K^T of the item has been issued: Q may be reloaded once they retire
+            __syncwarp();
+          }
           const uint32_t pb = pc % FA_P_BUFS, vs = vc % FA_V_STAGES;
           mbar_wait(&p_full[pb], (pc / FA_P_BUFS) & 1u);
           mbar_wait(&v_full[vs], (vc / FA_V_STAGES) & 1u);
           if (kt == 0) mbar_wait(o_empty, (it & 1u) ^ 1u);  // the previous item's O has been read
           tcgen05_fence_after();
-          const uint32_t pa = smem_u32(p_smem + pb * FA_P_BYTES), vb = smem_u32(v_smem + vs * FA_V_BYTES);
+          if (leader) {
+            const uint64_t dp = dp0 + static_cast<uint64_t>((pb * FA_P_BYTES) >> 4), dv = dv0 + static_cast<uint64_t>((vs * FA_V_BYTES) >> 4);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb)                    // two 64-key sub-tiles
+            for (int kb = 0; kb < 2; ++kb)                    // two 64-key sub-tiles
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + FA_O_COL, umma_smem_desc(pa + kb * (FA_BM * 128) + k * 32, 16, 1024),
-                        umma_smem_desc(vb + kb * (64 * 128) + k * (16 * 128), 64 * 128, 1024), idesc_o, (kt | kb | k) != 0 ? 1u : 0u);
-          umma_commit(&v_empty[vs]);
-          umma_commit(&p_empty[pb]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + FA_O_COL, dp + ((kb * (FA_BM * 128) + k * 32) >> 4), dv + ((kb * (64 * 128) + k * (16 * 128)) >> 4),
+                          idesc_o, (kt | kb | k) != 0 ? 1u : 0u);
+            umma_commit(&v_empty[vs]);
+            umma_commit(&p_empty[pb]);
+          }
+          __syncwarp();
           ++pc; ++vc;
         }
-        umma_commit(o_full);
+        if (leader) umma_commit(o_full);
+        __syncwarp();
       }
     }
   } else if (warp >= FA_EPI_WARP0) {

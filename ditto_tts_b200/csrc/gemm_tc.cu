@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();   // control warps run on warp-uniform values (see common.cuh: elect_one)
   const int lane = threadIdx.x & 31;
   const ClusterPos cp = cluster_pos(p.cm, p.cn);
   const int num_clusters = gridDim.x / cp.csize;
@@ -1152,22 +1152,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (whole warp, one elected lane issues) ===========================
     regs_shrink_ctrl();
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int st = cluster_id; st < num_super; st += num_clusters) {
-        const int sn = st % n_super;
-        const int rest = st / n_super;
-        const int smi = rest % m_super;
-        const int b = rest / m_super;
-        const int m_blk = smi * p.cm + cp.rm, n_blk = sn * p.cn + cp.rn;  // may lie past the edge: TMA zero-fills
-        const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
-        const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
-        const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int sn = st % n_super;
+      const int rest = st / n_super;
+      const int smi = rest % m_super;
+      const int b = rest / m_super;
+      const int m_blk = smi * p.cm + cp.rm, n_blk = sn * p.cn + cp.rn;  // may lie past the edge: TMA zero-fills
+      const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
+      const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
+      const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (leader) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -1194,44 +1195,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               }
             }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread) ===========================
+    // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
     regs_shrink_ctrl();
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, B_KN);
-      const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int st = cluster_id; st < num_super; st += num_clusters) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, B_KN);
+    const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
+    // operand descriptors of ring slot 0; a slot / k-step only adds to the 14-bit address field (16-byte units, no carry:
+    // shared memory ends below 256 KiB)
+    const uint64_t da0 = umma_smem_desc(smem_u32(smem), 16, 1024);
+    const uint64_t db0 = B_KN ? umma_smem_desc(smem_u32(smem) + A_STAGE_BYTES, BLOCK_K * 128, 1024)
+                              : umma_smem_desc(smem_u32(smem) + A_STAGE_BYTES, 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+        if (leader) {
+          const uint64_t da = da0 + static_cast<uint64_t>((stage * STAGE_BYTES) >> 4), db = db0 + static_cast<uint64_t>((stage * STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_KN ? umma_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                     : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, da + ((k * (UMMA_K * 2)) >> 4), db + ((B_KN ? k * (UMMA_K * 128) : k * (UMMA_K * 2)) >> 4), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
           // smem slot reusable once these MMAs retire -- announced to every CTA that may multicast into this slot
           if (cp.csize == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_mc(&empty_bar[stage], commit_mask);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= EPI_WARP0) {
     // =========================== epilogue: TMEM -> registers -> global ===========================
@@ -1337,9 +1343,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);   // provably warp-uniform (see common.cuh: elect_one)
   const int num_pairs = gridDim.x >> 1;
   const int pair_id = blockIdx.x >> 1;
 
@@ -1373,40 +1379,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   const int num_tiles = m_pairs * p.n_tiles;
 
   if (warp == 0) {
+    // TMA producer: whole warp on warp-uniform values, one elected lane issues
     regs_shrink_ctrl();
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      long long w_slot = 0;
-      const long long t_begin = (kDbgCounters && p.dbg) ? clock64() : 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-        const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
-        const int m0 = m_pair * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
-        const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (kDbgCounters && p.dbg) {
-            const long long t0 = clock64();
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            w_slot += clock64() - t0;
-          } else
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_slot = 0;
+    const long long t_begin = (kDbgCounters && p.dbg) ? clock64() : 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int n_blk = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+      const int m0 = m_pair * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+      const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        if (kDbgCounters && p.dbg) {
+          const long long t0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          w_slot += clock64() - t0;
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+        }
+        if (leader) {
           uint8_t* sa = smem + stage * P_STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
           tma_load_4d_2sm(&tmap_a, &full_bar[stage], sa, kb * BLOCK_K, m0, 0, 0);
           tma_load_4d_2sm(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, n0, 0, 0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      if (kDbgCounters && p.dbg && rank == 0) {
-        atomicAdd(p.dbg + 3, static_cast<unsigned long long>(w_slot));
-        atomicAdd(p.dbg + 4, static_cast<unsigned long long>(clock64() - t_begin));
-      }
+    }
+    if (kDbgCounters && p.dbg && rank == 0 && leader) {
+      atomicAdd(p.dbg + 3, static_cast<unsigned long long>(w_slot));
+      atomicAdd(p.dbg + 4, static_cast<unsigned long long>(clock64() - t_begin));
     }
   } else if (warp == 1) {
     regs_shrink_ctrl();
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {   // the leader CTA issues for the pair; whole warp on warp-uniform values, one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, false, false);
+      const uint64_t da0 = umma_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t db0 = umma_smem_desc(smem_u32(smem) + A_STAGE_BYTES, 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -1418,8 +1431,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           const long long t0 = clock64();
           mbar_wait(&tmem_empty[as], aphase ^ 1u);
           w_acc += clock64() - t0;
-        } else
-        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        } else {
+          mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        }
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -1427,24 +1441,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const long long t0 = clock64();
             mbar_wait(&full_bar[stage], phase);
             w_ops += clock64() - t0;
-          } else
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            mbar_wait(&full_bar[stage], phase);
           }
-          umma_commit_2sm(&empty_bar[stage]);
+          tcgen05_fence_after();
+          if (leader) {
+            const uint64_t da = da0 + static_cast<uint64_t>((stage * P_STAGE_BYTES) >> 4), db = db0 + static_cast<uint64_t>((stage * P_STAGE_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_2sm(d_tmem, da + ((k * (UMMA_K * 2)) >> 4), db + ((k * (UMMA_K * 2)) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_2sm(&tmem_full[as]);
+        if (leader) umma_commit_2sm(&tmem_full[as]);
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      if (kDbgCounters && p.dbg) {
+      if (kDbgCounters && p.dbg && leader) {
         atomicAdd(p.dbg + 0, static_cast<unsigned long long>(w_ops));
         atomicAdd(p.dbg + 1, static_cast<unsigned long long>(w_acc));
         atomicAdd(p.dbg + 2, static_cast<unsigned long long>(clock64() - t_begin));
@@ -1544,7 +1559,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stat_bar + 2);
   float* stat = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BARRIER_BYTES);  // [2][SM_MAX_CLUSTER][BLOCK_M]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   // cluster = cm tile rows x csize tile columns: CTA (rm, rank) computes query block mg * cm + rm against key tile `rank`;
   // Q blocks are multicast along a row, K blocks along a column, row maxima are exchanged along a row
@@ -1580,19 +1595,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (whole warp, one elected lane issues) ===========================
     regs_shrink_ctrl();
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters) {
-        const int m_blk = (item % m_groups) * p.cm + cp.rm;  // may lie past the last block (cluster padding): zero-filled
-        const int b = item / m_groups;
-        const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
-        const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
-        const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int m_blk = (item % m_groups) * p.cm + cp.rm;  // may lie past the last block (cluster padding): zero-filled
+      const int b = item / m_groups;
+      const int bo = b / p.batch_inner, bi = b - bo * p.batch_inner;
+      const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0;
+      const int bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (leader) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -1605,42 +1621,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (kb % p.cm == cp.rm)
               tma_load_4d_mc(&tmap_b, &full_bar[stage], sb, kb * BLOCK_K, rank * BLOCK_N, bbi, bbo, cp.col_mask);
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+    // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
     regs_shrink_ctrl();
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
-      for (int item = cluster_id; item < num_items; item += num_clusters) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
+    const uint64_t da0 = umma_smem_desc(smem_u32(smem), 16, 1024);
+    const uint64_t db0 = umma_smem_desc(smem_u32(smem) + A_STAGE_BYTES, 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint16_t commit_mask = static_cast<uint16_t>(cp.row_mask | cp.col_mask);
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+        if (leader) {
+          const uint64_t da = da0 + static_cast<uint64_t>((stage * STAGE_BYTES) >> 4), db = db0 + static_cast<uint64_t>((stage * STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, da + ((k * (UMMA_K * 2)) >> 4), db + ((k * (UMMA_K * 2)) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
           if (cp.csize == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_mc(&empty_bar[stage], commit_mask);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[as]);
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(&tmem_full[as]);
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= EPI_WARP0) {
     // =========================== softmax epilogue ===========================

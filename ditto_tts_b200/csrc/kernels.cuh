@@ -186,6 +186,20 @@ struct FlashAttnParams {
 bool flash_attn_supported(int d, int Tq, int Tk);
 int launch_flash_attn(const FlashAttnParams& p, cudaStream_t st);
 
+// ---- flash_attn768.cu: self-attention for ONE head of 768 + residual + the LayerNorm that follows, one kernel ---------
+struct Flash768Params {
+  const bf16* qkv = nullptr; int64_t ld = 0;   // [n_seq * T, ld]: q at column 0, k at 768 (both rotated), v at 1536 in the out_perm4 column order
+  int64_t n_seq = 0; int T = 0; int H = 0;
+  float alpha = 1.f;
+  float* h = nullptr;                          // [n_seq * T, 768] fp32 residual stream, updated in place
+  const float* gamma = nullptr; const float* beta = nullptr;   // LayerNorm after the attention (norm2)
+  bf16* u_out = nullptr;                       // [n_seq * T, 768] its bf16 output; nullptr: no LayerNorm stage
+  bool force_rescale = false;                  // tests: take the online-softmax rescale path whenever a tile raises the maximum
+  int tag = PC_TC_OTHER;
+};
+bool flash768_supported(int H, int heads, int T);
+int launch_flash768(const Flash768Params& p, cudaStream_t st);
+
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 // 4-D bf16 tensor map (cols, rows, inner batch, outer batch) with a (box_cols, box_rows, 1, 1) box, 128-B swizzle, zero OOB fill
 int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows);

@@ -218,6 +218,15 @@ int32_t ditto_adaln(const float* x, const float* time_emb, const float* text_emb
 int32_t ditto_rope(const float* t, const float* pos, float* out, int64_t batch, int64_t T, int64_t heads, int64_t head_dim,
                    void* stream);
 
+/* The attention core of DiT.forward for ONE head of 768 (DiT.py:117-139: softmax(alpha q k^T) v, no out_proj) + residual
+ * + the LayerNorm that follows (norm2, DiT.py:143) in one kernel; bf16 operands, fp32 accumulation / softmax / statistics.
+ * qkv [n_seq * T, ld] bf16: q at column 0 and k at column 768 (both already rotated), v at column 1536 with its columns in
+ * the order the fused QKV epilogue stores them: position 64 b + 8 kb + 2 q + e (kb < 8, q < 4, e < 2) holds column
+ * 64 b + 16 (kb / 2) + 4 q + 2 (kb % 2) + e.  h [n_seq * T, 768] fp32 in/out; u_out bf16 = LayerNorm(h) gamma + beta, or NULL.
+ * flags bit 0: take the online-softmax rescale path whenever a key tile raises a row maximum (tests). */
+int32_t ditto_attn_self768(const void* qkv, int64_t ld, int64_t n_seq, int64_t T, float alpha, float* h, const float* gamma,
+                           const float* beta, void* u_out, int32_t flags, void* stream);
+
 /* ---- single operators (unit-tested against the oracle; also usable on their own) --------------------- */
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5, biased variance; DiT.py:84,89,94).
  * gamma/beta may be NULL (no affine, DiT.py:23).  out_bf16 != 0: y is written as bf16. */
