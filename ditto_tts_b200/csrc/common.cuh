@@ -133,16 +133,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait (~4 s of SM clock): a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the box.
+// Bounded wait (~4 s of SM clock): a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the box.  No printf:
+// a call in the spin loop makes every wait an ABI call site and spills the 56-register control warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long start = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - start > 8000000000ll) {
-      printf("ditto: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
+    if ((++spins & 0x3FFu) == 0 && clock64() - start > 8000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

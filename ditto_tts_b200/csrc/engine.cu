@@ -1322,7 +1322,7 @@ int32_t ditto_attn_self768(const void* qkv, int64_t ld, int64_t n_seq, int64_t T
   DITTO_REQUIRE(qkv && h && n_seq > 0 && T > 0 && T < (1ll << 30), DITTO_E_BADARG, "attn_self768: bad argument");
   Flash768Params f;
   f.qkv = static_cast<const bf16*>(qkv); f.ld = ld; f.n_seq = n_seq; f.T = static_cast<int>(T); f.H = 768; f.alpha = alpha; f.h = h;
-  f.gamma = gamma; f.beta = beta; f.u_out = static_cast<bf16*>(u_out); f.force_rescale = (flags & 1) != 0; f.tag = PC_FLASH768;
+  f.gamma = gamma; f.beta = beta; f.u_out = static_cast<bf16*>(u_out); f.force_rescale = (flags & 1) != 0; f.dbg = flags >> 8; f.tag = PC_FLASH768;
   return launch_flash768(f, static_cast<cudaStream_t>(stream));
 }
 

@@ -195,6 +195,7 @@ struct Flash768Params {
   const float* gamma = nullptr; const float* beta = nullptr;   // LayerNorm after the attention (norm2)
   bf16* u_out = nullptr;                       // [n_seq * T, 768] its bf16 output; nullptr: no LayerNorm stage
   bool force_rescale = false;                  // tests: take the online-softmax rescale path whenever a tile raises the maximum
+  int dbg = 0;                                 // timing experiments (wrong results): ditto_attn_self768 flags >> 8
   int tag = PC_TC_OTHER;
 };
 bool flash768_supported(int H, int heads, int T);

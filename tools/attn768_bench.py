@@ -19,6 +19,7 @@ ap.add_argument("--n", type=int, default=32)
 ap.add_argument("--T", type=int, default=750)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--noln", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 H = 768
@@ -34,7 +35,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def run():
-    _lib.check(lib.ditto_attn_self768(P(qkv), 3 * H, a.n, a.T, 1.0 / math.sqrt(H), P(h), P(gamma), P(beta), P(u), a.flags, st))
+    _lib.check(lib.ditto_attn_self768(P(qkv), 3 * H, a.n, a.T, 1.0 / math.sqrt(H), P(h), P(gamma), P(beta), None if a.noln else P(u), a.flags, st))
 
 
 for _ in range(3):
