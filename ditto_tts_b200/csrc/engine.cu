@@ -500,10 +500,13 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
                          1.f, static_cast<int>(gs[gi].n_x * gs[gi].T), H, H, st));
   }
 
-  // the fused cross-attention kernel also produces norm3's output, so it is used only when EVERY group qualifies
-  bool fuse_cross = b16 && e->fused_cross && !dln;
-  for (int gi = 0; gi < ng && fuse_cross; ++gi)
-    fuse_cross = fold_active(e, gs[gi].S) && cross_fused_supported(gs[gi].T, gs[gi].S, H, e->heads);
+  // the fused cross-attention kernel also produces norm3's output; the decision is taken GROUP BY GROUP (one utterance with
+  // more than 64 text tokens must not push the whole ragged batch onto the three-kernel path): a group that does not
+  // qualify runs the composition and its own norm3 LayerNorm
+  const bool fuse_cross_any = b16 && e->fused_cross && !dln;
+  auto fuse_cross_group = [&](const SeqGroup& g) {
+    return fuse_cross_any && fold_active(e, g.S) && cross_fused_supported(g.T, g.S, H, e->heads);
+  };
   for (int i = l_begin; i < l_end; ++i) {
     const LayerPack& lp = e->layers[i];
     const bool last = (i == l_end - 1);
@@ -563,7 +566,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
           const int heads = e->heads;
           const int64_t Sp = round_up(S, 8);
-          if (fuse_cross) {
+          if (fuse_cross_group(grp)) {
             // scores + softmax + P.V + out bias + residual + norm3 in one kernel (cross_fused.cu); u is overwritten with LN3(h)
             CrossFusedParams f;
             f.u = ug; f.kfold = c.kfold0 + c.kfold_stride * i; f.kf_seq = S * H; f.vfold = c.vfold0 + c.vfold_stride * i; f.vf_seq = Sp * H;
@@ -619,10 +622,11 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, hg, false, H, e->LW(i, "cross_attn.out_proj.bias"), hg, H, 0, dln ? u : nullptr, H,
                           static_cast<int>(Mg), H, H, st, PC_TC_CROSS_OUT, dln ? w.lnstat : nullptr, w.ln_parts_h));
         }
+        // norm3 of a group that did not take the fused kernel (which writes it itself)                    DiT.py:151
+        if (!dln) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), ug, true, Mg, H, st));
       }
       DITTO_TRY(fork.end());
       // ---- gated MLP                                                                                  DiT.py:150-155
-      if (!dln && !fuse_cross) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, true, M, H, st));
       {
         TcGemmParams g;
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;

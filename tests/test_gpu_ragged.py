@@ -115,3 +115,24 @@ def test_ragged_rejects_bad_input(dev):
         RaggedBatch(m, [torch.zeros(4, 256)], [8])            # CPU tensor: no fallback
     with pytest.raises(D.DittoError):
         RaggedBatch(m, [], [])
+
+
+def test_ragged_cross_fusion_is_decided_per_group(dev):
+    """One utterance with more than 64 text tokens (cross_fused.cu covers S <= 64) must not push the whole mixed batch onto the
+    three-kernel cross-attention: the short-text groups keep the fused kernel, the long one takes the composition + its own
+    norm3 -- every utterance still equals the per-utterance (unpadded) oracle."""
+    from ditto_tts_b200 import _lib
+    cfg = O.OracleConfig(768, 2, 1, 256, 768, 20)
+    sd = O.make_state_dict(cfg, 61)
+    lengths, text_lens = [150, 300, 150, 90], [13, 100, 13, 64]
+    xs, texts = utterances(lengths, text_lens, cfg, 62)
+    t = torch.tensor([3, 19, 0, 7])
+    m = build_model(cfg, sd, "bf16", dev)
+    _lib.profile_start()
+    outs = m.forward_ragged([x.to(dev) for x in xs], [c.to(dev) for c in texts], t.to(dev))
+    prof = _lib.profile_stop()
+    assert "tc_gemm.cross_fused_ln" in prof and "tc_gemm.cross_pv" in prof, sorted(prof)
+    assert prof["tc_gemm.cross_fused_ln"]["launches"] == 2 * cfg.num_layers      # groups (150, 13) and (90, 64)
+    for i, (x, c) in enumerate(zip(xs, texts)):
+        ref = O.ditto_forward(sd, cfg, x[None], c[None], t[i:i + 1])[0]
+        assert rel(outs[i], ref) <= BAR["bf16"], (i, rel(outs[i], ref))

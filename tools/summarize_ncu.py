@@ -10,6 +10,7 @@ from collections import OrderedDict
 
 def short(name):
     name = re.sub(r"ditto::<unnamed>::|ditto::|void |\(anonymous namespace\)::", "", name)
+    name = re.sub(r"^.*?unnamed>::", "", name)
     name = re.sub(r"\(CUtensorMap_st.*", "", name)
     name = re.sub(r"\(.*", "", name)
     return name.strip()
