@@ -1341,7 +1341,7 @@ int32_t ditto_debug_option(const char* name, int32_t value) {
       {"no_flash768", &g_opt.no_flash768}, {"no_fused_cross", &g_opt.no_fused_cross}, {"defer_ln2", &g_opt.defer_ln2},
       {"pv_transpose", &g_opt.pv_transpose}, {"rope_table", &g_opt.rope_table}, {"rope_generic", &g_opt.rope_generic},
       {"glu_generic", &g_opt.glu_generic}, {"no_rope_fast32", &g_opt.no_rope_fast32}, {"no_pv_perm4", &g_opt.no_pv_perm4},
-      {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}};
+      {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}, {"flash768_quad", &g_opt.flash768_quad}};
   if (strcmp(name, "reset") == 0) { g_opt = DebugOptions(); return 0; }
   for (const Opt& o : opts)
     if (strcmp(name, o.n) == 0) { *o.p = value; return 0; }

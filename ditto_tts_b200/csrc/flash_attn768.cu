@@ -75,7 +75,31 @@ constexpr int F7_TMEM_COLS = 512;
 constexpr int F7_S_COL = F7_DH;       // 384
 constexpr float F7_TAU = 8.0f;        // lazy-rescale threshold, log2 units
 
+// Developer timeline (build with -DDITTO_F7_TRACE=1 through DITTO_NVCC_EXTRA; tools/f7_trace.py): cluster 0 records
+// (tag, item-relative SM clock) pairs of its MMA issuer, TMA producer and first softmax warp into the buffer handed to
+// ditto_debug_set_counters.  Compiled out by default.
+#ifndef DITTO_F7_TRACE
+#define DITTO_F7_TRACE 0
+#endif
+constexpr int F7_TR_MAX = 512;   // events per (CTA, role)
+constexpr int F7_TR_ROLES = 3;   // 0 MMA issuer, 1 softmax warp 0, 2 TMA producer
+struct F7Tr {
+  unsigned long long* b; int n; long long t0;
+  __device__ __forceinline__ void init(unsigned long long* buf, int rank, int role, bool on, long long t_sync) {
+    b = (DITTO_F7_TRACE && buf != nullptr && on) ? buf + (rank * F7_TR_ROLES + role) * F7_TR_MAX : nullptr; n = 0; t0 = t_sync;
+  }
+  __device__ __forceinline__ void ev(int kind, int j) {
+    if (DITTO_F7_TRACE && b != nullptr && n < F7_TR_MAX)
+      b[n++] = (static_cast<unsigned long long>(kind * 256 + (j & 255)) << 40) | (static_cast<unsigned long long>(clock64() - t0) & 0xFFFFFFFFFFull);
+  }
+  __device__ __forceinline__ void val(int kind, int j, long long v) {
+    if (DITTO_F7_TRACE && b != nullptr && n < F7_TR_MAX)
+      b[n++] = (static_cast<unsigned long long>(kind * 256 + (j & 255)) << 40) | (static_cast<unsigned long long>(v) & 0xFFFFFFFFFFull);
+  }
+};
+
 struct F7Dev {
+  unsigned long long* trace;
   int n_seq, T;
   int m_tiles, k_tiles, num_items;
   float alpha2;                       // alpha * log2(e)
@@ -83,7 +107,7 @@ struct F7Dev {
   const float* gamma; const float* beta;
   bf16* u_out;                        // [n_seq * T, 768] LayerNorm(h) (nullptr: no LayerNorm stage)
   int force_rescale;                  // tests: move the reference whenever a tile raises a row maximum
-  int dbg;                            // timing experiments only (WRONG results): bit 0 no reference chain, bit 1 no epilogue stores
+  int dbg;                            // timing experiments only (WRONG results): bit 0 no reference chain, bit 1 no residual loads, bit 2 no residual stores, bit 3 no LayerNorm-output stores
 };
 
 __device__ __forceinline__ void tmem_st_16x64(uint32_t taddr, const uint32_t (&r)[32]) {  // inverse of tmem_ld_16x64
@@ -193,6 +217,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
   f7_cluster_sync();   // the peer's barriers exist before the first st.async / bulk copy / commit reaches them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if ((p.dbg >> 8) != 0 && (first & 1)) {   // timing experiment: odd clusters start late (units of 2048 clocks)
+    const long long t_go = clock64() + (static_cast<long long>(p.dbg >> 8) << 11);
+    while (clock64() < t_go) {}
+  }
+  const long long t_sync = DITTO_F7_TRACE ? clock64() : 0;   // the cluster barrier released both CTAs at (about) the same moment
 
   if (warp == 0) {
     // =========================== TMA producer (whole warp, one elected lane issues) ===========================
@@ -200,6 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
     // constants and the barrier phase flips once per group of four.
     regs_shrink_ctrl();
     const bool leader = elect_one();
+    F7Tr tr; tr.init(p.trace, c, 2, first == 0 && leader, t_sync);
     uint32_t phase = 0;
     for (int item = first; item < p.num_items; item += num_clusters) {
       const int qt = item % p.m_tiles, seq = item / p.m_tiles;
@@ -219,6 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
           }
           phase ^= 1u;
         }
+        tr.ev(30, j);
       };
       auto load_v = [&](int j) {
 #pragma unroll
@@ -234,6 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
           __syncwarp();
         }
         phase ^= 1u;
+        tr.ev(31, j);
       };
       // same order as the MMA issuer: the first own score tile, then per key tile [the next own score tile] and the P.V
       if (c < KT) load_s(c);
@@ -259,14 +291,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
     const uint16_t peer_mask = static_cast<uint16_t>(1u << peer);
     uint32_t phase = 0;
     uint32_t it = 0, sc = 0, oc = 0, rc = 0, pvi = 0;   // items, own score tiles, own / peer probability tiles consumed, P.V issued
+    F7Tr tr; tr.init(p.trace, c, 0, first == 0 && leader, t_sync);
     auto issue_s = [&]() {
       mbar_wait(s_empty, (sc & 1u) ^ 1u);
       tcgen05_fence_after();
+      tr.ev(1, sc);
+      long long fw = 0;
 #pragma unroll 1
       for (int c4 = 0; c4 < F7_KCH / F7_STAGES; ++c4) {
 #pragma unroll
         for (int s = 0; s < F7_STAGES; ++s) {
-          mbar_wait(&ring_full[s], phase);
+          if (DITTO_F7_TRACE && tr.b) { const long long w0 = clock64(); mbar_wait(&ring_full[s], phase); fw += clock64() - w0; }
+          else mbar_wait(&ring_full[s], phase);
           tcgen05_fence_after();
           if (leader) {
 #pragma unroll
@@ -281,6 +317,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
       }
       if (leader) umma_commit(s_full);
       __syncwarp();
+      tr.ev(2, sc);
+      tr.val(6, sc, fw);
       ++sc;
     };
     auto issue_pv = [&](int j) {
@@ -295,10 +333,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
       }
       if (j == 0) mbar_wait(o_empty, (it & 1u) ^ 1u);         // the previous item's O has been drained
       tcgen05_fence_after();
+      tr.ev(3, j);
+      long long fw = 0;
       const uint64_t dp = dq0 + (own ? kToPOwn : kToPLand);
 #pragma unroll
       for (int s = 0; s < F7_VST; ++s) {
-        mbar_wait(&ring_full[s], phase);
+        if (DITTO_F7_TRACE && tr.b) { const long long w0 = clock64(); mbar_wait(&ring_full[s], phase); fw += clock64() - w0; }
+        else mbar_wait(&ring_full[s], phase);
         tcgen05_fence_after();
         if (leader) {
 #pragma unroll
@@ -321,6 +362,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
         else f7_commit_mc(p_free, peer_mask);
       }
       __syncwarp();
+      tr.ev(4, j);
+      tr.val(7, j, fw);
       if (own) ++oc; else ++rc;
       ++pvi;
     };
@@ -332,6 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
       }
       if (leader) umma_commit(o_full);
       __syncwarp();
+      tr.ev(5, it);
     }
   } else if (warp == 2) {
     // =========================== probability courier ===========================
@@ -357,6 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
     const bool writer = q == 0;
     const int col_half = c * F7_DH;
     uint32_t it = 0, sc = 0, oc = 0, rc = 0, pvc = 0;   // items, own score tiles, own / peer tiles, P.V issued (all tiles)
+    F7Tr tr; tr.init(p.trace, c, 1, first == 0 && ew == 0 && lane == 0, t_sync);
     // multiply this warp's O rows by (fA, fB): the previous P.V (global index pvc - 1) must have retired, the next one waits
     // for this warp.  (pv_done cycles through four barriers and every tile first waits for P.V(pvc - 4): a parity wait is
     // only unambiguous while the barrier is at most one completion behind -- or ahead.)
@@ -388,6 +433,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
       float* hA = p.h + growA * F7_D + col_half + q * 4;         // this thread's first output column of a 64-column chunk
       float* hB = hA + 8 * F7_D;
       // residual rows of this warp -> L2 while the tile computes (16 rows x 384 columns = 192 lines of 128 B)
+      if (!(p.dbg & 16))
       for (int i = lane; i < 16 * (F7_DH * 4 / 128); i += 32) {
         const int r = i / (F7_DH * 4 / 128), l = i - r * (F7_DH * 4 / 128);
         if (qt * F7_BM + trow + r < p.T)
@@ -406,6 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);                     // the scores are in registers: the next own S may be issued
+        tr.ev(10, sc);
         ++sc;
         have_s = true;
       };
@@ -413,6 +460,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
         // pacing: never more than four tiles ahead of the tensor pipe (keeps every parity wait below unambiguous, and the
         // accept / header barriers from completing twice before they are consumed)
         if (pvc >= 4) mbar_wait(&pv_done[pvc & 3u], ((pvc >> 2) - 1) & 1u);
+        tr.ev(20, j);
         if ((j & 1) != c) {
           // ---------------- a tile of the peer: adopt its reference ----------------
           // first take the next own score tile out of TMEM: it needs no reference yet, and the tensor pipe gets the buffer back
@@ -420,6 +468,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
           const uint32_t slot = rc & 1u;
           if (ew == 0 && lane == 0) mbar_expect_tx(&hdr_bar[slot], F7_BM * 4);
           if (!(p.dbg & 1)) mbar_wait(&hdr_bar[slot], (rc >> 1) & 1u);
+          tr.ev(11, j);
           const float nA = hdr_x[slot * F7_BM + rA], nB = hdr_x[slot * F7_BM + rB];
           if (j > 0) {
             const bool upA = nA != refA, upB = nB != refB;
@@ -473,6 +522,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
           f7_st_async(dsta, nA, barr);
           f7_st_async(dsta + 8 * 4, nB, barr);
         }
+        tr.ev(12, j);
         if (__any_sync(0xffffffffu, upA || upB)) {
           const float fA = upA ? ex2_approx(refA - nA) : 1.0f, fB = upB ? ex2_approx(refB - nB) : 1.0f;
           lA2.x *= fA; lA2.y *= fA; lB2.x *= fB; lB2.y *= fB;
@@ -481,6 +531,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
         refA = nA; refB = nB;
         // P = exp2(alpha2 s - ref) -> shared memory (K-major A operand, 128-B swizzle), row sums
         mbar_wait(p_free, (oc & 1u) ^ 1u);   // both CTAs' P.V of the previous own tile have retired (and the copy with them)
+        tr.ev(13, j);
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const uint32_t(&r)[32] = cb == 0 ? s0 : s1;
@@ -506,6 +557,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        tr.ev(14, j);
         ++oc;
       }
       // ---------------- total row sums: own partial + the peer's (both relative to the final references) ----------------
@@ -523,18 +575,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
       auto load_res = [&](int cb, float4(&f)[8]) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          f[jj] = okA ? *reinterpret_cast<const float4*>(hA + cb * 64 + jj * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-          f[4 + jj] = okB ? *reinterpret_cast<const float4*>(hB + cb * 64 + jj * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[jj] = (okA && !(p.dbg & 2)) ? *reinterpret_cast<const float4*>(hA + cb * 64 + jj * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[4 + jj] = (okB && !(p.dbg & 2)) ? *reinterpret_cast<const float4*>(hB + cb * 64 + jj * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
       load_res(0, f0);       // both requested before the waits below: their L2 latency hides behind the exchange / the last P.V
       load_res(1, f1);
       mbar_wait(&l_bar[par], (it >> 1) & 1u);
+      tr.ev(15, it);
       lA += l_x[par * F7_BM + rA];
       lB += l_x[par * F7_BM + rB];
       const float iA = 1.0f / lA, iB = 1.0f / lB;
       mbar_wait(o_full, it & 1u);
       tcgen05_fence_after();
+      tr.ev(16, it);
       float smA = 0.f, sqA = 0.f, smB = 0.f, sqB = 0.f;
       auto sweep1 = [&](int cb, const float4(&f)[8]) {
         uint32_t o[32];
@@ -552,8 +606,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
           vB.y = fmaf(iB, __uint_as_float(o[4 * k0 + 3]), f[4 + jj].y);
           vB.z = fmaf(iB, __uint_as_float(o[4 * k1 + 2]), f[4 + jj].z);
           vB.w = fmaf(iB, __uint_as_float(o[4 * k1 + 3]), f[4 + jj].w);
-          if (okA) *reinterpret_cast<float4*>(hA + cb * 64 + jj * 16) = vA;
-          if (okB) *reinterpret_cast<float4*>(hB + cb * 64 + jj * 16) = vB;
+          if (okA && !(p.dbg & 4)) *reinterpret_cast<float4*>(hA + cb * 64 + jj * 16) = vA;
+          if (okB && !(p.dbg & 4)) *reinterpret_cast<float4*>(hB + cb * 64 + jj * 16) = vB;
           smA += (vA.x + vA.y) + (vA.z + vA.w);
           sqA = fmaf(vA.x, vA.x, fmaf(vA.y, vA.y, fmaf(vA.z, vA.z, fmaf(vA.w, vA.w, sqA))));
           smB += (vB.x + vB.y) + (vB.z + vB.w);
@@ -572,6 +626,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
         sweep1(cb + 1, f1);
         if (cb + 3 < F7_DH / 64) load_res(cb + 3, f1);
       }
+      tr.ev(17, it);
       if (p.u_out != nullptr) {
         tmem_st_wait();
         // ---------------- LayerNorm statistics: this CTA has 384 of the 768 columns; the peer has the rest ----------------
@@ -586,6 +641,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
           f7_st_async(slot + 8 * 8 + 4, sqB, bar);
         }
         mbar_wait(&stat_bar[par], (it >> 1) & 1u);
+        tr.ev(18, it);
         const float2 xA = *reinterpret_cast<const float2*>(stat_x + (par * F7_BM + rA) * 2);
         const float2 xB = *reinterpret_cast<const float2*>(stat_x + (par * F7_BM + rB) * 2);
         const float inv_h = 1.0f / static_cast<float>(F7_D);
@@ -620,14 +676,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
                                fmaf((__uint_as_float(o[4 * k0 + 3]) - meanB) * rsB, gm[jj].y, bt[jj].y));
             wB.y = pack_bf16x2(fmaf((__uint_as_float(o[4 * k1 + 2]) - meanB) * rsB, gm[jj].z, bt[jj].z),
                                fmaf((__uint_as_float(o[4 * k1 + 3]) - meanB) * rsB, gm[jj].w, bt[jj].w));
-            if (okA) *reinterpret_cast<uint2*>(uA + cb * 64 + jj * 16) = wA;
-            if (okB) *reinterpret_cast<uint2*>(uB + cb * 64 + jj * 16) = wB;
+            if (okA && !(p.dbg & 8)) *reinterpret_cast<uint2*>(uA + cb * 64 + jj * 16) = wA;
+            if (okB && !(p.dbg & 8)) *reinterpret_cast<uint2*>(uB + cb * 64 + jj * 16) = wB;
           }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
+      tr.ev(19, it);
     }
   } else {
     regs_shrink_ctrl();  // warp 3 idles; the whole warpgroup has to execute the setmaxnreg
@@ -648,6 +705,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F7_THREADS, 1)
 bool flash768_supported(int H, int heads, int T) { return heads == 1 && H == F7_D && T >= 1; }
 
 int launch_flash768(const Flash768Params& q, cudaStream_t st) {
+  // four-CTA clusters (two cta_group::2 pairs, K / V loaded once per pair) when 256-row query tiles fit the sequence length
+  if (g_opt.flash768_quad != 1 && q.T >= 1 && (g_opt.flash768_quad == 2 || flash768_quad_preferred(q.T))) return launch_flash768_quad(q, st);
   DITTO_TRY(tc_gemm_init());
   DITTO_REQUIRE(flash768_supported(q.H, 1, q.T), DITTO_E_UNSUPPORTED, "flash768: single head of 768 only");
   DITTO_REQUIRE(q.qkv && q.h && q.n_seq >= 1 && q.ld % 8 == 0 && q.ld >= 3 * F7_D, DITTO_E_BADARG, "flash768: bad argument");
@@ -680,6 +739,7 @@ int launch_flash768(const Flash768Params& q, cudaStream_t st) {
   p.h = q.h; p.gamma = q.gamma; p.beta = q.beta; p.u_out = q.u_out;
   p.force_rescale = q.force_rescale ? 1 : 0;
   p.dbg = q.dbg;
+  p.trace = DITTO_F7_TRACE ? tc_gemm_debug_counters() : nullptr;
   // algorithmic flops: 4 T^2 d per utterance (the second Q K^T of the cluster is not counted); bytes: q, k, v read once, h
   // read + written, u written
   const double rows = static_cast<double>(q.n_seq) * q.T;

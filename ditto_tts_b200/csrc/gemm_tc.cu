@@ -1084,8 +1084,6 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ uint32_t cluster_ctarank();
-__device__ __forceinline__ void cluster_sync_all();
 
 struct ClusterPos {
   int csize, rm, rn;          // cluster size, this CTA's tile-row / tile-column inside the cluster
@@ -1297,40 +1295,6 @@ constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;  // 32 KiB
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + BARRIER_BYTES + 1024;
 static_assert(P_SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of an sm_100 CTA");
 static_assert((2 * P_STAGES + 4) * 8 + 4 <= BARRIER_BYTES, "barrier block too small");
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// arrive (once the issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
@@ -1998,6 +1962,7 @@ int launch_clustered(const void* func, int csize, int smem_bytes, int64_t num_wo
 }  // namespace
 
 void tc_gemm_set_debug_counters(unsigned long long* dev_ptr) { g_dbg = dev_ptr; }
+unsigned long long* tc_gemm_debug_counters() { return g_dbg; }
 int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
   return make_map(m, op, n_inner, n_outer, box_cols, box_rows);
 }

@@ -16,6 +16,8 @@ struct DebugOptions {
   // engine.cu (read by ditto_engine_create)
   int no_defer_ln = 0, no_fused_attn = 0, no_flash = 0, no_flash768 = 0, no_fused_cross = 0, defer_ln2 = 0, pv_transpose = 0,
       rope_table = 0, rope_generic = 0, glu_generic = 0, no_rope_fast32 = 0, no_pv_perm4 = 0, side_streams = -1, no_fused_ln = 0;
+  // flash_attn768.cu (read at launch time): 1 = always the two-CTA kernel, 2 = the four-CTA kernel whenever it is supported
+  int flash768_quad = 0;
 };
 extern DebugOptions g_opt;
 
@@ -23,6 +25,7 @@ extern DebugOptions g_opt;
 struct DeviceState {
   bool tc_init = false, xf_attr = false, fa_attr = false, f768_attr = false;
   int num_sms = 0;
+  int f768q_clusters = 0;   // co-resident four-CTA clusters of flash_attn768q_kernel (0: not queried yet, -1: cannot be scheduled)
 };
 DeviceState* device_state();  // state of the CURRENT device (nullptr + error set when cudaGetDevice fails)
 
@@ -199,12 +202,15 @@ struct Flash768Params {
   int tag = PC_TC_OTHER;
 };
 bool flash768_supported(int H, int heads, int T);
-int launch_flash768(const Flash768Params& p, cudaStream_t st);
+int launch_flash768(const Flash768Params& p, cudaStream_t st);   // picks the two- or the four-CTA kernel
+bool flash768_quad_preferred(int T);
+int launch_flash768_quad(const Flash768Params& p, cudaStream_t st);   // flash_attn768q.cu
 
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 // 4-D bf16 tensor map (cols, rows, inner batch, outer batch) with a (box_cols, box_rows, 1, 1) box, 128-B swizzle, zero OOB fill
 int tc_make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows);
 int tc_num_sms();
 void tc_gemm_set_debug_counters(unsigned long long* dev_ptr);  // ditto_debug_set_counters
+unsigned long long* tc_gemm_debug_counters();
 
 }  // namespace ditto

@@ -1,4 +1,4 @@
-"""GPU tests (-m gpu) of flash_attn768.cu through its C symbol ditto_attn_self768: self-attention of ONE head of 768
+"""GPU tests (-m gpu) of flash_attn768.cu / flash_attn768q.cu through its C symbol ditto_attn_self768: self-attention of ONE head of 768
 (reference: src/components/DiT.py:117-139, repo-default config) + residual + norm2 in one cluster kernel, against a plain
 PyTorch fp32 evaluation of the same formulas on the same bf16-rounded operands.  Covers partial query / key tiles, long
 sequences, and the online-softmax rescale path (forced, and provoked by keys whose scores grow along the sequence)."""
@@ -23,6 +23,15 @@ def ST():
 @pytest.fixture(scope="module")
 def dev():
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True, params=["pair", "quad"])
+def kernel_variant(request):
+    """Every test runs on both kernels: flash_attn768_kernel (two-CTA cluster, 128 query rows) and flash_attn768q_kernel (four-CTA
+    cluster of two cta_group::2 pairs, 256 query rows) -- the launcher otherwise picks by sequence length."""
+    _lib.debug_option("flash768_quad", 1 if request.param == "pair" else 2)
+    yield request.param
+    _lib.debug_option("flash768_quad", 0)
 
 
 def v_storage_order():
