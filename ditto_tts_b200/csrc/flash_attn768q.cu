@@ -420,12 +420,17 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
       const long long growA = static_cast<long long>(seq) * p.T + lrowA;
       float* hA = p.h + growA * Q7_D + col_half + q * 4;
       float* hB = hA + 8 * Q7_D;
-      if (!(p.dbg & 16))
-      for (int i = lane; i < 16 * (Q7_DH * 4 / 128); i += 32) {
-        const int r = i / (Q7_DH * 4 / 128), l = i - r * (Q7_DH * 4 / 128);
-        if (row0 + trow + r < p.T)
-          q7_prefetch_l2(p.h + (static_cast<long long>(seq) * p.T + row0 + trow + r) * Q7_D + col_half + l * 32);
-      }
+      // residual rows of this warp -> L2 while the tiles compute (16 rows x 384 columns = 192 lines of 128 B); issued after
+      // the first own tile's probabilities are out, not before: the score tile of this item is already waiting
+      auto prefetch_residual = [&]() {
+        if (p.dbg & 16) return;
+        for (int i = lane; i < 16 * (Q7_DH * 4 / 128); i += 32) {
+          const int r = i / (Q7_DH * 4 / 128), l = i - r * (Q7_DH * 4 / 128);
+          if (row0 + trow + r < p.T)
+            q7_prefetch_l2(p.h + (static_cast<long long>(seq) * p.T + row0 + trow + r) * Q7_D + col_half + l * 32);
+        }
+      };
+      if (c >= KT) prefetch_residual();
       tr.ev(24, it);
       float refA = 0.f, refB = 0.f;
       float2 lA2 = make_float2(0.f, 0.f), lB2 = make_float2(0.f, 0.f);
@@ -543,6 +548,7 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
           mbar_arrive_leader(p_full);
         }
         tr.ev(14, j);
+        if (j == c) prefetch_residual();
         ++oc;
       }
       // ---------------- total row sums ----------------
@@ -556,7 +562,7 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
         q7_st_async(dsta + 8 * 4, lB, barr);
       }
       // ---------------- epilogue sweep 1: h <- O / l + h, row statistics, h kept in TMEM ----------------
-      float4 f0[8], f1[8];
+      float4 f0[8], f1[8], f2[8];   // residual of three 64-column chunks in flight (rows A: [0, 4), rows B: [4, 8))
       auto load_res = [&](int cb, float4(&f)[8]) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -566,6 +572,7 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
       };
       load_res(0, f0);
       load_res(1, f1);
+      load_res(2, f2);
       mbar_wait(&l_bar[par], (it >> 1) & 1u);
       tr.ev(15, it);
       lA += l_x[par * Q7_BM + rA];
@@ -606,13 +613,13 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
         if (p.u_out != nullptr) q7_tmem_st_16x64(t_lane + cb * 64, o);
         tr.ev(22, cb);
       };
-#pragma unroll 1
-      for (int cb = 0; cb < Q7_DH / 64; cb += 2) {
-        sweep1(cb, f0);
-        if (cb + 2 < Q7_DH / 64) load_res(cb + 2, f0);
-        sweep1(cb + 1, f1);
-        if (cb + 3 < Q7_DH / 64) load_res(cb + 3, f1);
-      }
+      static_assert(Q7_DH / 64 == 6, "two rounds of three chunks");
+      sweep1(0, f0); load_res(3, f0);
+      sweep1(1, f1); load_res(4, f1);
+      sweep1(2, f2); load_res(5, f2);
+      sweep1(3, f0);
+      sweep1(4, f1);
+      sweep1(5, f2);
       tr.ev(17, it);
       if (p.u_out != nullptr) {
         q7_tmem_st_wait();

@@ -10,7 +10,9 @@
 //   QKV_ROPE  column-permuted q/k so that the RoPE partner (j, j+d/2) sits PD columns away in the tile  (DiT.py:52-72)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <unordered_map>
 #include <mutex>
 #include <tuple>
 #include <type_traits>
@@ -1873,6 +1875,18 @@ constexpr int kMaxDevices = 64;
 DeviceState g_dev_state[kMaxDevices];
 std::mutex g_dev_mutex;
 
+struct MapKey {
+  uint64_t v[9];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 0xBF58476D1CE4E5B9ull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+
 // 4-D bf16 map: dims (cols, rows, inner, outer), box (box_cols, box_rows, 1, 1), 128B swizzle, zero OOB fill.
 int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_outer, int box_cols, int box_rows) {
   DITTO_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, DITTO_E_BADARG, "tc_gemm: operand base must be 16-B aligned");
@@ -1888,6 +1902,17 @@ int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_out
                            static_cast<cuuint64_t>(outer_bytes)};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // A descriptor is a pure function of (base, extents, strides, box): an eager caller that steps a model in a loop asks for
+  // the same few dozen maps every step, so they are kept in a small per-thread cache (pointer/shape-keyed)
+  // instead of being re-encoded by the driver on every launch.  Graph replay never comes here.
+  const MapKey key{{reinterpret_cast<uint64_t>(op.ptr), dims[0], dims[1], dims[2], dims[3], strides[0], strides[1], strides[2],
+                    (static_cast<uint64_t>(box_cols) << 32) | static_cast<uint64_t>(box_rows)}};
+  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *m = it->second;
+    return 0;
+  }
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(op.ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1896,6 +1921,8 @@ int make_map(CUtensorMap* m, const TcOperand& op, int64_t n_inner, int64_t n_out
               std::to_string(op.cols) + " rows=" + std::to_string(op.rows) + " ld=" + std::to_string(op.ld) + ")");
     return DITTO_E_CUDA;
   }
+  if (cache.size() >= 2048) cache.clear();   // bounded: serving with ever-changing shapes / buffers just re-encodes
+  cache.emplace(key, *m);
   return 0;
 }
 
