@@ -71,6 +71,8 @@ SIGNATURES = {
     "ditto_layernorm": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _P]),
     "ditto_gemm_f32": (_I32, [_P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64, _I64, _P, _P, _F, _I64, _I64, _I64,
                               _I64, _P]),
+    "ditto_gemm_resid_ln_weight_row": (_I32, [_I32]),
+    "ditto_gemm_resid_ln": (_I32, [_P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "ditto_gemm_bf16": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _I64, _F, _I64, _I64, _I64, _P]),
     "ditto_cast_bf16": (_I32, [_P, _P, _I64, _P]),
     "ditto_vq_code_sqnorm": (_I32, [_P, _I64, _I64, _P, _P]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libditto_b200.so")
-SOURCES = ["engine.cu", "elementwise.cu", "gemm_f32.cu", "gemm_tc.cu", "cross_fused.cu", "flash_attn.cu", "flash_attn768.cu", "flash_attn768q.cu", "vq.cu"]
+SOURCES = ["engine.cu", "elementwise.cu", "gemm_f32.cu", "gemm_tc.cu", "gemm_resid_ln.cu", "cross_fused.cu", "flash_attn.cu", "flash_attn768.cu", "flash_attn768q.cu", "vq.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "ditto_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

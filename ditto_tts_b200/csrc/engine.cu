@@ -91,6 +91,7 @@ struct ditto_engine {
   bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   bool pv_perm4 = false;    // v columns stored in the order the float4 P.V epilogue wants (TcGemmParams::out_perm4)
   bool qkv_perm16 = false;  // QKV weight rows also permuted inside 64-row blocks for the lean RoPE epilogue (TcGemmParams::rope_perm16)
+  bool fc2_ln = false;      // fc2 + residual + the next block's norm1 in one cluster kernel (gemm_resid_ln.cu); w_fc2 rows in perm4 order
   bool flash768 = false;    // one head of 768 (repo default): self-attention + residual + norm2 in one cluster kernel (flash_attn768.cu)
   bool flash_attn = true;   // head_dim 64: self-attention without materialised scores (flash_attn.cu); DITTO_NO_FLASH=1 disables
   bool defer_ln2 = false;   // norm2 only: row statistics from the self-attention P.V epilogue, LayerNorm folded into cross_fused's scores
@@ -637,12 +638,23 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         g.tag = PC_TC_GLU;
         DITTO_TRY(launch_tc_gemm(g, st));
       }
+      if (e->fc2_ln) {
+        // h += fc2(hid) + b and, in the same kernel, the operand of what follows: norm1 of the next block (DiT.py:105) or,
+        // after the last block, the plain bf16 copy that proj_out reads
+        GemmResidLnParams f;
+        f.A = static_cast<bf16*>(w.hid); f.lda = 4 * H; f.W = lp.w_fc2; f.ldw = 4 * H; f.bias = e->LW(i, "mlp_fc2.bias");
+        f.h = w.h; f.ldh = H; f.M = static_cast<int>(M); f.N = H; f.K = 4 * H; f.tag = PC_TC_FC2;
+        if (last) { f.u = static_cast<bf16*>(w.xb16); f.ldu = H; }
+        else { f.gamma = e->LW(i + 1, "norm1.weight"); f.beta = e->LW(i + 1, "norm1.bias"); f.u = u; f.ldu = H; }
+        DITTO_TRY(launch_gemm_resid_ln(f, st));
+      } else {
       DITTO_TRY(tc_nt(static_cast<bf16*>(w.hid), 4 * H, lp.w_fc2, 4 * H, w.h, false, H, e->LW(i, "mlp_fc2.bias"), w.h, H, 0,
                       last ? static_cast<bf16*>(w.xb16) : (dln ? u : nullptr), H, static_cast<int>(M), H, 4 * H, st, PC_TC_FC2,
                       (dln && !last) ? w.lnstat : nullptr, w.ln_parts_h));
       ln1_parts = w.ln_parts_h;
       if (!last && !dln)
         DITTO_TRY(launch_layernorm(w.h, e->LW(i + 1, "norm1.weight"), e->LW(i + 1, "norm1.bias"), u, true, M, H, st));
+      }
     } else {
       float* u = static_cast<float*>(w.u);
       float* qkv = static_cast<float*>(w.qkv);
@@ -816,6 +828,7 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     e->pv_perm4 = e->qkv_perm16 && !e->pv_transpose && !e->defer_ln2 && e->d % 128 == 0 && !g_opt.no_pv_perm4;
     // needs the v columns in the 16-byte store order (pv_perm4) and the fused softmax machinery
     e->flash768 = e->fused_attn && e->pv_perm4 && !e->defer_ln && flash768_supported(e->H, e->heads, 1) && !g_opt.no_flash768;
+    e->fc2_ln = !e->defer_ln && gemm_resid_ln_supported(e->H, 4 * e->H) && !g_opt.no_fc2_ln;
   }
   build_expected(e);
   e->layers.resize(e->L);
@@ -984,8 +997,12 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
         qkv_perm[r] = base[blk * 64 + l];
       }
     }
-    int *d_glu = nullptr, *d_qkv = nullptr;
+    int *d_glu = nullptr, *d_qkv = nullptr, *d_fc2 = nullptr;
     float* cat = nullptr;
+    std::vector<int> fc2_perm(H);
+    for (int r = 0; r < H; ++r) fc2_perm[r] = e->fc2_ln ? gemm_resid_ln_weight_row(r) : r;
+    DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_fc2), sizeof(int) * fc2_perm.size()));
+    DITTO_CUDA(cudaMemcpyAsync(d_fc2, fc2_perm.data(), sizeof(int) * fc2_perm.size(), cudaMemcpyHostToDevice, st));
     DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_glu), sizeof(int) * glu_perm.size()));
     DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_qkv), sizeof(int) * qkv_perm.size()));
     DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&cat), sizeof(float) * (8ll * H * H + 8 * H)));
@@ -1014,7 +1031,12 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
                               e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), nullptr);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.in_proj_weight"), 3ll * H * H, &lp.wc_in);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.out_proj.weight"), static_cast<int64_t>(H) * H, &lp.wc_o);
-      if (!rc) rc = cast_new(e->LW(i, "mlp_fc2.weight"), 4ll * H * H, &lp.w_fc2);
+      if (!rc && e->fc2_ln) {   // rows in the order the float4 residual + LayerNorm epilogue wants (gemm_resid_ln.cu)
+        if (!lp.w_fc2) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.w_fc2), sizeof(bf16) * 4ll * H * H);
+        if (!rc) rc = launch_pack_rows(e->LW(i, "mlp_fc2.weight"), lp.w_fc2, nullptr, nullptr, d_fc2, H, 4 * H, st, nullptr, nullptr, nullptr);
+      } else if (!rc) {
+        rc = cast_new(e->LW(i, "mlp_fc2.weight"), 4ll * H * H, &lp.w_fc2);
+      }
       if (rc) break;
       cudaMemcpyAsync(cat, e->LW(i, "mlp_fc1.weight"), sizeof(float) * 4ll * H * H, cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(cat + 4ll * H * H, e->LW(i, "gate.weight"), sizeof(float) * 4ll * H * H, cudaMemcpyDeviceToDevice, st);
@@ -1026,6 +1048,7 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
     se = cudaStreamSynchronize(st);
     cudaFree(d_glu);
     cudaFree(d_qkv);
+    cudaFree(d_fc2);
     cudaFree(cat);
     if (rc) return rc;
     DITTO_CUDA(se);
@@ -1341,7 +1364,8 @@ int32_t ditto_debug_option(const char* name, int32_t value) {
       {"no_flash768", &g_opt.no_flash768}, {"no_fused_cross", &g_opt.no_fused_cross}, {"defer_ln2", &g_opt.defer_ln2},
       {"pv_transpose", &g_opt.pv_transpose}, {"rope_table", &g_opt.rope_table}, {"rope_generic", &g_opt.rope_generic},
       {"glu_generic", &g_opt.glu_generic}, {"no_rope_fast32", &g_opt.no_rope_fast32}, {"no_pv_perm4", &g_opt.no_pv_perm4},
-      {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}, {"flash768_quad", &g_opt.flash768_quad}};
+      {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}, {"flash768_quad", &g_opt.flash768_quad},
+      {"no_fc2_ln", &g_opt.no_fc2_ln}};
   if (strcmp(name, "reset") == 0) { g_opt = DebugOptions(); return 0; }
   for (const Opt& o : opts)
     if (strcmp(name, o.n) == 0) { *o.p = value; return 0; }
@@ -1365,6 +1389,18 @@ int32_t ditto_gemm_f32(const float* A, int64_t lda, int64_t strideA, const float
   p.C = C; p.ldc = ldc; p.sC_outer = strideC; p.bias = bias; p.resid = resid; p.ldr = ldc; p.sR_outer = strideC; p.alpha = alpha;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.batch_outer = static_cast<int>(batch);
   return launch_sgemm(p, static_cast<cudaStream_t>(stream));
+}
+
+int32_t ditto_gemm_resid_ln_weight_row(int32_t packed_row) { return packed_row >= 0 ? gemm_resid_ln_weight_row(packed_row) : -1; }
+int32_t ditto_gemm_resid_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* h, int64_t ldh,
+                            const float* gamma, const float* beta, void* u, int64_t ldu, int64_t M, int64_t N, int64_t K, void* stream) {
+  DITTO_REQUIRE(A && W && bias && h && M > 0 && M < (1ll << 31) && N > 0 && K > 0 && N < (1 << 20) && K < (1 << 24), DITTO_E_BADARG,
+                "gemm_resid_ln: bad argument");
+  GemmResidLnParams f;
+  f.A = static_cast<const bf16*>(A); f.lda = lda; f.W = static_cast<const bf16*>(W); f.ldw = ldw; f.bias = bias;
+  f.h = h; f.ldh = ldh; f.gamma = gamma; f.beta = beta; f.u = static_cast<bf16*>(u); f.ldu = ldu;
+  f.M = static_cast<int>(M); f.N = static_cast<int>(N); f.K = static_cast<int>(K);
+  return launch_gemm_resid_ln(f, static_cast<cudaStream_t>(stream));
 }
 
 int32_t ditto_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t out_bf16,

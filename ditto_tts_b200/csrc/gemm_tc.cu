@@ -1376,8 +1376,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
       }
     }
     if (kDbgCounters && p.dbg && rank == 0 && leader) {
-      atomicAdd(p.dbg + 3, static_cast<unsigned long long>(w_slot));
-      atomicAdd(p.dbg + 4, static_cast<unsigned long long>(clock64() - t_begin));
+      atomicAdd(p.dbg + EPI * 8 + 3, static_cast<unsigned long long>(w_slot));
+      atomicAdd(p.dbg + EPI * 8 + 4, static_cast<unsigned long long>(clock64() - t_begin));
     }
   } else if (warp == 1) {
     regs_shrink_ctrl();
@@ -1426,9 +1426,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
       if (kDbgCounters && p.dbg && leader) {
-        atomicAdd(p.dbg + 0, static_cast<unsigned long long>(w_ops));
-        atomicAdd(p.dbg + 1, static_cast<unsigned long long>(w_acc));
-        atomicAdd(p.dbg + 2, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(p.dbg + EPI * 8 + 0, static_cast<unsigned long long>(w_ops));
+        atomicAdd(p.dbg + EPI * 8 + 1, static_cast<unsigned long long>(w_acc));
+        atomicAdd(p.dbg + EPI * 8 + 2, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
   } else if (warp >= EPI_WARP0) {

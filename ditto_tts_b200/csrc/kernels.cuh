@@ -18,6 +18,8 @@ struct DebugOptions {
       rope_table = 0, rope_generic = 0, glu_generic = 0, no_rope_fast32 = 0, no_pv_perm4 = 0, side_streams = -1, no_fused_ln = 0;
   // flash_attn768.cu (read at launch time): 1 = always the two-CTA kernel, 2 = the four-CTA kernel whenever it is supported
   int flash768_quad = 0;
+  // engine.cu: fc2 + residual + next block's norm1 as separate launches (GEMM, LayerNorm) instead of gemm_resid_ln.cu
+  int no_fc2_ln = 0;
 };
 extern DebugOptions g_opt;
 
@@ -205,6 +207,21 @@ bool flash768_supported(int H, int heads, int T);
 int launch_flash768(const Flash768Params& p, cudaStream_t st);   // picks the two- or the four-CTA kernel
 bool flash768_quad_preferred(int T);
 int launch_flash768_quad(const Flash768Params& p, cudaStream_t st);   // flash_attn768q.cu
+
+// ---- gemm_resid_ln.cu: h += A W^T + b (fp32, in place) and u = LayerNorm(h) gamma + beta (bf16) in one cluster kernel ----
+struct GemmResidLnParams {
+  const bf16* A = nullptr; int64_t lda = 0;     // [M, K] bf16
+  const bf16* W = nullptr; int64_t ldw = 0;     // [N, K] bf16, rows in the perm4 order (gemm_resid_ln_weight_row)
+  const float* bias = nullptr;                  // [N], plain column order
+  float* h = nullptr; int64_t ldh = 0;          // [M, N] fp32 residual stream, updated in place
+  const float* gamma = nullptr; const float* beta = nullptr;   // LayerNorm after the update; gamma == nullptr: u = bf16(h)
+  bf16* u = nullptr; int64_t ldu = 0;           // [M, N] bf16 output (optional when gamma == nullptr)
+  int M = 0, N = 0, K = 0;
+  int tag = PC_TC_OTHER;
+};
+bool gemm_resid_ln_supported(int N, int K);
+int gemm_resid_ln_weight_row(int packed_row);   // source row of a packed weight row
+int launch_gemm_resid_ln(const GemmResidLnParams& p, cudaStream_t st);
 
 int tc_gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 // 4-D bf16 tensor map (cols, rows, inner batch, outer batch) with a (box_cols, box_rows, 1, 1) box, 128-B swizzle, zero OOB fill

@@ -243,6 +243,17 @@ int32_t ditto_gemm_f32(const float* A, int64_t lda, int64_t strideA, const float
 int32_t ditto_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                         int32_t out_bf16, const float* bias, const float* resid, int64_t ldr, float alpha,
                         int64_t M, int64_t N, int64_t K, void* stream);
+/* The gated MLP's second linear with what follows it, in one cluster kernel (csrc/gemm_resid_ln.cu; reference
+ * src/components/DiT.py:152-155 `x = residual + mlp_fc2(...)` and the next block's `norm1`, DiT.py:105):
+ *   h <- h + A W^T + bias          (fp32, in place; A [M,K] bf16, W [N,K] bf16)
+ *   u <- LayerNorm(h) gamma + beta (bf16; eps 1e-5, biased variance)   -- gamma == NULL: u <- bf16(h), u may be NULL
+ * N in {256, 512, 768, 1024}, K % 8 == 0.  W holds the rows of the nn.Linear weight in the order
+ * ditto_gemm_resid_ln_weight_row(r) -> source row of packed row r (a fixed permutation inside every 64-row block that
+ * makes a thread's accumulators four consecutive outputs); bias / gamma / beta / h / u are in plain column order. */
+int32_t ditto_gemm_resid_ln_weight_row(int32_t packed_row);
+int32_t ditto_gemm_resid_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* h, int64_t ldh,
+                            const float* gamma, const float* beta, void* u, int64_t ldu, int64_t M, int64_t N, int64_t K,
+                            void* stream);
 /* fp32 -> bf16 (round to nearest even) */
 int32_t ditto_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 

@@ -313,7 +313,7 @@ def test_fused_cross_attention_block(dev, B, T, S):
 
 
 @pytest.mark.parametrize("env", [{"xf_rows": 88}, {"defer_ln2": 1}, {"rope_generic": 1, "glu_generic": 1}, {"no_pv_perm4": 1},
-                                 {"no_flash768": 1}, {"no_fused_ln": 1}],
+                                 {"no_flash768": 1}, {"no_fused_ln": 1}, {"no_fc2_ln": 1}, {"flash768_quad": 1}],
                          ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
 def test_kernel_variants_behind_switches(dev, env):
     """Every developer switch of DESIGN.md section 9 selects a different kernel / weight packing for the same arithmetic: each

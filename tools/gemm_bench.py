@@ -43,11 +43,11 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print(f"gemm_bf16 M{M} N{N} K{K} f32out={f32out} resid={resid}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
 if "--counters" in sys.argv:  # where the paired kernel's MMA issuer / TMA producer spend their cycles
-    cnt = torch.zeros(5, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(64, dtype=torch.int64, device=dev)   # 8 counters per epilogue kind of the paired kernel
     _lib.check(lib.ditto_debug_set_counters(P(cnt)))
     run()
     torch.cuda.synchronize()
     _lib.check(lib.ditto_debug_set_counters(None))
-    c = cnt.tolist()
+    c = cnt.view(8, 8).sum(0).tolist()
     print(f"  mma issuer: wait operands {c[0] / max(c[2], 1):.1%}, wait accumulator {c[1] / max(c[2], 1):.1%} of {c[2]} cycles; "
           f"tma producer: wait slot {c[3] / max(c[4], 1):.1%} of {c[4]} cycles")

@@ -69,3 +69,16 @@ for k_, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
           f"{v['ms'] / tot:>7.1%}")
 print(f"{'sum (eager, profiled)':<24s}{'':>14s}{tot / P:>10.4f}")
 print("finite:", bool(torch.isfinite(graph.x).all()))
+if os.environ.get("DITTO_STEP_COUNTERS"):   # library built with -DDITTO_DBG_COUNTERS=1: where the paired GEMMs' control warps wait
+    import ctypes as C
+    cnt = torch.zeros(64, dtype=torch.int64, device=dev)
+    _lib.check(_lib.load().ditto_debug_set_counters(C.c_void_p(cnt.data_ptr())))
+    _lib.check(_lib.load().ditto_p_sample_rng(m.engine(), _ptr(graph.x), _ptr(graph.ctx), _ptr(graph.t), _ptr(graph.rng), 1, 3.0, B, T, S,
+                                              _ptr(graph.eps), _ptr(graph.x), _ptr(graph.ws), graph.ws.numel(), 1, _stream()))
+    torch.cuda.synchronize()
+    _lib.check(_lib.load().ditto_debug_set_counters(None))
+    names = {0: "store_f32", 1: "store_f32_resid (fc2, proj_out)", 2: "store_bf16", 3: "generic", 4: "geglu", 5: "qkv_rope"}
+    for e, c in enumerate(cnt.view(8, 8).tolist()):
+        if c[2]:
+            print(f"pair GEMM epilogue {names.get(e, e)}: MMA issuer waits operands {c[0] / c[2]:.1%}, accumulator {c[1] / c[2]:.1%}; "
+                  f"TMA producer waits slot {c[3] / max(c[4], 1):.1%}")
