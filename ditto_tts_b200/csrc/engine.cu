@@ -1365,7 +1365,7 @@ int32_t ditto_debug_option(const char* name, int32_t value) {
       {"pv_transpose", &g_opt.pv_transpose}, {"rope_table", &g_opt.rope_table}, {"rope_generic", &g_opt.rope_generic},
       {"glu_generic", &g_opt.glu_generic}, {"no_rope_fast32", &g_opt.no_rope_fast32}, {"no_pv_perm4", &g_opt.no_pv_perm4},
       {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}, {"flash768_quad", &g_opt.flash768_quad},
-      {"no_fc2_ln", &g_opt.no_fc2_ln}};
+      {"no_fc2_ln", &g_opt.no_fc2_ln}, {"dbg_nostore", &g_opt.dbg_nostore}};
   if (strcmp(name, "reset") == 0) { g_opt = DebugOptions(); return 0; }
   for (const Opt& o : opts)
     if (strcmp(name, o.n) == 0) { *o.p = value; return 0; }

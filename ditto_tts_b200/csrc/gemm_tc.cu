@@ -75,6 +75,7 @@ struct DevParams {
   int rope_fast;        // weights packed for the lean pd = 128 epilogue (TcGemmParams::rope_perm16)
   int glu_fast;         // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   int out_perm4;        // fp32 + residual result in the 16-byte column order (TcGemmParams::out_perm4)
+  int dbg_nostore;      // timing experiment (wrong results): the lean QKV+RoPE / GEGLU epilogues skip their global stores
   int stages;  // smem ring depth actually used (<= STAGES / P_STAGES)
   int cm, cn;  // 1-CTA kernels: cluster shape in tiles (cm x cn CTAs share operands by TMA multicast); 1 x 1 = no cluster
   const float* row_lsum; int row_lparts; long long sl_inner, sl_outer;  // optional per-row 1/sum scale (fast STORE paths)
@@ -545,6 +546,13 @@ __device__ __forceinline__ void sincos_reduced2(float2 a, float2& s, float2& c) 
 // quad writes whole 128-byte lines (was: 4-byte stores, 16 bytes per line and instruction -- the top stall of this
 // epilogue in ncu).  Biases follow the GEMM column (they are packed with the weight); rotary frequencies and output
 // addresses follow the output column.
+// 256-bit global store (sm_100+): eight packed bf16 pairs = 16 consecutive outputs; the address must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 template <bool FULL>
 __device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int lane, int half_sel, uint32_t t_row, long long row0, int n_blk,
                                                       long long out_off, const float* bias, uint64_t* full_bar, uint32_t full_parity) {
@@ -626,17 +634,30 @@ __device__ __forceinline__ void rope_epilogue_fast128(const DevParams& p, int la
         w2B[kb] = pack_bf16x2(y2B.x, y2B.y);
       }
     }
-    if (okA) {
-      reinterpret_cast<uint4*>(oA)[0] = make_uint4(w1A[0], w1A[1], w1A[2], w1A[3]);
-      reinterpret_cast<uint4*>(oA)[1] = make_uint4(w1A[4], w1A[5], w1A[6], w1A[7]);
-      reinterpret_cast<uint4*>(oA + off2)[0] = make_uint4(w2A[0], w2A[1], w2A[2], w2A[3]);
-      reinterpret_cast<uint4*>(oA + off2)[1] = make_uint4(w2A[4], w2A[5], w2A[6], w2A[7]);
+    // one 32-byte store per thread and block: a thread fills whole 32-byte sectors, a quad a whole 128-byte line (two
+    // 16-byte stores wrote half sectors each)
+    if (p.dbg_nostore == 2) {   // A/B: the two 16-byte stores per block of the first version
+      if (okA) {
+        reinterpret_cast<uint4*>(oA)[0] = make_uint4(w1A[0], w1A[1], w1A[2], w1A[3]);
+        reinterpret_cast<uint4*>(oA)[1] = make_uint4(w1A[4], w1A[5], w1A[6], w1A[7]);
+        reinterpret_cast<uint4*>(oA + off2)[0] = make_uint4(w2A[0], w2A[1], w2A[2], w2A[3]);
+        reinterpret_cast<uint4*>(oA + off2)[1] = make_uint4(w2A[4], w2A[5], w2A[6], w2A[7]);
+      }
+      if (okB) {
+        reinterpret_cast<uint4*>(oB)[0] = make_uint4(w1B[0], w1B[1], w1B[2], w1B[3]);
+        reinterpret_cast<uint4*>(oB)[1] = make_uint4(w1B[4], w1B[5], w1B[6], w1B[7]);
+        reinterpret_cast<uint4*>(oB + off2)[0] = make_uint4(w2B[0], w2B[1], w2B[2], w2B[3]);
+        reinterpret_cast<uint4*>(oB + off2)[1] = make_uint4(w2B[4], w2B[5], w2B[6], w2B[7]);
+      }
+    } else {
+    if (okA && !p.dbg_nostore) {
+      st_global_v8(oA, w1A);
+      st_global_v8(oA + off2, w2A);
     }
-    if (okB) {
-      reinterpret_cast<uint4*>(oB)[0] = make_uint4(w1B[0], w1B[1], w1B[2], w1B[3]);
-      reinterpret_cast<uint4*>(oB)[1] = make_uint4(w1B[4], w1B[5], w1B[6], w1B[7]);
-      reinterpret_cast<uint4*>(oB + off2)[0] = make_uint4(w2B[0], w2B[1], w2B[2], w2B[3]);
-      reinterpret_cast<uint4*>(oB + off2)[1] = make_uint4(w2B[4], w2B[5], w2B[6], w2B[7]);
+    if (okB && !p.dbg_nostore) {
+      st_global_v8(oB, w1B);
+      st_global_v8(oB + off2, w2B);
+    }
     }
   }
 }
@@ -2107,6 +2128,7 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
   p.stat_parts_item = static_cast<int>(ceil_div(q.N, 128));
   p.ln_stat = q.ln_stat; p.ln_parts = q.ln_parts; p.ln_inv_h = q.ln_width > 0 ? 1.0f / static_cast<float>(q.ln_width) : 0.f;
   p.ln_c = q.ln_c;
+  p.dbg_nostore = g_opt.dbg_nostore;
   if (q.stat_out != nullptr)
     DITTO_REQUIRE(q.epilogue == TC_EPI_STORE && q.resid && !q.out_bf16 && q.N % 2 == 0 && !g_force_generic &&
                       q.stat_parts == q.batch_inner * p.stat_parts_item && (q.batch_outer == 1 || q.stat_rows_outer >= q.M),
@@ -2132,8 +2154,10 @@ int launch_tc_gemm(const TcGemmParams& q, cudaStream_t st) {
                   DITTO_E_BADARG, "tc_gemm: glu_perm16 needs the GEGLU epilogue, no deferred LayerNorm, a bias and N % 256 == 0");
   if (q.rope_perm16)
     DITTO_REQUIRE(q.epilogue == TC_EPI_QKV_ROPE && (q.rope_pd == 128 || q.rope_pd == 32) && q.rope_freq != nullptr && q.ln_stat == nullptr &&
-                      q.N % BLOCK_N == 0 && q.hidden % BLOCK_N == 0 && q.out_bf16 && q.ldo % 8 == 0,
-                  DITTO_E_BADARG, "tc_gemm: rope_perm16 needs pd = 128, on-the-fly frequencies, no deferred LayerNorm, N and hidden % 256 == 0");
+                      q.N % BLOCK_N == 0 && q.hidden % BLOCK_N == 0 && q.out_bf16 && q.ldo % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(q.out) & 31) == 0 && (q.batch_inner * q.batch_outer == 1 || (q.so_inner % 16 == 0 && q.so_outer % 16 == 0)),
+                  DITTO_E_BADARG, "tc_gemm: rope_perm16 needs pd = 128 or 32, on-the-fly frequencies, no deferred LayerNorm, N and hidden % 256 == 0, "
+                                  "a 32-byte aligned output with a row stride of a multiple of 16 (32-byte stores)");
   // kernel variant: the lean compile-time epilogues cover the hot cases, anything else takes the generic one
   int ke;
   if (q.epilogue == TC_EPI_GEGLU) ke = K_GEGLU;

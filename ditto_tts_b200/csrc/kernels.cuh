@@ -10,7 +10,7 @@ namespace ditto {
 // reads the environment; tools / tests set these through the C-ABI before creating an engine.
 struct DebugOptions {
   // gemm_tc.cu (read at launch time)
-  int no_pair = 0, cluster_m = 0, cluster_n = 0, generic_epi = 0, stages_1cta = 0, stages_pair = 0, no_mcast = 0;
+  int no_pair = 0, cluster_m = 0, cluster_n = 0, generic_epi = 0, stages_1cta = 0, stages_pair = 0, no_mcast = 0, dbg_nostore = 0;
   // cross_fused.cu
   int xf_rows = 0;
   // engine.cu (read by ditto_engine_create)
