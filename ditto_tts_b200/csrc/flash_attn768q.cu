@@ -698,6 +698,37 @@ std::mutex g_q7_mutex;
 // The four-CTA kernel pays when 256-row query tiles do not pad much more than 128-row tiles would (T = 750: 768 = 768).
 bool flash768_quad_preferred(int T) { return round_up(T, 2 * Q7_BM) * 100 <= round_up(T, Q7_BM) * 120; }
 
+// co-resident four-CTA clusters on the current device (queried once per device); <= 0: cannot be scheduled
+static int q7_clusters(DeviceState* ds) {
+  std::lock_guard<std::mutex> lock(g_q7_mutex);
+  if (ds->f768q_clusters == 0) {
+    int n = 0;
+    if (cudaFuncSetAttribute(flash_attn768q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q7_SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 4;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.blockDim = dim3(Q7_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = Q7_SMEM_BYTES;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(static_cast<unsigned>(4 * std::max(ds->num_sms, 4)), 1, 1);
+      if (cudaOccupancyMaxActiveClusters(&n, flash_attn768q_kernel, &cfg) != cudaSuccess) n = 0;
+    }
+    (void)cudaGetLastError();
+    ds->f768q_clusters = n > 0 ? n : -1;
+  }
+  return ds->f768q_clusters;
+}
+
+bool flash768_quad_schedulable() {
+  if (tc_gemm_init() != 0) return false;
+  DeviceState* ds = device_state();
+  return ds != nullptr && q7_clusters(ds) > 0;
+}
+
 int launch_flash768_quad(const Flash768Params& q, cudaStream_t st) {
   DITTO_TRY(tc_gemm_init());
   DITTO_REQUIRE(flash768_supported(q.H, 1, q.T), DITTO_E_UNSUPPORTED, "flash768: single head of 768 only");
@@ -718,18 +749,8 @@ int launch_flash768_quad(const Flash768Params& q, cudaStream_t st) {
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  {
-    std::lock_guard<std::mutex> lock(g_q7_mutex);
-    if (ds->f768q_clusters == 0) {  // per device
-      DITTO_CUDA(cudaFuncSetAttribute(flash_attn768q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q7_SMEM_BYTES));
-      cfg.gridDim = dim3(static_cast<unsigned>(4 * ds->num_sms), 1, 1);
-      int n = 0;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, flash_attn768q_kernel, &cfg);
-      if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
-      ds->f768q_clusters = n > 0 ? n : -1;
-    }
-  }
-  DITTO_REQUIRE(ds->f768q_clusters > 0, DITTO_E_UNSUPPORTED, "flash768: four-CTA clusters cannot be scheduled on this device");
+  const int max_clusters = q7_clusters(ds);
+  DITTO_REQUIRE(max_clusters > 0, DITTO_E_UNSUPPORTED, "flash768: four-CTA clusters cannot be scheduled on this device");
   TcOperand Q, K, V;
   Q.ptr = q.qkv; Q.rows = q.T; Q.cols = Q7_D; Q.ld = q.ld; Q.s_outer = static_cast<int64_t>(q.T) * q.ld;
   K = Q; K.ptr = q.qkv + Q7_D;
@@ -752,7 +773,7 @@ int launch_flash768_quad(const Flash768Params& q, cudaStream_t st) {
   p.trace = DITTO_F7_TRACE ? tc_gemm_debug_counters() : nullptr;
   const double rows = static_cast<double>(q.n_seq) * q.T;
   ProfScope prof(q.tag, st, 4.0 * q.T * static_cast<double>(q.T) * Q7_D * q.n_seq, rows * Q7_D * (6.0 + 8.0 + (q.u_out ? 2.0 : 0.0)));
-  const int clusters = static_cast<int>(std::min<int64_t>(ds->f768q_clusters, items));
+  const int clusters = static_cast<int>(std::min<int64_t>(max_clusters, items));
   cfg.gridDim = dim3(static_cast<unsigned>(4 * clusters), 1, 1);
   void* args[4] = {&mq, &mk, &mv, &p};
   DITTO_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(flash_attn768q_kernel), args));

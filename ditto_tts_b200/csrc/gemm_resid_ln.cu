@@ -356,6 +356,40 @@ int gemm_resid_ln_weight_row(int r) {
   return blk * 64 + 16 * (kb / 2) + 4 * q + 2 * (kb % 2) + e;
 }
 
+// co-resident clusters of `csize` CTAs on the current device (queried once per device and size); <= 0: cannot be scheduled
+static int rl_clusters(int csize) {
+  DeviceState* ds = device_state();
+  int dev_id = 0;
+  if (ds == nullptr || cudaGetDevice(&dev_id) != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lock(g_rl_mutex);
+  auto key = std::make_pair(dev_id, csize);
+  auto it = g_rl_clusters.find(key);
+  if (it == g_rl_clusters.end()) {
+    int n = 0;
+    if (cudaFuncSetAttribute(tc_gemm_resid_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.blockDim = dim3(RL_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = RL_SMEM_BYTES;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(static_cast<unsigned>(csize * std::max(ds->num_sms, 1)), 1, 1);
+      if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_resid_ln_kernel, &cfg) != cudaSuccess) n = 0;
+    }
+    (void)cudaGetLastError();
+    it = g_rl_clusters.emplace(key, n > 0 ? n : -1).first;
+  }
+  return it->second;
+}
+
+bool gemm_resid_ln_schedulable(int N) {
+  return N > 0 && N % RL_BN == 0 && N / RL_BN <= RL_MAX_NT && tc_gemm_init() == 0 && rl_clusters(2 * (N / RL_BN)) > 0;
+}
+
 int launch_gemm_resid_ln(const GemmResidLnParams& q, cudaStream_t st) {
   DITTO_TRY(tc_gemm_init());
   DITTO_REQUIRE(q.A && q.W && q.h && q.bias && q.M > 0, DITTO_E_BADARG, "gemm_resid_ln: null argument");
@@ -388,21 +422,7 @@ int launch_gemm_resid_ln(const GemmResidLnParams& q, cudaStream_t st) {
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int clusters = 0;
-  {
-    std::lock_guard<std::mutex> lock(g_rl_mutex);
-    auto key = std::make_pair(dev_id, csize);
-    auto it = g_rl_clusters.find(key);
-    if (it == g_rl_clusters.end()) {
-      DITTO_CUDA(cudaFuncSetAttribute(tc_gemm_resid_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_BYTES));
-      cfg.gridDim = dim3(static_cast<unsigned>(csize * ds->num_sms), 1, 1);
-      int n = 0;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, tc_gemm_resid_ln_kernel, &cfg);
-      if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
-      it = g_rl_clusters.emplace(key, n > 0 ? n : -1).first;
-    }
-    clusters = it->second;
-  }
+  int clusters = rl_clusters(csize);
   DITTO_REQUIRE(clusters > 0, DITTO_E_UNSUPPORTED, "gemm_resid_ln: this cluster size cannot be scheduled on the device");
   TcOperand A, B;
   A.ptr = q.A; A.rows = q.M; A.cols = q.K; A.ld = q.lda;

@@ -206,6 +206,7 @@ struct Flash768Params {
 bool flash768_supported(int H, int heads, int T);
 int launch_flash768(const Flash768Params& p, cudaStream_t st);   // picks the two- or the four-CTA kernel
 bool flash768_quad_preferred(int T);
+bool flash768_quad_schedulable();   // four-CTA clusters fit the current device (else the two-CTA kernel is used)
 int launch_flash768_quad(const Flash768Params& p, cudaStream_t st);   // flash_attn768q.cu
 
 // ---- gemm_resid_ln.cu: h += A W^T + b (fp32, in place) and u = LayerNorm(h) gamma + beta (bf16) in one cluster kernel ----
@@ -220,6 +221,7 @@ struct GemmResidLnParams {
   int tag = PC_TC_OTHER;
 };
 bool gemm_resid_ln_supported(int N, int K);
+bool gemm_resid_ln_schedulable(int N);   // clusters of 2 N / 256 CTAs fit the current device
 int gemm_resid_ln_weight_row(int packed_row);   // source row of a packed weight row
 int launch_gemm_resid_ln(const GemmResidLnParams& p, cudaStream_t st);
 
