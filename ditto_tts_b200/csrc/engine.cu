@@ -70,6 +70,7 @@ struct Arena {
 
 struct LayerPack {
   bf16 *w_qkv = nullptr, *wc_in = nullptr, *wc_o = nullptr, *w_glu = nullptr, *w_fc2 = nullptr;
+  bf16* wc_o_p4 = nullptr;   // cross_attn.out_proj rows in the perm4 order of gemm_resid_ln.cu (fc2_ln engines; wc_o stays plain for the fold)
   float *b_qkv = nullptr, *b_glu = nullptr;  // permuted / interleaved copies
   // deferred LayerNorm (DITTO_F_DEFER_LN): w_qkv / w_glu carry gamma1 / gamma3, b_* carry W beta, c_* = row sums of the
   // scaled bf16 weights; wq_g / bq_g = cross-attention query projection with gamma2 / beta2 folded in (folded cross path)
@@ -563,6 +564,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           if (!dln2) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), ug, true, Mg, H, st));
         }
         void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
+        bool norm3_done = false;   // a fused kernel of this group also wrote norm3's output
         if (fold_active(e, S)) {
           // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
           const int heads = e->heads;
@@ -620,11 +622,21 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           const bf16* kc = static_cast<const bf16*>(kv);
           DITTO_TRY(attention_bf16(e, wg, qc, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, n, static_cast<int>(T),
                                    static_cast<int>(S), sqrt_inv_d, oc, true, H, T * H, nullptr, st, true));
+          if (e->fc2_ln && !dln) {
+            // out_proj + bias + residual AND norm3 in one cluster kernel (gemm_resid_ln.cu)                 DiT.py:148-151
+            GemmResidLnParams f;
+            f.A = oc; f.lda = H; f.W = lp.wc_o_p4; f.ldw = H; f.bias = e->LW(i, "cross_attn.out_proj.bias"); f.h = hg; f.ldh = H;
+            f.gamma = e->LW(i, "norm3.weight"); f.beta = e->LW(i, "norm3.bias"); f.u = ug; f.ldu = H;
+            f.M = static_cast<int>(Mg); f.N = H; f.K = H; f.tag = PC_TC_CROSS_OUT;
+            DITTO_TRY(launch_gemm_resid_ln(f, st));
+            norm3_done = true;
+          } else {
           DITTO_TRY(tc_nt(oc, H, lp.wc_o, H, hg, false, H, e->LW(i, "cross_attn.out_proj.bias"), hg, H, 0, dln ? u : nullptr, H,
                           static_cast<int>(Mg), H, H, st, PC_TC_CROSS_OUT, dln ? w.lnstat : nullptr, w.ln_parts_h));
+          }
         }
-        // norm3 of a group that did not take the fused kernel (which writes it itself)                    DiT.py:151
-        if (!dln) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), ug, true, Mg, H, st));
+        // norm3 of a group that did not take a fused kernel (which writes it itself)                      DiT.py:151
+        if (!dln && !norm3_done) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), ug, true, Mg, H, st));
       }
       DITTO_TRY(fork.end());
       // ---- gated MLP                                                                                  DiT.py:150-155
@@ -1031,6 +1043,10 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
                               e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), nullptr);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.in_proj_weight"), 3ll * H * H, &lp.wc_in);
       if (!rc) rc = cast_new(e->LW(i, "cross_attn.out_proj.weight"), static_cast<int64_t>(H) * H, &lp.wc_o);
+      if (!rc && e->fc2_ln) {
+        if (!lp.wc_o_p4) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.wc_o_p4), sizeof(bf16) * static_cast<int64_t>(H) * H);
+        if (!rc) rc = launch_pack_rows(e->LW(i, "cross_attn.out_proj.weight"), lp.wc_o_p4, nullptr, nullptr, d_fc2, H, H, st, nullptr, nullptr, nullptr);
+      }
       if (!rc && e->fc2_ln) {   // rows in the order the float4 residual + LayerNorm epilogue wants (gemm_resid_ln.cu)
         if (!lp.w_fc2) rc = dev_alloc(e, reinterpret_cast<void**>(&lp.w_fc2), sizeof(bf16) * 4ll * H * H);
         if (!rc) rc = launch_pack_rows(e->LW(i, "mlp_fc2.weight"), lp.w_fc2, nullptr, nullptr, d_fc2, H, 4 * H, st, nullptr, nullptr, nullptr);
