@@ -55,7 +55,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 enum ProfClass {
   PC_TC_PROJ_IN = 0, PC_TC_QKV, PC_TC_SELF_SCORES, PC_TC_SELF_PV, PC_TC_CROSS_Q, PC_TC_CROSS_SCORES, PC_TC_CROSS_PV,
   PC_TC_CROSS_OUT, PC_TC_GLU, PC_TC_FC2, PC_TC_PROJ_OUT, PC_TC_TEXT_KV, PC_TC_OTHER,
-  PC_SGEMM, PC_LAYERNORM, PC_ADALN, PC_ROPE, PC_SOFTMAX, PC_CFG_UPDATE, PC_ELEMENTWISE, PC_TC_CROSS_FUSED, PC_FLASH_ATTN, PC_FLASH768, PC_COUNT
+  PC_SGEMM, PC_LAYERNORM, PC_ADALN, PC_ROPE, PC_SOFTMAX, PC_CFG_UPDATE, PC_ELEMENTWISE, PC_TC_CROSS_FUSED, PC_FLASH_ATTN, PC_FLASH768,
+  PC_CROSS_FLASH, PC_COUNT
 };
 extern bool g_prof_enabled;
 struct ProfScope {  // records start/stop events around the launches issued in its lifetime (no-op unless enabled)

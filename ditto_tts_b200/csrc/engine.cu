@@ -39,7 +39,7 @@ const char* kProfNames[PC_COUNT] = {"tc_gemm.proj_in", "tc_gemm.qkv_rope", "tc_g
                                     "tc_gemm.cross_scores", "tc_gemm.cross_pv", "tc_gemm.cross_out", "tc_gemm.glu", "tc_gemm.fc2",
                                     "tc_gemm.proj_out", "tc_gemm.text_kv", "tc_gemm.other", "sgemm_f32", "layernorm", "adaln_ln",
                                     "rope", "softmax", "cfg_ddpm_update", "elementwise", "tc_gemm.cross_fused_ln", "tc_gemm.flash_attn",
-                                    "tc_gemm.flash768_ln"};
+                                    "tc_gemm.flash768_ln", "tc_gemm.cross_flash_ln"};
 }  // namespace
 ProfScope::ProfScope(int cls, cudaStream_t stream, double flops, double bytes) : st(stream) {
   if (!g_prof_enabled) return;
@@ -92,6 +92,7 @@ struct ditto_engine {
   bool glu_perm16 = false;  // [fc1; gate] rows packed for the lean GEGLU epilogue (TcGemmParams::glu_perm16)
   bool pv_perm4 = false;    // v columns stored in the order the float4 P.V epilogue wants (TcGemmParams::out_perm4)
   bool qkv_perm16 = false;  // QKV weight rows also permuted inside 64-row blocks for the lean RoPE epilogue (TcGemmParams::rope_perm16)
+  bool cross_flash = false; // folded cross-attention with 64 < S <= 256 text tokens through flash_attn768q<CROSS> (+ residual + norm3)
   bool fc2_ln = false;      // fc2 + residual + the next block's norm1 in one cluster kernel (gemm_resid_ln.cu); w_fc2 rows in perm4 order
   bool flash768 = false;    // one head of 768 (repo default): self-attention + residual + norm2 in one cluster kernel (flash_attn768.cu)
   bool flash_attn = true;   // head_dim 64: self-attention without materialised scores (flash_attn.cu); DITTO_NO_FLASH=1 disables
@@ -211,6 +212,11 @@ static bool fold_active(const ditto_engine* e, int64_t S) {
 static bool fold_ln_active(const ditto_engine* e, int64_t S) {
   const bool want = e->defer_ln || (e->defer_ln2 && cross_fused_supported(1, S, e->H, e->heads));
   return want && fold_active(e, S) && tc_scores_softmax_csize(static_cast<int>(S)) == 1;
+}
+// text lengths the fused single-key-tile kernel (cross_fused.cu, S <= 64) does not cover go through the flash-style kernel
+// (up to two key tiles); the V fold of such a context is built in that kernel's column order
+static bool cross_flash_active(const ditto_engine* e, int64_t S) {
+  return e->cross_flash && e->fused_cross && e->heads == 1 && S <= 256 && fold_active(e, S) && !cross_fused_supported(1, S, e->H, e->heads);
 }
 static CtxLayout ctx_layout(const ditto_engine* e, void* base, int64_t n, int64_t S) {
   Arena a(base);
@@ -569,6 +575,17 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           // scores = sqrt(1/d) (u Wq^T + bq) K^T == sqrt(1/d) u (K Wq)^T + sqrt(1/d) K bq ; out = P (V Wo^T) + bo
           const int heads = e->heads;
           const int64_t Sp = round_up(S, 8);
+          if (!dln && cross_flash_active(e, S)) {
+            // 64 < S <= 256: scores, online softmax, P (V Wo^T), + bo + residual AND norm3 in the flash-style cluster kernel
+            Flash768Params f;
+            f.qkv = ug; f.ld = H; f.n_seq = n; f.T = static_cast<int>(T); f.H = H; f.alpha = sqrt_inv_d; f.h = hg;
+            f.kfold = c.kfold0 + c.kfold_stride * i; f.kf_seq = S * H; f.vfold = c.vfold0 + c.vfold_stride * i; f.vf_seq = Sp * H;
+            f.vf_rows = static_cast<int>(Sp); f.Tk = static_cast<int>(S); f.kbias = c.sbias0 + c.sbias_stride * i; f.kb_seq = Sp;
+            f.out_bias = e->LW(i, "cross_attn.out_proj.bias");
+            f.gamma = e->LW(i, "norm3.weight"); f.beta = e->LW(i, "norm3.bias"); f.u_out = ug; f.tag = PC_CROSS_FLASH;
+            DITTO_TRY(launch_flash768_quad(f, st));
+            continue;
+          }
           if (fuse_cross_group(grp)) {
             // scores + softmax + P.V + out bias + residual + norm3 in one kernel (cross_fused.cu); u is overwritten with LN3(h)
             CrossFusedParams f;
@@ -841,6 +858,8 @@ int32_t ditto_engine_create(const ditto_config_t* cfg, ditto_engine_t** out) {
     // needs the v columns in the 16-byte store order (pv_perm4) and the fused softmax machinery
     e->flash768 = e->fused_attn && e->pv_perm4 && !e->defer_ln && flash768_supported(e->H, e->heads, 1) && !g_opt.no_flash768;
     e->fc2_ln = !e->defer_ln && gemm_resid_ln_supported(e->H, 4 * e->H) && !g_opt.no_fc2_ln && gemm_resid_ln_schedulable(e->H);
+    // needs the perm4-packed out-projection (packed with the fc2_ln weights) for the V fold and four-CTA clusters
+    e->cross_flash = e->flash768 && e->fc2_ln && e->fold_cross && !e->defer_ln2 && !g_opt.no_cross_flash && flash768_quad_schedulable();
   }
   build_expected(e);
   e->layers.resize(e->L);
@@ -1131,7 +1150,8 @@ int32_t ditto_text_context(ditto_engine_t* e, const float* text_emb, int64_t n, 
         // vfold[seq, h*Sp + s, :] = V[seq][:, h*d:(h+1)*d] (S x d) @ Wo[:, h*d:(h+1)*d]^T
         TcGemmParams v;
         v.A.ptr = kvb + H; v.A.rows = S; v.A.cols = d; v.A.ld = 2 * H; v.A.s_inner = d; v.A.s_outer = S * 2 * H;
-        v.B.ptr = e->layers[i].wc_o; v.B.rows = H; v.B.cols = d; v.B.ld = H; v.B.s_inner = d; v.B.s_outer = 0;
+        v.B.ptr = cross_flash_active(e, S) ? e->layers[i].wc_o_p4 : e->layers[i].wc_o;   // output columns in the consumer's order
+        v.B.rows = H; v.B.cols = d; v.B.ld = H; v.B.s_inner = d; v.B.s_outer = 0;
         v.M = static_cast<int>(S); v.N = H; v.K = d; v.batch_inner = heads; v.batch_outer = static_cast<int>(n);
         v.out = vf; v.out_bf16 = true; v.ldo = H; v.so_inner = Sp * H; v.so_outer = static_cast<int64_t>(heads) * Sp * H;
         v.tag = PC_TC_TEXT_KV;
@@ -1381,7 +1401,7 @@ int32_t ditto_debug_option(const char* name, int32_t value) {
       {"pv_transpose", &g_opt.pv_transpose}, {"rope_table", &g_opt.rope_table}, {"rope_generic", &g_opt.rope_generic},
       {"glu_generic", &g_opt.glu_generic}, {"no_rope_fast32", &g_opt.no_rope_fast32}, {"no_pv_perm4", &g_opt.no_pv_perm4},
       {"side_streams", &g_opt.side_streams}, {"no_fused_ln", &g_opt.no_fused_ln}, {"flash768_quad", &g_opt.flash768_quad},
-      {"no_fc2_ln", &g_opt.no_fc2_ln}, {"dbg_nostore", &g_opt.dbg_nostore}};
+      {"no_fc2_ln", &g_opt.no_fc2_ln}, {"no_cross_flash", &g_opt.no_cross_flash}, {"dbg_nostore", &g_opt.dbg_nostore}};
   if (strcmp(name, "reset") == 0) { g_opt = DebugOptions(); return 0; }
   for (const Opt& o : opts)
     if (strcmp(name, o.n) == 0) { *o.p = value; return 0; }

@@ -89,7 +89,10 @@ struct Q7Tr {
 struct Q7Dev {
   unsigned long long* trace;
   int n_seq, T;
+  int Tk;                             // keys per sequence (self-attention: T; cross-attention: text tokens S)
   int m_tiles, k_tiles, num_items;    // m_tiles: 256-row query tiles per utterance
+  const float* kbias; long long kb_seq;   // CROSS: additive score bias per key [n_seq, kb_seq] (already scaled; folded k-bias)
+  const float* obias;                 // CROSS: output bias [768] (cross_attn.out_proj.bias)
   float alpha2;
   float* h;
   const float* gamma; const float* beta;
@@ -127,6 +130,11 @@ __device__ __forceinline__ void q7_bulk_copy_to_peer(uint32_t remote_dst, uint32
 }
 __device__ __forceinline__ void q7_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// CROSS = false: self-attention (q, k, v = column thirds of the QKV GEMM output).  CROSS = true: the folded cross-attention
+// of a single-head model with 64 < S <= 256 text tokens (DiT.py:141-151 -> torch MHA math path):
+//   h <- h + softmax(alpha u (K Wq)^T + kbias) (V Wo^T) + bo ;  u <- LayerNorm(h) gamma3 + beta3
+// q = u (norm2 output, overwritten in place with norm3's), k = K-fold [S, 768], v = V-fold [Sp, 768] in the perm4 column order.
+template <bool CROSS>
 __global__ void __launch_bounds__(Q7_THREADS, 1)
     flash_attn768q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, const Q7Dev p) {
@@ -478,7 +486,27 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
         if (!have_s) load_scores();
         have_s = false;
         const int c0 = j * Q7_BN + q2;
-        const bool full = j * Q7_BN + Q7_BN <= p.T;
+        const bool full = j * Q7_BN + Q7_BN <= p.Tk;
+        const float a2 = CROSS ? 1.0f : p.alpha2;   // CROSS: the accumulators are turned into alpha2 s + bias first
+        if (CROSS) {
+          const float* kbp = p.kbias + static_cast<long long>(seq) * p.kb_seq;
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const int cc = c0 + kb * 8;
+            const float b0 = cc < p.Tk ? __ldg(kbp + cc) * 1.4426950408889634f : 0.f;
+            const float b1 = cc + 1 < p.Tk ? __ldg(kbp + cc + 1) * 1.4426950408889634f : 0.f;
+            const float b2 = cc + 64 < p.Tk ? __ldg(kbp + cc + 64) * 1.4426950408889634f : 0.f;
+            const float b3 = cc + 65 < p.Tk ? __ldg(kbp + cc + 65) * 1.4426950408889634f : 0.f;
+            s0[4 * kb] = __float_as_uint(fmaf(__uint_as_float(s0[4 * kb]), p.alpha2, b0));
+            s0[4 * kb + 1] = __float_as_uint(fmaf(__uint_as_float(s0[4 * kb + 1]), p.alpha2, b1));
+            s0[4 * kb + 2] = __float_as_uint(fmaf(__uint_as_float(s0[4 * kb + 2]), p.alpha2, b0));
+            s0[4 * kb + 3] = __float_as_uint(fmaf(__uint_as_float(s0[4 * kb + 3]), p.alpha2, b1));
+            s1[4 * kb] = __float_as_uint(fmaf(__uint_as_float(s1[4 * kb]), p.alpha2, b2));
+            s1[4 * kb + 1] = __float_as_uint(fmaf(__uint_as_float(s1[4 * kb + 1]), p.alpha2, b3));
+            s1[4 * kb + 2] = __float_as_uint(fmaf(__uint_as_float(s1[4 * kb + 2]), p.alpha2, b2));
+            s1[4 * kb + 3] = __float_as_uint(fmaf(__uint_as_float(s1[4 * kb + 3]), p.alpha2, b3));
+          }
+        }
         float mA = -INFINITY, mB = -INFINITY;
         if (full) {
 #pragma unroll
@@ -492,14 +520,14 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {
             const int cc = c0 + kb * 8;
-            if (cc < p.T) { mA = fmaxf(mA, __uint_as_float(s0[4 * kb])); mB = fmaxf(mB, __uint_as_float(s0[4 * kb + 2])); }
-            if (cc + 1 < p.T) { mA = fmaxf(mA, __uint_as_float(s0[4 * kb + 1])); mB = fmaxf(mB, __uint_as_float(s0[4 * kb + 3])); }
-            if (cc + 64 < p.T) { mA = fmaxf(mA, __uint_as_float(s1[4 * kb])); mB = fmaxf(mB, __uint_as_float(s1[4 * kb + 2])); }
-            if (cc + 65 < p.T) { mA = fmaxf(mA, __uint_as_float(s1[4 * kb + 1])); mB = fmaxf(mB, __uint_as_float(s1[4 * kb + 3])); }
+            if (cc < p.Tk) { mA = fmaxf(mA, __uint_as_float(s0[4 * kb])); mB = fmaxf(mB, __uint_as_float(s0[4 * kb + 2])); }
+            if (cc + 1 < p.Tk) { mA = fmaxf(mA, __uint_as_float(s0[4 * kb + 1])); mB = fmaxf(mB, __uint_as_float(s0[4 * kb + 3])); }
+            if (cc + 64 < p.Tk) { mA = fmaxf(mA, __uint_as_float(s1[4 * kb])); mB = fmaxf(mB, __uint_as_float(s1[4 * kb + 2])); }
+            if (cc + 65 < p.Tk) { mA = fmaxf(mA, __uint_as_float(s1[4 * kb + 1])); mB = fmaxf(mB, __uint_as_float(s1[4 * kb + 3])); }
           }
         }
-        mA = quad_max(mA) * p.alpha2;
-        mB = quad_max(mB) * p.alpha2;
+        mA = quad_max(mA) * a2;
+        mB = quad_max(mB) * a2;
         const bool upA = j > 0 && (mA > refA + Q7_TAU || (p.force_rescale && mA > refA));
         const bool upB = j > 0 && (mB > refB + Q7_TAU || (p.force_rescale && mB > refB));
         const float nA = (j == 0 || upA) ? mA : refA, nB = (j == 0 || upB) ? mB : refB;
@@ -526,14 +554,14 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
           uint8_t* pbp = p_own + cb * (Q7_BM * 128) + rB * 128 + q2 * 2;
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {
-            float2 eA = make_float2(ex2_approx(fmaf(__uint_as_float(r[4 * kb]), p.alpha2, -refA)),
-                                    ex2_approx(fmaf(__uint_as_float(r[4 * kb + 1]), p.alpha2, -refA)));
-            float2 eB = make_float2(ex2_approx(fmaf(__uint_as_float(r[4 * kb + 2]), p.alpha2, -refB)),
-                                    ex2_approx(fmaf(__uint_as_float(r[4 * kb + 3]), p.alpha2, -refB)));
+            float2 eA = make_float2(ex2_approx(fmaf(__uint_as_float(r[4 * kb]), a2, -refA)),
+                                    ex2_approx(fmaf(__uint_as_float(r[4 * kb + 1]), a2, -refA)));
+            float2 eB = make_float2(ex2_approx(fmaf(__uint_as_float(r[4 * kb + 2]), a2, -refB)),
+                                    ex2_approx(fmaf(__uint_as_float(r[4 * kb + 3]), a2, -refB)));
             if (!full) {
               const int cc = c0 + cb * 64 + kb * 8;
-              if (cc >= p.T) { eA.x = 0.f; eB.x = 0.f; }
-              if (cc + 1 >= p.T) { eA.y = 0.f; eB.y = 0.f; }
+              if (cc >= p.Tk) { eA.x = 0.f; eB.x = 0.f; }
+              if (cc + 1 >= p.Tk) { eA.y = 0.f; eB.y = 0.f; }
             }
             lA2 = __fadd2_rn(lA2, eA);
             lB2 = __fadd2_rn(lB2, eB);
@@ -585,6 +613,11 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
       auto sweep1 = [&](int cb, const float4(&f)[8]) {
         uint32_t o[32];
         tmem_ld_16x64(t_lane + cb * 64, o);
+        float4 ob[4];
+        if (CROSS) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) ob[jj] = __ldg(reinterpret_cast<const float4*>(p.obias + col_half + q * 4 + cb * 64 + jj * 16));
+        }
         tmem_ld_wait();
         tr.ev(21, cb);
 #pragma unroll
@@ -599,6 +632,10 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
           vB.y = fmaf(iB, __uint_as_float(o[4 * k0 + 3]), f[4 + jj].y);
           vB.z = fmaf(iB, __uint_as_float(o[4 * k1 + 2]), f[4 + jj].z);
           vB.w = fmaf(iB, __uint_as_float(o[4 * k1 + 3]), f[4 + jj].w);
+          if (CROSS) {   // + out_proj bias (the torch MHA output projection, folded into V)
+            vA.x += ob[jj].x; vA.y += ob[jj].y; vA.z += ob[jj].z; vA.w += ob[jj].w;
+            vB.x += ob[jj].x; vB.y += ob[jj].y; vB.z += ob[jj].z; vB.w += ob[jj].w;
+          }
           if (okA && !(p.dbg & 4)) *reinterpret_cast<float4*>(hA + cb * 64 + jj * 16) = vA;
           if (okB && !(p.dbg & 4)) *reinterpret_cast<float4*>(hB + cb * 64 + jj * 16) = vB;
           smA += (vA.x + vA.y) + (vA.z + vA.w);
@@ -703,7 +740,8 @@ static int q7_clusters(DeviceState* ds) {
   std::lock_guard<std::mutex> lock(g_q7_mutex);
   if (ds->f768q_clusters == 0) {
     int n = 0;
-    if (cudaFuncSetAttribute(flash_attn768q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q7_SMEM_BYTES) == cudaSuccess) {
+    if (cudaFuncSetAttribute(flash_attn768q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q7_SMEM_BYTES) == cudaSuccess &&
+        cudaFuncSetAttribute(flash_attn768q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q7_SMEM_BYTES) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -715,7 +753,7 @@ static int q7_clusters(DeviceState* ds) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       cfg.gridDim = dim3(static_cast<unsigned>(4 * std::max(ds->num_sms, 4)), 1, 1);
-      if (cudaOccupancyMaxActiveClusters(&n, flash_attn768q_kernel, &cfg) != cudaSuccess) n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, flash_attn768q_kernel<false>, &cfg) != cudaSuccess) n = 0;
     }
     (void)cudaGetLastError();
     ds->f768q_clusters = n > 0 ? n : -1;
@@ -732,7 +770,11 @@ bool flash768_quad_schedulable() {
 int launch_flash768_quad(const Flash768Params& q, cudaStream_t st) {
   DITTO_TRY(tc_gemm_init());
   DITTO_REQUIRE(flash768_supported(q.H, 1, q.T), DITTO_E_UNSUPPORTED, "flash768: single head of 768 only");
-  DITTO_REQUIRE(q.qkv && q.h && q.n_seq >= 1 && q.ld % 8 == 0 && q.ld >= 3 * Q7_D, DITTO_E_BADARG, "flash768: bad argument");
+  const bool cross = q.kfold != nullptr;
+  DITTO_REQUIRE(q.qkv && q.h && q.n_seq >= 1 && q.ld % 8 == 0 && q.ld >= (cross ? 1 : 3) * Q7_D, DITTO_E_BADARG, "flash768: bad argument");
+  DITTO_REQUIRE(!cross || (q.vfold && q.kbias && q.out_bias && q.Tk >= 1 && q.Tk <= 256 && q.vf_rows >= q.Tk && q.kb_seq >= q.Tk &&
+                           q.kf_seq % 8 == 0 && q.vf_seq % 8 == 0 && (reinterpret_cast<uintptr_t>(q.out_bias) & 15) == 0),
+                DITTO_E_BADARG, "flash768 (cross-attention): folded keys / values, score bias and output bias for 1..256 text tokens");
   DITTO_REQUIRE(q.u_out == nullptr || (q.gamma && q.beta), DITTO_E_BADARG, "flash768: LayerNorm output needs gamma and beta");
   DITTO_REQUIRE((reinterpret_cast<uintptr_t>(q.h) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.u_out) & 7) == 0, DITTO_E_BADARG,
                 "flash768: h must be 16-byte, u 8-byte aligned");
@@ -755,14 +797,20 @@ int launch_flash768_quad(const Flash768Params& q, cudaStream_t st) {
   Q.ptr = q.qkv; Q.rows = q.T; Q.cols = Q7_D; Q.ld = q.ld; Q.s_outer = static_cast<int64_t>(q.T) * q.ld;
   K = Q; K.ptr = q.qkv + Q7_D;
   V = Q; V.ptr = q.qkv + 2 * Q7_D;
+  if (cross) {
+    K.ptr = q.kfold; K.rows = q.Tk; K.ld = Q7_D; K.s_outer = q.kf_seq;
+    V.ptr = q.vfold; V.rows = q.Tk; V.ld = Q7_D; V.s_outer = q.vf_seq;   // rows past Tk: zero-filled by TMA
+  }
   CUtensorMap mq, mk, mv;
   DITTO_TRY(tc_make_map(&mq, Q, 1, q.n_seq, Q7_BK, Q7_BM));
   DITTO_TRY(tc_make_map(&mk, K, 1, q.n_seq, Q7_BK, Q7_BN / 2));
   DITTO_TRY(tc_make_map(&mv, V, 1, q.n_seq, 64, Q7_VKEYS));
   Q7Dev p;
   p.n_seq = static_cast<int>(q.n_seq); p.T = q.T;
+  p.Tk = cross ? q.Tk : q.T;
+  p.kbias = q.kbias; p.kb_seq = q.kb_seq; p.obias = q.out_bias;
   p.m_tiles = static_cast<int>(ceil_div(q.T, 2 * Q7_BM));
-  p.k_tiles = static_cast<int>(ceil_div(q.T, Q7_BN));
+  p.k_tiles = static_cast<int>(ceil_div(p.Tk, Q7_BN));
   const int64_t items = static_cast<int64_t>(p.m_tiles) * q.n_seq;
   DITTO_REQUIRE(items < (1ll << 31), DITTO_E_UNSUPPORTED, "flash768: too many work items");
   p.num_items = static_cast<int>(items);
@@ -772,11 +820,13 @@ int launch_flash768_quad(const Flash768Params& q, cudaStream_t st) {
   p.dbg = q.dbg;
   p.trace = DITTO_F7_TRACE ? tc_gemm_debug_counters() : nullptr;
   const double rows = static_cast<double>(q.n_seq) * q.T;
-  ProfScope prof(q.tag, st, 4.0 * q.T * static_cast<double>(q.T) * Q7_D * q.n_seq, rows * Q7_D * (6.0 + 8.0 + (q.u_out ? 2.0 : 0.0)));
+  ProfScope prof(q.tag, st, 4.0 * q.T * static_cast<double>(p.Tk) * Q7_D * q.n_seq,
+                 rows * Q7_D * ((cross ? 2.0 : 6.0) + 8.0 + (q.u_out ? 2.0 : 0.0)) + (cross ? 4.0 * q.n_seq * static_cast<double>(p.Tk) * Q7_D : 0.0));
   const int clusters = static_cast<int>(std::min<int64_t>(max_clusters, items));
   cfg.gridDim = dim3(static_cast<unsigned>(4 * clusters), 1, 1);
   void* args[4] = {&mq, &mk, &mv, &p};
-  DITTO_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(flash_attn768q_kernel), args));
+  DITTO_CUDA(cudaLaunchKernelExC(&cfg, cross ? reinterpret_cast<const void*>(flash_attn768q_kernel<true>)
+                                             : reinterpret_cast<const void*>(flash_attn768q_kernel<false>), args));
   count_launch();
   return 0;
 }

@@ -20,6 +20,8 @@ struct DebugOptions {
   int flash768_quad = 0;
   // engine.cu: fc2 + residual + next block's norm1 as separate launches (GEMM, LayerNorm) instead of gemm_resid_ln.cu
   int no_fc2_ln = 0;
+  // engine.cu: cross-attention with 64 < S <= 256 text tokens as scores+softmax / P.V / LayerNorm launches instead of flash_attn768q<CROSS>
+  int no_cross_flash = 0;
 };
 extern DebugOptions g_opt;
 
@@ -199,6 +201,13 @@ struct Flash768Params {
   float* h = nullptr;                          // [n_seq * T, 768] fp32 residual stream, updated in place
   const float* gamma = nullptr; const float* beta = nullptr;   // LayerNorm after the attention (norm2)
   bf16* u_out = nullptr;                       // [n_seq * T, 768] its bf16 output; nullptr: no LayerNorm stage
+  // cross-attention mode (four-CTA kernel only; kfold != nullptr): qkv = the query operand u [n_seq * T, ld] (its first 768
+  // columns), keys / values = the folded text projections of ditto_text_context, one score bias per key, an output bias
+  const bf16* kfold = nullptr; int64_t kf_seq = 0;                  // [n_seq][Tk, 768]         K Wq
+  const bf16* vfold = nullptr; int64_t vf_seq = 0; int vf_rows = 0; // [n_seq][vf_rows, 768]    V Wo^T, columns in the perm4 order, zero rows past Tk
+  int Tk = 0;                                                       // text tokens (<= 256)
+  const float* kbias = nullptr; int64_t kb_seq = 0;                 // [n_seq][kb_seq] additive score bias (already scaled)
+  const float* out_bias = nullptr;                                  // [768]
   bool force_rescale = false;                  // tests: take the online-softmax rescale path whenever a tile raises the maximum
   int dbg = 0;                                 // timing experiments (wrong results): ditto_attn_self768 flags >> 8
   int tag = PC_TC_OTHER;

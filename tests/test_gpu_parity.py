@@ -312,8 +312,33 @@ def test_fused_cross_attention_block(dev, B, T, S):
     assert rel(outs[True], outs[False]) <= 6e-3     # same operands, different rounding points of P / LN statistics
 
 
+@pytest.mark.parametrize("B,T,S", [(2, 750, 65), (1, 300, 100), (2, 257, 128), (1, 130, 129), (1, 2250, 192), (2, 90, 256)])
+def test_flash_cross_attention_block(dev, B, T, S):
+    """flash_attn768q<CROSS> (64 < S <= 256 text tokens: scores, online softmax over up to two key tiles, P (V Wo^T), + bo +
+    residual + norm3 in one cluster kernel) against the oracle and against the three-kernel composition (no_cross_flash)."""
+    cfg = O.OracleConfig(768, 2, 1, 256, 768, 50)
+    sd = O.make_state_dict(cfg, 23)
+    x, text, _ = O.make_inputs(B, T, S, cfg, 24)
+    t = torch.arange(B) * 11 + 5
+    want = O.ditto_forward(sd, cfg, x, text, t)
+    outs = {}
+    for fused in (True, False):
+        _lib.debug_option("no_cross_flash", 0 if fused else 1)
+        try:
+            m = build_model(cfg, sd, "bf16", dev)
+            _lib.profile_start()
+            outs[fused] = m(x.to(dev), text.to(dev), t.to(dev))
+            prof = _lib.profile_stop()
+        finally:
+            _lib.debug_option("reset", 0)
+        assert ("tc_gemm.cross_flash_ln" in prof) == fused, sorted(prof)
+        assert ("tc_gemm.cross_pv" in prof) == (not fused)
+        assert rel(outs[fused], want) <= BAR["bf16"], rel(outs[fused], want)
+    assert rel(outs[True], outs[False]) <= 6e-3
+
+
 @pytest.mark.parametrize("env", [{"xf_rows": 88}, {"defer_ln2": 1}, {"rope_generic": 1, "glu_generic": 1}, {"no_pv_perm4": 1},
-                                 {"no_flash768": 1}, {"no_fused_ln": 1}, {"no_fc2_ln": 1}, {"flash768_quad": 1}],
+                                 {"no_flash768": 1}, {"no_fused_ln": 1}, {"no_fc2_ln": 1}, {"flash768_quad": 1}, {"no_cross_flash": 1}],
                          ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
 def test_kernel_variants_behind_switches(dev, env):
     """Every developer switch of DESIGN.md section 9 selects a different kernel / weight packing for the same arithmetic: each

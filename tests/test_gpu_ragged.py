@@ -119,8 +119,8 @@ def test_ragged_rejects_bad_input(dev):
 
 def test_ragged_cross_fusion_is_decided_per_group(dev):
     """One utterance with more than 64 text tokens (cross_fused.cu covers S <= 64) must not push the whole mixed batch onto the
-    three-kernel cross-attention: the short-text groups keep the fused kernel, the long one takes the composition + its own
-    norm3 -- every utterance still equals the per-utterance (unpadded) oracle."""
+    three-kernel cross-attention: the short-text groups keep the fused kernel, the long one takes the flash-style cluster kernel
+    (flash_attn768q<CROSS>, which also writes its norm3) -- every utterance still equals the per-utterance (unpadded) oracle."""
     from ditto_tts_b200 import _lib
     cfg = O.OracleConfig(768, 2, 1, 256, 768, 20)
     sd = O.make_state_dict(cfg, 61)
@@ -131,8 +131,10 @@ def test_ragged_cross_fusion_is_decided_per_group(dev):
     _lib.profile_start()
     outs = m.forward_ragged([x.to(dev) for x in xs], [c.to(dev) for c in texts], t.to(dev))
     prof = _lib.profile_stop()
-    assert "tc_gemm.cross_fused_ln" in prof and "tc_gemm.cross_pv" in prof, sorted(prof)
+    # the long-text group: the flash-style cluster kernel (64 < S <= 256), not the three-kernel composition
+    assert "tc_gemm.cross_fused_ln" in prof and "tc_gemm.cross_flash_ln" in prof and "tc_gemm.cross_pv" not in prof, sorted(prof)
     assert prof["tc_gemm.cross_fused_ln"]["launches"] == 2 * cfg.num_layers      # groups (150, 13) and (90, 64)
+    assert prof["tc_gemm.cross_flash_ln"]["launches"] == cfg.num_layers          # group (300, 100)
     for i, (x, c) in enumerate(zip(xs, texts)):
         ref = O.ditto_forward(sd, cfg, x[None], c[None], t[i:i + 1])[0]
         assert rel(outs[i], ref) <= BAR["bf16"], (i, rel(outs[i], ref))
