@@ -678,6 +678,8 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
         const float meanA = (smA + xA.x) * inv_h, meanB = (smB + xB.x) * inv_h;
         const float rsA = rsqrtf(fmaxf(fmaf(-meanA, meanA, (sqA + xA.y) * inv_h), 0.f) + 1e-5f);
         const float rsB = rsqrtf(fmaxf(fmaf(-meanB, meanB, (sqB + xB.y) * inv_h), 0.f) + 1e-5f);
+        const float2 aA2 = make_float2(rsA, rsA), cA2 = make_float2(-meanA * rsA, -meanA * rsA);
+        const float2 aB2 = make_float2(rsB, rsB), cB2 = make_float2(-meanB * rsB, -meanB * rsB);
         bf16* uA = p.u_out + growA * Q7_D + col_half + q * 4;
         bf16* uB = uA + 8 * Q7_D;
         const float* gp = p.gamma + col_half + q * 4;
@@ -697,15 +699,18 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int k0 = 2 * jj, k1 = 2 * jj + 1;
+            // (o - mean) rstd gamma + beta as two packed FMAs per column pair: o a + c with a = rstd, c = -mean rstd, then * gamma + beta
+            const float2 g01 = make_float2(gm[jj].x, gm[jj].y), g23 = make_float2(gm[jj].z, gm[jj].w);
+            const float2 b01 = make_float2(bt[jj].x, bt[jj].y), b23 = make_float2(bt[jj].z, bt[jj].w);
+            const float2 yA0 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k0]), __uint_as_float(o[4 * k0 + 1])), aA2, cA2), g01, b01);
+            const float2 yA1 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k1]), __uint_as_float(o[4 * k1 + 1])), aA2, cA2), g23, b23);
+            const float2 yB0 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k0 + 2]), __uint_as_float(o[4 * k0 + 3])), aB2, cB2), g01, b01);
+            const float2 yB1 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k1 + 2]), __uint_as_float(o[4 * k1 + 3])), aB2, cB2), g23, b23);
             uint2 wA, wB;
-            wA.x = pack_bf16x2(fmaf((__uint_as_float(o[4 * k0]) - meanA) * rsA, gm[jj].x, bt[jj].x),
-                               fmaf((__uint_as_float(o[4 * k0 + 1]) - meanA) * rsA, gm[jj].y, bt[jj].y));
-            wA.y = pack_bf16x2(fmaf((__uint_as_float(o[4 * k1]) - meanA) * rsA, gm[jj].z, bt[jj].z),
-                               fmaf((__uint_as_float(o[4 * k1 + 1]) - meanA) * rsA, gm[jj].w, bt[jj].w));
-            wB.x = pack_bf16x2(fmaf((__uint_as_float(o[4 * k0 + 2]) - meanB) * rsB, gm[jj].x, bt[jj].x),
-                               fmaf((__uint_as_float(o[4 * k0 + 3]) - meanB) * rsB, gm[jj].y, bt[jj].y));
-            wB.y = pack_bf16x2(fmaf((__uint_as_float(o[4 * k1 + 2]) - meanB) * rsB, gm[jj].z, bt[jj].z),
-                               fmaf((__uint_as_float(o[4 * k1 + 3]) - meanB) * rsB, gm[jj].w, bt[jj].w));
+            wA.x = pack_bf16x2(yA0.x, yA0.y);
+            wA.y = pack_bf16x2(yA1.x, yA1.y);
+            wB.x = pack_bf16x2(yB0.x, yB0.y);
+            wB.y = pack_bf16x2(yB1.x, yB1.y);
             if (okA && !(p.dbg & 8)) *reinterpret_cast<uint2*>(uA + cb * 64 + jj * 16) = wA;
             if (okB && !(p.dbg & 8)) *reinterpret_cast<uint2*>(uB + cb * 64 + jj * 16) = wB;
           }

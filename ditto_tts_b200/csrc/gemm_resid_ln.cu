@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(RL_THREADS, 1)
             gm[jj] = __ldg(reinterpret_cast<const float4*>(p.gamma + colw + cb * 64 + jj * 16));
             bt[jj] = __ldg(reinterpret_cast<const float4*>(p.beta + colw + cb * 64 + jj * 16));
           }
-          const float mA = mean[2 * hh], rA = rstd[2 * hh], mB = mean[2 * hh + 1], rB = rstd[2 * hh + 1];
+          const float2 aA2 = make_float2(rstd[2 * hh], rstd[2 * hh]), cA2 = make_float2(-mean[2 * hh] * rstd[2 * hh], -mean[2 * hh] * rstd[2 * hh]);
+          const float2 aB2 = make_float2(rstd[2 * hh + 1], rstd[2 * hh + 1]),
+                       cB2 = make_float2(-mean[2 * hh + 1] * rstd[2 * hh + 1], -mean[2 * hh + 1] * rstd[2 * hh + 1]);
           bf16* ua = u0 + static_cast<long long>(16 * hh) * p.ldu + cb * 64;
           bf16* ub = ua + 8 * p.ldu;
           const bool okA = ok[2 * hh], okB = ok[2 * hh + 1];
@@ -310,15 +312,18 @@ __global__ void __launch_bounds__(RL_THREADS, 1)
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int k0 = 2 * jj, k1 = 2 * jj + 1;
+            // (o - mean) rstd gamma + beta as two packed FMAs per column pair: o a + c with a = rstd, c = -mean rstd, then * gamma + beta
+            const float2 g01 = make_float2(gm[jj].x, gm[jj].y), g23 = make_float2(gm[jj].z, gm[jj].w);
+            const float2 b01 = make_float2(bt[jj].x, bt[jj].y), b23 = make_float2(bt[jj].z, bt[jj].w);
+            const float2 yA0 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k0]), __uint_as_float(o[4 * k0 + 1])), aA2, cA2), g01, b01);
+            const float2 yA1 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k1]), __uint_as_float(o[4 * k1 + 1])), aA2, cA2), g23, b23);
+            const float2 yB0 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k0 + 2]), __uint_as_float(o[4 * k0 + 3])), aB2, cB2), g01, b01);
+            const float2 yB1 = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(o[4 * k1 + 2]), __uint_as_float(o[4 * k1 + 3])), aB2, cB2), g23, b23);
             uint2 wA, wB;
-            wA.x = pack_bf16x2(fmaf((__uint_as_float(o[4 * k0]) - mA) * rA, gm[jj].x, bt[jj].x),
-                               fmaf((__uint_as_float(o[4 * k0 + 1]) - mA) * rA, gm[jj].y, bt[jj].y));
-            wA.y = pack_bf16x2(fmaf((__uint_as_float(o[4 * k1]) - mA) * rA, gm[jj].z, bt[jj].z),
-                               fmaf((__uint_as_float(o[4 * k1 + 1]) - mA) * rA, gm[jj].w, bt[jj].w));
-            wB.x = pack_bf16x2(fmaf((__uint_as_float(o[4 * k0 + 2]) - mB) * rB, gm[jj].x, bt[jj].x),
-                               fmaf((__uint_as_float(o[4 * k0 + 3]) - mB) * rB, gm[jj].y, bt[jj].y));
-            wB.y = pack_bf16x2(fmaf((__uint_as_float(o[4 * k1 + 2]) - mB) * rB, gm[jj].z, bt[jj].z),
-                               fmaf((__uint_as_float(o[4 * k1 + 3]) - mB) * rB, gm[jj].w, bt[jj].w));
+            wA.x = pack_bf16x2(yA0.x, yA0.y);
+            wA.y = pack_bf16x2(yA1.x, yA1.y);
+            wB.x = pack_bf16x2(yB0.x, yB0.y);
+            wB.y = pack_bf16x2(yB1.x, yB1.y);
             if (okA) *reinterpret_cast<uint2*>(ua + jj * 16) = wA;
             if (okB) *reinterpret_cast<uint2*>(ub + jj * 16) = wB;
           }
