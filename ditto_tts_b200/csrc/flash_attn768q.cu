@@ -684,17 +684,15 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
         bf16* uB = uA + 8 * Q7_D;
         const float* gp = p.gamma + col_half + q * 4;
         const float* bp = p.beta + col_half + q * 4;
-#pragma unroll 1
-        for (int cb = 0; cb < Q7_DH / 64; ++cb) {
-          uint32_t o[32];
-          tmem_ld_16x64(t_lane + cb * 64, o);
+        // the TMEM load of chunk cb + 1 is in flight while chunk cb is normalised and stored (tcgen05.wait::ld waits for every
+        // outstanding load, so the next load is issued right after the wait and consumed one iteration later)
+        auto sweep2 = [&](int cb, const uint32_t(&o)[32]) {
           float4 gm[4], bt[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             gm[jj] = __ldg(reinterpret_cast<const float4*>(gp + cb * 64 + jj * 16));
             bt[jj] = __ldg(reinterpret_cast<const float4*>(bp + cb * 64 + jj * 16));
           }
-          tmem_ld_wait();
           tr.ev(23, cb);
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
@@ -713,6 +711,20 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
             wB.y = pack_bf16x2(yB1.x, yB1.y);
             if (okA && !(p.dbg & 8)) *reinterpret_cast<uint2*>(uA + cb * 64 + jj * 16) = wA;
             if (okB && !(p.dbg & 8)) *reinterpret_cast<uint2*>(uB + cb * 64 + jj * 16) = wB;
+          }
+        };
+        {
+          uint32_t o0[32], o1[32];
+          tmem_ld_16x64(t_lane, o0);
+          tmem_ld_wait();
+#pragma unroll 1
+          for (int cb = 0; cb < Q7_DH / 64; cb += 2) {
+            tmem_ld_16x64(t_lane + (cb + 1) * 64, o1);
+            sweep2(cb, o0);
+            tmem_ld_wait();
+            if (cb + 2 < Q7_DH / 64) tmem_ld_16x64(t_lane + (cb + 2) * 64, o0);
+            sweep2(cb + 1, o1);
+            tmem_ld_wait();
           }
         }
       }
