@@ -108,6 +108,7 @@ struct ditto_engine {
   std::vector<void*> owned;                 // everything else cudaMalloc'ed by the engine
   float *time_table = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *rope_freq = nullptr, *coef = nullptr, *qs_buf = nullptr;
   bf16 *w_in16 = nullptr, *w_out16 = nullptr;
+  bf16* w_out_p4 = nullptr;   // proj_out rows in the perm4 order of gemm_resid_ln.cu (fc2_ln engines)
   std::vector<LayerPack> layers;
   // ragged batches: the per-group launches (small attention kernels) are spread over side streams so that groups overlap
   // on the GPU; fork/join with events, which CUDA-graph capture turns into parallel branches.  The mutex serialises the
@@ -732,7 +733,13 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
     return 0;
   }
   // eps = x_skip + proj_out(h)                                              DiTTO.py:93-94
-  if (b16) {
+  if (b16 && e->fc2_ln && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    GemmResidLnParams f;
+    f.A = static_cast<bf16*>(w.xb16); f.lda = H; f.W = e->w_out_p4; f.ldw = H; f.bias = e->W("proj_out.bias"); f.h = out; f.ldh = H;
+    f.resid = w.xskip; f.ldr = H; f.resid_mod = ragged ? 0 : g0.n_x * g0.T;
+    f.M = static_cast<int>(M); f.N = H; f.K = H; f.tag = PC_TC_PROJ_OUT;
+    DITTO_TRY(launch_gemm_resid_ln(f, st));
+  } else if (b16) {
     DITTO_TRY(tc_nt(static_cast<bf16*>(w.xb16), H, e->w_out16, H, out, false, H, e->W("proj_out.bias"), w.xskip, H,
                     ragged ? 0 : g0.n_x * g0.T, nullptr, 0, static_cast<int>(M), H, H, st, PC_TC_PROJ_OUT));
   } else {
@@ -984,6 +991,20 @@ int32_t ditto_engine_finalize(ditto_engine_t* e, void* stream) {
     if (!e->blocks_only) {
       DITTO_TRY(cast_new(e->W("proj_in.weight"), static_cast<int64_t>(H) * H, &e->w_in16));
       DITTO_TRY(cast_new(e->W("proj_out.weight"), static_cast<int64_t>(H) * H, &e->w_out16));
+      if (e->fc2_ln) {   // eps = x_skip + proj_out(h) through the float4-epilogue GEMM of gemm_resid_ln.cu (no LayerNorm stage)
+        std::vector<int> perm(H);
+        for (int r = 0; r < H; ++r) perm[r] = gemm_resid_ln_weight_row(r);
+        int* d_perm = nullptr;
+        DITTO_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_perm), sizeof(int) * H));
+        DITTO_CUDA(cudaMemcpyAsync(d_perm, perm.data(), sizeof(int) * H, cudaMemcpyHostToDevice, st));
+        int rc2 = 0;
+        if (!e->w_out_p4) rc2 = dev_alloc(e, reinterpret_cast<void**>(&e->w_out_p4), sizeof(bf16) * static_cast<int64_t>(H) * H);
+        if (!rc2) rc2 = launch_pack_rows(e->W("proj_out.weight"), e->w_out_p4, nullptr, nullptr, d_perm, H, H, st, nullptr, nullptr, nullptr);
+        cudaError_t se2 = cudaStreamSynchronize(st);
+        cudaFree(d_perm);
+        if (rc2) return rc2;
+        DITTO_CUDA(se2);
+      }
     }
     // row permutations (host-built, tiny)
     std::vector<int> glu_perm(8 * H), qkv_perm(3 * H);

@@ -49,7 +49,8 @@ struct RlDev {
   int M, N, K;
   int n_tiles, m_pairs, num_kb;
   const float* bias;                 // [N], output-column order
-  float* h; long long ldh;           // [M, N] fp32, read (residual) and written in place
+  float* h; long long ldh;           // [M, N] fp32 output; also the residual (in place) unless `resid` is given
+  const float* resid; long long ldr; int resid_mod;   // optional separate residual, row r reads resid[r % resid_mod] (0: r)
   const float* gamma; const float* beta;   // nullptr: no normalisation
   bf16* u; long long ldu;            // [M, N] bf16 output (may be nullptr when gamma == nullptr)
   float inv_n;
@@ -203,9 +204,18 @@ __global__ void __launch_bounds__(RL_THREADS, 1)
       for (int i = 0; i < 4; ++i) ok[i] = r0 + 8 * i < p.M;
       // one step = (hh, cb): 16 rows (r0 + 16 hh, + 8) x 64 columns (cb); residual of the next step requested one step ahead
       float4 f0[8], f1[8];
+      // residual rows: the output rows themselves (in place), or rows of a separate tensor that repeats with period resid_mod
+      // (x_skip is shared by the conditional / unconditional halves of a CFG batch)
+      const float* rrow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = r0 + 8 * i;
+        rrow[i] = p.resid == nullptr ? p.h + static_cast<long long>(rr) * p.ldh + colw
+                                     : p.resid + static_cast<long long>(p.resid_mod > 0 ? rr % p.resid_mod : rr) * p.ldr + colw;
+      }
       auto load_res = [&](int hh, int cb, float4(&f)[8]) {
-        const float* ra = h0 + static_cast<long long>(16 * hh) * p.ldh + cb * 64;
-        const float* rb = ra + 8 * p.ldh;
+        const float* ra = rrow[2 * hh] + cb * 64;
+        const float* rb = rrow[2 * hh + 1] + cb * 64;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           f[jj] = ok[2 * hh] ? *reinterpret_cast<const float4*>(ra + jj * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -400,6 +410,8 @@ int launch_gemm_resid_ln(const GemmResidLnParams& q, cudaStream_t st) {
   DITTO_REQUIRE(q.A && q.W && q.h && q.bias && q.M > 0, DITTO_E_BADARG, "gemm_resid_ln: null argument");
   DITTO_REQUIRE(gemm_resid_ln_supported(q.N, q.K), DITTO_E_UNSUPPORTED, "gemm_resid_ln: N must be 256, 512, 768 or 1024 and K a multiple of 8");
   DITTO_REQUIRE(q.gamma == nullptr || (q.beta != nullptr && q.u != nullptr), DITTO_E_BADARG, "gemm_resid_ln: LayerNorm needs gamma, beta and u");
+  DITTO_REQUIRE(q.resid == nullptr || (q.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(q.resid) & 15) == 0 && q.resid_mod >= 0 && q.resid_mod < (1ll << 31)),
+                DITTO_E_BADARG, "gemm_resid_ln: separate residual must be 16-byte aligned with a row stride that is a multiple of 4");
   DITTO_REQUIRE(q.ldh % 4 == 0 && (q.u == nullptr || q.ldu % 4 == 0) && (reinterpret_cast<uintptr_t>(q.h) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(q.u) & 7) == 0 && (reinterpret_cast<uintptr_t>(q.bias) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(q.gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.beta) & 15) == 0,
@@ -414,6 +426,7 @@ int launch_gemm_resid_ln(const GemmResidLnParams& q, cudaStream_t st) {
   p.m_pairs = static_cast<int>(ceil_div(q.M, 2 * RL_BM));
   p.num_kb = static_cast<int>(ceil_div(q.K, RL_BK));
   p.bias = q.bias; p.h = q.h; p.ldh = q.ldh; p.gamma = q.gamma; p.beta = q.beta; p.u = q.u; p.ldu = q.ldu;
+  p.resid = q.resid; p.ldr = q.ldr; p.resid_mod = static_cast<int>(q.resid_mod);
   p.inv_n = 1.0f / static_cast<float>(q.N);
   const int csize = 2 * p.n_tiles;
   cudaLaunchConfig_t cfg = {};

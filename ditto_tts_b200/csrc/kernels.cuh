@@ -223,7 +223,8 @@ struct GemmResidLnParams {
   const bf16* A = nullptr; int64_t lda = 0;     // [M, K] bf16
   const bf16* W = nullptr; int64_t ldw = 0;     // [N, K] bf16, rows in the perm4 order (gemm_resid_ln_weight_row)
   const float* bias = nullptr;                  // [N], plain column order
-  float* h = nullptr; int64_t ldh = 0;          // [M, N] fp32 residual stream, updated in place
+  float* h = nullptr; int64_t ldh = 0;          // [M, N] fp32 residual stream, updated in place (or the output when `resid` is set)
+  const float* resid = nullptr; int64_t ldr = 0; int64_t resid_mod = 0;   // optional separate residual: row r reads resid[r % resid_mod] (0: row r)
   const float* gamma = nullptr; const float* beta = nullptr;   // LayerNorm after the update; gamma == nullptr: u = bf16(h)
   bf16* u = nullptr; int64_t ldu = 0;           // [M, N] bf16 output (optional when gamma == nullptr)
   int M = 0, N = 0, K = 0;
