@@ -546,6 +546,10 @@ __device__ __forceinline__ void sincos_reduced2(float2 a, float2& s, float2& c) 
 // quad writes whole 128-byte lines (was: 4-byte stores, 16 bytes per line and instruction -- the top stall of this
 // epilogue in ncu).  Biases follow the GEMM column (they are packed with the weight); rotary frequencies and output
 // addresses follow the output column.
+// 128-bit global store with the cache-streaming (evict-first) policy
+__device__ __forceinline__ void st_global_cs_v4(void* ptr, const uint32_t (&w)[4]) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
 // 256-bit global store (sm_100+): eight packed bf16 pairs = 16 consecutive outputs; the address must be 32-byte aligned
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
@@ -716,8 +720,10 @@ __device__ __forceinline__ void geglu_epilogue_fast(const DevParams& p, int lane
         wB[j] = pack_bf16x2(oB.x, oB.y);
       }
       bf16* o = outp + static_cast<long long>(hh * 16) * p.ldo + cb * 32;
-      if (FULL || row0 + hh * 16 + g < p.M) *reinterpret_cast<uint4*>(o) = make_uint4(wA[0], wA[1], wA[2], wA[3]);
-      if (FULL || row0 + hh * 16 + g + 8 < p.M) *reinterpret_cast<uint4*>(o + 8 * p.ldo) = make_uint4(wB[0], wB[1], wB[2], wB[3]);
+      // streaming stores: the hidden activations (147 MB at C2, 2.4 GB at C4) are read once by fc2 and must not push the A
+      // row blocks, which 24 column tiles re-read, out of L2
+      if (FULL || row0 + hh * 16 + g < p.M) st_global_cs_v4(o, wA);
+      if (FULL || row0 + hh * 16 + g + 8 < p.M) st_global_cs_v4(o + 8 * p.ldo, wB);
     }
   }
 }
