@@ -257,13 +257,96 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same for the hot case (bf16 operand, fused LN1, no deferred statistics, H = NV * 128): the row's float4 slots are a
+// compile-time count, so there are no predicated slots and the per-slot address arithmetic folds into immediates (933 -> ~450 warp
+// instructions per row).
+template <int NV>
+__global__ void __launch_bounds__(256)
+    adaln_ln_fast_kernel(const float* __restrict__ x, int64_t n_x, const float* __restrict__ time_table,
+                         const float* __restrict__ text_mod, const int64_t* __restrict__ t, int steps,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ h,
+                         bf16* __restrict__ u, bf16* __restrict__ xcast, int64_t n_seq, int T, bool xcast_all, int* __restrict__ row_pos) {
+  constexpr int H = NV * 128;
+  constexpr float kInvH = 1.0f / static_cast<float>(H);
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_seq * T) return;
+  const int64_t seq = row / T;
+  const int64_t pos = row - seq * T;
+  const int64_t xrow = (seq % n_x) * T + pos;
+  int64_t tt = t != nullptr ? t[seq] : seq;
+  tt = tt < 0 ? 0 : (tt >= steps ? steps - 1 : tt);
+  const float4* xr = reinterpret_cast<const float4*>(x + xrow * H) + lane;
+  const float4* tm = reinterpret_cast<const float4*>(time_table + tt * 2 * H) + lane;
+  const float4* xm = reinterpret_cast<const float4*>(text_mod + seq * 2 * H) + lane;
+  float4 v[NV], sc[NV], sh[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {   // requested before the first reduction: their latency hides behind the statistics of x
+    const float4 ts = __ldg(tm + i * 32), tb = __ldg(tm + H / 4 + i * 32);
+    const float4 xs = __ldg(xm + i * 32), xb = __ldg(xm + H / 4 + i * 32);
+    // scale = 1 + time_scale + text_scale ; shift = time_shift + text_shift   (DiT.py:34-35, same order)
+    sc[i] = make_float4((1.f + ts.x) + xs.x, (1.f + ts.y) + xs.y, (1.f + ts.z) + xs.z, (1.f + ts.w) + xs.w);
+    sh[i] = make_float4(tb.x + xb.x, tb.y + xb.y, tb.z + xb.z, tb.w + xb.w);
+  }
+  if (xcast != nullptr && (xcast_all || seq < n_x)) {
+    uint2* xc = reinterpret_cast<uint2*>(xcast + (xcast_all ? row : xrow) * H) + lane;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xc[i * 32] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+  if (row_pos != nullptr && lane == 0) row_pos[row] = static_cast<int>(pos);
+  auto stats = [&](float& mean, float& rstd) {   // two-pass, the same arithmetic as row_stats
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(sm) * kInvH;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    rstd = rsqrtf(warp_sum(q) * kInvH + 1e-5f);
+  };
+  float mean, rstd;
+  stats(mean, rstd);
+  float4* hr = reinterpret_cast<float4*>(h + row * H) + lane;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x = (v[i].x - mean) * rstd * sc[i].x + sh[i].x;
+    v[i].y = (v[i].y - mean) * rstd * sc[i].y + sh[i].y;
+    v[i].z = (v[i].z - mean) * rstd * sc[i].z + sh[i].z;
+    v[i].w = (v[i].w - mean) * rstd * sc[i].w + sh[i].w;
+    hr[i * 32] = v[i];
+  }
+  stats(mean, rstd);
+  const float4* gp = reinterpret_cast<const float4*>(gamma) + lane;
+  const float4* bp = reinterpret_cast<const float4*>(beta) + lane;
+  uint2* ur = reinterpret_cast<uint2*>(u + row * H) + lane;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(gp + i * 32), b = __ldg(bp + i * 32);
+    ur[i * 32] = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
+                            pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+  }
+}
+
 int launch_adaln_ln(const float* x, int64_t n_x, const float* time_table, const float* text_mod, const int64_t* t,
                     int steps, const float* gamma, const float* beta, float* h, void* u, bool u_bf16, bf16* xcast,
                     int64_t n_seq, int T, int H, cudaStream_t st, float2* stat, bool xcast_all, int* row_pos) {
   DITTO_REQUIRE(H % 4 == 0 && H <= LN_MAXV * 128, DITTO_E_UNSUPPORTED, "adaln: need H % 4 == 0 and H <= 1024");
   const unsigned blocks = static_cast<unsigned>(ceil_div(n_seq * T, 8));
   ProfScope prof(PC_ADALN, st, 0.0, static_cast<double>(n_seq) * T * H * (u_bf16 ? 10 + 2 : 12));
-  if (u_bf16)
+  if (u_bf16 && u != nullptr && stat == nullptr && gamma != nullptr && beta != nullptr && (H == 768 || H == 256 || H == 512 || H == 1024)) {
+    bf16* ub = static_cast<bf16*>(u);
+    switch (H) {   // compile-time row width: no predicated slots
+      case 768: adaln_ln_fast_kernel<6><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h, ub, xcast, n_seq, T, xcast_all, row_pos); break;
+      case 256: adaln_ln_fast_kernel<2><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h, ub, xcast, n_seq, T, xcast_all, row_pos); break;
+      case 512: adaln_ln_fast_kernel<4><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h, ub, xcast, n_seq, T, xcast_all, row_pos); break;
+      default: adaln_ln_fast_kernel<8><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h, ub, xcast, n_seq, T, xcast_all, row_pos); break;
+    }
+  } else if (u_bf16)
     adaln_ln_kernel<bf16><<<blocks, 256, 0, st>>>(x, n_x, time_table, text_mod, t, steps, gamma, beta, h,
                                                   static_cast<bf16*>(u), xcast, n_seq, T, H, stat, xcast_all, row_pos);
   else
