@@ -9,7 +9,10 @@ def apply_opts(argv=None):
     rest, applied = [], {}
     i = 0
     while i < len(argv):
-        if argv[i] == "--opt" and i + 1 < len(argv):
+        if argv[i] == "--lib" and i + 1 < len(argv):      # a differently built library (e.g. the timeline-trace build)
+            _lib.LIB_PATH = argv[i + 1]
+            i += 2
+        elif argv[i] == "--opt" and i + 1 < len(argv):
             k, _, v = argv[i + 1].partition("=")
             _lib.debug_option(k, int(v or 1))
             applied[k] = int(v or 1)
