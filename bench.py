@@ -505,6 +505,23 @@ def run_ours(args):
               "rtf_10s_utterance_batch_latency": ms2_step * K / 1e3 / 10.0,
               "clocks": {k: ck2.get(k) for k in ("sm_mhz", "sm_max_mhz", "samples", "reasons")}}
         del job2
+    # ---------------- one 10 s utterance alone (the metric's RTF half: latency of a single request) ----------------
+    single = None
+    if world == 1 and args.workload == "c4" and not args.no_c2:
+        job1 = UniformJob(torch, D, model, sampler, 1, FRAMES_10S, TEXT_LEN, K, dev, 201)
+        ms1, rep1, _, _ = timed_job(torch, job1, K, W, barrier, min_ms=300.0)
+        ms1_job = ms1 / rep1
+        job1.e2e_once()
+        barrier()
+        f0.record()
+        job1.e2e_once()
+        f1.record()
+        barrier()
+        single = {"workload": f"one 10 s utterance (B=1, T={FRAMES_10S}, S={TEXT_LEN}), {K}-step CFG sampling", "job_latency_ms": ms1_job,
+                  "rtf": ms1_job / 1e3 / 10.0, "ms_per_step": ms1_job / K, "repeats": rep1,
+                  "e2e_latency_ms": f0.elapsed_time(f1), "e2e_rtf": f0.elapsed_time(f1) / 1e3 / 10.0,
+                  "launches_per_step": int(job1.launches_per_step)}
+        del job1
     clocks.stop()
 
     # ---------------- reduce over ranks: time = max, frames / flops = sum ----------------
@@ -586,6 +603,8 @@ def run_ours(args):
         }
         if c2 is not None:
             line["c2"] = c2
+        if single is not None:
+            line["rtf"]["single_utterance"] = single
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
