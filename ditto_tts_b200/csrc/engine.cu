@@ -1416,7 +1416,7 @@ int32_t ditto_debug_option(const char* name, int32_t value) {
   struct Opt { const char* n; int* p; };
   const Opt opts[] = {
       {"no_pair", &g_opt.no_pair}, {"cluster_m", &g_opt.cluster_m}, {"cluster_n", &g_opt.cluster_n}, {"generic_epi", &g_opt.generic_epi},
-      {"stages_1cta", &g_opt.stages_1cta}, {"stages_pair", &g_opt.stages_pair}, {"no_mcast", &g_opt.no_mcast}, {"xf_rows", &g_opt.xf_rows},
+      {"stages_1cta", &g_opt.stages_1cta}, {"stages_pair", &g_opt.stages_pair}, {"no_mcast", &g_opt.no_mcast}, {"xf_rows", &g_opt.xf_rows}, {"xf_prefetch", &g_opt.xf_prefetch},
       {"no_defer_ln", &g_opt.no_defer_ln}, {"no_fused_attn", &g_opt.no_fused_attn}, {"no_flash", &g_opt.no_flash},
       {"no_flash768", &g_opt.no_flash768}, {"no_fused_cross", &g_opt.no_fused_cross}, {"defer_ln2", &g_opt.defer_ln2},
       {"pv_transpose", &g_opt.pv_transpose}, {"rope_table", &g_opt.rope_table}, {"rope_generic", &g_opt.rope_generic},

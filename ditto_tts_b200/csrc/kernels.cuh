@@ -13,6 +13,7 @@ struct DebugOptions {
   int no_pair = 0, cluster_m = 0, cluster_n = 0, generic_epi = 0, stages_1cta = 0, stages_pair = 0, no_mcast = 0, dbg_nostore = 0;
   // cross_fused.cu
   int xf_rows = 0;
+  int xf_prefetch = 0;   // > 0: L2 prefetch of the residual stream, n half-chunk jobs ahead (experiment; off by default)
   // engine.cu (read by ditto_engine_create)
   int no_defer_ln = 0, no_fused_attn = 0, no_flash = 0, no_flash768 = 0, no_fused_cross = 0, defer_ln2 = 0, pv_transpose = 0,
       rope_table = 0, rope_generic = 0, glu_generic = 0, no_rope_fast32 = 0, no_pv_perm4 = 0, side_streams = -1, no_fused_ln = 0;
