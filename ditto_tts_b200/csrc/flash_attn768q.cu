@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
             umma_commit_2sm_mc(&ring_empty[stage], own_mask);
           }
           __syncwarp();
+          tr.ev(8 + s, j);
           if (++stage == Q7_STAGES) { stage = 0; phase ^= 1u; }
         }
         if (leader) {
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
     uint32_t it = 0, sc = 0, oc = 0, rc = 0, pvc = 0;
     Q7Tr tr; tr.init(p.trace, rank, 1, first == 0 && ew == 0 && lane == 0, t_sync);
     auto rescale_o = [&](float fA, float fB) {
+      tr.ev(25, static_cast<int>(pvc));
       mbar_wait(&pv_done[(pvc - 1) & 3u], ((pvc - 1) >> 2) & 1u);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -598,9 +600,11 @@ __global__ void __launch_bounds__(Q7_THREADS, 1)
           f[4 + jj] = (okB && !(p.dbg & 2)) ? *reinterpret_cast<const float4*>(hB + cb * 64 + jj * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
+      tr.ev(26, it);
       load_res(0, f0);
       load_res(1, f1);
       load_res(2, f2);
+      tr.ev(27, it);
       mbar_wait(&l_bar[par], (it >> 1) & 1u);
       tr.ev(15, it);
       lA += l_x[par * Q7_BM + rA];

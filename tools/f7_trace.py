@@ -47,7 +47,7 @@ _lib.check(lib.ditto_debug_set_counters(P(buf)))
 run()
 torch.cuda.synchronize()
 _lib.check(lib.ditto_debug_set_counters(None))
-KIND = {1: "S.begin", 2: "S.issued", 3: "PV.ready", 4: "PV.issued", 5: "item.issued", 6: "S.feedwait", 7: "PV.feedwait",
+KIND = {8: "PV.stage0_issued", 9: "PV.stage1_issued", 25: "sm.rescale_o", 26: "sm.res_loads_begin", 27: "sm.res_loads_issued", 1: "S.begin", 2: "S.issued", 3: "PV.ready", 4: "PV.issued", 5: "item.issued", 6: "S.feedwait", 7: "PV.feedwait",
         10: "sm.scores_in_regs", 11: "sm.hdr_recv", 12: "sm.decision_sent", 13: "sm.p_free", 14: "sm.P_written", 15: "sm.l_recv",
         16: "sm.o_full", 17: "sm.sweep1_done", 18: "sm.stat_recv", 19: "sm.item_done", 20: "sm.tile_begin", 21: "sm.sweep1_ld", 22: "sm.sweep1_st", 23: "sm.sweep2_ld", 24: "sm.prefetched",
         30: "tma.S_loads_issued", 31: "tma.V_loads_issued"}
