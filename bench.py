@@ -106,6 +106,24 @@ def traffic_for(kernel_class):
     return (float(v) if v is not None else None), t.get("_source", "profiles/traffic.json")
 
 
+def per_class_roofline(prof, peak_tflops, peak_gbs):
+    """Every kernel class of the profiled steps against ITS roofline: the bound is whichever of (algorithmic flops / tensor peak)
+    and (algorithmic bytes / HBM copy peak) takes longer, `frac` = that time / the measured time.  Flops and bytes are what the
+    launchers declare (no credit for padding rows; bytes = the tensors a launch must read and write once)."""
+    out = {}
+    for name, v in sorted(prof.items()):
+        t = v["ms"] / 1e3
+        if t <= 0.0:
+            continue
+        t_tensor = v["flops"] / (peak_tflops * 1e12) if v["flops"] else 0.0
+        t_hbm = v["bytes"] / (peak_gbs * 1e9) if v["bytes"] else 0.0
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        ach = v["flops"] / t / 1e12 if bound == "tensor" else v["bytes"] / t / 1e9
+        out[name] = {"bound": bound, "achieved": round(ach, 1), "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                     "frac": round(max(t_tensor, t_hbm) / t, 3)}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started well before the timed region (nvidia-smi needs up
     to a second to come up on an 8-GPU box); summary() keeps the samples whose arrival time falls inside the timed region."""
@@ -577,6 +595,7 @@ def run_ours(args):
                                    "frac_of_burst": step_tflops_gpu / peaks["burst"],
                                    "frac_of_sustained": step_tflops_gpu / peaks["sustained"]},
                     "per_class_ms_per_step": {k_: round(v["ms"] / prof_steps, 4) for k_, v in sorted(prof.items())},
+                    "per_class": per_class_roofline(prof, peak, peaks["hbm"]),
                     "per_class_launches_per_step": {k_: v["launches"] // prof_steps for k_, v in sorted(prof.items())}}
         cpu = None
         if world == 1:

@@ -70,3 +70,16 @@ def test_traffic_file_names_known_profile_classes():
     keys = [k for k in t if not k.startswith("_")]
     assert "tc_gemm.glu" in keys                       # the dominant kernel of the bench line
     assert all(isinstance(t[k], float) and t[k] > 0 for k in keys)
+
+
+def test_per_class_roofline_picks_the_longer_bound():
+    """A GEMM class is held to the tensor peak, a streaming class to the HBM copy peak; frac = roofline time / measured time."""
+    prof = {"tc_gemm.glu": {"ms": 2.0, "flops": 2.0e12, "bytes": 1.0e9, "launches": 1},      # 2 TFLOP in 2 ms = 1000 TFLOP/s
+            "adaln_ln": {"ms": 1.0, "flops": 0.0, "bytes": 5.0e9, "launches": 1},            # 5 GB in 1 ms = 5000 GB/s
+            "idle": {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0}}
+    out = bench.per_class_roofline(prof, 1400.0, 6500.0)
+    assert "idle" not in out
+    assert out["tc_gemm.glu"]["bound"] == "tensor" and out["tc_gemm.glu"]["unit"] == "TFLOP/s"
+    assert abs(out["tc_gemm.glu"]["achieved"] - 1000.0) < 1e-6 and abs(out["tc_gemm.glu"]["frac"] - 1000.0 / 1400.0) < 1e-3
+    assert out["adaln_ln"]["bound"] == "hbm" and abs(out["adaln_ln"]["frac"] - 5000.0 / 6500.0) < 1e-3
+    assert all(0.0 < v["frac"] <= 1.0 for v in out.values())
