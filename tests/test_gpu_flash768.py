@@ -81,6 +81,16 @@ def test_flash768_vs_torch(dev, n, T):
     assert finite and eo <= 1e-2 and eh <= 3e-3 and eu <= 6e-3, (eo, eh, eu)
 
 
+@pytest.mark.parametrize("n,T", [(70, 750), (200, 40), (150, 100), (12, 2250)])
+def test_flash768_many_items_per_cluster(dev, n, T):
+    """More work items than co-resident clusters: every cluster walks through several items, so the hand-overs between the
+    epilogue of one item and the key loop of the next (TMEM, probability buffers, exchange slots, barrier phases) are exercised
+    under load -- the single-item shapes above cannot see a hazard there.  Run twice: such hazards are timing dependent."""
+    for seed in (0, 1):
+        eo, eh, eu, finite = run(dev, n, T, seed=seed)
+        assert finite and eo <= 1e-2 and eh <= 3e-3 and eu <= 6e-3, (seed, eo, eh, eu)
+
+
 @pytest.mark.parametrize("n,T", [(2, 750), (1, 300), (1, 1500)])
 def test_flash768_rescale_path(dev, n, T):
     """(i) forced: every tile that raises a row maximum rescales O in TMEM; (ii) provoked: keys scaled x4 per 128-key tile, so
