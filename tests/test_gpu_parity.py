@@ -337,6 +337,31 @@ def test_flash_cross_attention_block(dev, B, T, S):
     assert rel(outs[True], outs[False]) <= 6e-3
 
 
+@pytest.mark.parametrize("B,T,S,switch,cls", [(48, 750, 64, "no_fused_cross", "tc_gemm.cross_fused_ln"),
+                                              (24, 750, 100, "no_cross_flash", "tc_gemm.cross_flash_ln"),
+                                              (40, 750, 64, "no_flash768", "tc_gemm.flash768_ln")])
+def test_fused_blocks_under_load_match_their_compositions(dev, B, T, S, switch, cls):
+    """The one-kernel blocks with several tiles / items per CTA or cluster (the shapes above give each CTA a single one, where a
+    hand-over hazard between consecutive tiles cannot show) against the separate-kernel composition of the same arithmetic."""
+    cfg = O.OracleConfig(768, 2, 1, 256, 768, 50)
+    sd = O.make_state_dict(cfg, 25)
+    x, text, _ = O.make_inputs(B, T, S, cfg, 26)
+    t = (torch.arange(B) * 5 + 1) % 50
+    outs = {}
+    for fused in (True, False):
+        _lib.debug_option(switch, 0 if fused else 1)
+        try:
+            m = build_model(cfg, sd, "bf16", dev)
+            _lib.profile_start()
+            outs[fused] = m(x.to(dev), text.to(dev), t.to(dev))
+            prof = _lib.profile_stop()
+        finally:
+            _lib.debug_option("reset", 0)
+        assert (cls in prof) == fused, sorted(prof)
+    assert torch.isfinite(outs[True]).all()
+    assert rel(outs[True], outs[False]) <= 6e-3, rel(outs[True], outs[False])
+
+
 @pytest.mark.parametrize("env", [{"xf_rows": 88}, {"defer_ln2": 1}, {"rope_generic": 1, "glu_generic": 1}, {"no_pv_perm4": 1},
                                  {"no_flash768": 1}, {"no_fused_ln": 1}, {"no_fc2_ln": 1}, {"flash768_quad": 1}, {"no_cross_flash": 1}],
                          ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
