@@ -64,6 +64,9 @@ SIGNATURES = {
     "ditto_p_sample_ragged": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _I32, _F, _P, _P, _P, _I64, _P]),
     "ditto_p_sample_ragged_rng": (_I32, [_P, _P, C.POINTER(SeqGroup), _I64, _P, _P, _I32, _F, _P, _P, _P, _I64, _I32, _P]),
     "ditto_dit_block": (_I32, [_P, _I32, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "ditto_attn_self": (_I32, [_P, _I32, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "ditto_attn_cross": (_I32, [_P, _I32, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "ditto_gated_mlp": (_I32, [_P, _I32, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P]),
     "ditto_adaln_workspace_bytes": (_I64, [_I64, _I64, _I64, _I64]),
     "ditto_adaln": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
     "ditto_rope": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),

@@ -455,10 +455,14 @@ struct Fork {
 // ng == 1 is the uniform batch of ditto_forward (x shared between CFG branches through n_x).
 // block_layer >= 0: ONE DiT block on its own (DiT.forward, DiT.py:100-157 -> ditto_dit_block): x [n, T, H] is the block's input
 // residual stream, out its output; no AdaLN / proj_in / proj_out, t unused.
+// block_stage (block_layer >= 0 only): 0 = the whole block; 1 / 2 / 3 = its self-attention / cross-attention / gated-MLP
+// section alone, each from its own LayerNorm to its residual add (DiT.py:103-139 / :141-148 / :150-155).
 static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGroup* gs, int ng, float* out, void* workspace,
-                        int64_t workspace_bytes, cudaStream_t st, int block_layer = -1) {
+                        int64_t workspace_bytes, cudaStream_t st, int block_layer = -1, int block_stage = 0) {
   const int H = e->H, d = e->d;
   const bool block_only = block_layer >= 0;
+  const int stage = block_only ? block_stage : 0;
+  const bool do_self = stage == 0 || stage == 1, do_cross = stage == 0 || stage == 2, do_mlp = stage == 0 || stage == 3;
   const int l_begin = block_only ? block_layer : 0, l_end = block_only ? block_layer + 1 : e->L;
   Workspace w = ws_layout(e, workspace, gs, ng);
   const int64_t M = w.M;
@@ -481,7 +485,9 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
   if (block_only) {
     DITTO_REQUIRE(!ragged && !dln, DITTO_E_UNSUPPORTED, "dit_block: uniform batches without DITTO_F_DEFER_LN only");
     DITTO_CUDA(cudaMemcpyAsync(w.h, x, static_cast<size_t>(M) * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    DITTO_TRY(launch_layernorm(w.h, e->LW(l_begin, "norm1.weight"), e->LW(l_begin, "norm1.bias"), w.u, b16, M, H, st));  // DiT.py:105
+    const char* nw = stage == 2 ? "norm2.weight" : stage == 3 ? "norm3.weight" : "norm1.weight";     // DiT.py:105 / :143 / :152
+    const char* nb = stage == 2 ? "norm2.bias" : stage == 3 ? "norm3.bias" : "norm1.bias";
+    DITTO_TRY(launch_layernorm(w.h, e->LW(l_begin, nw), e->LW(l_begin, nb), w.u, b16, M, H, st));
   }
   // AdaLN + LN1 of block 0 (+ bf16 copy of x for proj_in)                 DiTTO.py:86, DiT.py:25-40,105
   DITTO_TRY(fork.begin(block_only ? 0 : ng));
@@ -523,7 +529,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
       bf16* u = static_cast<bf16*>(w.u);
       bf16* qkv = static_cast<bf16*>(w.qkv);
       // ---- self-attention: QKV projection (+RoPE), softmax(QK^T/sqrt d)V, + residual (no out_proj)   DiT.py:103-139
-      {
+      if (do_self) {
         TcGemmParams g;
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
         g.B.ptr = lp.w_qkv; g.B.rows = 3 * H; g.B.cols = H; g.B.ld = H;
@@ -557,7 +563,9 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         // norm2 deferred for this group (context built with the gamma2-folded K): whole-model DITTO_F_DEFER_LN, or norm2 only
         const bool dln2 = dln ? dln2_all : fold_ln_active(e, S);
         float2* lnstat_g = w.lnstat ? w.lnstat + grp.row0 * std::max(w.ln_parts_h, w.ln_parts_attn) : nullptr;
-        if (e->flash768 && !dln2 && flash768_supported(H, e->heads, static_cast<int>(T))) {
+        if (!do_self) {
+          // stand-alone cross-attention / MLP section: u already holds that section's LayerNorm of the input
+        } else if (e->flash768 && !dln2 && flash768_supported(H, e->heads, static_cast<int>(T))) {
           // scores, softmax, P.V, + residual AND norm2 in one kernel: no S / P in HBM, no LayerNorm launch     DiT.py:117-143
           Flash768Params f;
           f.qkv = q; f.ld = 3 * H; f.n_seq = n; f.T = static_cast<int>(T); f.H = H; f.alpha = inv_sqrt_d; f.h = hg;
@@ -570,6 +578,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
           // ---- cross-attention (torch MHA math path)                                                   DiT.py:141-148
           if (!dln2) DITTO_TRY(launch_layernorm(hg, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), ug, true, Mg, H, st));
         }
+        if (!do_cross) continue;
         void* kv = static_cast<char*>(c.kv0) + c.kv_stride * i;
         bool norm3_done = false;   // a fused kernel of this group also wrote norm3's output
         if (fold_active(e, S)) {
@@ -658,6 +667,7 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
       }
       DITTO_TRY(fork.end());
       // ---- gated MLP                                                                                  DiT.py:150-155
+      if (!do_mlp) continue;
       {
         TcGemmParams g;
         g.A.ptr = u; g.A.rows = M; g.A.cols = H; g.A.ld = H;
@@ -690,9 +700,10 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
       float* qkv = static_cast<float*>(w.qkv);
       float* qc = static_cast<float*>(w.qc);
       float* oc = static_cast<float*>(w.oc);
+      if (do_self)
       DITTO_TRY(sgemm_nt(u, H, e->LW(i, "attn.in_proj_weight"), H, qkv, 3 * H, e->LW(i, "attn.in_proj_bias"), nullptr, 0, 1.f,
                          static_cast<int>(M), 3 * H, H, st));
-      for (int gi = 0; gi < ng; ++gi) {
+      for (int gi = 0; gi < ng && do_self; ++gi) {
         const SeqGroup& g = gs[gi];
         const Workspace wg = group_view(e, w, g);
         float* q = qkv + g.row0 * 3 * H;
@@ -702,10 +713,11 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         DITTO_TRY(attention_f32(e, wg, q, 3 * H, T * 3 * H, q + H, 3 * H, T * 3 * H, q + 2 * H, 3 * H, T * 3 * H, g.n, static_cast<int>(T),
                                 static_cast<int>(T), inv_sqrt_d, hg, H, T * H, hg, st));
       }
-      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, false, M, H, st));
+      if (do_self && do_cross) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm2.weight"), e->LW(i, "norm2.bias"), u, false, M, H, st));
+      if (do_cross)
       DITTO_TRY(sgemm_nt(u, H, e->LW(i, "cross_attn.in_proj_weight"), H, qc, H, e->LW(i, "cross_attn.in_proj_bias"), nullptr, 0, 1.f,
                          static_cast<int>(M), H, H, st));
-      for (int gi = 0; gi < ng; ++gi) {
+      for (int gi = 0; gi < ng && do_cross; ++gi) {
         const SeqGroup& g = gs[gi];
         const Workspace wg = group_view(e, w, g);
         const CtxLayout c = ctx_layout(e, const_cast<void*>(g.ctx), g.n, g.S);
@@ -714,9 +726,11 @@ static int forward_impl(ditto_engine* e, const float* x, const int64_t* t, SeqGr
         DITTO_TRY(attention_f32(e, wg, qc + g.row0 * H, H, T * H, kc, 2 * H, S * 2 * H, kc + H, 2 * H, S * 2 * H, g.n, static_cast<int>(T),
                                 static_cast<int>(S), sqrt_inv_d, oc + g.row0 * H, H, T * H, nullptr, st));
       }
+      if (do_cross)
       DITTO_TRY(sgemm_nt(oc, H, e->LW(i, "cross_attn.out_proj.weight"), H, w.h, H, e->LW(i, "cross_attn.out_proj.bias"), w.h, H, 1.f,
                          static_cast<int>(M), H, H, st));
-      DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, false, M, H, st));
+      if (do_cross && do_mlp) DITTO_TRY(launch_layernorm(w.h, e->LW(i, "norm3.weight"), e->LW(i, "norm3.bias"), u, false, M, H, st));
+      if (!do_mlp) continue;
       DITTO_TRY(sgemm_nt(u, H, e->LW(i, "mlp_fc1.weight"), H, w.fc1, 4 * H, e->LW(i, "mlp_fc1.bias"), nullptr, 0, 1.f, static_cast<int>(M),
                          4 * H, H, st));
       DITTO_TRY(sgemm_nt(u, H, e->LW(i, "gate.weight"), H, w.gate, 4 * H, e->LW(i, "gate.bias"), nullptr, 0, 1.f, static_cast<int>(M),
@@ -1359,6 +1373,30 @@ int32_t ditto_dit_block(ditto_engine_t* e, int32_t layer, const float* x, const 
   SeqGroup g;
   g.n = n_seq; g.n_x = n_seq; g.T = T; g.S = S; g.ctx = ctx;
   return forward_impl(e, x, nullptr, &g, 1, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), layer);
+}
+
+// the three sections of DiT.forward on their own: LayerNorm -> section -> + residual
+static int32_t dit_section(ditto_engine_t* e, int32_t layer, int stage, const char* what, const float* x, const void* ctx, int64_t n_seq,
+                           int64_t T, int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  DITTO_REQUIRE(e && x && ctx && out && workspace, DITTO_E_BADARG, std::string(what) + ": null argument");
+  DITTO_REQUIRE(e->finalized, DITTO_E_STATE, std::string(what) + ": engine not finalized");
+  DITTO_REQUIRE(layer >= 0 && layer < e->L, DITTO_E_BADARG, std::string(what) + ": layer out of range");
+  DITTO_REQUIRE(n_seq > 0 && T > 0 && S > 0 && T <= e->maxT, DITTO_E_BADARG, std::string(what) + ": bad sizes");
+  SeqGroup g;
+  g.n = n_seq; g.n_x = n_seq; g.T = T; g.S = S; g.ctx = ctx;
+  return forward_impl(e, x, nullptr, &g, 1, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), layer, stage);
+}
+int32_t ditto_attn_self(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T, int64_t S, float* out,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  return dit_section(e, layer, 1, "attn_self", x, ctx, n_seq, T, S, out, workspace, workspace_bytes, stream);
+}
+int32_t ditto_attn_cross(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T, int64_t S, float* out,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  return dit_section(e, layer, 2, "attn_cross", x, ctx, n_seq, T, S, out, workspace, workspace_bytes, stream);
+}
+int32_t ditto_gated_mlp(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T, int64_t S, float* out,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  return dit_section(e, layer, 3, "gated_mlp", x, ctx, n_seq, T, S, out, workspace, workspace_bytes, stream);
 }
 
 int64_t ditto_adaln_workspace_bytes(int64_t n_seq, int64_t H, int64_t time_dim, int64_t text_dim) {

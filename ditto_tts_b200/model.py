@@ -148,15 +148,32 @@ class DiT(nn.Module):
             std = self.rotary(T, x.device)
             if tuple(rotary_pos.shape) != tuple(std.shape) or not torch.equal(rotary_pos.to(std), std):
                 raise DittoError("DiT.forward: rotary_pos must equal RotaryEmbedding.forward(seq_len) (positions 0..T-1)")
+        return self._run("ditto_dit_block", x, text_emb)
+
+    def _run(self, symbol, x, text_emb):
+        n, T, _ = x.shape
         host, layer = self._engine_host()
-        lib = _lib.load()
         ctx = host.text_context(text_emb, name="block_ctx", T_hint=T)
         out = torch.empty_like(x)
         with torch.cuda.device(x.device):
             ws = host.workspace(n, T, text_emb.shape[1])
-            _lib.check(lib.ditto_dit_block(host.engine(), layer, _ptr(x), _ptr(ctx), n, T, text_emb.shape[1], _ptr(out), _ptr(ws),
-                                           ws.numel(), _stream()), "ditto_dit_block")
+            _lib.check(getattr(_lib.load(), symbol)(host.engine(), layer, _ptr(x), _ptr(ctx), n, T, text_emb.shape[1], _ptr(out), _ptr(ws),
+                                                    ws.numel(), _stream()), symbol)
         return out
+
+    @torch.no_grad()
+    def section(self, name, x, text_emb):
+        """One of the three sections of the block on its own, LayerNorm to residual add (``ditto_attn_self`` / ``ditto_attn_cross`` /
+        ``ditto_gated_mlp``): name "self" (DiT.py:103-139), "cross" (:141-148) or "mlp" (:150-155); forward == the three in order.
+        ``text_emb`` [n,S,text_dim] is needed by every section (it sizes the workspace), only "cross" reads it."""
+        symbol = {"self": "ditto_attn_self", "cross": "ditto_attn_cross", "mlp": "ditto_gated_mlp"}.get(name)
+        if symbol is None:
+            raise DittoError("DiT.section: name must be 'self', 'cross' or 'mlp'")
+        x = _need_cuda_f32("x", x)
+        text_emb = _need_cuda_f32("text_emb", text_emb)
+        if x.dim() != 3 or text_emb.dim() != 3 or x.shape[0] != text_emb.shape[0]:
+            raise DittoError("expected x [n,T,H] and text_emb [n,S,text_dim] with the same n")
+        return self._run(symbol, x, text_emb)
 
     def _engine_host(self):
         if self._owner is not None:

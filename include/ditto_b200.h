@@ -206,6 +206,19 @@ int32_t ditto_p_sample_ragged_rng(ditto_engine_t* e, const float* x, const ditto
  * engine's own table = RotaryEmbedding.forward(T) (DiT.py:56-59).  ctx: ditto_text_context of the block's text_emb. */
 int32_t ditto_dit_block(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T,
                         int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* The three sections of that block on their own, each from its LayerNorm to its residual add, same arguments as
+ * ditto_dit_block (ditto_attn_self / ditto_attn_cross):
+ *   ditto_attn_self   x + merge_heads(softmax(rope(q) rope(k)^T / sqrt(d)) v),  q|k|v = norm1(x) attn.in_proj     DiT.py:103-139
+ *   ditto_attn_cross  x + MHA(norm2(x), text, text) (torch math path, out_proj applied)                         DiT.py:141-148
+ *   ditto_gated_mlp   x + fc2(GELU_erf(fc1(u)) * sigmoid(gate(u))),  u = norm3(x)                               DiT.py:150-155
+ * They run the same kernels as the block (flash-style attention, folded / fused cross-attention, GLU GEMM + fc2 cluster GEMM);
+ * ditto_dit_block == the three in this order. */
+int32_t ditto_attn_self(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T,
+                        int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t ditto_attn_cross(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T,
+                         int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t ditto_gated_mlp(ditto_engine_t* e, int32_t layer, const float* x, const void* ctx, int64_t n_seq, int64_t T,
+                        int64_t S, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 /* GlobalAdaLN.forward(x, time_emb, text_emb) (DiT.py:25-40), no engine needed: x [n_seq, T, H], time_emb [n_seq, time_dim],
  * text_emb [n_seq, S, text_dim]; w_time [2H, time_dim], b_time [2H] = time_mlp.1.*; w_text [2H, text_dim], b_text [2H] =
  * text_mlp.1.*; out [n_seq, T, H] (may alias x). */

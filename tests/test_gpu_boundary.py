@@ -113,6 +113,34 @@ def test_standalone_dit_block_and_adaln_vs_oracle(dev, hidden, heads, T, S):
     assert rel(blk(x.to(dev), text.to(dev)), O.dit_block(sd, 0, x, text, O.rotary_angles(T, hidden // heads), heads)) <= BAR["bf16"]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("hidden,heads,T,S", [(768, 1, 300, 20), (768, 1, 257, 100), (768, 12, 130, 9), (256, 4, 77, 33)])
+def test_block_sections_vs_oracle(dev, hidden, heads, T, S, precision):
+    """ditto_attn_self / ditto_attn_cross / ditto_gated_mlp (the three sections of DiT.forward, DiT.py:103-139 / :141-148 /
+    :150-155) against the oracle's self_attention / cross_attention / gated_mlp on the same input, through every attention
+    path (one 768-wide head with the fused and the flash-style cross-attention, head_dim 64, generic), and their composition
+    against the whole block."""
+    cfg = O.OracleConfig(hidden, 2, heads, 64, hidden, 50)
+    sd = O.make_state_dict(cfg, 31)
+    m = build_model(cfg, sd, precision, dev)
+    g = torch.Generator().manual_seed(32)
+    x, text = torch.randn(2, T, hidden, generator=g), torch.randn(2, S, hidden, generator=g)
+    rot = O.rotary_angles(T, hidden // heads)
+    blk, pre = m.blocks[1], "blocks.1."
+    xd, td = x.to(dev), text.to(dev)
+    want = {"self": O.self_attention(sd, pre, x, rot, heads), "cross": O.cross_attention(sd, pre, x, text, heads),
+            "mlp": O.gated_mlp(sd, pre, x)}
+    for name in ("self", "cross", "mlp"):
+        got = blk.section(name, xd, td)
+        assert rel(got, want[name]) <= BAR[precision], (name, rel(got, want[name]))
+    chained = blk.section("mlp", blk.section("cross", blk.section("self", xd, td), td), td)
+    whole = blk(xd, td)
+    assert rel(chained, whole) <= (1e-5 if precision == "fp32" else 6e-3)
+    assert rel(whole, O.dit_block(sd, 1, x, text, rot, heads)) <= BAR[precision]
+    with pytest.raises(D.DittoError):
+        blk.section("attn", xd, td)
+
+
 @pytest.mark.parametrize("b,T,h,d", [(2, 24, 2, 32), (1, 750, 1, 768), (3, 5, 12, 64)])
 def test_apply_rope_vs_oracle(dev, b, T, h, d):
     g = torch.Generator().manual_seed(3)
